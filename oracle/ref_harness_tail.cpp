@@ -1,0 +1,274 @@
+// ref_harness_tail.cpp -- TEST INFRASTRUCTURE ONLY (oracle side; never linked into the product).
+//
+// This file is appended (by oracle/build_ref.sh) AFTER the untouched reference translation unit
+// /root/reference/src/main.cpp, which is streamed into the compiler through `sed` (to flip the
+// compile-time #define switches at src/main.cpp:50,54,55,100) with `main` renamed to
+// `reference_main`.  Because it lives in the same TU it can call the reference's file-scope
+// `static` procedures (src/main.cpp:201-241) and read its `static` global arrays
+// (src/main.cpp:83-197) directly.  Nothing of the reference is copied: this tail only *calls* it.
+//
+// Exported C symbols (ctypes-friendly) let the tests and the golden-vector generator drive the
+// reference stage by stage, exactly in the order of the reference main loop (src/main.cpp:596-663).
+
+#include <map>
+#include <string>
+
+extern "C" {
+
+// ---- life cycle -------------------------------------------------------------------------------
+// mirrors src/main.cpp:511-537 (+ device updates are no-ops on the CPU build)
+int ref_open(const char *datafile, const char *gridfile, const char *logfile, int nthreads)
+{
+    log_open(logfile ? logfile : "/dev/null");
+#ifdef _OPENMP
+    omp_set_num_threads(nthreads > 0 ? nthreads : 1);
+#endif
+    readDataFile((char *)datafile);
+    readGridFile((char *)gridfile);
+    initializeWeight();
+    initializeFluid();
+    initializeWall();
+    initializeDomain();
+    // The reference leaves several malloc'ed arrays unwritten for some particle classes
+    // (DensityA/GravityCenter of solids, the [2][*] rows of the 2D tensors, Force before step 0...).
+    // Fresh large mallocs are zero pages in practice; make that explicit so dumps are reproducible.
+    return 0;
+}
+
+// mirrors src/main.cpp:564-570
+void ref_init(void)
+{
+    calculateInitialNeighbor();
+    calculateNeighbor();
+    calculateDensityA();
+    calculateGravityCenter();
+    calculateDensityP();
+    calculateLamesconstant();
+    calculateNormalizer();
+}
+
+// one procedure by name (stage-level parity)
+int ref_call(const char *name)
+{
+    static std::map<std::string, void (*)()> tab;
+    if (tab.empty()) {
+        tab["calculateWall"] = calculateWall;
+        tab["calculatePeriodicBoundary"] = calculatePeriodicBoundary;
+        tab["resetForce"] = resetForce;
+        tab["resetAccel"] = resetAccel;
+        tab["calculateNeighbor"] = calculateNeighbor;
+        tab["calculateInitialNeighbor"] = calculateInitialNeighbor;
+        tab["calculateDensityA"] = calculateDensityA;
+        tab["calculateGravityCenter"] = calculateGravityCenter;
+        tab["calculateDensityP"] = calculateDensityP;
+        tab["calculateDivergenceP"] = calculateDivergenceP;
+        tab["calculatePhysicalCoefficients"] = calculatePhysicalCoefficients;
+        tab["calculatePressureP"] = calculatePressureP;
+        tab["calculatePressureA"] = calculatePressureA;
+        tab["calculateDiffuseInterface"] = calculateDiffuseInterface;
+        tab["calculateViscosityV"] = calculateViscosityV;
+        tab["calculateGravity"] = calculateGravity;
+        tab["calculateInterfaceForce"] = calculateInterfaceForce;
+        tab["calculateAcceleration"] = calculateAcceleration;
+        tab["calculateConvection"] = calculateConvection;
+        tab["calculateElasticDeformationVector"] = calculateElasticDeformationVector;
+        tab["calculateStress"] = calculateStress;
+        tab["calculateStressForce"] = calculateStressForce;
+        tab["updateElasticPosition"] = updateElasticPosition;
+        tab["calculateLamesconstant"] = calculateLamesconstant;
+        tab["calculateNormalizer"] = calculateNormalizer;
+        tab["calculateVirialStressAtParticle"] = calculateVirialStressAtParticle;
+    }
+    std::map<std::string, void (*)()>::iterator it = tab.find(name);
+    if (it == tab.end()) return -1;
+    it->second();
+    return 0;
+}
+
+// The loop body of src/main.cpp:596-663 + 685-686, without file output.
+// stop_after_fluid!=0 returns right after calculateConvection (before the solid sub-steps).
+int ref_step(int nsteps, int stop_after_fluid)
+{
+    for (int s = 0; s < nsteps; ++s) {
+        calculateWall();
+        calculatePeriodicBoundary();
+        resetForce();
+        resetAccel();
+        calculateNeighbor();
+        calculateDensityA();
+        calculateGravityCenter();
+        calculateDensityP();
+        calculateDivergenceP();
+        calculatePhysicalCoefficients();
+        calculatePressureP();
+        calculatePressureA();
+        calculateDiffuseInterface();
+        calculateViscosityV();
+        calculateGravity();
+        calculateInterfaceForce();
+        calculateAcceleration();
+        calculateConvection();
+        if (stop_after_fluid) return 0;
+        int substeps = (int)(Dt / Elastic_Dt + 0.5);
+        for (int substep = 0; substep < substeps; ++substep) {
+            calculateElasticDeformationVector();
+            calculateStress();
+            calculateStressForce();
+            updateElasticPosition();
+        }
+        Time += Dt;
+    }
+    return 0;
+}
+
+void ref_write_prof(const char *fn) { writeProfFile((char *)fn); }
+void ref_write_vtk(const char *fn) { writeVtkFile((char *)fn); }
+
+// ---- introspection ----------------------------------------------------------------------------
+int ref_int(const char *name)
+{
+    std::string s(name);
+    if (s == "ParticleCount") return ParticleCount;
+    if (s == "FluidParticleBegin") return FluidParticleBegin;
+    if (s == "FluidParticleEnd") return FluidParticleEnd;
+    if (s == "StructureParticleBegin") return StructureParticleBegin;
+    if (s == "StructureParticleEnd") return StructureParticleEnd;
+    if (s == "WallParticleBegin") return WallParticleBegin;
+    if (s == "WallParticleEnd") return WallParticleEnd;
+    if (s == "CellCounts") return CellCounts;
+    if (s == "CellCount0") return CellCount[0];
+    if (s == "CellCount1") return CellCount[1];
+    if (s == "CellCount2") return CellCount[2];
+    if (s == "PowerParticleCount") return PowerParticleCount;
+    if (s == "MAX_NEIGHBOR_COUNT") return MAX_NEIGHBOR_COUNT;
+#ifdef TWO_DIMENSIONAL
+    if (s == "dim") return 2;
+#else
+    if (s == "dim") return 3;
+#endif
+#ifdef Bar_Module
+    if (s == "module") return 1;
+#elif defined(DAM_Module)
+    if (s == "module") return 2;
+#else
+    if (s == "module") return 0;
+#endif
+    return -999999;
+}
+
+double ref_double(const char *name)
+{
+    std::string s(name);
+    if (s == "Time") return Time;
+    if (s == "Dt") return Dt;
+    if (s == "Elastic_Dt") return Elastic_Dt;
+    if (s == "EndTime") return EndTime;
+    if (s == "OutputInterval") return OutputInterval;
+    if (s == "VtkOutputInterval") return VtkOutputInterval;
+    if (s == "ParticleSpacing") return ParticleSpacing;
+    if (s == "ParticleVolume") return ParticleVolume;
+    if (s == "MaxRadius") return MaxRadius;
+    if (s == "RadiusA") return RadiusA;
+    if (s == "RadiusG") return RadiusG;
+    if (s == "RadiusP") return RadiusP;
+    if (s == "RadiusV") return RadiusV;
+    if (s == "Swa") return Swa;
+    if (s == "Swg") return Swg;
+    if (s == "Swp") return Swp;
+    if (s == "Swv") return Swv;
+    if (s == "N0a") return N0a;
+    if (s == "N0p") return N0p;
+    if (s == "R2g") return R2g;
+    if (s == "CofK") return CofK;
+    if (s == "CellWidth") return CellWidth;
+    return -9.99e99;
+}
+
+void ref_set_double(const char *name, double v)
+{
+    std::string s(name);
+    if (s == "Time") Time = v;
+    else if (s == "Dt") Dt = v;
+    else if (s == "Elastic_Dt") Elastic_Dt = v;
+    else if (s == "EndTime") EndTime = v;
+}
+
+// raw pointer to a global array (the caller knows the shape from the name)
+void *ref_ptr(const char *name)
+{
+    std::string s(name);
+    if (s == "Property") return Property;
+    if (s == "Mass") return Mass;
+    if (s == "Position") return Position;
+    if (s == "InitialPosition") return InitialPosition;
+    if (s == "Velocity") return Velocity;
+    if (s == "Force") return Force;
+    if (s == "Acceleration") return Acceleration;
+    if (s == "NeighborCount") return NeighborCount;
+    if (s == "Neighbor") return Neighbor;
+    if (s == "InitialStructureNeighborCount") return InitialStructureNeighborCount;
+    if (s == "InitialStructureNeighbor") return InitialStructureNeighbor;
+    if (s == "CellIndex") return CellIndex;
+    if (s == "CellParticle") return CellParticle;
+    if (s == "CellParticleBegin") return CellParticleBegin;
+    if (s == "CellParticleEnd") return CellParticleEnd;
+    if (s == "DensityA") return DensityA;
+    if (s == "GravityCenter") return GravityCenter;
+    if (s == "PressureA") return PressureA;
+    if (s == "VolStrainP") return VolStrainP;
+    if (s == "DivergenceP") return DivergenceP;
+    if (s == "PressureP") return PressureP;
+    if (s == "Mu") return Mu;
+    if (s == "Lambda") return Lambda;
+    if (s == "Kappa") return Kappa;
+    if (s == "LambdaLames") return LambdaLames;
+    if (s == "MuLames") return MuLames;
+    if (s == "Normalizer") return Normalizer;
+    if (s == "DeformGradient") return DeformGradient;
+    if (s == "Strain") return Strain;
+    if (s == "Stress") return Stress;
+    if (s == "DomainMin") return DomainMin;
+    if (s == "DomainMax") return DomainMax;
+    if (s == "DomainWidth") return DomainWidth;
+    if (s == "CofA") return CofA;
+    if (s == "Density") return Density;
+    if (s == "BulkModulus") return BulkModulus;
+    if (s == "BulkViscosity") return BulkViscosity;
+    if (s == "ShearViscosity") return ShearViscosity;
+    if (s == "SurfaceTension") return SurfaceTension;
+    if (s == "YoungModulus") return YoungModulus;
+    if (s == "PoissonRatio") return PoissonRatio;
+    if (s == "InteractionRatio") return InteractionRatio;
+    if (s == "Gravity") return Gravity;
+    if (s == "WallCenter") return WallCenter;
+    if (s == "WallVelocity") return WallVelocity;
+    if (s == "WallOmega") return WallOmega;
+    if (s == "WallRotation") return WallRotation;
+    return 0;
+}
+
+// zero the arrays the reference never initialises (see ref_open comment); call after ref_open
+void ref_zero_uninitialised(void)
+{
+    const int n = ParticleCount;
+    memset(DensityA, 0, sizeof(double) * n);
+    memset(GravityCenter, 0, sizeof(double) * n * DIM);
+    memset(PressureA, 0, sizeof(double) * n);
+    memset(VolStrainP, 0, sizeof(double) * n);
+    memset(DivergenceP, 0, sizeof(double) * n);
+    memset(PressureP, 0, sizeof(double) * n);
+    memset(Force, 0, sizeof(double) * n * DIM);
+    memset(Acceleration, 0, sizeof(double) * n * DIM);
+    memset(Normalizer, 0, sizeof(double) * n * DIM * DIM);
+    memset(DeformGradient, 0, sizeof(double) * n * DIM * DIM);
+    memset(Strain, 0, sizeof(double) * n * DIM * DIM);
+    memset(Stress, 0, sizeof(double) * n * DIM * DIM);
+    memset(LambdaLames, 0, sizeof(double) * n);
+    memset(MuLames, 0, sizeof(double) * n);
+    memset(NeighborCount, 0, sizeof(int) * n);
+    memset(InitialStructureNeighborCount, 0, sizeof(int) * n);
+    memset(VirialPressureAtParticle, 0, sizeof(double) * n);
+    memset(VirialStressAtParticle, 0, sizeof(double) * n * DIM * DIM);
+}
+
+} // extern "C"
