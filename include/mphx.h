@@ -1,0 +1,208 @@
+/* mphx.h -- C-ABI boundary of the B200-native explicit MPH / total-Lagrangian FSI step.
+ *
+ * The reference (Ryo1011gd/ParticleMethod_FSI) has no plugin/FFI interface: its hot path is 22
+ * `static void f(void)` procedures on file-scope globals, called in fixed order by main()
+ * (src/main.cpp:596-663).  The stable external contract is the CLI (src/main.cpp:501-508), the
+ * file formats (.data :729-786, .grid/.prof :788-982, .vtk :984-1189) and that call order.  This
+ * header is the extern-"C" layer a maintainer would bind instead of the OpenACC regions: plain
+ * pointers and sizes, no C++/torch types, error codes instead of exit(1).
+ *
+ * Every entry point cites the reference interface it replaces.  Arrays crossing the boundary use
+ * the reference's own layout: AoS `double[N][3]` vectors, `double[N][3][3]` tensors, `int[N]`
+ * scalars, ORIGINAL (file) particle order.  The library owns all device memory (cell-sorted SoA).
+ *
+ * There is NO CPU fallback: without an sm_100 device every compute entry point returns
+ * MPHX_ERR_NO_DEVICE.  The file-format and host-constant functions need no GPU.
+ */
+#ifndef MPHX_H_INCLUDED
+#define MPHX_H_INCLUDED
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPHX_TYPE_COUNT 6 /* src/main.cpp:68  (fluid 0-1, structure 2-3, wall 4-5; :69-74) */
+#define MPHX_VERSION 100
+
+/* ---- error codes ---------------------------------------------------------------------------- */
+enum {
+    MPHX_OK = 0,
+    MPHX_ERR_INVALID = -1,    /* bad argument / state                                         */
+    MPHX_ERR_NO_DEVICE = -2,  /* no CUDA device of compute capability 10.x (no CPU fallback)  */
+    MPHX_ERR_CUDA = -3,       /* a CUDA call failed; see mphx_last_error()                    */
+    MPHX_ERR_IO = -4,         /* file could not be opened / parsed  (src/errorfunc.cpp:19-31) */
+    MPHX_ERR_NOMEM = -5,      /* host or device allocation failed   (src/errorfunc.cpp:8-17)  */
+    MPHX_ERR_UNSUPPORTED = -6,/* configuration outside the supported envelope                 */
+    MPHX_ERR_OVERFLOW = -7    /* neighbour capacity exceeded (reference only counts, :1766)   */
+};
+
+/* ---- parameters ----------------------------------------------------------------------------- */
+/* clamp module: the reference selects it with a compile-time #define (src/main.cpp:54-59);
+ * here it is a run-time field.  Only the modules of the BASELINE configs are supported. */
+enum { MPHX_MODULE_NONE = 0, MPHX_MODULE_BAR = 1 /* :54, clamp x0[0]<0.001 :1919 */,
+       MPHX_MODULE_DAM = 2 /* :55, clamp x0[1]<0.002 :1968 */ };
+
+/* ref_compat bits: reproduce reference quirks (SURVEY.md Q-list).  Default: all on. */
+enum { MPHX_COMPAT_DOUBLE_UPDATE = 1 /* Q1: updateElasticPosition advances twice, :2070-2079 */ };
+
+typedef struct mphx_params {
+    int dim;            /* 2 or 3: `#define TWO_DIMENSIONAL` src/main.cpp:50                   */
+    int clamp_module;   /* MPHX_MODULE_*                                                       */
+    int ref_compat;     /* MPHX_COMPAT_* bits                                                  */
+    int reserved0;
+    double time0;             /* Time from line 1 of the grid file          :797               */
+    double dt;                /* Dt                                          :743              */
+    double elastic_dt;        /* ElasticDt                                   :744              */
+    double particle_spacing;  /* l0, grid header                             :799-801          */
+    double domain_min[3];     /*                                             :802-804          */
+    double domain_max[3];
+    double radius_ratio_a;    /* RadiusRatioA (= RadiusRatioG, :1193)         :748             */
+    double radius_ratio_p;    /*                                             :750              */
+    double radius_ratio_v;    /*                                             :751              */
+    double density[MPHX_TYPE_COUNT];          /* :752 */
+    double bulk_modulus[MPHX_TYPE_COUNT];     /* :753 */
+    double bulk_viscosity[MPHX_TYPE_COUNT];   /* :754 */
+    double shear_viscosity[MPHX_TYPE_COUNT];  /* :755 */
+    double surface_tension[MPHX_TYPE_COUNT];  /* :756 (file gives types 0,1,4,5) */
+    double young_modulus[MPHX_TYPE_COUNT];    /* :757 (file gives types 2..5)    */
+    double poisson_ratio[MPHX_TYPE_COUNT];    /* :758 */
+    double interaction_ratio[MPHX_TYPE_COUNT][MPHX_TYPE_COUNT]; /* :759-764 */
+    double gravity[3];                        /* :765 */
+    double wall_center[MPHX_TYPE_COUNT][3];   /* :766-767 (Wall6 -> type 4, Wall7 -> type 5) */
+    double wall_velocity[MPHX_TYPE_COUNT][3];
+    double wall_omega[MPHX_TYPE_COUNT][3];
+} mphx_params;
+
+/* what the driver (not the step) needs from the .data file: src/main.cpp:745-747 */
+typedef struct mphx_run_control {
+    double output_interval;     /* OutputInterval    */
+    double vtk_output_interval; /* VtkOutputInterval */
+    double end_time;            /* EndTime           */
+} mphx_run_control;
+
+/* host-side constants computed once by the reference's initialize* procedures; they must be
+ * bit-identical to the reference (initializeWeight :1191-1309, initializeFluid :1312-1341,
+ * initializeWall :1371-1410, initializeDomain :1412-1469). */
+typedef struct mphx_constants {
+    double particle_volume;                 /* :806-808 */
+    double radius_a, radius_g, radius_p, radius_v, max_radius;
+    double swa, swg, swp, swv, r2g, n0a, n0p;
+    double cof_k, cof_a[MPHX_TYPE_COUNT];
+    double wall_rotation[MPHX_TYPE_COUNT][3][3];
+    double domain_max[3], domain_width[3];  /* after the integer-cell fix-up :1431-1440 */
+    double cell_width;
+    int cell_count[3];
+    int cell_counts;                        /* product (int, like :1429)     */
+    int n0a_count, n0p_count;               /* lattice points inside the radius (logged :1258,1303) */
+    int stencil_range;                      /* ceil((MaxRadius+MARGIN)/CellWidth) :1744 */
+} mphx_constants;
+
+/* Host views for download: any pointer may be NULL (= not wanted).  Shapes as in the reference
+ * (src/main.cpp:102-115,154-164,184-196); everything in ORIGINAL particle order. */
+typedef struct mphx_host_views {
+    int *property;        /* [N]       */
+    double *position;     /* [N][3]    */
+    double *velocity;     /* [N][3]    */
+    double *force;        /* [N][3]    */
+    double *acceleration; /* [N][3]    */
+    double *pressure_p;   /* [N]       */
+    double *vol_strain_p; /* [N]       */
+    double *divergence_p; /* [N]       */
+    double *density_a;    /* [N]       */
+    double *gravity_center; /* [N][3]  */
+    double *pressure_a;   /* [N]       */
+    int *neighbor_count;  /* [N]  NeighborCount with the reference's bit-exact predicate :1764-1772 */
+    int *initial_structure_neighbor_count; /* [N] :1608-1616 */
+    int *cell_index;      /* [N]  CellId of the particle's bucket :1671-1674 */
+    double *normalizer;       /* [N][3][3] */
+    double *deform_gradient;  /* [N][3][3] */
+    double *strain;           /* [N][3][3] */
+    double *stress;           /* [N][3][3] */
+    double *lambda_lames;     /* [N] */
+    double *mu_lames;         /* [N] */
+} mphx_host_views;
+
+typedef struct mphx_ctx mphx_ctx;
+
+/* ---- misc ----------------------------------------------------------------------------------- */
+int mphx_version(void);
+const char *mphx_strerror(int code);
+/* last CUDA / IO diagnostic text of the calling thread ("" if none) */
+const char *mphx_last_error(void);
+/* number of visible sm_100 devices (0 when there is none or no driver) */
+int mphx_device_count(void);
+
+/* ---- file formats (host only; replaces readDataFile/readGridFile/writeProfFile/writeVtkFile) -- */
+void mphx_params_default(mphx_params *p, mphx_run_control *rc);
+/* src/main.cpp:729-786.  Unknown lines are reported through `on_invalid_line` (may be NULL),
+ * exactly the lines the reference logs as `Invalid line in data file`. */
+int mphx_read_data_file(const char *filename, mphx_params *p, mphx_run_control *rc,
+                        void (*on_invalid_line)(const char *line, void *user), void *user);
+/* src/main.cpp:788-929.  Allocates the four arrays with malloc (free with mphx_free_host);
+ * fills time0, particle_spacing, domain_* of *p. */
+int mphx_read_grid_file(const char *filename, mphx_params *p, int *n_out, int **property,
+                        double **position, double **initial_position, double **velocity);
+void mphx_free_host(void *ptr);
+/* src/main.cpp:957-982 (byte-identical text) */
+int mphx_write_prof_file(const char *filename, double time, const mphx_params *p, int n,
+                         const int *property, const double *position,
+                         const double *initial_position, const double *velocity);
+/* src/main.cpp:984-1189 (byte-identical text incl. the duplicated `velocity` section) */
+int mphx_write_vtk_file(const char *filename, int n, const double *initial_position,
+                        const mphx_host_views *fields);
+/* first..last index of each particle class, src/main.cpp:909-929; ranges[6] =
+ * {FluidBegin,FluidEnd,StructureBegin,StructureEnd,WallBegin,WallEnd} (-1 when absent) */
+void mphx_class_ranges(int n, const int *property, int ranges[6]);
+
+/* ---- host constants (no GPU needed) ----------------------------------------------------------- */
+/* initializeWeight/Fluid/Wall/Domain, src/main.cpp:1191-1469 */
+int mphx_compute_constants(const mphx_params *p, mphx_constants *c);
+
+/* ---- context life cycle ------------------------------------------------------------------------ */
+/* replaces `acc enter data` (src/main.cpp:775-784, 830-891) */
+int mphx_create(mphx_ctx **ctx, const mphx_params *p, int device);
+/* replaces `acc exit data` (src/main.cpp:704-723) */
+void mphx_destroy(mphx_ctx *ctx);
+/* replaces `acc update device` (src/main.cpp:549-560, 946-950).  The caller keeps its arrays. */
+int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *position,
+                const double *initial_position, const double *velocity);
+/* replaces src/main.cpp:534-537 + 564-570 (initialize*, calculateInitialNeighbor, first
+ * calculateNeighbor/DensityA/GravityCenter/DensityP, calculateLamesconstant, calculateNormalizer) */
+int mphx_init(mphx_ctx *ctx);
+int mphx_get_constants(const mphx_ctx *ctx, mphx_constants *c);
+
+/* ---- the hot path ------------------------------------------------------------------------------ */
+/* `nsteps` iterations of the loop body src/main.cpp:596-663 followed by Time += Dt (:685).
+ * Enqueues on the context's stream and returns; use mphx_sync (or mphx_download) to wait. */
+int mphx_step(mphx_ctx *ctx, int nsteps);
+/* debugging / stage parity: one step that stops after calculateConvection (:647), i.e. without
+ * the solid sub-steps and without advancing Time */
+int mphx_step_fluid_only(mphx_ctx *ctx);
+int mphx_sync(mphx_ctx *ctx);
+double mphx_time(const mphx_ctx *ctx);
+int mphx_set_time(mphx_ctx *ctx, double time);
+/* replaces `acc update host` (src/main.cpp:987-989); un-permutes to original particle order */
+int mphx_download(mphx_ctx *ctx, const mphx_host_views *views);
+
+/* ---- parity / debug ------------------------------------------------------------------------------ */
+/* The neighbour SETS of calculateNeighbor (src/main.cpp:1730-1810) with its bit-exact predicate,
+ * as CSR in original particle ids, each row sorted ascending.  offsets has N+1 entries.
+ * ids may be NULL to query the total size (returned through offsets[N]). */
+int mphx_debug_neighbors(mphx_ctx *ctx, long long *offsets, int *ids, long long ids_capacity);
+/* InitialStructureNeighbor of calculateInitialNeighbor (src/main.cpp:1497-1644), rows sorted */
+int mphx_debug_initial_structure_neighbors(mphx_ctx *ctx, long long *offsets, int *ids,
+                                           long long ids_capacity);
+
+/* accumulated device time per phase in milliseconds, same split as the reference timer block
+ * (src/main.cpp:695-700): [0] neighbour search, [1] explicit calculation, [2] virial, [3] other */
+int mphx_get_timers(mphx_ctx *ctx, double ms[4]);
+/* number of kernel launches issued by mphx_step since mphx_create (for bench.py gpu_launches) */
+long long mphx_launch_count(const mphx_ctx *ctx);
+/* algorithmic HBM bytes of one step for the resident case (SURVEY.md 8(d) model):
+ * N_f*368 + N_w*260 + N_s*(344+384*n_sub) */
+double mphx_algorithmic_bytes_per_step(const mphx_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPHX_H_INCLUDED */
