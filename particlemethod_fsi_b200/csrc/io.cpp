@@ -1,0 +1,325 @@
+// io.cpp -- the reference's file formats at the drop-in boundary (host only, no GPU needed).
+//
+//   .data  key/value text     readDataFile   src/main.cpp:729-786
+//   .grid  particle text      readGridFile   src/main.cpp:788-929   (written by generator.cpp:839-862)
+//   .prof  same layout        writeProfFile  src/main.cpp:957-982
+//   .vtk   legacy ASCII       writeVtkFile   src/main.cpp:984-1189
+//
+// Output text must be byte-identical to the reference's, so the printf conversions (%e, %d, the
+// float casts of the VTK fields, the duplicated `velocity` block, the blank lines) are kept.
+#include <cerrno>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mphx.h"
+#include "mphx_internal.h"
+
+extern "C" void mphx_params_default(mphx_params *p, mphx_run_control *rc)
+{
+    if (p) {
+        std::memset(p, 0, sizeof(*p));
+        p->dim = 2;                      // the shipped build defines TWO_DIMENSIONAL (:50)
+        p->clamp_module = MPHX_MODULE_BAR; // and Bar_Module (:54)
+        p->ref_compat = MPHX_COMPAT_DOUBLE_UPDATE;
+        p->dt = 1.0e100;         // :91
+        p->elastic_dt = 1.0e100; // :92
+    }
+    if (rc) std::memset(rc, 0, sizeof(*rc));
+}
+
+namespace {
+
+struct DataKey {
+    const char *key;
+    int count;
+    double *dst[9];
+};
+
+// one `else if (sscanf(buf, " Key %lf ...") == count)` arm of :743-767
+bool match_key(const char *line, const DataKey &k)
+{
+    std::string fmt = " ";
+    fmt += k.key;
+    for (int i = 0; i < k.count; ++i) fmt += " %lf";
+    double *d = const_cast<double **>(k.dst)[0];
+    (void)d;
+    int got = 0;
+    switch (k.count) {
+    case 1: got = std::sscanf(line, fmt.c_str(), k.dst[0]); break;
+    case 3: got = std::sscanf(line, fmt.c_str(), k.dst[0], k.dst[1], k.dst[2]); break;
+    case 4: got = std::sscanf(line, fmt.c_str(), k.dst[0], k.dst[1], k.dst[2], k.dst[3]); break;
+    case 6: got = std::sscanf(line, fmt.c_str(), k.dst[0], k.dst[1], k.dst[2], k.dst[3], k.dst[4], k.dst[5]); break;
+    default: return false;
+    }
+    return got == k.count;
+}
+
+bool match_wall(const char *line, const char *name, mphx_params *p, int t)
+{
+    std::string fmt = std::string(" ") + name + "  Center %lf %lf %lf Velocity %lf %lf %lf Omega %lf %lf %lf";
+    double *c = p->wall_center[t], *v = p->wall_velocity[t], *w = p->wall_omega[t];
+    return std::sscanf(line, fmt.c_str(), &c[0], &c[1], &c[2], &v[0], &v[1], &v[2], &w[0], &w[1], &w[2]) == 9;
+}
+
+} // namespace
+
+extern "C" int mphx_read_data_file(const char *filename, mphx_params *p, mphx_run_control *rc,
+                                   void (*on_invalid_line)(const char *, void *), void *user)
+{
+    if (!filename || !p || !rc) return MPHX_ERR_INVALID;
+    FILE *fp = std::fopen(filename, "r");
+    if (!fp) {
+        mphx::set_last_error(std::string("cannot open data file ") + filename);
+        return MPHX_ERR_IO;
+    }
+    double *D = p->density, *K = p->bulk_modulus, *L = p->bulk_viscosity, *M = p->shear_viscosity;
+    double *S = p->surface_tension, *Y = p->young_modulus, *Po = p->poisson_ratio;
+    std::vector<DataKey> keys = {
+        {"Dt", 1, {&p->dt}},
+        {"ElasticDt", 1, {&p->elastic_dt}},
+        {"OutputInterval", 1, {&rc->output_interval}},
+        {"VtkOutputInterval", 1, {&rc->vtk_output_interval}},
+        {"EndTime", 1, {&rc->end_time}},
+        {"RadiusRatioA", 1, {&p->radius_ratio_a}},
+        {"RadiusRatioP", 1, {&p->radius_ratio_p}},
+        {"RadiusRatioV", 1, {&p->radius_ratio_v}},
+        {"Density", 6, {&D[0], &D[1], &D[2], &D[3], &D[4], &D[5]}},
+        {"BulkModulus", 6, {&K[0], &K[1], &K[2], &K[3], &K[4], &K[5]}},
+        {"BulkViscosity", 6, {&L[0], &L[1], &L[2], &L[3], &L[4], &L[5]}},
+        {"ShearViscosity", 6, {&M[0], &M[1], &M[2], &M[3], &M[4], &M[5]}},
+        {"SurfaceTension", 4, {&S[0], &S[1], &S[4], &S[5]}},       // :756
+        {"YoungModulus", 4, {&Y[2], &Y[3], &Y[4], &Y[5]}},         // :757
+        {"PoissonRatio", 4, {&Po[2], &Po[3], &Po[4], &Po[5]}},     // :758
+    };
+    static const char *ir_names[6] = {"InteractionRatio(Type0)", "InteractionRatio(Type1)",
+                                      "InteractionRatio(Type2)", "InteractionRatio(Type3)",
+                                      "InteractionRatio(Type4)", "InteractionRatio(Type5)"};
+    for (int t = 0; t < 6; ++t) {
+        double *r = p->interaction_ratio[t];
+        keys.push_back({ir_names[t], 6, {&r[0], &r[1], &r[2], &r[3], &r[4], &r[5]}});
+    }
+    keys.push_back({"Gravity", 3, {&p->gravity[0], &p->gravity[1], &p->gravity[2]}});
+
+    char buf[1024];
+    while (!std::feof(fp) && !std::ferror(fp)) {
+        if (std::fgets(buf, sizeof(buf), fp) == NULL) continue;
+        if (buf[0] == '#') continue;
+        bool ok = false;
+        for (size_t i = 0; i < keys.size() && !ok; ++i) ok = match_key(buf, keys[i]);
+        if (!ok) ok = match_wall(buf, "Wall6", p, 4); // :766
+        if (!ok) ok = match_wall(buf, "Wall7", p, 5); // :767
+        if (!ok && on_invalid_line) on_invalid_line(buf, user); // :769
+    }
+    std::fclose(fp);
+    return MPHX_OK;
+}
+
+extern "C" void mphx_free_host(void *ptr) { std::free(ptr); }
+
+extern "C" void mphx_class_ranges(int n, const int *property, int ranges[6])
+{
+    for (int i = 0; i < 6; ++i) ranges[i] = -1;
+    for (int i = 0; i < n; ++i) {
+        const int t = property[i];
+        const int cls = (0 <= t && t < 2) ? 0 : (2 <= t && t < 4) ? 1 : (4 <= t && t < 6) ? 2 : -1;
+        if (cls < 0) continue;
+        if (ranges[2 * cls] == -1) ranges[2 * cls] = i;
+        ranges[2 * cls + 1] = i + 1;
+    }
+}
+
+extern "C" int mphx_read_grid_file(const char *filename, mphx_params *p, int *n_out, int **property,
+                                   double **position, double **initial_position, double **velocity)
+{
+    if (!filename || !p || !n_out || !property || !position || !initial_position || !velocity)
+        return MPHX_ERR_INVALID;
+    FILE *fp = std::fopen(filename, "r");
+    if (!fp) {
+        mphx::set_last_error(std::string("cannot open grid file ") + filename);
+        return MPHX_ERR_IO;
+    }
+    char buf[1024];
+    int n = 0;
+    if (!std::fgets(buf, sizeof(buf), fp)) { std::fclose(fp); return MPHX_ERR_IO; }
+    std::sscanf(buf, "%lf", &p->time0); // :797
+    if (!std::fgets(buf, sizeof(buf), fp)) { std::fclose(fp); return MPHX_ERR_IO; }
+    if (std::sscanf(buf, "%d  %lf  %lf %lf %lf  %lf %lf %lf", &n, &p->particle_spacing, // :799-804
+                    &p->domain_min[0], &p->domain_max[0], &p->domain_min[1], &p->domain_max[1],
+                    &p->domain_min[2], &p->domain_max[2]) != 8 || n < 0) {
+        std::fclose(fp);
+        mphx::set_last_error("malformed grid header");
+        return MPHX_ERR_IO;
+    }
+    const size_t N = (size_t)n;
+    int *t = (int *)std::calloc(N ? N : 1, sizeof(int));
+    double *x = (double *)std::calloc(N ? 3 * N : 1, sizeof(double));
+    double *x0 = (double *)std::calloc(N ? 3 * N : 1, sizeof(double));
+    double *v = (double *)std::calloc(N ? 3 * N : 1, sizeof(double));
+    if (!t || !x || !x0 || !v) {
+        std::free(t); std::free(x); std::free(x0); std::free(v);
+        std::fclose(fp);
+        return MPHX_ERR_NOMEM;
+    }
+    for (size_t i = 0; i < N; ++i) { // :896-904; strtol/strtod parse exactly like %d/%lf
+        if (!std::fgets(buf, sizeof(buf), fp)) break;
+        char *s = buf, *e;
+        t[i] = (int)std::strtol(s, &e, 10);
+        if (e == s) continue;
+        s = e;
+        double vals[9];
+        int k = 0;
+        for (; k < 9; ++k) {
+            vals[k] = std::strtod(s, &e);
+            if (e == s) break;
+            s = e;
+        }
+        for (int d = 0; d < 3; ++d) {
+            if (d < k) x[3 * i + d] = vals[d];
+            if (3 + d < k) x0[3 * i + d] = vals[3 + d];
+            if (6 + d < k) v[3 * i + d] = vals[6 + d];
+        }
+    }
+    std::fclose(fp);
+    *n_out = n;
+    *property = t;
+    *position = x;
+    *initial_position = x0;
+    *velocity = v;
+    return MPHX_OK;
+}
+
+namespace {
+// big buffered writer: at 10M particles the per-line fprintf of the reference dominates wall time
+struct Out {
+    FILE *fp;
+    std::vector<char> buf;
+    size_t used = 0;
+    explicit Out(FILE *f) : fp(f), buf(1 << 22) {}
+    char *reserve(size_t n)
+    {
+        if (used + n > buf.size()) flush();
+        return buf.data() + used;
+    }
+    void flush()
+    {
+        if (used) std::fwrite(buf.data(), 1, used, fp);
+        used = 0;
+    }
+    void puts(const char *s)
+    {
+        size_t n = std::strlen(s);
+        std::memcpy(reserve(n), s, n);
+        used += n;
+    }
+};
+} // namespace
+
+extern "C" int mphx_write_prof_file(const char *filename, double time, const mphx_params *p, int n,
+                                    const int *property, const double *position,
+                                    const double *initial_position, const double *velocity)
+{
+    if (!filename || !p || n < 0) return MPHX_ERR_INVALID;
+    FILE *fp = std::fopen(filename, "w");
+    if (!fp) {
+        mphx::set_last_error(std::string("cannot open prof file ") + filename);
+        return MPHX_ERR_IO;
+    }
+    Out o(fp);
+    o.used += std::snprintf(o.reserve(64), 64, "%e\n", time);
+    o.used += std::snprintf(o.reserve(256), 256, "%d %e %e %e %e %e %e %e\n", n, p->particle_spacing,
+                            p->domain_min[0], p->domain_max[0], p->domain_min[1], p->domain_max[1],
+                            p->domain_min[2], p->domain_max[2]);
+    for (int i = 0; i < n; ++i) {
+        const double *x = position + 3 * (size_t)i, *x0 = initial_position + 3 * (size_t)i;
+        const double *v = velocity + 3 * (size_t)i;
+        o.used += std::snprintf(o.reserve(320), 320, "%d %e %e %e %e %e %e  %e %e %e\n", property[i],
+                                x[0], x[1], x[2], x0[0], x0[1], x0[2], v[0], v[1], v[2]);
+    }
+    o.flush();
+    std::fflush(fp);
+    std::fclose(fp);
+    return MPHX_OK;
+}
+
+extern "C" int mphx_write_vtk_file(const char *filename, int n, const double *initial_position,
+                                   const mphx_host_views *f)
+{
+    if (!filename || !f || n < 0 || !initial_position) return MPHX_ERR_INVALID;
+    if (!f->property || !f->position || !f->velocity || !f->force || !f->acceleration || !f->stress ||
+        !f->strain || !f->neighbor_count || !f->initial_structure_neighbor_count)
+        return MPHX_ERR_INVALID;
+    FILE *fp = std::fopen(filename, "w");
+    if (!fp) {
+        mphx::set_last_error(std::string("cannot open vtk file ") + filename);
+        return MPHX_ERR_IO;
+    }
+    Out o(fp);
+    char *b;
+    auto vec3f = [&](const double *a) { // "%e %e %e\n" of three float-cast values
+        b = o.reserve(128);
+        o.used += std::snprintf(b, 128, "%e %e %e\n", (float)a[0], (float)a[1], (float)a[2]);
+    };
+    o.puts("# vtk DataFile Version 2.0\n");
+    o.puts("Unstructured Grid Example\n");
+    o.puts("ASCII\n");
+    o.puts("DATASET UNSTRUCTURED_GRID\n");
+    o.used += std::snprintf(o.reserve(64), 64, "POINTS %d float\n", n);
+    for (int i = 0; i < n; ++i) vec3f(f->position + 3 * (size_t)i);
+    o.used += std::snprintf(o.reserve(64), 64, "CELLS %d %d\n", n, 2 * n);
+    for (int i = 0; i < n; ++i) o.used += std::snprintf(o.reserve(32), 32, "1 %d ", i);
+    o.puts("\n");
+    o.used += std::snprintf(o.reserve(64), 64, "CELL_TYPES %d\n", n);
+    for (int i = 0; i < n; ++i) o.puts("1 ");
+    o.puts("\n");
+    o.puts("\n");
+    o.used += std::snprintf(o.reserve(64), 64, "POINT_DATA %d\n", n);
+    o.puts("SCALARS label float 1\n");
+    o.puts("LOOKUP_TABLE default\n");
+    for (int i = 0; i < n; ++i) o.used += std::snprintf(o.reserve(32), 32, "%d\n", f->property[i]);
+    o.puts("\n");
+    o.puts("\n");
+    o.puts("VECTORS displacement float\n");
+    for (int i = 0; i < n; ++i) {
+        const double *x = f->position + 3 * (size_t)i, *x0 = initial_position + 3 * (size_t)i;
+        const double d[3] = {x[0] - x0[0], x[1] - x0[1], x[2] - x0[2]};
+        vec3f(d);
+    }
+    for (int pass = 0; pass < 2; ++pass) { // stress00..22 then strain00..22  (:1030-1047)
+        const double *T = pass == 0 ? f->stress : f->strain;
+        const char *nm = pass == 0 ? "stress" : "strain";
+        for (int a = 0; a < 3; ++a)
+            for (int c = 0; c < 3; ++c) {
+                o.puts("\n");
+                o.used += std::snprintf(o.reserve(64), 64, " SCALARS %s%d%d float \n", nm, a, c);
+                o.puts("LOOKUP_TABLE default\n");
+                for (int i = 0; i < n; ++i)
+                    o.used += std::snprintf(o.reserve(32), 32, "%e\n", (float)T[9 * (size_t)i + 3 * a + c]);
+            }
+    }
+    o.puts("VECTORS velocity float\n");
+    for (int i = 0; i < n; ++i) vec3f(f->velocity + 3 * (size_t)i);
+    o.puts("\n");
+    o.puts("VECTORS accel float\n");
+    for (int i = 0; i < n; ++i) vec3f(f->acceleration + 3 * (size_t)i);
+    o.puts("\n");
+    o.puts("SCALARS Initialneighbor float 1\n");
+    o.puts("LOOKUP_TABLE default\n");
+    for (int i = 0; i < n; ++i)
+        o.used += std::snprintf(o.reserve(32), 32, "%d\n", f->initial_structure_neighbor_count[i]);
+    o.puts("SCALARS neighbor float 1\n");
+    o.puts("LOOKUP_TABLE default\n");
+    for (int i = 0; i < n; ++i) o.used += std::snprintf(o.reserve(32), 32, "%d\n", f->neighbor_count[i]);
+    o.puts("VECTORS velocity float\n"); // Q8: the section appears twice (:1062 and :1169)
+    for (int i = 0; i < n; ++i) vec3f(f->velocity + 3 * (size_t)i);
+    o.puts("\n");
+    o.puts("VECTORS force float\n");
+    for (int i = 0; i < n; ++i) vec3f(f->force + 3 * (size_t)i);
+    o.puts("\n");
+    o.flush();
+    std::fflush(fp);
+    std::fclose(fp);
+    return MPHX_OK;
+}

@@ -1,0 +1,829 @@
+// mphx.cu -- context, step orchestration and the extern-"C" layer (include/mphx.h).
+//
+// One context drives one B200.  All state lives on the device as cell-sorted SoA; the host only
+// keeps scalars (Time, wall centres) and enqueues kernels on the context's stream.
+// There is no CPU fallback: every compute entry point fails with MPHX_ERR_NO_DEVICE / MPHX_ERR_CUDA
+// when no sm_100 device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "kernels.cuh"
+#include "mphx.h"
+#include "mphx_internal.h"
+
+namespace mphx {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_last_error(std::string(#call) + ": " + cudaGetErrorString(e_));                    \
+            return MPHX_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+constexpr int kBlock = 128;
+static inline int nblk(long long n, int b = kBlock) { return (int)((n + b - 1) / b); }
+
+struct Ctx {
+    mphx_params p;
+    mphx_constants c;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int n = 0, nf = 0, ns = 0, nw = 0;
+    int ranges[6];
+    bool uploaded = false, inited = false, surface_tension = false;
+    double time = 0.0;
+    double wall_center[kTypeCount][3];
+    long long launches = 0;
+    long long steps_done = 0;
+
+    GridDesc grid;
+    Phys phys;
+    Particles S{}, T{}; // S: current cell-sorted state, T: scratch (permute target / pre-step positions)
+    double *bx = nullptr, *by = nullptr, *bz = nullptr; // positions the buckets were built from
+    int *cellCount = nullptr, *cellStart = nullptr, *slot = nullptr, *tmpIdx = nullptr, *blockSums = nullptr;
+    int scan_blocks = 0;
+    double *P = nullptr, *volStrain = nullptr, *divP = nullptr;
+    double *densA = nullptr, *gcx = nullptr, *gcy = nullptr, *gcz = nullptr, *PA = nullptr;
+    double *fx = nullptr, *fy = nullptr, *fz = nullptr, *ax = nullptr, *ay = nullptr, *az = nullptr;
+    Solid sol{};
+    double *d_inv_density = nullptr;
+    double *d_x0_orig = nullptr; // InitialPosition, original order AoS (for re-upload / debugging)
+    std::vector<void *> allocs;
+
+    // phase timers (src/main.cpp:695-700 split)
+    bool timing = false;
+    std::vector<cudaEvent_t> ev;
+    double ms[4] = {0, 0, 0, 0};
+
+    template <class Tp> int alloc(Tp **ptr, size_t count)
+    {
+        void *q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(Tp));
+        if (e != cudaSuccess) {
+            set_last_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+            return MPHX_ERR_NOMEM;
+        }
+        allocs.push_back(q);
+        *ptr = (Tp *)q;
+        return MPHX_OK;
+    }
+};
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                                                      \
+    do {                                                                                           \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                 \
+        ++(ctx)->launches;                                                                         \
+    } while (0)
+
+static int alloc_particles(Ctx *c, Particles *p, size_t n)
+{
+    int rc = 0;
+    rc |= c->alloc(&p->x, n); rc |= c->alloc(&p->y, n); rc |= c->alloc(&p->z, n);
+    rc |= c->alloc(&p->vx, n); rc |= c->alloc(&p->vy, n); rc |= c->alloc(&p->vz, n);
+    rc |= c->alloc(&p->type, n); rc |= c->alloc(&p->id, n); rc |= c->alloc(&p->key, n);
+    return rc ? MPHX_ERR_NOMEM : MPHX_OK;
+}
+
+// stencil columns: all (dx,dy) within `range` whose buckets can hold a particle within the list
+// cut-off of some particle of the home bucket; per column the half-length along the run axis.
+static int build_stencil(GridDesc &g, double cutoff)
+{
+    const int R = g.range;
+    const double cut2 = (cutoff / g.cellw) * (cutoff / g.cellw) * (1.0 + 1e-9) + 1e-9;
+    auto gap = [](int d) { const int a = std::abs(d) - 1; return a > 0 ? (double)a : 0.0; };
+    int ns = 0;
+    if (g.dim == 3) {
+        for (int dx = -R; dx <= R; ++dx)
+            for (int dy = -R; dy <= R; ++dy) {
+                const double m2 = gap(dx) * gap(dx) + gap(dy) * gap(dy);
+                if (m2 > cut2) continue;
+                int h = 0;
+                for (int dz = 0; dz <= R; ++dz)
+                    if (m2 + gap(dz) * gap(dz) <= cut2) h = dz;
+                if (ns >= kMaxStencil) return MPHX_ERR_UNSUPPORTED;
+                g.sdx[ns] = (signed char)dx; g.sdy[ns] = (signed char)dy; g.sh[ns] = (signed char)h;
+                ++ns;
+            }
+    } else {
+        for (int dx = -R; dx <= R; ++dx) {
+            const double m2 = gap(dx) * gap(dx);
+            if (m2 > cut2) continue;
+            int h = 0;
+            for (int dy = 0; dy <= R; ++dy)
+                if (m2 + gap(dy) * gap(dy) <= cut2) h = dy;
+            if (ns >= kMaxStencil) return MPHX_ERR_UNSUPPORTED;
+            g.sdx[ns] = (signed char)dx; g.sdy[ns] = 0; g.sh[ns] = (signed char)h;
+            ++ns;
+        }
+    }
+    g.nsten = ns;
+    return MPHX_OK;
+}
+
+static int setup_constants(Ctx *c)
+{
+    const mphx_params &p = c->p;
+    int rc = mphx_compute_constants(&p, &c->c);
+    if (rc) return rc;
+    const mphx_constants &k = c->c;
+    GridDesc &g = c->grid;
+    std::memset(&g, 0, sizeof(g));
+    g.dim = p.dim;
+    g.nx = k.cell_count[0]; g.ny = k.cell_count[1]; g.nz = k.cell_count[2];
+    g.ncells = k.cell_counts;
+    g.range = k.stencil_range;
+    g.cellw = k.cell_width;
+    for (int d = 0; d < 3; ++d) { g.mn[d] = p.domain_min[d]; g.W[d] = k.domain_width[d]; }
+    const double cutoff = k.max_radius + 0.1 * p.particle_spacing; // MaxRadius+MARGIN (:116,:1765)
+    rc = build_stencil(g, cutoff);
+    if (rc) { set_last_error("stencil too large (radius ratio too big)"); return rc; }
+    // every traversed axis must hold the whole stencil once (otherwise the reference itself visits
+    // buckets several times, :1751-1755)
+    const int need = 2 * g.range + 1;
+    if (g.nx < need || g.ny < need || (p.dim == 3 && g.nz < need)) {
+        set_last_error("domain narrower than the neighbour stencil");
+        return MPHX_ERR_UNSUPPORTED;
+    }
+    Phys &ph = c->phys;
+    std::memset(&ph, 0, sizeof(ph));
+    const bool two_d = p.dim == 2;
+    auto hd = [&](double h) { return two_d ? h * h : h * h * h; };
+    ph.dt = p.dt; ph.vol = k.particle_volume; ph.l0 = p.particle_spacing;
+    ph.rp2 = k.radius_p * k.radius_p; ph.irp = 1.0 / k.radius_p;
+    ph.cwp = 1.0 / k.swp * 1.0 / hd(k.radius_p); ph.cdp = ph.cwp * (-2.0 / k.radius_p);
+    ph.rv2 = k.radius_v * k.radius_v; ph.irv = 1.0 / k.radius_v;
+    ph.cdv = (1.0 / k.swv * 1.0 / hd(k.radius_v)) * (-2.0 / k.radius_v);
+    ph.ra2 = k.radius_a * k.radius_a; ph.ira = 1.0 / k.radius_a;
+    ph.cwa = 1.0 / k.swa * 1.0 / hd(k.radius_a);
+    ph.cwg = 1.0 / k.swg * 1.0 / hd(k.radius_g); ph.cdg = ph.cwg * (-2.0 / k.radius_g);
+    ph.r2g = k.r2g; ph.rg = k.radius_g;
+    ph.n0p = k.n0p; ph.n0a = k.n0a; ph.cofk = k.cof_k;
+    const double cd = two_d ? 8.0 : 10.0; // :2510 / :2512
+    c->surface_tension = false;
+    for (int t = 0; t < kTypeCount; ++t) {
+        ph.mass[t] = p.density[t] * k.particle_volume; // :2105
+        ph.inv_density[t] = 1.0 / p.density[t];        // :2877
+        ph.bulk[t] = p.bulk_modulus[t];
+        ph.lambda[t] = p.bulk_viscosity[t];
+        ph.cofa[t] = k.cof_a[t];
+        if (k.cof_a[t] != 0.0) c->surface_tension = true;
+        for (int u = 0; u < kTypeCount; ++u) {
+            const double mi = p.shear_viscosity[t], mj = p.shear_viscosity[u];
+            ph.viscpair[t][u] = cd * (2.0 * (mi * mj) / (mi + mj)) * k.particle_volume; // :2505
+            ph.ratio[t][u] = p.interaction_ratio[t][u];
+        }
+    }
+    for (int d = 0; d < 3; ++d) ph.g[d] = p.gravity[d];
+    return MPHX_OK;
+}
+
+// ---- bucket rebuild: K1 key/count, K2 scan, K3 scatter, K4 permute -------------------------------
+static int rebuild_buckets(Ctx *c, bool prestep_motion)
+{
+    const int n = c->n;
+    CK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * (size_t)c->grid.ncells, c->stream));
+    WallMotion wm;
+    std::memset(&wm, 0, sizeof(wm));
+    wm.dt = c->p.dt;
+    wm.active = (prestep_motion && c->time < 0.2 && c->nw > 0) ? 1 : 0; // Q7 (:3037)
+    if (wm.active)
+        for (int t = 0; t < kTypeCount; ++t)
+            for (int d = 0; d < 3; ++d) {
+                wm.center[t][d] = c->wall_center[t][d];
+                wm.vel[t][d] = c->p.wall_velocity[t][d];
+                wm.omega[t][d] = c->p.wall_omega[t][d];
+                for (int e = 0; e < 3; ++e) wm.R[t][d][e] = c->c.wall_rotation[t][d][e];
+            }
+    LAUNCH(c, k_prestep, nblk(n), kBlock, n, c->S, c->sol, c->grid, wm, prestep_motion ? 1 : 0, c->cellCount, c->slot);
+    if (prestep_motion) // :3066-3070 (host mirror of the wall centres)
+        for (int t = 4; t < kTypeCount; ++t)
+            for (int d = 0; d < 3; ++d) c->wall_center[t][d] += c->p.wall_velocity[t][d] * c->p.dt;
+    const int nc = c->grid.ncells;
+    LAUNCH(c, k_scan_reduce, c->scan_blocks, kScanThreads, c->cellCount, nc, c->blockSums);
+    LAUNCH(c, k_scan_top, 1, kScanThreads, c->blockSums, c->scan_blocks);
+    LAUNCH(c, k_scan_apply, c->scan_blocks, kScanThreads, c->cellCount, nc, c->blockSums, c->cellStart);
+    LAUNCH(c, k_scatter_index, nblk(n), kBlock, n, c->S.key, c->slot, c->cellStart, c->tmpIdx);
+    LAUNCH(c, k_permute, nblk(n), kBlock, n, c->S, c->T, c->cellStart, c->tmpIdx);
+    std::swap(c->S, c->T);
+    c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+static int run_pass1(Ctx *c)
+{
+    const int n = c->n;
+#define P1(D, ST) LAUNCH(c, (k_pass1<D, ST>), nblk(n), kBlock, n, c->S, c->cellStart, c->grid, c->phys, c->P, c->volStrain, \
+                         c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA)
+    if (c->p.dim == 3) { if (c->surface_tension) P1(3, true); else P1(3, false); }
+    else               { if (c->surface_tension) P1(2, true); else P1(2, false); }
+#undef P1
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+static int run_pass2(Ctx *c)
+{
+    const int n = c->n;
+#define P2(D, ST) LAUNCH(c, (k_pass2<D, ST>), nblk(n), kBlock, n, c->S, c->cellStart, c->grid, c->phys, c->P, c->PA, c->gcx, \
+                         c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, c->fy, c->fz, c->ax,  \
+                         c->ay, c->az, c->sol)
+    if (c->p.dim == 3) { if (c->surface_tension) P2(3, true); else P2(3, false); }
+    else               { if (c->surface_tension) P2(2, true); else P2(2, false); }
+#undef P2
+    // S keeps type/id/key of this step's order and takes the integrated x,v; T keeps the pre-step
+    // (bucket) positions for the neighbour-count diagnostics.
+    std::swap(c->S.x, c->T.x); std::swap(c->S.y, c->T.y); std::swap(c->S.z, c->T.z);
+    std::swap(c->S.vx, c->T.vx); std::swap(c->S.vy, c->T.vy); std::swap(c->S.vz, c->T.vz);
+    c->bx = c->T.x; c->by = c->T.y; c->bz = c->T.z;
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+static int run_solid_substeps(Ctx *c)
+{
+    if (c->ns <= 0) return MPHX_OK;
+    const int substeps = (int)(c->p.dt / c->p.elastic_dt + 0.5); // :653
+    const mphx_constants &k = c->c;
+    const double cw = c->phys.cwp;
+    const int ns = c->ns;
+    const int dbl = (c->p.ref_compat & MPHX_COMPAT_DOUBLE_UPDATE) ? 1 : 0;
+    for (int s = 0; s < substeps; ++s) {
+        if (c->p.dim == 3) {
+            LAUNCH(c, k_solid_pass1<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw);
+            LAUNCH(c, k_solid_pass2<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw,
+                   c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);
+        } else {
+            LAUNCH(c, k_solid_pass1<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw);
+            LAUNCH(c, k_solid_pass2<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw,
+                   c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);
+        }
+    }
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+static void timer_mark(Ctx *c)
+{
+    if (!c->timing) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, c->stream);
+    c->ev.push_back(e);
+}
+static void timer_resolve(Ctx *c)
+{
+    if (c->ev.empty()) return;
+    cudaStreamSynchronize(c->stream);
+    // events come in groups of 4 per step: start, after rebuild, after fluid, after solid
+    for (size_t i = 0; i + 3 < c->ev.size(); i += 4) {
+        float a = 0, b = 0, d = 0;
+        cudaEventElapsedTime(&a, c->ev[i], c->ev[i + 1]);
+        cudaEventElapsedTime(&b, c->ev[i + 1], c->ev[i + 2]);
+        cudaEventElapsedTime(&d, c->ev[i + 2], c->ev[i + 3]);
+        c->ms[0] += a;
+        c->ms[1] += b + d;
+    }
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    c->ev.clear();
+}
+
+static int one_step(Ctx *c, bool fluid_only)
+{
+    int rc;
+    timer_mark(c);
+    if ((rc = rebuild_buckets(c, true))) return rc; // calculateWall, PeriodicBoundary, resets, calculateNeighbor
+    timer_mark(c);
+    if ((rc = run_pass1(c))) return rc;             // DensityA..DivergenceP, coefficients, PressureP/A
+    if ((rc = run_pass2(c))) return rc;             // force sums, gravity, interface, acceleration, convection
+    timer_mark(c);
+    if (!fluid_only) {
+        if ((rc = run_solid_substeps(c))) return rc;
+        c->time += c->p.dt; // :685
+        ++c->steps_done;
+    }
+    timer_mark(c);
+    if (c->ev.size() >= 4096) timer_resolve(c);
+    return MPHX_OK;
+}
+
+// ---- initial structure lists (calculateInitialNeighbor :1497-1644) + Lame + Normalizer ----------
+static int exact_lists(Ctx *c, bool structure_only, bool xy_only, int row_base, int nrows,
+                       std::vector<long long> &offsets, int **d_ids_out, long long *total_out)
+{
+    // neighbour sets over the positions the buckets were last built from
+    const int n = c->n;
+    int *d_counts = nullptr;
+    long long *d_off = nullptr;
+    CK(cudaMalloc(&d_counts, sizeof(int) * (size_t)std::max(nrows, 1)));
+    CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)std::max(nrows, 1), c->stream));
+    const double cut = c->c.max_radius + 0.1 * c->p.particle_spacing;
+    const double cutoff2 = cut * cut; // (MaxRadius+MARGIN)*(MaxRadius+MARGIN) :1765
+    const Particles &S = c->S;
+    if (c->p.dim == 3)
+        LAUNCH(c, (k_neighbors_exact<3, 0>), nblk(n), kBlock, n, c->bx, c->by, c->bz, S.type, S.id, S.key, c->cellStart, c->grid,
+               cutoff2, structure_only ? 1 : 0, xy_only ? 1 : 0, row_base, d_counts, (const long long *)nullptr, (int *)nullptr);
+    else
+        LAUNCH(c, (k_neighbors_exact<2, 0>), nblk(n), kBlock, n, c->bx, c->by, c->bz, S.type, S.id, S.key, c->cellStart, c->grid,
+               cutoff2, structure_only ? 1 : 0, xy_only ? 1 : 0, row_base, d_counts, (const long long *)nullptr, (int *)nullptr);
+    std::vector<int> counts((size_t)std::max(nrows, 1));
+    CK(cudaMemcpyAsync(counts.data(), d_counts, sizeof(int) * (size_t)std::max(nrows, 1), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    offsets.assign((size_t)nrows + 1, 0);
+    for (int r = 0; r < nrows; ++r) offsets[r + 1] = offsets[r] + counts[r];
+    const long long total = offsets[nrows];
+    *total_out = total;
+    cudaFree(d_counts);
+    if (!d_ids_out) return MPHX_OK;
+    int *d_ids = nullptr;
+    CK(cudaMalloc(&d_ids, sizeof(int) * (size_t)std::max<long long>(total, 1)));
+    CK(cudaMalloc(&d_off, sizeof(long long) * ((size_t)nrows + 1)));
+    CK(cudaMemcpyAsync(d_off, offsets.data(), sizeof(long long) * ((size_t)nrows + 1), cudaMemcpyHostToDevice, c->stream));
+    if (c->p.dim == 3)
+        LAUNCH(c, (k_neighbors_exact<3, 1>), nblk(n), kBlock, n, c->bx, c->by, c->bz, S.type, S.id, S.key, c->cellStart, c->grid,
+               cutoff2, structure_only ? 1 : 0, xy_only ? 1 : 0, row_base, (int *)nullptr, d_off, d_ids);
+    else
+        LAUNCH(c, (k_neighbors_exact<2, 1>), nblk(n), kBlock, n, c->bx, c->by, c->bz, S.type, S.id, S.key, c->cellStart, c->grid,
+               cutoff2, structure_only ? 1 : 0, xy_only ? 1 : 0, row_base, (int *)nullptr, d_off, d_ids);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    cudaFree(d_off);
+    *d_ids_out = d_ids;
+    return MPHX_OK;
+}
+
+static int init_solid(Ctx *c, const double *d_x03_orig)
+{
+    if (c->ns <= 0) return MPHX_OK;
+    const int n = c->n, ns = c->ns;
+    int rc;
+    // buckets over InitialPosition: temporarily load x0 into the position arrays.  S is still in
+    // original order here (id == index; no rebuild has happened since the first upload).
+    double *sx = nullptr, *sy = nullptr, *sz = nullptr;
+    CK(cudaMalloc(&sx, sizeof(double) * n)); CK(cudaMalloc(&sy, sizeof(double) * n)); CK(cudaMalloc(&sz, sizeof(double) * n));
+    CK(cudaMemcpyAsync(sx, c->S.x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(sy, c->S.y, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(sz, c->S.z, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
+    LAUNCH(c, k_split_vec3, nblk(n), kBlock, n, d_x03_orig, c->S.x, c->S.y, c->S.z);
+    // solids read their position from the solid arrays in k_prestep: point them at x0 for this build
+    Solid tmp = c->sol;
+    tmp.x = c->sol.x0; tmp.y = c->sol.y0; tmp.z = c->sol.z0;
+    Solid keep = c->sol;
+    c->sol = tmp;
+    rc = rebuild_buckets(c, false);
+    c->sol = keep;
+    if (rc) return rc;
+    std::vector<long long> off;
+    int *d_ids = nullptr;
+    long long total = 0;
+    rc = exact_lists(c, true, c->p.dim == 2, c->sol.sb, ns, off, &d_ids, &total);
+    if (rc) return rc;
+    std::vector<int> ids((size_t)std::max<long long>(total, 1));
+    CK(cudaMemcpy(ids.data(), d_ids, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost));
+    cudaFree(d_ids);
+    if (total > 0x7fffffffLL) return MPHX_ERR_UNSUPPORTED;
+    std::vector<int> off32((size_t)ns + 1);
+    for (int s = 0; s <= ns; ++s) off32[s] = (int)off[s];
+    // transpose: roff/rnbr (rows = particles that list s), ascending
+    std::vector<int> roff((size_t)ns + 1, 0), rnbr((size_t)std::max<long long>(total, 1));
+    for (long long k = 0; k < total; ++k) ++roff[ids[k] + 1];
+    for (int s = 0; s < ns; ++s) roff[s + 1] += roff[s];
+    {
+        std::vector<int> fill(roff.begin(), roff.end() - 1);
+        for (int s = 0; s < ns; ++s)
+            for (int k = off32[s]; k < off32[s + 1]; ++k) rnbr[fill[ids[k]]++] = s;
+    }
+    int e = 0;
+    e |= c->alloc(&c->sol.off, (size_t)ns + 1); e |= c->alloc(&c->sol.nbr, (size_t)total);
+    e |= c->alloc(&c->sol.roff, (size_t)ns + 1); e |= c->alloc(&c->sol.rnbr, (size_t)total);
+    if (e) return MPHX_ERR_NOMEM;
+    CK(cudaMemcpy(c->sol.off, off32.data(), sizeof(int) * ((size_t)ns + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->sol.nbr, ids.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->sol.roff, roff.data(), sizeof(int) * ((size_t)ns + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->sol.rnbr, rnbr.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice));
+    // Lame constants per particle (:2533-2539)
+    {
+        std::vector<int> ht(ns);
+        CK(cudaMemcpy(ht.data(), c->sol.type, sizeof(int) * ns, cudaMemcpyDeviceToHost));
+        std::vector<double> lam(ns), mu(ns);
+        for (int s = 0; s < ns; ++s) {
+            const double E = c->p.young_modulus[ht[s]], v = c->p.poisson_ratio[ht[s]];
+            lam[s] = (E * v) / ((1.0 + v) * (1.0 - 2.0 * v));
+            mu[s] = E / (2.0 * (1.0 + v));
+        }
+        CK(cudaMemcpy(c->sol.lam, lam.data(), sizeof(double) * ns, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->sol.mu, mu.data(), sizeof(double) * ns, cudaMemcpyHostToDevice));
+    }
+    const mphx_constants &k = c->c;
+    if (c->p.dim == 3)
+        LAUNCH(c, k_solid_normalizer<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->phys.cwp);
+    else
+        LAUNCH(c, k_solid_normalizer<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->phys.cwp);
+    CK(cudaGetLastError());
+    // restore the current positions (the arrays are now in x0-bucket order): gather through the ids
+    LAUNCH(c, k_restore_by_id, nblk(n), kBlock, n, c->S.id, sx, sy, sz, c->S.x, c->S.y, c->S.z);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    cudaFree(sx); cudaFree(sy); cudaFree(sz);
+    return MPHX_OK;
+}
+
+} // namespace mphx
+
+using namespace mphx;
+
+// =================================================================================================
+extern "C" {
+
+int mphx_version(void) { return MPHX_VERSION; }
+
+const char *mphx_strerror(int code)
+{
+    switch (code) {
+    case MPHX_OK: return "ok";
+    case MPHX_ERR_INVALID: return "invalid argument or state";
+    case MPHX_ERR_NO_DEVICE: return "no sm_100 CUDA device (there is no CPU fallback)";
+    case MPHX_ERR_CUDA: return "CUDA error";
+    case MPHX_ERR_IO: return "file error";
+    case MPHX_ERR_NOMEM: return "out of memory";
+    case MPHX_ERR_UNSUPPORTED: return "unsupported configuration";
+    case MPHX_ERR_OVERFLOW: return "neighbour capacity exceeded";
+    default: return "unknown error";
+    }
+}
+
+const char *mphx_last_error(void) { return g_last_error.c_str(); }
+
+int mphx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
+{
+    if (!out || !p) return MPHX_ERR_INVALID;
+    *out = nullptr;
+    if (p->dim != 2 && p->dim != 3) return MPHX_ERR_INVALID;
+    if (p->clamp_module < 0 || p->clamp_module > 2) return MPHX_ERR_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        set_last_error("no CUDA device visible; mphx has no CPU fallback");
+        return MPHX_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) return MPHX_ERR_INVALID;
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) {
+        set_last_error("device is not compute capability 10.x; libmphx.so carries sm_100a code only");
+        return MPHX_ERR_NO_DEVICE;
+    }
+    Ctx *c = new Ctx();
+    c->p = *p;
+    c->device = device;
+    c->time = p->time0;
+    for (int t = 0; t < kTypeCount; ++t)
+        for (int d = 0; d < 3; ++d) c->wall_center[t][d] = p->wall_center[t][d];
+    int rc = setup_constants(c);
+    if (rc) { delete c; return rc; }
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_last_error("cudaSetDevice/cudaStreamCreate failed");
+        delete c;
+        return MPHX_ERR_CUDA;
+    }
+    c->timing = std::getenv("MPHX_TIMING") != nullptr;
+    *out = reinterpret_cast<mphx_ctx *>(c);
+    return MPHX_OK;
+}
+
+void mphx_destroy(mphx_ctx *ctx)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    for (void *q : c->allocs) cudaFree(q);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *position,
+                const double *initial_position, const double *velocity)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || n <= 0 || !property || !position || !initial_position || !velocity) return MPHX_ERR_INVALID;
+    if (c->uploaded && n != c->n) return MPHX_ERR_INVALID; // re-upload must keep the particle count
+    CK(cudaSetDevice(c->device));
+    for (int i = 0; i < n; ++i)
+        if (property[i] < 0 || property[i] >= kTypeCount) { set_last_error("particle type outside 0..5"); return MPHX_ERR_INVALID; }
+    int r[6];
+    mphx_class_ranges(n, property, r);
+    // each class must be one contiguous block of the file order, as the reference's range loops
+    // (src/main.cpp:909-929, e.g. :2922, :2442) assume
+    for (int cls = 0; cls < 3; ++cls)
+        for (int i = std::max(r[2 * cls], 0); i < r[2 * cls + 1]; ++i) {
+            const int t = property[i];
+            const int k = t < 2 ? 0 : t < 4 ? 1 : 2;
+            if (k != cls) { set_last_error("particle classes are not contiguous in file order"); return MPHX_ERR_UNSUPPORTED; }
+        }
+    const bool first = !c->uploaded;
+    if (first) {
+        c->n = n;
+        std::memcpy(c->ranges, r, sizeof(r));
+        c->nf = r[0] >= 0 ? r[1] - r[0] : 0;
+        c->ns = r[2] >= 0 ? r[3] - r[2] : 0;
+        c->nw = r[4] >= 0 ? r[5] - r[4] : 0;
+        int e = 0;
+        e |= alloc_particles(c, &c->S, n);
+        e |= alloc_particles(c, &c->T, n);
+        e |= c->alloc(&c->cellCount, (size_t)c->grid.ncells);
+        e |= c->alloc(&c->cellStart, (size_t)c->grid.ncells + 1);
+        c->scan_blocks = (int)(((long long)c->grid.ncells + kScanChunk - 1) / kScanChunk);
+        e |= c->alloc(&c->blockSums, (size_t)c->scan_blocks + 1);
+        e |= c->alloc(&c->slot, n); e |= c->alloc(&c->tmpIdx, n);
+        e |= c->alloc(&c->P, n); e |= c->alloc(&c->volStrain, n); e |= c->alloc(&c->divP, n);
+        e |= c->alloc(&c->fx, n); e |= c->alloc(&c->fy, n); e |= c->alloc(&c->fz, n);
+        e |= c->alloc(&c->ax, n); e |= c->alloc(&c->ay, n); e |= c->alloc(&c->az, n);
+        e |= c->alloc(&c->densA, n); e |= c->alloc(&c->gcx, n); e |= c->alloc(&c->gcy, n);
+        e |= c->alloc(&c->gcz, n); e |= c->alloc(&c->PA, n);
+        e |= c->alloc(&c->d_inv_density, kTypeCount);
+        e |= c->alloc(&c->d_x0_orig, (size_t)3 * n);
+        Solid &so = c->sol;
+        so.ns = c->ns; so.sb = c->ns > 0 ? r[2] : 0;
+        const size_t ns = (size_t)c->ns;
+        double **sv[] = {&so.x, &so.y, &so.z, &so.vx, &so.vy, &so.vz, &so.x0, &so.y0, &so.z0, &so.fx, &so.fy, &so.fz, &so.lam, &so.mu};
+        for (double **q : sv) e |= c->alloc(q, ns);
+        double **st[] = {&so.Linv, &so.Fm, &so.E, &so.S, &so.Pk};
+        for (double **q : st) e |= c->alloc(q, 9 * ns);
+        e |= c->alloc(&so.type, ns);
+        if (e) return MPHX_ERR_NOMEM;
+        CK(cudaMemcpy(c->d_inv_density, c->phys.inv_density, sizeof(double) * kTypeCount, cudaMemcpyHostToDevice));
+        double *zs[] = {c->P, c->volStrain, c->divP, c->fx, c->fy, c->fz, c->ax, c->ay, c->az, c->densA, c->gcx, c->gcy, c->gcz, c->PA};
+        for (double *q : zs) CK(cudaMemsetAsync(q, 0, sizeof(double) * n, c->stream));
+        for (double **q : st) CK(cudaMemsetAsync(*q, 0, sizeof(double) * 9 * std::max<size_t>(ns, 1), c->stream));
+    }
+    // stage AoS host arrays, split to SoA on the device
+    int *d_t = nullptr;
+    double *d_x = nullptr, *d_v = nullptr;
+    CK(cudaMalloc(&d_t, sizeof(int) * n));
+    CK(cudaMalloc(&d_x, sizeof(double) * 3 * (size_t)n));
+    CK(cudaMalloc(&d_v, sizeof(double) * 3 * (size_t)n));
+    CK(cudaMemcpyAsync(d_t, property, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_x, position, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_v, velocity, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_x0_orig, initial_position, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_upload_split, nblk(n), kBlock, n, d_t, d_x, d_v, c->S);
+    if (c->ns > 0) LAUNCH(c, k_solid_upload, nblk(c->ns), kBlock, c->sol, d_t, d_x, c->d_x0_orig, d_v);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    cudaFree(d_t); cudaFree(d_x); cudaFree(d_v);
+    c->uploaded = true;
+    if (!first && c->inited) {
+        // state replaced on an initialised context: rebuild the buckets (no wall motion / wrap)
+        int rc = rebuild_buckets(c, false);
+        if (rc) return rc;
+    }
+    return MPHX_OK;
+}
+
+int mphx_init(mphx_ctx *ctx)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->uploaded) return MPHX_ERR_INVALID;
+    if (c->inited) return MPHX_OK;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = init_solid(c, c->d_x0_orig))) return rc; // calculateInitialNeighbor, Lame, Normalizer
+    // first calculateNeighbor + density sums on the initial positions (:565-568): gives
+    // NeighborCount / PressureP for the `output.vtk` written before the loop (:572)
+    if ((rc = rebuild_buckets(c, false))) return rc;
+    if ((rc = run_pass1(c))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    c->inited = true;
+    return MPHX_OK;
+}
+
+int mphx_get_constants(const mphx_ctx *ctx, mphx_constants *k)
+{
+    const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+    if (!c || !k) return MPHX_ERR_INVALID;
+    *k = c->c;
+    return MPHX_OK;
+}
+
+int mphx_step(mphx_ctx *ctx, int nsteps)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->inited || nsteps < 0) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    for (int s = 0; s < nsteps; ++s) {
+        int rc = one_step(c, false);
+        if (rc) return rc;
+    }
+    return MPHX_OK;
+}
+
+int mphx_step_fluid_only(mphx_ctx *ctx)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->inited) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    return one_step(c, true);
+}
+
+int mphx_sync(mphx_ctx *ctx)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+double mphx_time(const mphx_ctx *ctx) { return ctx ? reinterpret_cast<const Ctx *>(ctx)->time : 0.0; }
+
+int mphx_set_time(mphx_ctx *ctx, double t)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return MPHX_ERR_INVALID;
+    c->time = t;
+    return MPHX_OK;
+}
+
+int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !v || !c->uploaded) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const int n = c->n, ns = c->ns;
+    const size_t N = (size_t)n;
+    double *d3 = nullptr, *d1 = nullptr, *d9 = nullptr;
+    int *di = nullptr;
+    CK(cudaMalloc(&d3, sizeof(double) * 3 * N));
+    CK(cudaMalloc(&d1, sizeof(double) * N));
+    CK(cudaMalloc(&di, sizeof(int) * N));
+    const Particles &S = c->S;
+    const Solid &so = c->sol;
+    int rc = MPHX_OK;
+    auto vec3 = [&](double *host, const double *a, const double *b, const double *cc, const double *sa, const double *sb_, const double *sc) -> int {
+        if (!host) return MPHX_OK;
+        LAUNCH(c, k_gather_vec3, nblk(n), kBlock, n, S.id, a, b, cc, d3);
+        if (ns > 0 && sa) LAUNCH(c, k_solid_vec3_to_orig, nblk(ns), kBlock, so, sa, sb_, sc, d3);
+        CK(cudaMemcpyAsync(host, d3, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return MPHX_OK;
+    };
+    auto scal = [&](double *host, const double *a) -> int {
+        if (!host) return MPHX_OK;
+        LAUNCH(c, k_gather_scalar, nblk(n), kBlock, n, S.id, a, d1);
+        CK(cudaMemcpyAsync(host, d1, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return MPHX_OK;
+    };
+    auto ints = [&](int *host, const int *a) -> int {
+        if (!host) return MPHX_OK;
+        LAUNCH(c, k_gather_int, nblk(n), kBlock, n, S.id, a, di);
+        CK(cudaMemcpyAsync(host, di, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return MPHX_OK;
+    };
+    auto tens = [&](double *host, const double *M) -> int {
+        if (!host) return MPHX_OK;
+        if (!d9) { CK(cudaMalloc(&d9, sizeof(double) * 9 * N)); }
+        CK(cudaMemsetAsync(d9, 0, sizeof(double) * 9 * N, c->stream));
+        if (ns > 0) LAUNCH(c, k_solid_tensor_to_orig, nblk(ns), kBlock, so, M, d9);
+        CK(cudaMemcpyAsync(host, d9, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return MPHX_OK;
+    };
+    auto solid_scal = [&](double *host, const double *a) -> int {
+        if (!host) return MPHX_OK;
+        CK(cudaMemsetAsync(d1, 0, sizeof(double) * N, c->stream));
+        if (ns > 0) LAUNCH(c, k_solid_scalar_to_orig, nblk(ns), kBlock, so, a, d1);
+        CK(cudaMemcpyAsync(host, d1, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        return MPHX_OK;
+    };
+    do {
+        if ((rc = ints(v->property, S.type))) break;
+        if ((rc = vec3(v->position, S.x, S.y, S.z, so.x, so.y, so.z))) break;
+        if ((rc = vec3(v->velocity, S.vx, S.vy, S.vz, so.vx, so.vy, so.vz))) break;
+        if ((rc = vec3(v->force, c->fx, c->fy, c->fz, so.fx, so.fy, so.fz))) break;
+        if ((rc = vec3(v->acceleration, c->ax, c->ay, c->az, nullptr, nullptr, nullptr))) break;
+        if ((rc = scal(v->pressure_p, c->P))) break;
+        if ((rc = scal(v->vol_strain_p, c->volStrain))) break;
+        if ((rc = scal(v->divergence_p, c->divP))) break;
+        if ((rc = scal(v->density_a, c->densA))) break;
+        if ((rc = vec3(v->gravity_center, c->gcx, c->gcy, c->gcz, nullptr, nullptr, nullptr))) break;
+        if ((rc = scal(v->pressure_a, c->PA))) break;
+        if ((rc = ints(v->cell_index, S.key))) break;
+        if (v->neighbor_count) {
+            if (!c->inited) { rc = MPHX_ERR_INVALID; break; }
+            std::vector<long long> off;
+            long long total = 0;
+            if ((rc = exact_lists(c, false, false, 0, n, off, nullptr, &total))) break;
+            for (int i = 0; i < n; ++i) v->neighbor_count[i] = (int)(off[i + 1] - off[i]);
+        }
+        if (v->initial_structure_neighbor_count) {
+            CK(cudaMemsetAsync(di, 0, sizeof(int) * N, c->stream));
+            if (ns > 0 && so.off) LAUNCH(c, k_solid_rowlen_to_orig, nblk(ns), kBlock, so, di);
+            CK(cudaMemcpyAsync(v->initial_structure_neighbor_count, di, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+        }
+        if ((rc = tens(v->normalizer, so.Linv))) break;
+        if ((rc = tens(v->deform_gradient, so.Fm))) break;
+        if ((rc = tens(v->strain, so.E))) break;
+        if ((rc = tens(v->stress, so.S))) break;
+        if ((rc = solid_scal(v->lambda_lames, so.lam))) break;
+        if ((rc = solid_scal(v->mu_lames, so.mu))) break;
+    } while (0);
+    cudaFree(d3); cudaFree(d1); cudaFree(di);
+    if (d9) cudaFree(d9);
+    if (rc == MPHX_OK) { CK(cudaGetLastError()); }
+    return rc;
+}
+
+int mphx_debug_neighbors(mphx_ctx *ctx, long long *offsets, int *ids, long long cap)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->inited || !offsets) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    std::vector<long long> off;
+    long long total = 0;
+    int *d_ids = nullptr;
+    int rc = exact_lists(c, false, false, 0, c->n, off, ids ? &d_ids : nullptr, &total);
+    if (rc) return rc;
+    std::memcpy(offsets, off.data(), sizeof(long long) * ((size_t)c->n + 1));
+    if (ids) {
+        if (cap < total) { cudaFree(d_ids); return MPHX_ERR_OVERFLOW; }
+        CK(cudaMemcpy(ids, d_ids, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost));
+        cudaFree(d_ids);
+    }
+    return MPHX_OK;
+}
+
+int mphx_debug_initial_structure_neighbors(mphx_ctx *ctx, long long *offsets, int *ids, long long cap)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->inited || !offsets) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const int n = c->n, ns = c->ns, sb = c->sol.sb;
+    std::vector<int> off32((size_t)ns + 1, 0);
+    if (ns > 0) CK(cudaMemcpy(off32.data(), c->sol.off, sizeof(int) * ((size_t)ns + 1), cudaMemcpyDeviceToHost));
+    for (int i = 0; i <= n; ++i) {
+        const int s = i - sb;
+        offsets[i] = (ns > 0 && s >= 0) ? off32[std::min(s, ns)] : 0;
+    }
+    const long long total = ns > 0 ? off32[ns] : 0;
+    if (ids) {
+        if (cap < total) return MPHX_ERR_OVERFLOW;
+        if (total > 0) {
+            CK(cudaMemcpy(ids, c->sol.nbr, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost));
+            for (long long k = 0; k < total; ++k) ids[k] += sb;
+        }
+    }
+    return MPHX_OK;
+}
+
+int mphx_get_timers(mphx_ctx *ctx, double ms[4])
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !ms) return MPHX_ERR_INVALID;
+    cudaSetDevice(c->device);
+    timer_resolve(c);
+    for (int i = 0; i < 4; ++i) ms[i] = c->ms[i];
+    return MPHX_OK;
+}
+
+long long mphx_launch_count(const mphx_ctx *ctx) { return ctx ? reinterpret_cast<const Ctx *>(ctx)->launches : 0; }
+
+double mphx_algorithmic_bytes_per_step(const mphx_ctx *ctx)
+{
+    const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+    if (!c) return 0.0;
+    const int nsub = (int)(c->p.dt / c->p.elastic_dt + 0.5);
+    return 368.0 * c->nf + 260.0 * c->nw + (344.0 + 384.0 * nsub) * c->ns;
+}
+
+} // extern "C"

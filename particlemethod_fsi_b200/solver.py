@@ -1,0 +1,267 @@
+"""Host-side binding of libmphx.so (the extern-"C" layer of include/mphx.h) -- plumbing only.
+
+There is no Python or CPU implementation of the step here: every compute call goes to the CUDA
+library, and importing this module fails loudly when the library has not been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmphx.so")
+
+
+class MphxError(RuntimeError):
+    def __init__(self, what: str, code: int, lib=None):
+        msg = f"{what}: error {code}"
+        if lib is not None:
+            msg = f"{what}: {lib.mphx_strerror(code).decode()} [{code}] {lib.mphx_last_error().decode()}"
+        super().__init__(msg)
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C particlemethod_fsi_b200/csrc`). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, ip, dp = C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)
+    L.mphx_version.restype = C.c_int
+    L.mphx_strerror.argtypes = [C.c_int]
+    L.mphx_strerror.restype = C.c_char_p
+    L.mphx_last_error.restype = C.c_char_p
+    L.mphx_device_count.restype = C.c_int
+    L.mphx_params_default.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.RunControl)]
+    L.mphx_params_default.restype = None
+    L.mphx_read_data_file.argtypes = [C.c_char_p, C.POINTER(abi.Params), C.POINTER(abi.RunControl), vp, vp]
+    L.mphx_read_grid_file.argtypes = [C.c_char_p, C.POINTER(abi.Params), ip, C.POINTER(ip), C.POINTER(dp),
+                                      C.POINTER(dp), C.POINTER(dp)]
+    L.mphx_free_host.argtypes = [vp]
+    L.mphx_free_host.restype = None
+    L.mphx_write_prof_file.argtypes = [C.c_char_p, C.c_double, C.POINTER(abi.Params), C.c_int, vp, vp, vp, vp]
+    L.mphx_write_vtk_file.argtypes = [C.c_char_p, C.c_int, vp, C.POINTER(abi.HostViews)]
+    L.mphx_class_ranges.argtypes = [C.c_int, vp, C.POINTER(C.c_int * 6)]
+    L.mphx_class_ranges.restype = None
+    L.mphx_compute_constants.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Constants)]
+    L.mphx_create.argtypes = [C.POINTER(vp), C.POINTER(abi.Params), C.c_int]
+    L.mphx_destroy.argtypes = [vp]
+    L.mphx_destroy.restype = None
+    L.mphx_upload.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.mphx_init.argtypes = [vp]
+    L.mphx_get_constants.argtypes = [vp, C.POINTER(abi.Constants)]
+    L.mphx_step.argtypes = [vp, C.c_int]
+    L.mphx_step_fluid_only.argtypes = [vp]
+    L.mphx_sync.argtypes = [vp]
+    L.mphx_time.argtypes = [vp]
+    L.mphx_time.restype = C.c_double
+    L.mphx_set_time.argtypes = [vp, C.c_double]
+    L.mphx_download.argtypes = [vp, C.POINTER(abi.HostViews)]
+    L.mphx_debug_neighbors.argtypes = [vp, vp, vp, C.c_longlong]
+    L.mphx_debug_initial_structure_neighbors.argtypes = [vp, vp, vp, C.c_longlong]
+    L.mphx_get_timers.argtypes = [vp, C.POINTER(C.c_double * 4)]
+    L.mphx_launch_count.argtypes = [vp]
+    L.mphx_launch_count.restype = C.c_longlong
+    L.mphx_algorithmic_bytes_per_step.argtypes = [vp]
+    L.mphx_algorithmic_bytes_per_step.restype = C.c_double
+    return L
+
+
+lib = _load()
+
+
+def _ck(what: str, rc: int):
+    if rc != abi.MPHX_OK:
+        raise MphxError(what, rc, lib)
+
+
+# ---- file formats / host constants (no GPU needed) ---------------------------------------------
+def read_data_file(fn: str, dim: int = 2, module: int = abi.MODULE_BAR):
+    """readDataFile (src/main.cpp:729-786) -> (Params, RunControl, [invalid lines])"""
+    p, rc = abi.Params(), abi.RunControl()
+    lib.mphx_params_default(C.byref(p), C.byref(rc))
+    p.dim, p.clamp_module = dim, module
+    bad = []
+    CB = C.CFUNCTYPE(None, C.c_char_p, C.c_void_p)
+    cb = CB(lambda line, _u: bad.append(line.decode(errors="replace")))
+    _ck("mphx_read_data_file", lib.mphx_read_data_file(fn.encode(), C.byref(p), C.byref(rc), C.cast(cb, C.c_void_p), None))
+    return p, rc, bad
+
+
+def read_grid_file(fn: str, p: abi.Params):
+    """readGridFile (src/main.cpp:788-929): fills p.time0/spacing/domain, returns (type, x, x0, v)"""
+    n = C.c_int()
+    t = C.POINTER(C.c_int)()
+    x, x0, v = (C.POINTER(C.c_double)() for _ in range(3))
+    _ck("mphx_read_grid_file", lib.mphx_read_grid_file(fn.encode(), C.byref(p), C.byref(n), C.byref(t), C.byref(x),
+                                                        C.byref(x0), C.byref(v)))
+    N = n.value
+    try:
+        T = np.ctypeslib.as_array(t, shape=(max(N, 1),))[:N].copy()
+        X = np.ctypeslib.as_array(x, shape=(max(N, 1), 3))[:N].copy()
+        X0 = np.ctypeslib.as_array(x0, shape=(max(N, 1), 3))[:N].copy()
+        V = np.ctypeslib.as_array(v, shape=(max(N, 1), 3))[:N].copy()
+    finally:
+        for q in (t, x, x0, v):
+            lib.mphx_free_host(C.cast(q, C.c_void_p))
+    return T, X, X0, V
+
+
+def write_prof_file(fn: str, time: float, p: abi.Params, property, position, initial_position, velocity):
+    t = np.ascontiguousarray(property, dtype=np.int32)
+    x, x0, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (position, initial_position, velocity))
+    _ck("mphx_write_prof_file", lib.mphx_write_prof_file(fn.encode(), time, C.byref(p), t.shape[0], t.ctypes.data,
+                                                         x.ctypes.data, x0.ctypes.data, v.ctypes.data))
+
+
+def _views(n: int, fields: dict):
+    hv = abi.HostViews()
+    keep = {}
+    for name, arr in fields.items():
+        shape, is_int = abi.VIEW_FIELDS[name]
+        a = np.ascontiguousarray(arr, dtype=np.int32 if is_int else np.float64)
+        assert a.shape == (n,) + shape, (name, a.shape)
+        keep[name] = a
+        setattr(hv, name, a.ctypes.data_as(C.POINTER(C.c_int if is_int else C.c_double)))
+    return hv, keep
+
+
+def write_vtk_file(fn: str, initial_position, fields: dict):
+    x0 = np.ascontiguousarray(initial_position, dtype=np.float64)
+    hv, _keep = _views(x0.shape[0], fields)
+    _ck("mphx_write_vtk_file", lib.mphx_write_vtk_file(fn.encode(), x0.shape[0], x0.ctypes.data, C.byref(hv)))
+
+
+def compute_constants(p: abi.Params) -> abi.Constants:
+    k = abi.Constants()
+    _ck("mphx_compute_constants", lib.mphx_compute_constants(C.byref(p), C.byref(k)))
+    return k
+
+
+def class_ranges(property) -> list:
+    t = np.ascontiguousarray(property, dtype=np.int32)
+    r = (C.c_int * 6)()
+    lib.mphx_class_ranges(t.shape[0], t.ctypes.data, C.byref(r))
+    return list(r)
+
+
+def device_count() -> int:
+    return lib.mphx_device_count()
+
+
+# ---- the solver context ---------------------------------------------------------------------------
+VTK_FIELDS = ("property", "position", "velocity", "force", "acceleration", "stress", "strain",
+              "neighbor_count", "initial_structure_neighbor_count")
+
+
+class Solver:
+    """One context = one B200.  Mirrors the reference's sequence: create (readDataFile/readGridFile
+    results), upload (`acc update device`), init (initialize* + the calls of src/main.cpp:564-570),
+    step (loop body :596-663), download (`acc update host`)."""
+
+    def __init__(self, params: abi.Params, device: int = 0):
+        self.params = params
+        self._ctx = C.c_void_p()
+        _ck("mphx_create", lib.mphx_create(C.byref(self._ctx), C.byref(params), device))
+        self.n = 0
+
+    @classmethod
+    def from_case(cls, case, device: int = 0, init: bool = True):
+        s = cls(case.params, device)
+        s.upload(case.property, case.position, case.initial_position, case.velocity)
+        if init:
+            s.init()
+        return s
+
+    def close(self):
+        if self._ctx:
+            lib.mphx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, property, position, initial_position, velocity):
+        t = np.ascontiguousarray(property, dtype=np.int32)
+        x, x0, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (position, initial_position, velocity))
+        assert x.shape == (t.shape[0], 3) and x0.shape == x.shape and v.shape == x.shape
+        _ck("mphx_upload", lib.mphx_upload(self._ctx, t.shape[0], t.ctypes.data, x.ctypes.data, x0.ctypes.data,
+                                           v.ctypes.data))
+        self.n = t.shape[0]
+
+    def init(self):
+        _ck("mphx_init", lib.mphx_init(self._ctx))
+
+    def constants(self) -> abi.Constants:
+        k = abi.Constants()
+        _ck("mphx_get_constants", lib.mphx_get_constants(self._ctx, C.byref(k)))
+        return k
+
+    def step(self, nsteps: int = 1, sync: bool = False):
+        _ck("mphx_step", lib.mphx_step(self._ctx, nsteps))
+        if sync:
+            self.sync()
+
+    def step_fluid_only(self):
+        _ck("mphx_step_fluid_only", lib.mphx_step_fluid_only(self._ctx))
+
+    def sync(self):
+        _ck("mphx_sync", lib.mphx_sync(self._ctx))
+
+    @property
+    def time(self) -> float:
+        return lib.mphx_time(self._ctx)
+
+    @time.setter
+    def time(self, t: float):
+        _ck("mphx_set_time", lib.mphx_set_time(self._ctx, t))
+
+    def download(self, *names, out: dict | None = None) -> dict:
+        fields = {}
+        for nm in names:
+            shape, is_int = abi.VIEW_FIELDS[nm]
+            if out is not None and nm in out:
+                fields[nm] = out[nm]
+            else:
+                fields[nm] = np.empty((self.n,) + shape, dtype=np.int32 if is_int else np.float64)
+        hv, keep = _views(self.n, fields)
+        _ck("mphx_download", lib.mphx_download(self._ctx, C.byref(hv)))
+        return keep
+
+    def neighbors(self):
+        """(offsets[N+1], ids) -- neighbour sets of calculateNeighbor, rows sorted ascending"""
+        off = np.zeros(self.n + 1, dtype=np.int64)
+        _ck("mphx_debug_neighbors", lib.mphx_debug_neighbors(self._ctx, off.ctypes.data, None, 0))
+        ids = np.empty(max(int(off[-1]), 1), dtype=np.int32)
+        _ck("mphx_debug_neighbors", lib.mphx_debug_neighbors(self._ctx, off.ctypes.data, ids.ctypes.data, ids.shape[0]))
+        return off, ids[: int(off[-1])]
+
+    def initial_structure_neighbors(self):
+        off = np.zeros(self.n + 1, dtype=np.int64)
+        _ck("mphx_debug_initial_structure_neighbors",
+            lib.mphx_debug_initial_structure_neighbors(self._ctx, off.ctypes.data, None, 0))
+        ids = np.empty(max(int(off[-1]), 1), dtype=np.int32)
+        _ck("mphx_debug_initial_structure_neighbors",
+            lib.mphx_debug_initial_structure_neighbors(self._ctx, off.ctypes.data, ids.ctypes.data, ids.shape[0]))
+        return off, ids[: int(off[-1])]
+
+    def timers_ms(self):
+        ms = (C.c_double * 4)()
+        _ck("mphx_get_timers", lib.mphx_get_timers(self._ctx, C.byref(ms)))
+        return list(ms)
+
+    @property
+    def launch_count(self) -> int:
+        return lib.mphx_launch_count(self._ctx)
+
+    @property
+    def algorithmic_bytes_per_step(self) -> float:
+        return lib.mphx_algorithmic_bytes_per_step(self._ctx)
