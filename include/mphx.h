@@ -131,6 +131,9 @@ const char *mphx_strerror(int code);
 const char *mphx_last_error(void);
 /* number of visible sm_100 devices (0 when there is none or no driver) */
 int mphx_device_count(void);
+/* sizeof of the boundary structs, for FFI layout checks: 0 params, 1 run_control, 2 constants,
+ * 3 host_views */
+int mphx_abi_sizeof(int which);
 
 /* ---- file formats (host only; replaces readDataFile/readGridFile/writeProfFile/writeVtkFile) -- */
 void mphx_params_default(mphx_params *p, mphx_run_control *rc);

@@ -94,7 +94,7 @@ VIEW_FIELDS = {
 
 # every symbol include/mphx.h declares (tests/test_abi.py parses the header and compares)
 EXPORTS = [
-    "mphx_version", "mphx_strerror", "mphx_last_error", "mphx_device_count",
+    "mphx_version", "mphx_strerror", "mphx_last_error", "mphx_device_count", "mphx_abi_sizeof",
     "mphx_params_default", "mphx_read_data_file", "mphx_read_grid_file", "mphx_free_host",
     "mphx_write_prof_file", "mphx_write_vtk_file", "mphx_class_ranges",
     "mphx_compute_constants",

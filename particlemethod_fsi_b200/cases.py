@@ -205,8 +205,28 @@ def fsi3d(l0: float, tank=(1.6, 0.8, 1.0), water=(0.6, 0.5, 1.0), plate_x: float
 def fsi3d_mini() -> Case:
     """small 3D FSI case for parity tests (about 15k particles)."""
     l0 = 4.0e-3
-    return fsi3d(l0, tank=(0.20, 0.10, 0.048), water=(0.06, 0.08, 0.048), plate_x=0.10,
-                 plate_layers=3, plate_h=0.04, elastic_dt_ratio=5, z_walls=False)
+    c = fsi3d(l0, tank=(0.20, 0.10, 0.048), water=(0.06, 0.08, 0.048), plate_x=0.10,
+              plate_layers=3, plate_h=0.04, elastic_dt_ratio=5, z_walls=False)
+    c.name = "fsi3d_mini"
+    return c
+
+
+def tiny2d() -> Case:
+    """about 1.3k particles: 2D water column + clamped plate + walls (golden-fixture case)"""
+    l0 = 2.0e-3
+    c = fsi2d(l0, tank=(0.10, 0.06), water=(0.03, 0.04), plate_x=0.05, plate_t=3 * l0, plate_h=0.024,
+              elastic_dt=2.0e-5)
+    c.name = "tiny2d"
+    return c
+
+
+def tiny3d() -> Case:
+    """about 2.5k particles: 3D water block + clamped plate + walls, periodic span (golden-fixture case)"""
+    l0 = 4.0e-3
+    c = fsi3d(l0, tank=(0.12, 0.06, 0.032), water=(0.036, 0.044, 0.032), plate_x=0.06, plate_layers=3,
+              plate_h=0.028, elastic_dt_ratio=5, z_walls=False)
+    c.name = "tiny3d"
+    return c
 
 
 def fsi3d_for_count(n_target: float, **kw) -> Case:

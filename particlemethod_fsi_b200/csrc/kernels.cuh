@@ -452,15 +452,19 @@ k_pass2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys 
                 F0 += A0; F1 += A1; F2 += A2;
             }
         });
+    // gravity + explicit integration in the reference's operand order (explicitly rounded, so a
+    // particle whose force sum is exact -- e.g. a solid far from any fluid -- moves bit-identically)
     const double m = ph.mass[ti];
     double nx = xi, ny = yi, nz = zi, nvx = vxi, nvy = vyi, nvz = vzi;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0;
     if (!is_wall_type(ti)) { // gravity on fluid and solid (:2922-2935)
-        F0 += m * ph.g[0]; F1 += m * ph.g[1]; F2 += m * ph.g[2];
-        nvx = vxi + F0 / m * ph.dt; nvy = vyi + F1 / m * ph.dt; nvz = vzi + F2 / m * ph.dt; // :2944-2954
+        F0 = __dadd_rn(F0, __dmul_rn(m, ph.g[0])); F1 = __dadd_rn(F1, __dmul_rn(m, ph.g[1])); F2 = __dadd_rn(F2, __dmul_rn(m, ph.g[2]));
+        nvx = __dadd_rn(vxi, __dmul_rn(__ddiv_rn(F0, m), ph.dt)); // :2944-2954
+        nvy = __dadd_rn(vyi, __dmul_rn(__ddiv_rn(F1, m), ph.dt));
+        nvz = __dadd_rn(vzi, __dmul_rn(__ddiv_rn(F2, m), ph.dt));
         if (!solid_i) { // :1897-1906
-            a0 = F0 / m; a1 = F1 / m; a2 = F2 / m;
-            nx = xi + nvx * ph.dt; ny = yi + nvy * ph.dt; nz = zi + nvz * ph.dt;
+            a0 = __ddiv_rn(F0, m); a1 = __ddiv_rn(F1, m); a2 = __ddiv_rn(F2, m);
+            nx = __dadd_rn(xi, __dmul_rn(nvx, ph.dt)); ny = __dadd_rn(yi, __dmul_rn(nvy, ph.dt)); nz = __dadd_rn(zi, __dmul_rn(nvz, ph.dt));
         } else {
             const int s = p.id[i] - sol.sb;
             sol.vx[s] = nvx; sol.vy[s] = nvy; sol.vz[s] = nvz;
@@ -518,17 +522,35 @@ k_neighbors_exact(int n, const double *__restrict__ X, const double *__restrict_
 
 // ------------------------------------------------------------------------------------------------
 // total-Lagrangian solid.  M(k) = plane k of a 3x3 SoA tensor.
+//
+// The reference-configuration lists are static and hold at most one particle per bucket, so the
+// reference's accumulation ORDER can be reproduced exactly (rows are stored in its stencil order).
+// The solid kernels therefore use explicitly rounded operations in the reference's operand order
+// (no FMA contraction): given identical inputs they return the reference's bits.  This matters
+// because E = (F^T F - I)/2 cancels ~5 digits at small strain, so any re-association shows up at
+// 1e-11 relative per sub-step.
 #define MPHX_T(M, r, c, s, ns) (M)[(size_t)(3 * (r) + (c)) * (ns) + (s)]
 
-__device__ __forceinline__ double tl_weight(int DIMS, double x0, double x1, double x2, double radius, double cw)
+namespace ex {
+__device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+} // namespace ex
+
+// weight() :268-295 -- always the pressure normaliser Swp; 2D ignores the third component.
+// cw = (1.0/Swp)*(1.0/radius^d) evaluated on the host in that order.
+template <int DIMS>
+__device__ __forceinline__ double tl_weight(double x0, double x1, double x2, double radius, double cw)
 {
-    // weight() :268-295 -- always the pressure normaliser Swp; 2D ignores the third component
-    const double r2 = (DIMS == 2) ? (x0 * x0 + x1 * x1) : (x0 * x0 + x1 * x1 + x2 * x2);
-    const double q = sqrt(r2) / radius;
-    return cw * ((1.0 - q) * (1.0 - q));
+    double r2 = ex::add(ex::mul(x0, x0), ex::mul(x1, x1)); // 0.0 + x0*x0 is exact
+    if (DIMS == 3) r2 = ex::add(r2, ex::mul(x2, x2));
+    const double q = ex::div(sqrt(r2), radius);
+    const double omq = ex::sub(1.0, q);
+    return ex::mul(cw, ex::mul(omq, omq));
 }
 
-// calculateNormalizer :2544-2653 (once).  cw = (1/Swp)*(1/RP^d)
+// calculateNormalizer :2544-2653 (once)
 template <int DIMS>
 __global__ void k_solid_normalizer(Solid so, double W0, double W1, double W2, double radius, double cw)
 {
@@ -539,32 +561,34 @@ __global__ void k_solid_normalizer(Solid so, double W0, double W1, double W2, do
     for (int k = so.off[s]; k < so.off[s + 1]; ++k) {
         const int j = so.nbr[k];
         // Q2: three components are accumulated even in 2D (the reference tests a misspelt macro)
-        const double d[3] = {minimg(so.x0[j] - xi0, W0), minimg(so.y0[j] - yi0, W1), minimg(so.z0[j] - zi0, W2)};
-        const double w = tl_weight(DIMS, d[0], d[1], d[2], radius, cw);
+        const double d[3] = {minimg_exact(so.x0[j], xi0, W0), minimg_exact(so.y0[j], yi0, W1), minimg_exact(so.z0[j], zi0, W2)};
+        const double w = tl_weight<DIMS>(d[0], d[1], d[2], radius, cw);
         for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) A[a][b] += w * d[a] * d[b];
+            for (int b = 0; b < 3; ++b) A[a][b] = ex::add(A[a][b], ex::mul(ex::mul(w, d[a]), d[b]));
     }
+    using namespace ex;
     if (DIMS == 2) { // :2592-2621
         const double a = A[0][0], b = A[0][1], c = A[1][0], d = A[1][1];
-        const double det = a * d - b * c;
-        if (det != 0.0) { A[0][0] = d / det; A[0][1] = -b / det; A[1][0] = -c / det; A[1][1] = a / det; }
+        const double det = sub(mul(a, d), mul(b, c));
+        if (det != 0.0) { A[0][0] = div(d, det); A[0][1] = div(-b, det); A[1][0] = div(-c, det); A[1][1] = div(a, det); }
         else { A[0][0] = 1.0; A[0][1] = 0.0; A[1][0] = 0.0; A[1][1] = 1.0; }
     } else { // :2624-2650
-        const double det = A[0][0] * (A[1][1] * A[2][2] - A[1][2] * A[2][1]) - A[0][1] * (A[1][0] * A[2][2] - A[1][2] * A[2][0]) +
-                           A[0][2] * (A[1][0] * A[2][1] - A[1][1] * A[2][0]);
+        const double det = add(sub(mul(A[0][0], sub(mul(A[1][1], A[2][2]), mul(A[1][2], A[2][1]))),
+                                   mul(A[0][1], sub(mul(A[1][0], A[2][2]), mul(A[1][2], A[2][0])))),
+                               mul(A[0][2], sub(mul(A[1][0], A[2][1]), mul(A[1][1], A[2][0]))));
         if (det != 0.0) {
             double B[3][3];
-            B[0][0] = A[1][1] * A[2][2] - A[1][2] * A[2][1];
-            B[0][1] = -A[1][0] * A[2][2] + A[1][2] * A[2][0];
-            B[0][2] = A[1][0] * A[2][1] - A[1][1] * A[2][0];
-            B[1][0] = -A[0][1] * A[2][2] + A[0][2] * A[2][1];
-            B[1][1] = A[0][0] * A[2][2] - A[0][2] * A[2][0];
-            B[1][2] = -A[0][0] * A[2][1] + A[0][1] * A[2][0];
-            B[2][0] = A[0][1] * A[1][2] - A[0][2] * A[1][1];
-            B[2][1] = -A[0][0] * A[1][2] + A[0][2] * A[1][0];
-            B[2][2] = A[0][0] * A[1][1] - A[0][1] * A[1][0];
+            B[0][0] = sub(mul(A[1][1], A[2][2]), mul(A[1][2], A[2][1]));
+            B[0][1] = add(mul(-A[1][0], A[2][2]), mul(A[1][2], A[2][0]));
+            B[0][2] = sub(mul(A[1][0], A[2][1]), mul(A[1][1], A[2][0]));
+            B[1][0] = add(mul(-A[0][1], A[2][2]), mul(A[0][2], A[2][1]));
+            B[1][1] = sub(mul(A[0][0], A[2][2]), mul(A[0][2], A[2][0]));
+            B[1][2] = add(mul(-A[0][0], A[2][1]), mul(A[0][1], A[2][0]));
+            B[2][0] = sub(mul(A[0][1], A[1][2]), mul(A[0][2], A[1][1]));
+            B[2][1] = add(mul(-A[0][0], A[1][2]), mul(A[0][2], A[1][0]));
+            B[2][2] = sub(mul(A[0][0], A[1][1]), mul(A[0][1], A[1][0]));
             for (int a = 0; a < 3; ++a)
-                for (int b = 0; b < 3; ++b) A[a][b] = B[a][b] / det;
+                for (int b = 0; b < 3; ++b) A[a][b] = div(B[a][b], det);
         }
     }
     for (int a = 0; a < 3; ++a)
@@ -576,22 +600,25 @@ __global__ void k_solid_normalizer(Solid so, double W0, double W1, double W2, do
 template <int DIMS>
 __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double radius, double cw)
 {
+    using namespace ex;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= so.ns) return;
     const int ns = so.ns;
     const double xi0 = so.x0[s], yi0 = so.y0[s], zi0 = so.z0[s];
-    double ui[3] = {minimg(so.x[s] - xi0, W0), minimg(so.y[s] - yi0, W1), DIMS == 3 ? minimg(so.z[s] - zi0, W2) : 0.0};
+    const double ui[3] = {minimg_exact(so.x[s], xi0, W0), minimg_exact(so.y[s], yi0, W1),
+                          DIMS == 3 ? minimg_exact(so.z[s], zi0, W2) : 0.0};
     double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     for (int k = so.off[s]; k < so.off[s + 1]; ++k) {
         const int j = so.nbr[k];
         const double xj0 = so.x0[j], yj0 = so.y0[j], zj0 = so.z0[j];
-        double d0[3] = {minimg(xj0 - xi0, W0), minimg(yj0 - yi0, W1), DIMS == 3 ? minimg(zj0 - zi0, W2) : 0.0};
-        double uj[3] = {minimg(so.x[j] - xj0, W0), minimg(so.y[j] - yj0, W1), DIMS == 3 ? minimg(so.z[j] - zj0, W2) : 0.0};
+        const double d0[3] = {minimg_exact(xj0, xi0, W0), minimg_exact(yj0, yi0, W1), DIMS == 3 ? minimg_exact(zj0, zi0, W2) : 0.0};
+        const double uj[3] = {minimg_exact(so.x[j], xj0, W0), minimg_exact(so.y[j], yj0, W1),
+                              DIMS == 3 ? minimg_exact(so.z[j], zj0, W2) : 0.0};
         double d[3];
-        for (int a = 0; a < DIMS; ++a) d[a] = d0[a] + (uj[a] - ui[a]);
-        const double w = tl_weight(DIMS, d0[0], d0[1], d0[2], radius, cw);
+        for (int a = 0; a < DIMS; ++a) d[a] = add(d0[a], sub(uj[a], ui[a])); // :2716
+        const double w = tl_weight<DIMS>(d0[0], d0[1], d0[2], radius, cw);
         for (int a = 0; a < DIMS; ++a)
-            for (int b = 0; b < DIMS; ++b) G[a][b] += w * d[a] * d0[b];
+            for (int b = 0; b < DIMS; ++b) G[a][b] = add(G[a][b], mul(mul(w, d[a]), d0[b])); // :2726
     }
     double L[3][3], F[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     for (int a = 0; a < 3; ++a)
@@ -599,28 +626,28 @@ __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double 
     for (int a = 0; a < DIMS; ++a)
         for (int b = 0; b < DIMS; ++b) {
             double sum = 0.0;
-            for (int k = 0; k < DIMS; ++k) sum += G[a][k] * L[k][b];
+            for (int k = 0; k < DIMS; ++k) sum = add(sum, mul(G[a][k], L[k][b])); // :2743
             F[a][b] = sum;
         }
     double E[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, tr = 0.0;
     for (int a = 0; a < DIMS; ++a)
         for (int b = 0; b < DIMS; ++b) {
             double sum = 0.0;
-            for (int k = 0; k < DIMS; ++k) sum += F[k][a] * F[k][b];
-            E[a][b] = 0.5 * (sum - (a == b ? 1.0 : 0.0));
-            if (a == b) tr += E[a][b];
+            for (int k = 0; k < DIMS; ++k) sum = add(sum, mul(F[k][a], F[k][b])); // :2780
+            E[a][b] = mul(0.5, sub(sum, (a == b ? 1.0 : 0.0)));
+            if (a == b) tr = add(tr, E[a][b]);
         }
     const double mu = so.mu[s], lam = so.lam[s];
     for (int a = 0; a < DIMS; ++a)
         for (int b = 0; b < DIMS; ++b) {
-            S[a][b] = 2.0 * mu * E[a][b];
-            if (a == b) S[a][b] += lam * tr;
+            S[a][b] = mul(mul(2.0, mu), E[a][b]); // :2804
+            if (a == b) S[a][b] = add(S[a][b], mul(lam, tr));
         }
     for (int a = 0; a < DIMS; ++a)
         for (int b = 0; b < DIMS; ++b) {
             double sum = 0.0;
             for (int k = 0; k < DIMS; ++k)
-                for (int l = 0; l < DIMS; ++l) sum += F[a][k] * S[k][l] * L[l][b];
+                for (int l = 0; l < DIMS; ++l) sum = add(sum, mul(mul(F[a][k], S[k][l]), L[l][b])); // :2847
             MPHX_T(so.Pk, a, b, s, ns) = sum;
             MPHX_T(so.Fm, a, b, s, ns) = F[a][b];
             MPHX_T(so.E, a, b, s, ns) = E[a][b];
@@ -629,45 +656,55 @@ __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double 
 }
 
 // K8 "solid pass 2": the reference scatters  v_i += w P_i x0_ij /rho_i dt,  v_j -= (same)/rho_j dt
-// with atomics (:2855-2887); here every particle GATHERS its own-row terms and, through the
-// transposed list, the terms other rows would have scattered to it (deterministic, no atomics).
+// serially / with atomics (:2855-2887); here every particle GATHERS, in the reference's serial
+// order, the terms of rows j<s that list s, then its own row, then rows j>s (transposed list), so
+// the result is deterministic, atomic-free and equal to the reference's CPU bits.
 // Then updateElasticPosition (:1916-2081) incl. the clamp modules and quirk Q1.
 template <int DIMS>
 __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double radius, double cw, double edt,
                               int module, int double_update, const double *__restrict__ inv_density)
 {
+    using namespace ex;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= so.ns) return;
     const int ns = so.ns;
     const double xi0 = so.x0[s], yi0 = so.y0[s], zi0 = so.z0[s];
-    double Pi[3][3];
-    for (int a = 0; a < 3; ++a)
-        for (int b = 0; b < 3; ++b) Pi[a][b] = (a < DIMS && b < DIMS) ? MPHX_T(so.Pk, a, b, s, ns) : 0.0;
-    double acc[3] = {0.0, 0.0, 0.0};
-    for (int k = so.off[s]; k < so.off[s + 1]; ++k) { // own row: + w (P_i x0_ij)
-        const int j = so.nbr[k];
-        double d0[3] = {minimg(so.x0[j] - xi0, W0), minimg(so.y0[j] - yi0, W1), DIMS == 3 ? minimg(so.z0[j] - zi0, W2) : 0.0};
-        const double w = tl_weight(DIMS, d0[0], d0[1], d0[2], radius, cw);
-        for (int a = 0; a < DIMS; ++a) {
-            double f = 0.0;
-            for (int b = 0; b < DIMS; ++b) f += Pi[a][b] * d0[b];
-            acc[a] += f * w;
-        }
-    }
-    for (int k = so.roff[s]; k < so.roff[s + 1]; ++k) { // rows j that list s: - w (P_j x0_js)
-        const int j = so.rnbr[k];
-        const double xj0 = so.x0[j], yj0 = so.y0[j], zj0 = so.z0[j];
-        double d0[3] = {minimg(xi0 - xj0, W0), minimg(yi0 - yj0, W1), DIMS == 3 ? minimg(zi0 - zj0, W2) : 0.0};
-        const double w = tl_weight(DIMS, d0[0], d0[1], d0[2], radius, cw);
-        for (int a = 0; a < DIMS; ++a) {
-            double f = 0.0;
-            for (int b = 0; b < DIMS; ++b) f += MPHX_T(so.Pk, a, b, j, ns) * d0[b];
-            acc[a] -= f * w;
-        }
-    }
     const double ir = inv_density[so.type[s]];
-    double v[3] = {so.vx[s] + ir * acc[0] * edt, so.vy[s] + ir * acc[1] * edt, so.vz[s] + ir * acc[2] * edt};
+    double v[3] = {so.vx[s], so.vy[s], so.vz[s]};
+    auto scattered_from = [&](int j) { // row j lists s:  v_s -= invRho_s * (w P_j x0_js) * dt
+        const double xj0 = so.x0[j], yj0 = so.y0[j], zj0 = so.z0[j];
+        const double d0[3] = {minimg_exact(xi0, xj0, W0), minimg_exact(yi0, yj0, W1), DIMS == 3 ? minimg_exact(zi0, zj0, W2) : 0.0};
+        const double w = tl_weight<DIMS>(d0[0], d0[1], d0[2], radius, cw);
+        for (int a = 0; a < DIMS; ++a) {
+            double f = 0.0;
+            for (int b = 0; b < DIMS; ++b) f = add(f, mul(MPHX_T(so.Pk, a, b, j, ns), d0[b]));
+            f = mul(f, w);
+            v[a] = sub(v[a], mul(mul(ir, f), edt)); // :2885
+        }
+    };
+    int k = so.roff[s];
+    const int kend = so.roff[s + 1];
+    for (; k < kend && so.rnbr[k] < s; ++k) scattered_from(so.rnbr[k]);
+    {
+        double Pi[3][3];
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) Pi[a][b] = (a < DIMS && b < DIMS) ? MPHX_T(so.Pk, a, b, s, ns) : 0.0;
+        for (int q = so.off[s]; q < so.off[s + 1]; ++q) { // own row: v_s += invRho_s * (w P_s x0_sj) * dt
+            const int j = so.nbr[q];
+            const double d0[3] = {minimg_exact(so.x0[j], xi0, W0), minimg_exact(so.y0[j], yi0, W1),
+                                  DIMS == 3 ? minimg_exact(so.z0[j], zi0, W2) : 0.0};
+            const double w = tl_weight<DIMS>(d0[0], d0[1], d0[2], radius, cw);
+            for (int a = 0; a < DIMS; ++a) {
+                double f = 0.0;
+                for (int b = 0; b < DIMS; ++b) f = add(f, mul(Pi[a][b], d0[b]));
+                f = mul(f, w);
+                v[a] = add(v[a], mul(mul(ir, f), edt)); // :2883
+            }
+        }
+    }
+    for (; k < kend; ++k) scattered_from(so.rnbr[k]);
     double x[3] = {so.x[s], so.y[s], so.z[s]};
+    // Acceleration of solids is 0 (:2892): v += 0*dt leaves v unchanged
     if (module != 0) {
         const bool clamped = (module == 1) ? (xi0 < 0.001) : (yi0 < 0.002); // :1919 / :1968
         if (clamped) {
@@ -675,12 +712,12 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
             v[0] = v[1] = v[2] = 0.0;
             so.fx[s] = 0.0; so.fy[s] = 0.0; so.fz[s] = 0.0;
         } else {
-            for (int a = 0; a < 3; ++a) x[a] += v[a] * edt; // Acceleration of solids is 0 (:2892)
+            for (int a = 0; a < 3; ++a) x[a] = add(x[a], mul(v[a], edt));
         }
         if (double_update) // Q1 (:2070-2079)
-            for (int a = 0; a < 3; ++a) x[a] += v[a] * edt;
+            for (int a = 0; a < 3; ++a) x[a] = add(x[a], mul(v[a], edt));
     } else {
-        for (int a = 0; a < 3; ++a) x[a] += v[a] * edt;
+        for (int a = 0; a < 3; ++a) x[a] = add(x[a], mul(v[a], edt));
     }
     so.x[s] = x[0]; so.y[s] = x[1]; so.z[s] = x[2];
     so.vx[s] = v[0]; so.vy[s] = v[1]; so.vz[s] = v[2];

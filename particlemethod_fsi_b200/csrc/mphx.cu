@@ -59,6 +59,7 @@ struct Ctx {
     double *fx = nullptr, *fy = nullptr, *fz = nullptr, *ax = nullptr, *ay = nullptr, *az = nullptr;
     Solid sol{};
     double *d_inv_density = nullptr;
+    double cw_tl = 0.0; // weight() prefactor (1.0/Swp)*(1.0/RP^d), src/main.cpp:291/293
     double *d_x0_orig = nullptr; // InitialPosition, original order AoS (for re-upload / debugging)
     std::vector<void *> allocs;
 
@@ -186,6 +187,7 @@ static int setup_constants(Ctx *c)
         }
     }
     for (int d = 0; d < 3; ++d) ph.g[d] = p.gravity[d];
+    c->cw_tl = (1.0 / k.swp) * (1.0 / hd(k.radius_p));
     return MPHX_OK;
 }
 
@@ -257,7 +259,7 @@ static int run_solid_substeps(Ctx *c)
     if (c->ns <= 0) return MPHX_OK;
     const int substeps = (int)(c->p.dt / c->p.elastic_dt + 0.5); // :653
     const mphx_constants &k = c->c;
-    const double cw = c->phys.cwp;
+    const double cw = c->cw_tl;
     const int ns = c->ns;
     const int dbl = (c->p.ref_compat & MPHX_COMPAT_DOUBLE_UPDATE) ? 1 : 0;
     for (int s = 0; s < substeps; ++s) {
@@ -396,6 +398,45 @@ static int init_solid(Ctx *c, const double *d_x03_orig)
     if (total > 0x7fffffffLL) return MPHX_ERR_UNSUPPORTED;
     std::vector<int> off32((size_t)ns + 1);
     for (int s = 0; s <= ns; ++s) off32[s] = (int)off[s];
+    // Store every row in the reference's list order: buckets jCX, jCY, jCZ ascending over the
+    // stencil offsets (:1591-1620).  The reference configuration holds at most one solid particle per
+    // bucket (lattice at cell spacing); if a bucket ever holds several, ties fall back to id order.
+    {
+        std::vector<double> hx0(ns), hy0(ns), hz0(ns);
+        CK(cudaMemcpy(hx0.data(), c->sol.x0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hy0.data(), c->sol.y0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(hz0.data(), c->sol.z0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
+        const GridDesc &g = c->grid;
+        auto coord = [](double x, double mn, double cw, int n) {
+            int v = ((int)std::floor((x - mn) / cw)) % n;
+            return (v % n + n) % n;
+        };
+        std::vector<int> cx(ns), cy(ns), cz(ns);
+        for (int s = 0; s < ns; ++s) {
+            cx[s] = coord(hx0[s], g.mn[0], g.cellw, g.nx);
+            cy[s] = coord(hy0[s], g.mn[1], g.cellw, g.ny);
+            cz[s] = g.dim == 3 ? coord(hz0[s], g.mn[2], g.cellw, g.nz) : 0;
+        }
+        const int R = g.range, span = 2 * R + 1;
+        auto off1 = [&](int cj, int ci, int n) {
+            int d = cj - ci;
+            if (d > R) d -= n;
+            if (d < -R) d += n;
+            return d + R;
+        };
+        std::vector<std::pair<long long, int>> row;
+        for (int s = 0; s < ns; ++s) {
+            row.clear();
+            for (int q = off32[s]; q < off32[s + 1]; ++q) {
+                const int j = ids[q];
+                const long long key = ((long long)off1(cx[j], cx[s], g.nx) * span + off1(cy[j], cy[s], g.ny)) * span +
+                                      (g.dim == 3 ? off1(cz[j], cz[s], g.nz) : 0);
+                row.emplace_back(key, j);
+            }
+            std::sort(row.begin(), row.end());
+            for (size_t q = 0; q < row.size(); ++q) ids[off32[s] + q] = row[q].second;
+        }
+    }
     // transpose: roff/rnbr (rows = particles that list s), ascending
     std::vector<int> roff((size_t)ns + 1, 0), rnbr((size_t)std::max<long long>(total, 1));
     for (long long k = 0; k < total; ++k) ++roff[ids[k] + 1];
@@ -428,9 +469,9 @@ static int init_solid(Ctx *c, const double *d_x03_orig)
     }
     const mphx_constants &k = c->c;
     if (c->p.dim == 3)
-        LAUNCH(c, k_solid_normalizer<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->phys.cwp);
+        LAUNCH(c, k_solid_normalizer<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->cw_tl);
     else
-        LAUNCH(c, k_solid_normalizer<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->phys.cwp);
+        LAUNCH(c, k_solid_normalizer<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->cw_tl);
     CK(cudaGetLastError());
     // restore the current positions (the arrays are now in x0-bucket order): gather through the ids
     LAUNCH(c, k_restore_by_id, nblk(n), kBlock, n, c->S.id, sx, sy, sz, c->S.x, c->S.y, c->S.z);
@@ -476,6 +517,17 @@ int mphx_device_count(void)
         if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
     }
     return ok;
+}
+
+int mphx_abi_sizeof(int which)
+{
+    switch (which) {
+    case 0: return (int)sizeof(mphx_params);
+    case 1: return (int)sizeof(mphx_run_control);
+    case 2: return (int)sizeof(mphx_constants);
+    case 3: return (int)sizeof(mphx_host_views);
+    default: return -1;
+    }
 }
 
 int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
@@ -580,7 +632,8 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         CK(cudaMemcpy(c->d_inv_density, c->phys.inv_density, sizeof(double) * kTypeCount, cudaMemcpyHostToDevice));
         double *zs[] = {c->P, c->volStrain, c->divP, c->fx, c->fy, c->fz, c->ax, c->ay, c->az, c->densA, c->gcx, c->gcy, c->gcz, c->PA};
         for (double *q : zs) CK(cudaMemsetAsync(q, 0, sizeof(double) * n, c->stream));
-        for (double **q : st) CK(cudaMemsetAsync(*q, 0, sizeof(double) * 9 * std::max<size_t>(ns, 1), c->stream));
+        if (ns > 0)
+            for (double **q : st) CK(cudaMemsetAsync(*q, 0, sizeof(double) * 9 * ns, c->stream));
     }
     // stage AoS host arrays, split to SoA on the device
     int *d_t = nullptr;
@@ -801,6 +854,7 @@ int mphx_debug_initial_structure_neighbors(mphx_ctx *ctx, long long *offsets, in
         if (total > 0) {
             CK(cudaMemcpy(ids, c->sol.nbr, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost));
             for (long long k = 0; k < total; ++k) ids[k] += sb;
+            for (int q = 0; q < ns; ++q) std::sort(ids + off32[q], ids + off32[q + 1]);
         }
     }
     return MPHX_OK;

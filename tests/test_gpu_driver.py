@@ -1,0 +1,64 @@
+"""The drop-in executable (same CLI as the reference, src/main.cpp:501-508) end to end on the GPU:
+its .prof/.vtk files against the text the reference executable wrote for the same inputs."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from particlemethod_fsi_b200 import cases
+
+pytestmark = pytest.mark.gpu
+EXE = os.path.join(ROOT, "particlemethod_fsi_b200", "Mph_Elastic_Explicit")
+
+
+def _gold(name):
+    return gzip.open(os.path.join(GOLDEN, name + ".gz"), "rb").read().decode()
+
+
+def _numbers(txt):
+    out = []
+    for tok in txt.split():
+        try:
+            out.append(float(tok))
+        except ValueError:
+            out.append(float(abs(hash(tok)) % 1000))
+    return np.array(out)
+
+
+@pytest.mark.parametrize("name,dim,module", [("tiny2d", "2", "dam"), ("tiny3d", "3", "dam")])
+def test_driver_outputs_match_reference_cli(name, dim, module, tmp_path):
+    c = getattr(cases, name)()
+    c.rc.end_time = 3.5 * c.params.dt
+    c.rc.output_interval = 2.0 * c.params.dt
+    c.rc.vtk_output_interval = 3.0 * c.params.dt
+    cases.write_grid_file(str(tmp_path / "c.grid"), c)
+    cases.write_data_file(str(tmp_path / "t.data"), c.params, c.rc)
+    r = subprocess.run([EXE, "t.data", "c.grid", "t%03d.prof", "t%03d.vtk", "t.log", "4", dim, module],
+                       cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    produced = sorted(f for f in os.listdir(tmp_path) if f.endswith((".prof", ".vtk")))
+    assert produced == ["output.vtk", "t000.prof", "t000.vtk", "t002.prof", "t003.vtk"]   # quirk Q8 naming
+    # state before the first step: byte-identical
+    assert (tmp_path / "t000.prof").read_text() == _gold(f"{name}_t000.prof")
+    assert (tmp_path / "output.vtk").read_text() == _gold(f"{name}_output.vtk")
+    for fn in ("t002.prof", "t000.vtk", "t003.vtk"):
+        mine, gold = (tmp_path / fn).read_text(), _gold(f"{name}_{fn}")
+        ml, gl = mine.splitlines(), gold.splitlines()
+        assert len(ml) == len(gl), fn
+        # identical layout: every non-numeric line (headers, section names) equal
+        for a, b in zip(ml, gl):
+            if a != b:
+                assert a[:1].isdigit() or a[:1] == "-", (fn, a, b)
+        a, b = _numbers(mine), _numbers(gold)
+        assert a.shape == b.shape
+        # %e prints 7 digits (and the vtk casts to float): values agree to print precision
+        assert np.abs(a - b).max() <= 2e-6 * max(1.0, np.abs(b).max()), fn
+        same = sum(x == y for x, y in zip(ml, gl)) / len(gl)
+        assert same > 0.97, (fn, same)
+    log = (tmp_path / "t.log").read_text()
+    for key in ("neighbor search:", "explicit calculation:", "virial calculation:", "other calculation:", "total:",
+                "total (check):", "N0p ="):
+        assert key in log
