@@ -169,6 +169,10 @@ void mphx_destroy(mphx_ctx *ctx);
 /* replaces `acc update device` (src/main.cpp:549-560, 946-950).  The caller keeps its arrays. */
 int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *position,
                 const double *initial_position, const double *velocity);
+/* per-step variant of the above for a caller that keeps the state on the host: replaces Position
+ * and Velocity only (original order, [N][3]); asynchronous on the context's stream, so pass
+ * page-locked buffers and keep them alive until the next mphx_sync/mphx_download */
+int mphx_upload_state(mphx_ctx *ctx, const double *position, const double *velocity);
 /* replaces src/main.cpp:534-537 + 564-570 (initialize*, calculateInitialNeighbor, first
  * calculateNeighbor/DensityA/GravityCenter/DensityP, calculateLamesconstant, calculateNormalizer) */
 int mphx_init(mphx_ctx *ctx);
@@ -196,8 +200,15 @@ int mphx_debug_neighbors(mphx_ctx *ctx, long long *offsets, int *ids, long long 
 int mphx_debug_initial_structure_neighbors(mphx_ctx *ctx, long long *offsets, int *ids,
                                            long long ids_capacity);
 
-/* accumulated device time per phase in milliseconds, same split as the reference timer block
- * (src/main.cpp:695-700): [0] neighbour search, [1] explicit calculation, [2] virial, [3] other */
+/* `nsteps` steps bracketed by CUDA events on the context's stream (the stream the kernels are
+ * launched on); returns the device time of the whole region in milliseconds after synchronising. */
+int mphx_timed_steps(mphx_ctx *ctx, int nsteps, double *elapsed_ms);
+/* per-phase device timers (CUDA events on the context's stream around each phase of every step):
+ * off by default; switching on resets the accumulators */
+int mphx_set_timing(mphx_ctx *ctx, int on);
+/* accumulated device milliseconds: [0] bucket rebuild (the reference's "neighbor search" timer,
+ * src/main.cpp:611), [1] pass 1, [2] pass 2, [3] solid sub-steps ([1]+[2]+[3] = its "explicit
+ * calculation" timer, :669) */
 int mphx_get_timers(mphx_ctx *ctx, double ms[4]);
 /* number of kernel launches issued by mphx_step since mphx_create (for bench.py gpu_launches) */
 long long mphx_launch_count(const mphx_ctx *ctx);

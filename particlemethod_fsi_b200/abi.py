@@ -98,8 +98,8 @@ EXPORTS = [
     "mphx_params_default", "mphx_read_data_file", "mphx_read_grid_file", "mphx_free_host",
     "mphx_write_prof_file", "mphx_write_vtk_file", "mphx_class_ranges",
     "mphx_compute_constants",
-    "mphx_create", "mphx_destroy", "mphx_upload", "mphx_init", "mphx_get_constants",
+    "mphx_create", "mphx_destroy", "mphx_upload", "mphx_upload_state", "mphx_init", "mphx_get_constants",
     "mphx_step", "mphx_step_fluid_only", "mphx_sync", "mphx_time", "mphx_set_time", "mphx_download",
     "mphx_debug_neighbors", "mphx_debug_initial_structure_neighbors",
-    "mphx_get_timers", "mphx_launch_count", "mphx_algorithmic_bytes_per_step",
+    "mphx_timed_steps", "mphx_set_timing", "mphx_get_timers", "mphx_launch_count", "mphx_algorithmic_bytes_per_step",
 ]

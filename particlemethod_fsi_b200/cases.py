@@ -170,7 +170,7 @@ def fsi2d(l0: float = 1.0e-3, tank=(0.4, 0.3), water=(0.1, 0.2), plate_x: float 
 
 def fsi3d(l0: float, tank=(1.6, 0.8, 1.0), water=(0.6, 0.5, 1.0), plate_x: float = 0.9,
           plate_layers: int = 4, plate_h: float = 0.3, elastic_dt_ratio: int = 5, dt: float = 1.0e-4,
-          z_walls: bool = True) -> Case:
+          z_walls: bool = True, _count_only: bool = False):
     """C4/C5: 3D dam break on an elastic plate.  x = flow/slab axis, y = up (gravity -y), z = span.
 
     The plate root is embedded three layers into the floor so that the DAM_Module clamp
@@ -193,6 +193,11 @@ def fsi3d(l0: float, tank=(1.6, 0.8, 1.0), water=(0.6, 0.5, 1.0), plate_x: float
         Cuboid(4, (Lx, 0.0, zlo), (Lx + w, Ly, zhi), l0),
     ]
     m = 7 * l0
+    if _count_only:
+        if z_walls:
+            cubs.append(Cuboid(4, (-w, -w, -w), (Lx + w, Ly, 0.0), l0))
+            cubs.append(Cuboid(4, (-w, -w, Lz), (Lx + w, Ly, Lz + w), l0))
+        return cubs
     if z_walls:
         cubs.append(Cuboid(4, (-w, -w, -w), (Lx + w, Ly, 0.0), l0))
         cubs.append(Cuboid(4, (-w, -w, Lz), (Lx + w, Ly, Lz + w), l0))
@@ -230,12 +235,19 @@ def tiny3d() -> Case:
 
 
 def fsi3d_for_count(n_target: float, **kw) -> Case:
-    """scale l0 so that the default 3D geometry has about n_target particles."""
-    ref_l0 = 0.02
-    c = fsi3d(ref_l0, **kw)
-    l0 = ref_l0 * (c.n / float(n_target)) ** (1.0 / 3.0)
-    l0 = float("%.3e" % l0)
-    return fsi3d(l0, **kw)
+    """scale l0 so that the default 3D geometry has about n_target particles (walls scale with the
+    surface, so the spacing is found by a few fixed-point iterations on coarse counts)"""
+    def count(l0):
+        n = 0
+        for cub in fsi3d(l0, **kw, _count_only=True):
+            n += int(np.prod([len(_axis(cub.lower[d], cub.upper[d], cub.spacing)) for d in range(3)]))
+        return n
+    l0 = 0.02
+    for _ in range(6):
+        l0 = float("%.4e" % (l0 * (count(l0) / float(n_target)) ** (1.0 / 3.0)))
+    c = fsi3d(l0, **kw)
+    c.name = "fsi3d_%dk" % round(c.n / 1000)
+    return c
 
 
 # ---- file formats (Python side: only for building inputs / reading results in tests) ------------

@@ -746,6 +746,20 @@ __global__ void k_solid_upload(Solid so, const int *__restrict__ type, const dou
     so.fx[s] = so.fy[s] = so.fz[s] = 0.0;
     so.type[s] = type[i];
 }
+// host state (original order AoS) -> current sorted slots (+ the solid arrays)
+__global__ void k_upload_state(int n, Particles p, Solid sol, const double *__restrict__ x3, const double *__restrict__ v3)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int id = p.id[q];
+    const size_t o = 3 * (size_t)id;
+    const double x = x3[o], y = x3[o + 1], z = x3[o + 2], vx = v3[o], vy = v3[o + 1], vz = v3[o + 2];
+    p.x[q] = x; p.y[q] = y; p.z[q] = z; p.vx[q] = vx; p.vy[q] = vy; p.vz[q] = vz;
+    if (is_structure_type(p.type[q])) {
+        const int s = id - sol.sb;
+        sol.x[s] = x; sol.y[s] = y; sol.z[s] = z; sol.vx[s] = vx; sol.vy[s] = vy; sol.vz[s] = vz;
+    }
+}
 __global__ void k_split_vec3(int n, const double *__restrict__ a3, double *__restrict__ x, double *__restrict__ y,
                              double *__restrict__ z)
 {

@@ -101,6 +101,7 @@ int main(int argc, char *argv[])
     log_printf("N0p = %e, count=%d\n", k.n0p, k.n0p_count); // :1303
     if ((rc = mphx_upload(ctx, n, property, position, initial_position, velocity))) die("mphx_upload", rc);
     if ((rc = mphx_init(ctx))) die("mphx_init", rc);
+    mphx_set_timing(ctx, 1);
 
     const size_t N = (size_t)n;
     std::vector<double> force(3 * N), accel(3 * N), stress(9 * N), strain(9 * N);
@@ -168,7 +169,7 @@ int main(int argc, char *argv[])
         time_t t = time(NULL);
         log_printf("end main roop at %s\n", ctime(&t));
         // same six lines as src/main.cpp:695-700; times are wall/device seconds of this process
-        const double neigh = ms[0] * 1e-3, expl = (ms[0] > 0 ? ms[1] * 1e-3 : sStep);
+        const double neigh = ms[0] * 1e-3, expl = (ms[0] > 0 ? (ms[1] + ms[2] + ms[3]) * 1e-3 : sStep);
         log_printf("neighbor search:         %lf [CPU sec]\n", neigh);
         log_printf("explicit calculation:    %lf [CPU sec]\n", expl);
         log_printf("virial calculation:      %lf [CPU sec]\n", 0.0);

@@ -61,12 +61,16 @@ struct Ctx {
     double *d_inv_density = nullptr;
     double cw_tl = 0.0; // weight() prefactor (1.0/Swp)*(1.0/RP^d), src/main.cpp:291/293
     double *d_x0_orig = nullptr; // InitialPosition, original order AoS (for re-upload / debugging)
+    double *stage3a = nullptr, *stage3b = nullptr, *stage1 = nullptr, *stage9 = nullptr; // AoS staging (lazy)
+    int *stagei = nullptr;
+    bool buckets_valid = false; // cellStart / bx,by,bz describe the positions currently held
     std::vector<void *> allocs;
 
     // phase timers (src/main.cpp:695-700 split)
     bool timing = false;
     std::vector<cudaEvent_t> ev;
     double ms[4] = {0, 0, 0, 0};
+    cudaEvent_t tev[2] = {nullptr, nullptr};
 
     template <class Tp> int alloc(Tp **ptr, size_t count)
     {
@@ -220,6 +224,7 @@ static int rebuild_buckets(Ctx *c, bool prestep_motion)
     LAUNCH(c, k_permute, nblk(n), kBlock, n, c->S, c->T, c->cellStart, c->tmpIdx);
     std::swap(c->S, c->T);
     c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
+    c->buckets_valid = true;
     CK(cudaGetLastError());
     return MPHX_OK;
 }
@@ -289,15 +294,13 @@ static void timer_resolve(Ctx *c)
 {
     if (c->ev.empty()) return;
     cudaStreamSynchronize(c->stream);
-    // events come in groups of 4 per step: start, after rebuild, after fluid, after solid
-    for (size_t i = 0; i + 3 < c->ev.size(); i += 4) {
-        float a = 0, b = 0, d = 0;
-        cudaEventElapsedTime(&a, c->ev[i], c->ev[i + 1]);
-        cudaEventElapsedTime(&b, c->ev[i + 1], c->ev[i + 2]);
-        cudaEventElapsedTime(&d, c->ev[i + 2], c->ev[i + 3]);
-        c->ms[0] += a;
-        c->ms[1] += b + d;
-    }
+    // events come in groups of 5 per step: start, after rebuild, after pass 1, after pass 2, after solid
+    for (size_t i = 0; i + 4 < c->ev.size(); i += 5)
+        for (int k = 0; k < 4; ++k) {
+            float a = 0;
+            cudaEventElapsedTime(&a, c->ev[i + k], c->ev[i + k + 1]);
+            c->ms[k] += a;
+        }
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     c->ev.clear();
 }
@@ -309,6 +312,7 @@ static int one_step(Ctx *c, bool fluid_only)
     if ((rc = rebuild_buckets(c, true))) return rc; // calculateWall, PeriodicBoundary, resets, calculateNeighbor
     timer_mark(c);
     if ((rc = run_pass1(c))) return rc;             // DensityA..DivergenceP, coefficients, PressureP/A
+    timer_mark(c);
     if ((rc = run_pass2(c))) return rc;             // force sums, gravity, interface, acceleration, convection
     timer_mark(c);
     if (!fluid_only) {
@@ -317,7 +321,7 @@ static int one_step(Ctx *c, bool fluid_only)
         ++c->steps_done;
     }
     timer_mark(c);
-    if (c->ev.size() >= 4096) timer_resolve(c);
+    if (c->ev.size() >= 5000) timer_resolve(c);
     return MPHX_OK;
 }
 
@@ -563,6 +567,7 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
         return MPHX_ERR_CUDA;
     }
     c->timing = std::getenv("MPHX_TIMING") != nullptr;
+    for (int k = 0; k < 2; ++k) cudaEventCreate(&c->tev[k]);
     *out = reinterpret_cast<mphx_ctx *>(c);
     return MPHX_OK;
 }
@@ -574,6 +579,7 @@ void mphx_destroy(mphx_ctx *ctx)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) if (c->tev[k]) cudaEventDestroy(c->tev[k]);
     for (void *q : c->allocs) cudaFree(q);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -659,6 +665,24 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
     return MPHX_OK;
 }
 
+// replace Position and Velocity of every particle (original order) on an initialised context:
+// the per-step host->device path of a caller that owns the state on the host
+int mphx_upload_state(mphx_ctx *ctx, const double *position, const double *velocity)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->inited || !position || !velocity) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    const size_t N = (size_t)c->n;
+    if (!c->stage3a && c->alloc(&c->stage3a, 3 * N)) return MPHX_ERR_NOMEM;
+    if (!c->stage3b && c->alloc(&c->stage3b, 3 * N)) return MPHX_ERR_NOMEM;
+    CK(cudaMemcpyAsync(c->stage3a, position, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->stage3b, velocity, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_upload_state, nblk(c->n), kBlock, c->n, c->S, c->sol, c->stage3a, c->stage3b);
+    c->buckets_valid = false;
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
 int mphx_init(mphx_ctx *ctx)
 {
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
@@ -693,6 +717,37 @@ int mphx_step(mphx_ctx *ctx, int nsteps)
         int rc = one_step(c, false);
         if (rc) return rc;
     }
+    return MPHX_OK;
+}
+
+int mphx_timed_steps(mphx_ctx *ctx, int nsteps, double *elapsed_ms)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->inited || nsteps < 0 || !elapsed_ms) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->tev[0], c->stream));
+    for (int s = 0; s < nsteps; ++s) {
+        int rc = one_step(c, false);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(c->tev[1], c->stream));
+    CK(cudaEventSynchronize(c->tev[1]));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->tev[0], c->tev[1]));
+    *elapsed_ms = ms;
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+int mphx_set_timing(mphx_ctx *ctx, int on)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return MPHX_ERR_INVALID;
+    cudaSetDevice(c->device);
+    timer_resolve(c);
+    c->timing = on != 0;
+    if (on) for (int k = 0; k < 4; ++k) c->ms[k] = 0.0;
     return MPHX_OK;
 }
 
@@ -731,11 +786,11 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     CK(cudaSetDevice(c->device));
     const int n = c->n, ns = c->ns;
     const size_t N = (size_t)n;
-    double *d3 = nullptr, *d1 = nullptr, *d9 = nullptr;
-    int *di = nullptr;
-    CK(cudaMalloc(&d3, sizeof(double) * 3 * N));
-    CK(cudaMalloc(&d1, sizeof(double) * N));
-    CK(cudaMalloc(&di, sizeof(int) * N));
+    if (!c->stage3a && c->alloc(&c->stage3a, 3 * N)) return MPHX_ERR_NOMEM;
+    if (!c->stage1 && c->alloc(&c->stage1, N)) return MPHX_ERR_NOMEM;
+    if (!c->stagei && c->alloc(&c->stagei, N)) return MPHX_ERR_NOMEM;
+    double *d3 = c->stage3a, *d1 = c->stage1, *d9 = c->stage9;
+    int *di = c->stagei;
     const Particles &S = c->S;
     const Solid &so = c->sol;
     int rc = MPHX_OK;
@@ -763,7 +818,10 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     };
     auto tens = [&](double *host, const double *M) -> int {
         if (!host) return MPHX_OK;
-        if (!d9) { CK(cudaMalloc(&d9, sizeof(double) * 9 * N)); }
+        if (!d9) {
+            if (c->alloc(&c->stage9, 9 * N)) return MPHX_ERR_NOMEM;
+            d9 = c->stage9;
+        }
         CK(cudaMemsetAsync(d9, 0, sizeof(double) * 9 * N, c->stream));
         if (ns > 0) LAUNCH(c, k_solid_tensor_to_orig, nblk(ns), kBlock, so, M, d9);
         CK(cudaMemcpyAsync(host, d9, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, c->stream));
@@ -793,6 +851,7 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         if ((rc = ints(v->cell_index, S.key))) break;
         if (v->neighbor_count) {
             if (!c->inited) { rc = MPHX_ERR_INVALID; break; }
+            if (!c->buckets_valid && (rc = rebuild_buckets(c, false))) break;
             std::vector<long long> off;
             long long total = 0;
             if ((rc = exact_lists(c, false, false, 0, n, off, nullptr, &total))) break;
@@ -811,8 +870,6 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         if ((rc = solid_scal(v->lambda_lames, so.lam))) break;
         if ((rc = solid_scal(v->mu_lames, so.mu))) break;
     } while (0);
-    cudaFree(d3); cudaFree(d1); cudaFree(di);
-    if (d9) cudaFree(d9);
     if (rc == MPHX_OK) { CK(cudaGetLastError()); }
     return rc;
 }

@@ -53,6 +53,7 @@ def _load():
     L.mphx_destroy.argtypes = [vp]
     L.mphx_destroy.restype = None
     L.mphx_upload.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.mphx_upload_state.argtypes = [vp, vp, vp]
     L.mphx_init.argtypes = [vp]
     L.mphx_get_constants.argtypes = [vp, C.POINTER(abi.Constants)]
     L.mphx_step.argtypes = [vp, C.c_int]
@@ -64,6 +65,8 @@ def _load():
     L.mphx_download.argtypes = [vp, C.POINTER(abi.HostViews)]
     L.mphx_debug_neighbors.argtypes = [vp, vp, vp, C.c_longlong]
     L.mphx_debug_initial_structure_neighbors.argtypes = [vp, vp, vp, C.c_longlong]
+    L.mphx_timed_steps.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
+    L.mphx_set_timing.argtypes = [vp, C.c_int]
     L.mphx_get_timers.argtypes = [vp, C.POINTER(C.c_double * 4)]
     L.mphx_launch_count.argtypes = [vp]
     L.mphx_launch_count.restype = C.c_longlong
@@ -197,6 +200,23 @@ class Solver:
                                            v.ctypes.data))
         self.n = t.shape[0]
 
+    def upload_state(self, position, velocity):
+        """per-step H2D of Position/Velocity (original order); arrays must stay alive until sync"""
+        assert position.dtype == np.float64 and velocity.dtype == np.float64
+        assert position.flags.c_contiguous and velocity.flags.c_contiguous
+        _ck("mphx_upload_state", lib.mphx_upload_state(self._ctx, position.ctypes.data, velocity.ctypes.data))
+
+    def upload_state_ptr(self, position_ptr: int, velocity_ptr: int):
+        _ck("mphx_upload_state", lib.mphx_upload_state(self._ctx, position_ptr, velocity_ptr))
+
+    def download_ptr(self, **ptrs):
+        """download into raw host pointers (e.g. torch pinned tensors): name=int address"""
+        hv = abi.HostViews()
+        for nm, ptr in ptrs.items():
+            _shape, is_int = abi.VIEW_FIELDS[nm]
+            setattr(hv, nm, C.cast(ptr, C.POINTER(C.c_int if is_int else C.c_double)))
+        _ck("mphx_download", lib.mphx_download(self._ctx, C.byref(hv)))
+
     def init(self):
         _ck("mphx_init", lib.mphx_init(self._ctx))
 
@@ -252,6 +272,15 @@ class Solver:
         _ck("mphx_debug_initial_structure_neighbors",
             lib.mphx_debug_initial_structure_neighbors(self._ctx, off.ctypes.data, ids.ctypes.data, ids.shape[0]))
         return off, ids[: int(off[-1])]
+
+    def timed_steps(self, nsteps: int) -> float:
+        """device milliseconds (CUDA events on the context's stream) of `nsteps` steps"""
+        ms = C.c_double()
+        _ck("mphx_timed_steps", lib.mphx_timed_steps(self._ctx, nsteps, C.byref(ms)))
+        return ms.value
+
+    def set_timing(self, on: bool):
+        _ck("mphx_set_timing", lib.mphx_set_timing(self._ctx, 1 if on else 0))
 
     def timers_ms(self):
         ms = (C.c_double * 4)()
