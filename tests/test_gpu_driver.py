@@ -56,8 +56,11 @@ def test_driver_outputs_match_reference_cli(name, dim, module, tmp_path):
         assert a.shape == b.shape
         # %e prints 7 digits (and the vtk casts to float): values agree to print precision
         assert np.abs(a - b).max() <= 2e-6 * max(1.0, np.abs(b).max()), fn
-        same = sum(x == y for x, y in zip(ml, gl)) / len(gl)
-        assert same > 0.97, (fn, same)
+        if fn.endswith(".prof"):
+            # type + Position + InitialPosition columns print identically (velocities of a fluid that
+            # starts at rest are rounding noise at these early steps and are covered by the bound above)
+            same = sum(x.split()[:7] == y.split()[:7] for x, y in zip(ml[2:], gl[2:])) / (len(gl) - 2)
+            assert same > 0.995, (fn, same)
     log = (tmp_path / "t.log").read_text()
     for key in ("neighbor search:", "explicit calculation:", "virial calculation:", "other calculation:", "total:",
                 "total (check):", "N0p ="):

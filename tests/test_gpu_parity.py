@@ -232,7 +232,8 @@ def test_scale_properties_3d_300k():
     g1 = s.download("position", "velocity", "force", "property")
     assert np.isfinite(g1["position"]).all() and np.isfinite(g1["velocity"]).all()
     walls = g1["property"] >= 4
-    assert np.array_equal(g1["position"][walls], case.position[walls])      # walls do not move (V=0)
+    # walls do not move (V=0) -- up to the ulp the reference's wrap (x-min)+min itself introduces (:3330)
+    assert np.abs(g1["position"][walls] - case.position[walls]).max() < 1e-15
     # particles stay inside the periodic box
     for d in range(3):
         assert (g1["position"][:, d] >= p.domain_min[d]).all() and (g1["position"][:, d] <= p.domain_max[d]).all()
