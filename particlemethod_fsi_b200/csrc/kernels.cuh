@@ -62,6 +62,7 @@ struct WallMotion {
 struct Particles {
     double *x, *y, *z, *vx, *vy, *vz;
     int *type, *id, *key;
+    float4 *pf; // (position - DomainMin)/CellWidth in fp32 + type bits: input of the sweep's fp32 filter
 };
 
 // total-Lagrangian solid, static order (solid-local index s = original id - sb)
@@ -244,7 +245,7 @@ __global__ void k_scatter_index(int n, const int *__restrict__ key, const int *_
 // K4: permute the SoA into bucket order; inside a bucket particles are ordered by original id, which
 // makes the layout (and therefore every floating-point sum) independent of atomic arrival order.
 __global__ void k_permute(int n, Particles src, Particles dst, const int *__restrict__ cellStart,
-                          const int *__restrict__ tmpIdx)
+                          const int *__restrict__ tmpIdx, GridDesc g)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
@@ -261,9 +262,14 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
             if (rank == want) { s = sa; break; }
         }
     }
-    dst.x[q] = src.x[s]; dst.y[q] = src.y[s]; dst.z[q] = src.z[s];
+    const double x = src.x[s], y = src.y[s], z = src.z[s];
+    const int t = src.type[s];
+    dst.x[q] = x; dst.y[q] = y; dst.z[q] = z;
     dst.vx[q] = src.vx[s]; dst.vy[q] = src.vy[s]; dst.vz[q] = src.vz[s];
-    dst.type[q] = src.type[s]; dst.id[q] = src.id[s]; dst.key[q] = k;
+    dst.type[q] = t; dst.id[q] = src.id[s]; dst.key[q] = k;
+    const double icw = 1.0 / g.cellw;
+    dst.pf[q] = make_float4((float)((x - g.mn[0]) * icw), (float)((y - g.mn[1]) * icw), (float)((z - g.mn[2]) * icw),
+                            __int_as_float(t));
 }
 
 // ------------------------------------------------------------------------------------------------

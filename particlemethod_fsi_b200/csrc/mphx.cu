@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
+#include "sweep.cuh"
 #include "mphx.h"
 #include "mphx_internal.h"
 
@@ -63,7 +64,9 @@ struct Ctx {
     double *d_x0_orig = nullptr; // InitialPosition, original order AoS (for re-upload / debugging)
     double *stage3a = nullptr, *stage3b = nullptr, *stage1 = nullptr, *stage9 = nullptr; // AoS staging (lazy)
     int *stagei = nullptr;
-    bool buckets_valid = false; // cellStart / bx,by,bz describe the positions currently held
+    bool buckets_valid = false;
+    int sweep_version = 2; // MPHX_SWEEP=1 selects the simple one-phase sweeps (A/B debugging only)
+    int sweep_batch = 12;  // stencil columns per filter/drain batch (3D) // cellStart / bx,by,bz describe the positions currently held
     std::vector<void *> allocs;
 
     // phase timers (src/main.cpp:695-700 split)
@@ -98,6 +101,7 @@ static int alloc_particles(Ctx *c, Particles *p, size_t n)
     rc |= c->alloc(&p->x, n); rc |= c->alloc(&p->y, n); rc |= c->alloc(&p->z, n);
     rc |= c->alloc(&p->vx, n); rc |= c->alloc(&p->vy, n); rc |= c->alloc(&p->vz, n);
     rc |= c->alloc(&p->type, n); rc |= c->alloc(&p->id, n); rc |= c->alloc(&p->key, n);
+    rc |= c->alloc(&p->pf, n);
     return rc ? MPHX_ERR_NOMEM : MPHX_OK;
 }
 
@@ -221,7 +225,7 @@ static int rebuild_buckets(Ctx *c, bool prestep_motion)
     LAUNCH(c, k_scan_top, 1, kScanThreads, c->blockSums, c->scan_blocks);
     LAUNCH(c, k_scan_apply, c->scan_blocks, kScanThreads, c->cellCount, nc, c->blockSums, c->cellStart);
     LAUNCH(c, k_scatter_index, nblk(n), kBlock, n, c->S.key, c->slot, c->cellStart, c->tmpIdx);
-    LAUNCH(c, k_permute, nblk(n), kBlock, n, c->S, c->T, c->cellStart, c->tmpIdx);
+    LAUNCH(c, k_permute, nblk(n), kBlock, n, c->S, c->T, c->cellStart, c->tmpIdx, c->grid);
     std::swap(c->S, c->T);
     c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
     c->buckets_valid = true;
@@ -229,14 +233,39 @@ static int rebuild_buckets(Ctx *c, bool prestep_motion)
     return MPHX_OK;
 }
 
+// squared cut-off (bucket units) of the sweep's fp32 filter: the exact cut-off plus a margin that
+// covers the rounding of the fp32 bucket coordinates (<= 2 ulp at the largest coordinate, per axis)
+// and of the fp32 distance arithmetic, so the filter is a superset of the fp64 predicate.
+static float filter_radius2(const Ctx *c, double rmax)
+{
+    const GridDesc &g = c->grid;
+    const double R = rmax / g.cellw;
+    const double big = (double)std::max(std::max(g.nx, g.ny), std::max(g.nz, 4)) + 2.0 * g.range + 2.0;
+    const double delta = std::ldexp(big, -22);           // 2 ulp_f32(big) per coordinate, both particles
+    const double margin = 2.0 * std::sqrt(3.0) * (R + 1.0) * (2.0 * delta) + 3.0 * (2.0 * delta) * (2.0 * delta) +
+                          8.0 * std::ldexp((R + 1.0) * (R + 1.0), -23) + 1e-6;
+    return (float)(R * R + margin) * (1.0f + 1e-6f);
+}
+
 static int run_pass1(Ctx *c)
 {
     const int n = c->n;
+    const mphx_constants &k = c->c;
+    if (c->sweep_version == 1) {
 #define P1(D, ST) LAUNCH(c, (k_pass1<D, ST>), nblk(n), kBlock, n, c->S, c->cellStart, c->grid, c->phys, c->P, c->volStrain, \
                          c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA)
-    if (c->p.dim == 3) { if (c->surface_tension) P1(3, true); else P1(3, false); }
-    else               { if (c->surface_tension) P1(2, true); else P1(2, false); }
+        if (c->p.dim == 3) { if (c->surface_tension) P1(3, true); else P1(3, false); }
+        else               { if (c->surface_tension) P1(2, true); else P1(2, false); }
 #undef P1
+    } else {
+        const float f2 = filter_radius2(c, c->surface_tension ? std::max(k.radius_p, k.radius_a) : k.radius_p);
+        const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
+#define P1(D, ST) LAUNCH(c, (k_pass1_v2<D, ST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
+                         batch, c->P, c->volStrain, c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA)
+        if (c->p.dim == 3) { if (c->surface_tension) P1(3, true); else P1(3, false); }
+        else               { if (c->surface_tension) P1(2, true); else P1(2, false); }
+#undef P1
+    }
     CK(cudaGetLastError());
     return MPHX_OK;
 }
@@ -244,12 +273,26 @@ static int run_pass1(Ctx *c)
 static int run_pass2(Ctx *c)
 {
     const int n = c->n;
+    const mphx_constants &k = c->c;
+    if (c->sweep_version == 1) {
 #define P2(D, ST) LAUNCH(c, (k_pass2<D, ST>), nblk(n), kBlock, n, c->S, c->cellStart, c->grid, c->phys, c->P, c->PA, c->gcx, \
                          c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, c->fy, c->fz, c->ax,  \
                          c->ay, c->az, c->sol)
-    if (c->p.dim == 3) { if (c->surface_tension) P2(3, true); else P2(3, false); }
-    else               { if (c->surface_tension) P2(2, true); else P2(2, false); }
+        if (c->p.dim == 3) { if (c->surface_tension) P2(3, true); else P2(3, false); }
+        else               { if (c->surface_tension) P2(2, true); else P2(2, false); }
 #undef P2
+    } else {
+        double rmax = std::max(k.radius_p, k.radius_v);
+        if (c->surface_tension) rmax = std::max(rmax, k.radius_a);
+        const float f2 = filter_radius2(c, rmax);
+        const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
+#define P2(D, ST) LAUNCH(c, (k_pass2_v2<D, ST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
+                         batch, c->P, c->PA, c->gcx, c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, \
+                         c->fy, c->fz, c->ax, c->ay, c->az, c->sol)
+        if (c->p.dim == 3) { if (c->surface_tension) P2(3, true); else P2(3, false); }
+        else               { if (c->surface_tension) P2(2, true); else P2(2, false); }
+#undef P2
+    }
     // S keeps type/id/key of this step's order and takes the integrated x,v; T keeps the pre-step
     // (bucket) positions for the neighbour-count diagnostics.
     std::swap(c->S.x, c->T.x); std::swap(c->S.y, c->T.y); std::swap(c->S.z, c->T.z);
@@ -567,6 +610,8 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
         return MPHX_ERR_CUDA;
     }
     c->timing = std::getenv("MPHX_TIMING") != nullptr;
+    if (const char *e = std::getenv("MPHX_SWEEP")) c->sweep_version = std::atoi(e) == 1 ? 1 : 2;
+    if (const char *e = std::getenv("MPHX_SWEEP_BATCH")) c->sweep_batch = std::max(1, std::atoi(e));
     for (int k = 0; k < 2; ++k) cudaEventCreate(&c->tev[k]);
     *out = reinterpret_cast<mphx_ctx *>(c);
     return MPHX_OK;
