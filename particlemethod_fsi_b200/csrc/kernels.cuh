@@ -72,8 +72,16 @@ struct Solid {
     double *Linv, *Fm, *E, *S, *Pk; // 9 planes of ns doubles each: M[k*ns+s], k = 3*row+col
     double *lam, *mu;
     int *type;
-    int *off, *nbr;   // InitialStructureNeighbor as CSR (solid-local ids, rows ascending)
-    int *roff, *rnbr; // transpose: rows = particles that list s
+    int *off, *nbr;   // InitialStructureNeighbor as CSR (solid-local ids, rows in the reference's list order)
+    int *roff, *rnbr; // transpose: rows = particles that list s (ascending)
+    // The sub-step kernels read the lists in ELL layout (entry kk of row s at [kk*ns + s]: coalesced
+    // across the threads of a warp) together with static per-pair data of the reference
+    // configuration computed once: x0_ij and weight(x0_ij).
+    int *len, *rlen;                 // row lengths
+    int *enbr, *ernbr;               // ELL neighbour ids (own rows / transposed rows)
+    double *d0x, *d0y, *d0z, *w;     // own rows
+    double *rd0x, *rd0y, *rd0z, *rw; // transposed: x0_js as row j computes it
+    double *ux, *uy, *uz;            // displacement u = minimg(x - x0) of the current positions
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -144,7 +152,12 @@ __global__ void k_prestep(int n, Particles p, Solid sol, GridDesc g, WallMotion 
         z = __dadd_rn(mod_exact(__dsub_rn(z, g.mn[2]), g.W[2]), g.mn[2]);
     }
     p.x[i] = x; p.y[i] = y; p.z[i] = z;
-    if (s >= 0) { sol.x[s] = x; sol.y[s] = y; sol.z[s] = z; }
+    if (s >= 0) {
+        sol.x[s] = x; sol.y[s] = y; sol.z[s] = z;
+        sol.ux[s] = minimg_exact(x, sol.x0[s], g.W[0]); // :2712, from the (wrapped) position the sub-steps start from
+        sol.uy[s] = minimg_exact(y, sol.y0[s], g.W[1]);
+        sol.uz[s] = minimg_exact(z, sol.z0[s], g.W[2]);
+    }
     const int k = cell_key(g, x, y, z);
     p.key[i] = k;
     slot[i] = atomicAdd(&cellCount[k], 1);
@@ -610,19 +623,17 @@ __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double 
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= so.ns) return;
     const int ns = so.ns;
-    const double xi0 = so.x0[s], yi0 = so.y0[s], zi0 = so.z0[s];
-    const double ui[3] = {minimg_exact(so.x[s], xi0, W0), minimg_exact(so.y[s], yi0, W1),
-                          DIMS == 3 ? minimg_exact(so.z[s], zi0, W2) : 0.0};
+    const double ui[3] = {so.ux[s], so.uy[s], DIMS == 3 ? so.uz[s] : 0.0};
     double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int k = so.off[s]; k < so.off[s + 1]; ++k) {
-        const int j = so.nbr[k];
-        const double xj0 = so.x0[j], yj0 = so.y0[j], zj0 = so.z0[j];
-        const double d0[3] = {minimg_exact(xj0, xi0, W0), minimg_exact(yj0, yi0, W1), DIMS == 3 ? minimg_exact(zj0, zi0, W2) : 0.0};
-        const double uj[3] = {minimg_exact(so.x[j], xj0, W0), minimg_exact(so.y[j], yj0, W1),
-                              DIMS == 3 ? minimg_exact(so.z[j], zj0, W2) : 0.0};
+    const int len = so.len[s];
+    for (int kk = 0; kk < len; ++kk) {
+        const size_t k = (size_t)kk * ns + s;
+        const int j = so.enbr[k];
+        const double d0[3] = {so.d0x[k], so.d0y[k], DIMS == 3 ? so.d0z[k] : 0.0};
+        const double uj[3] = {so.ux[j], so.uy[j], DIMS == 3 ? so.uz[j] : 0.0};
         double d[3];
         for (int a = 0; a < DIMS; ++a) d[a] = add(d0[a], sub(uj[a], ui[a])); // :2716
-        const double w = tl_weight<DIMS>(d0[0], d0[1], d0[2], radius, cw);
+        const double w = so.w[k];
         for (int a = 0; a < DIMS; ++a)
             for (int b = 0; b < DIMS; ++b) G[a][b] = add(G[a][b], mul(mul(w, d[a]), d0[b])); // :2726
     }
@@ -677,10 +688,10 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
     const double xi0 = so.x0[s], yi0 = so.y0[s], zi0 = so.z0[s];
     const double ir = inv_density[so.type[s]];
     double v[3] = {so.vx[s], so.vy[s], so.vz[s]};
-    auto scattered_from = [&](int j) { // row j lists s:  v_s -= invRho_s * (w P_j x0_js) * dt
-        const double xj0 = so.x0[j], yj0 = so.y0[j], zj0 = so.z0[j];
-        const double d0[3] = {minimg_exact(xi0, xj0, W0), minimg_exact(yi0, yj0, W1), DIMS == 3 ? minimg_exact(zi0, zj0, W2) : 0.0};
-        const double w = tl_weight<DIMS>(d0[0], d0[1], d0[2], radius, cw);
+    auto scattered_from = [&](int kk, int j) { // row j lists s:  v_s -= invRho_s * (w P_j x0_js) * dt
+        const size_t k = (size_t)kk * ns + s;
+        const double d0[3] = {so.rd0x[k], so.rd0y[k], DIMS == 3 ? so.rd0z[k] : 0.0};
+        const double w = so.rw[k];
         for (int a = 0; a < DIMS; ++a) {
             double f = 0.0;
             for (int b = 0; b < DIMS; ++b) f = add(f, mul(MPHX_T(so.Pk, a, b, j, ns), d0[b]));
@@ -688,18 +699,22 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
             v[a] = sub(v[a], mul(mul(ir, f), edt)); // :2885
         }
     };
-    int k = so.roff[s];
-    const int kend = so.roff[s + 1];
-    for (; k < kend && so.rnbr[k] < s; ++k) scattered_from(so.rnbr[k]);
+    int kr = 0;
+    const int rlen = so.rlen[s];
+    for (; kr < rlen; ++kr) {
+        const int j = so.ernbr[(size_t)kr * ns + s];
+        if (j >= s) break;
+        scattered_from(kr, j);
+    }
     {
         double Pi[3][3];
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) Pi[a][b] = (a < DIMS && b < DIMS) ? MPHX_T(so.Pk, a, b, s, ns) : 0.0;
-        for (int q = so.off[s]; q < so.off[s + 1]; ++q) { // own row: v_s += invRho_s * (w P_s x0_sj) * dt
-            const int j = so.nbr[q];
-            const double d0[3] = {minimg_exact(so.x0[j], xi0, W0), minimg_exact(so.y0[j], yi0, W1),
-                                  DIMS == 3 ? minimg_exact(so.z0[j], zi0, W2) : 0.0};
-            const double w = tl_weight<DIMS>(d0[0], d0[1], d0[2], radius, cw);
+        const int len = so.len[s];
+        for (int kk = 0; kk < len; ++kk) { // own row: v_s += invRho_s * (w P_s x0_sj) * dt
+            const size_t q = (size_t)kk * ns + s;
+            const double d0[3] = {so.d0x[q], so.d0y[q], DIMS == 3 ? so.d0z[q] : 0.0};
+            const double w = so.w[q];
             for (int a = 0; a < DIMS; ++a) {
                 double f = 0.0;
                 for (int b = 0; b < DIMS; ++b) f = add(f, mul(Pi[a][b], d0[b]));
@@ -708,7 +723,7 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
             }
         }
     }
-    for (; k < kend; ++k) scattered_from(so.rnbr[k]);
+    for (; kr < rlen; ++kr) scattered_from(kr, so.ernbr[(size_t)kr * ns + s]);
     double x[3] = {so.x[s], so.y[s], so.z[s]};
     // Acceleration of solids is 0 (:2892): v += 0*dt leaves v unchanged
     if (module != 0) {
@@ -727,6 +742,39 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
     }
     so.x[s] = x[0]; so.y[s] = x[1]; so.z[s] = x[2];
     so.vx[s] = v[0]; so.vy[s] = v[1]; so.vz[s] = v[2];
+    so.ux[s] = minimg_exact(x[0], xi0, W0); so.uy[s] = minimg_exact(x[1], yi0, W1); so.uz[s] = minimg_exact(x[2], zi0, W2);
+}
+
+// static pair data of the reference configuration (once, after the lists are known)
+template <int DIMS>
+__global__ void k_solid_pairs(Solid so, double W0, double W1, double W2, double radius, double cw)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= so.ns) return;
+    const double xi0 = so.x0[s], yi0 = so.y0[s], zi0 = so.z0[s];
+    const int ns = so.ns;
+    int kk = 0;
+    for (int c = so.off[s]; c < so.off[s + 1]; ++c, ++kk) {
+        const int j = so.nbr[c];
+        const size_t k = (size_t)kk * ns + s;
+        const double a = minimg_exact(so.x0[j], xi0, W0), b = minimg_exact(so.y0[j], yi0, W1);
+        const double cc = DIMS == 3 ? minimg_exact(so.z0[j], zi0, W2) : 0.0;
+        so.enbr[k] = j;
+        so.d0x[k] = a; so.d0y[k] = b; so.d0z[k] = cc;
+        so.w[k] = tl_weight<DIMS>(a, b, cc, radius, cw);
+    }
+    so.len[s] = kk;
+    kk = 0;
+    for (int c = so.roff[s]; c < so.roff[s + 1]; ++c, ++kk) {
+        const int j = so.rnbr[c]; // row j lists s: x0_js = Mod(x0_s - x0_j ...) as row j computes it
+        const size_t k = (size_t)kk * ns + s;
+        const double a = minimg_exact(xi0, so.x0[j], W0), b = minimg_exact(yi0, so.y0[j], W1);
+        const double cc = DIMS == 3 ? minimg_exact(zi0, so.z0[j], W2) : 0.0;
+        so.ernbr[k] = j;
+        so.rd0x[k] = a; so.rd0y[k] = b; so.rd0z[k] = cc;
+        so.rw[k] = tl_weight<DIMS>(a, b, cc, radius, cw);
+    }
+    so.rlen[s] = kk;
 }
 
 // ------------------------------------------------------------------------------------------------

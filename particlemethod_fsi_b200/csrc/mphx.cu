@@ -496,6 +496,19 @@ static int init_solid(Ctx *c, const double *d_x03_orig)
     int e = 0;
     e |= c->alloc(&c->sol.off, (size_t)ns + 1); e |= c->alloc(&c->sol.nbr, (size_t)total);
     e |= c->alloc(&c->sol.roff, (size_t)ns + 1); e |= c->alloc(&c->sol.rnbr, (size_t)total);
+    {
+        int maxlen = 0, rmaxlen = 0;
+        for (int s = 0; s < ns; ++s) {
+            maxlen = std::max(maxlen, off32[s + 1] - off32[s]);
+            rmaxlen = std::max(rmaxlen, roff[s + 1] - roff[s]);
+        }
+        double **pd[] = {&c->sol.d0x, &c->sol.d0y, &c->sol.d0z, &c->sol.w};
+        for (double **q : pd) e |= c->alloc(q, (size_t)maxlen * ns);
+        double **pr[] = {&c->sol.rd0x, &c->sol.rd0y, &c->sol.rd0z, &c->sol.rw};
+        for (double **q : pr) e |= c->alloc(q, (size_t)rmaxlen * ns);
+        e |= c->alloc(&c->sol.enbr, (size_t)maxlen * ns); e |= c->alloc(&c->sol.ernbr, (size_t)rmaxlen * ns);
+        e |= c->alloc(&c->sol.len, (size_t)ns); e |= c->alloc(&c->sol.rlen, (size_t)ns);
+    }
     if (e) return MPHX_ERR_NOMEM;
     CK(cudaMemcpy(c->sol.off, off32.data(), sizeof(int) * ((size_t)ns + 1), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->sol.nbr, ids.data(), sizeof(int) * (size_t)total, cudaMemcpyHostToDevice));
@@ -515,6 +528,10 @@ static int init_solid(Ctx *c, const double *d_x03_orig)
         CK(cudaMemcpy(c->sol.mu, mu.data(), sizeof(double) * ns, cudaMemcpyHostToDevice));
     }
     const mphx_constants &k = c->c;
+    if (c->p.dim == 3)
+        LAUNCH(c, k_solid_pairs<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->cw_tl);
+    else
+        LAUNCH(c, k_solid_pairs<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->cw_tl);
     if (c->p.dim == 3)
         LAUNCH(c, k_solid_normalizer<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->cw_tl);
     else
@@ -674,7 +691,8 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         Solid &so = c->sol;
         so.ns = c->ns; so.sb = c->ns > 0 ? r[2] : 0;
         const size_t ns = (size_t)c->ns;
-        double **sv[] = {&so.x, &so.y, &so.z, &so.vx, &so.vy, &so.vz, &so.x0, &so.y0, &so.z0, &so.fx, &so.fy, &so.fz, &so.lam, &so.mu};
+        double **sv[] = {&so.x, &so.y, &so.z, &so.vx, &so.vy, &so.vz, &so.x0, &so.y0, &so.z0, &so.fx, &so.fy, &so.fz, &so.lam, &so.mu,
+                         &so.ux, &so.uy, &so.uz};
         for (double **q : sv) e |= c->alloc(q, ns);
         double **st[] = {&so.Linv, &so.Fm, &so.E, &so.S, &so.Pk};
         for (double **q : st) e |= c->alloc(q, 9 * ns);

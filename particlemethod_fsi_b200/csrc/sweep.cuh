@@ -59,16 +59,23 @@ __device__ __forceinline__ void sweep(SweepShared &sm, const GridDesc &g, const 
 
     int cnt = 0;
     auto drain = [&]() {
-        for (int s = 0; s < cnt; ++s) {
-            const int j = (int)sm.q[s][tid];
-            double dx = X[j] - xi, dy = Y[j] - yi, dz = Z[j] - zi;
+        // two queue entries per trip: both position loads are issued before either is used
+        for (int s = 0; s < cnt; s += 2) {
+            const bool two = s + 1 < cnt;
+            const int j0 = (int)sm.q[s][tid];
+            const int j1 = two ? (int)sm.q[s + 1][tid] : j0;
+            double dx0 = X[j0] - xi, dy0 = Y[j0] - yi, dz0 = Z[j0] - zi;
+            double dx1 = X[j1] - xi, dy1 = Y[j1] - yi, dz1 = Z[j1] - zi;
             if (warp_wraps) {
-                dx = dx > hW0 ? dx - W0 : (dx < -hW0 ? dx + W0 : dx);
-                dy = dy > hW1 ? dy - W1 : (dy < -hW1 ? dy + W1 : dy);
-                dz = dz > hW2 ? dz - W2 : (dz < -hW2 ? dz + W2 : dz);
+                dx0 = dx0 > hW0 ? dx0 - W0 : (dx0 < -hW0 ? dx0 + W0 : dx0);
+                dy0 = dy0 > hW1 ? dy0 - W1 : (dy0 < -hW1 ? dy0 + W1 : dy0);
+                dz0 = dz0 > hW2 ? dz0 - W2 : (dz0 < -hW2 ? dz0 + W2 : dz0);
+                dx1 = dx1 > hW0 ? dx1 - W0 : (dx1 < -hW0 ? dx1 + W0 : dx1);
+                dy1 = dy1 > hW1 ? dy1 - W1 : (dy1 < -hW1 ? dy1 + W1 : dy1);
+                dz1 = dz1 > hW2 ? dz1 - W2 : (dz1 < -hW2 ? dz1 + W2 : dz1);
             }
-            const double r2 = dx * dx + dy * dy + dz * dz;
-            hit(j, dx, dy, dz, r2);
+            hit(j0, dx0, dy0, dz0, dx0 * dx0 + dy0 * dy0 + dz0 * dz0);
+            if (two) hit(j1, dx1, dy1, dz1, dx1 * dx1 + dy1 * dy1 + dz1 * dz1);
         }
         cnt = 0;
     };
