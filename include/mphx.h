@@ -216,6 +216,29 @@ long long mphx_launch_count(const mphx_ctx *ctx);
  * N_f*368 + N_w*260 + N_s*(344+384*n_sub) */
 double mphx_algorithmic_bytes_per_step(const mphx_ctx *ctx);
 
+/* ---- multi-GPU: one context per x-slab (the reference has no distributed path) ---
+ * Protocol per step, identical on every rank (buffers are DEVICE pointers owned by the caller;
+ * "left"/"right" are the ring neighbours along x; messages hold 7 doubles per particle):
+ *   mphx_slab_begin      -> emigrants packed            -> exchange -> mphx_slab_append(ghost=0)
+ *   mphx_slab_pack_halo  -> halo layers packed          -> exchange -> mphx_slab_append(ghost=1)
+ *   mphx_slab_build_pass1-> PressureP of halo + solids  -> exchange + all-reduce(solP)
+ *   mphx_slab_pass2      -> solid (v,F) updates         -> all-reduce(solbuf)
+ *   mphx_slab_finish     (solid sub-steps, Time += Dt)
+ * The host side of this protocol lives in particlemethod_fsi_b200/slab.py. */
+int mphx_set_stream(mphx_ctx *ctx, void *cuda_stream);
+int mphx_slab_configure(mphx_ctx *ctx, int rank, int nranks, int col_lo, int col_hi, int capacity,
+                        int msg_capacity);
+int mphx_slab_begin(mphx_ctx *ctx, double *send_left, double *send_right, int *counts);
+int mphx_slab_append(mphx_ctx *ctx, const double *from_left, int n_left, const double *from_right,
+                     int n_right, int ghost);
+int mphx_slab_pack_halo(mphx_ctx *ctx, double *send_left, double *send_right, int *counts);
+int mphx_slab_build_pass1(mphx_ctx *ctx, int n_left, int n_right, double *send_left, double *send_right,
+                          double *solP);
+int mphx_slab_pass2(mphx_ctx *ctx, const double *from_left, const double *from_right, const double *solP,
+                    double *solbuf);
+int mphx_slab_finish(mphx_ctx *ctx, const double *solbuf);
+int mphx_slab_info(mphx_ctx *ctx, int out[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,9 +22,13 @@ namespace mphx {
 constexpr int kMaxStencil = 128;
 constexpr int kTypeCount = 6;
 
-__host__ __device__ inline bool is_structure_type(int t) { return t >= 2 && t < 4; }
-__host__ __device__ inline bool is_fluid_type(int t) { return t >= 0 && t < 2; }
-__host__ __device__ inline bool is_wall_type(int t) { return t >= 4 && t < 6; }
+// particle type as stored on the device: the reference's Property (0..5) in the low three bits; bit 3
+// marks a ghost copy received from a neighbouring slab (never integrated, dropped every step)
+constexpr int kGhost = 8;
+__host__ __device__ inline int real_type(int t) { return t & 7; }
+__host__ __device__ inline bool is_structure_type(int t) { return (t & 7) >= 2 && (t & 7) < 4; }
+__host__ __device__ inline bool is_fluid_type(int t) { return (t & 7) >= 0 && (t & 7) < 2; }
+__host__ __device__ inline bool is_wall_type(int t) { return (t & 7) >= 4 && (t & 7) < 6; }
 
 struct GridDesc {
     int dim;        // 2 or 3
@@ -32,7 +36,12 @@ struct GridDesc {
     int ncells;
     int nsten; // stencil columns
     int range; // ceil((MaxRadius+MARGIN)/CellWidth)  src/main.cpp:1744
-    int pad;
+    int slab;  // 1: this context holds one x-slab of a multi-GPU run (see slab.inc)
+    // slab mode: nx is the LOCAL column count (owned columns [range, nx-range) + one halo of `range`
+    // columns each side), xoff the global column of local column 0 (may be negative / wrap), nxg the
+    // global column count, mn[0] the local origin mn0g + xoff*cellw.  Otherwise nxg=nx, xoff=0.
+    int nxg, xoff;
+    double mn0g;
     double mn[3], W[3], cellw;
     // stencil columns.  3D: (dx,dy) with half-length sh along z.  2D: dx with half-length sh along y.
     signed char sdx[kMaxStencil], sdy[kMaxStencil], sh[kMaxStencil];
@@ -100,13 +109,35 @@ __device__ __forceinline__ int cell_coord_exact(double x, double mn, double cw, 
     int c = __double2int_rz(floor(__ddiv_rn(__dsub_rn(x, mn), cw))) % n; // :1671
     return (c % n + n) % n;                                               // CellId wrap
 }
-__device__ __forceinline__ int cell_key(const GridDesc &g, double x, double y, double z)
+// bucket key.  Buckets [0,ncells) are real; ncells = "parked" (a replicated solid outside this slab and
+// its halo: kept, never traversed); ncells+1 = "dead" (ghosts of the previous step, particles that
+// migrated away: dropped by the next permute).  *col receives the local x column.
+__device__ __forceinline__ int cell_key(const GridDesc &g, double x, double y, double z, int *col = nullptr)
 {
-    const int cx = cell_coord_exact(x, g.mn[0], g.cellw, g.nx);
+    int cx = cell_coord_exact(x, g.mn0g, g.cellw, g.nxg);
+    if (g.slab) {
+        cx -= g.xoff;
+        if (cx < 0) cx += g.nxg;
+        else if (cx >= g.nxg) cx -= g.nxg;
+    }
+    if (col) *col = cx;
+    if (cx >= g.nx) return g.ncells;
     const int cy = cell_coord_exact(y, g.mn[1], g.cellw, g.ny);
     if (g.dim == 2) return cx * g.ny + cy;
     const int cz = cell_coord_exact(z, g.mn[2], g.cellw, g.nz);
     return (cx * g.ny + cy) * g.nz + cz;
+}
+__device__ __forceinline__ int key_column(const GridDesc &g, int key) { return g.dim == 2 ? key / g.ny : key / (g.ny * g.nz); }
+__device__ __forceinline__ bool column_owned(const GridDesc &g, int cx) { return !g.slab || (cx >= g.range && cx < g.nx - g.range); }
+// the reference's CellId (global) of a local key
+__device__ __forceinline__ int global_key(const GridDesc &g, int key)
+{
+    if (!g.slab) return key;
+    const int per = g.dim == 2 ? g.ny : g.ny * g.nz;
+    int cx = key / per + g.xoff;
+    if (cx < 0) cx += g.nxg;
+    else if (cx >= g.nxg) cx -= g.nxg;
+    return cx * per + key % per;
 }
 // plain (FMA-allowed) minimum image for the 1e-10 paths
 __device__ __forceinline__ double minimg(double d, double W)
@@ -119,12 +150,33 @@ __device__ __forceinline__ double minimg(double d, double W)
 // ------------------------------------------------------------------------------------------------
 // K0/K1: pre-step.  wall kinematics (t<0.2), periodic wrap, bucket key, per-bucket count + slot.
 // Solids take their state from the solid arrays (they are integrated there).
+// Slab mode: ghosts of the previous step die; fluid/wall particles whose column left the owned
+// range are packed for the neighbouring slab (migration) and die here.
+struct SlabSend {
+    double *buf[2]; // [0] to the left neighbour, [1] to the right; 7 doubles per particle (AoS)
+    int *count;     // count[0], count[1]  (+ count[2] = error flags)
+    int capacity;   // particles per buffer
+};
+constexpr int kMsgDoubles = 7;
+__device__ __forceinline__ void pack_particle(double *dst, double x, double y, double z, double vx, double vy, double vz,
+                                              int type, int id)
+{
+    dst[0] = x; dst[1] = y; dst[2] = z; dst[3] = vx; dst[4] = vy; dst[5] = vz;
+    dst[6] = __longlong_as_double(((long long)real_type(type) << 32) | (long long)(unsigned)id);
+}
+
 __global__ void k_prestep(int n, Particles p, Solid sol, GridDesc g, WallMotion wm, int do_wrap,
-                          int *__restrict__ cellCount, int *__restrict__ slot)
+                          int *__restrict__ cellCount, int *__restrict__ slot, SlabSend snd)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int t = p.type[i];
+    if (t & kGhost) { // last step's halo copy
+        const int k = g.ncells + 1;
+        p.key[i] = k;
+        slot[i] = atomicAdd(&cellCount[k], 1);
+        return;
+    }
     double x = p.x[i], y = p.y[i], z = p.z[i];
     int s = -1;
     if (is_structure_type(t)) {
@@ -147,7 +199,7 @@ __global__ void k_prestep(int n, Particles p, Solid sol, GridDesc g, WallMotion 
         z = __dadd_rn(__dadd_rn(q2, wm.center[t][2]), __dmul_rn(V[2], wm.dt));
     }
     if (do_wrap) { // :3330
-        x = __dadd_rn(mod_exact(__dsub_rn(x, g.mn[0]), g.W[0]), g.mn[0]);
+        x = __dadd_rn(mod_exact(__dsub_rn(x, g.mn0g), g.W[0]), g.mn0g);
         y = __dadd_rn(mod_exact(__dsub_rn(y, g.mn[1]), g.W[1]), g.mn[1]);
         z = __dadd_rn(mod_exact(__dsub_rn(z, g.mn[2]), g.W[2]), g.mn[2]);
     }
@@ -158,9 +210,101 @@ __global__ void k_prestep(int n, Particles p, Solid sol, GridDesc g, WallMotion 
         sol.uy[s] = minimg_exact(y, sol.y0[s], g.W[1]);
         sol.uz[s] = minimg_exact(z, sol.z0[s], g.W[2]);
     }
-    const int k = cell_key(g, x, y, z);
+    int col;
+    int k = cell_key(g, x, y, z, &col);
+    if (g.slab && s < 0 && !column_owned(g, col)) { // migrate: hand the particle to the neighbouring slab
+        const int dir = (col < g.range) ? 0 : ((col >= g.nx - g.range && col < g.nx) ? 1 : -1);
+        if (dir < 0) atomicOr(&snd.count[2], 1); // moved further than one halo width: lost
+        else {
+            const int q = atomicAdd(&snd.count[dir], 1);
+            if (q < snd.capacity) pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, x, y, z, p.vx[i], p.vy[i], p.vz[i], t, p.id[i]);
+            else atomicOr(&snd.count[2], 2);
+        }
+        k = g.ncells + 1;
+    }
     p.key[i] = k;
     slot[i] = atomicAdd(&cellCount[k], 1);
+}
+
+// slab mode: append particles received from a neighbour (migrants: ghost_flag 0; halo copies:
+// ghost_flag kGhost, x shifted by +-W across the periodic seam so separations need no wrap in x)
+__global__ void k_unpack_particles(int base, int count, const double *__restrict__ buf, double xshift, int ghost_flag,
+                                   Particles p, GridDesc g, int *__restrict__ cellCount, int *__restrict__ slot,
+                                   int *__restrict__ err)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    const double *m = buf + (size_t)kMsgDoubles * q;
+    const int i = base + q;
+    const double x = m[0] + xshift, y = m[1], z = m[2];
+    const long long meta = __double_as_longlong(m[6]);
+    p.x[i] = x; p.y[i] = y; p.z[i] = z; p.vx[i] = m[3]; p.vy[i] = m[4]; p.vz[i] = m[5];
+    p.type[i] = (int)(meta >> 32) | ghost_flag;
+    p.id[i] = (int)(meta & 0xffffffffLL);
+    int col;
+    int k = cell_key(g, x, y, z, &col);
+    const bool owned = column_owned(g, col);
+    if (k >= g.ncells || (ghost_flag ? owned : !owned)) { atomicOr(err, 4); k = g.ncells + 1; }
+    p.key[i] = k;
+    slot[i] = atomicAdd(&cellCount[k], 1);
+}
+
+// slab mode: pack the owned fluid/wall particles within one halo width of the slab faces
+__global__ void k_halo_pack(int n, Particles p, GridDesc g, SlabSend snd, int *__restrict__ haloSrc0, int *__restrict__ haloSrc1)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = p.key[i], t = p.type[i];
+    if (k >= g.ncells || (t & kGhost) || is_structure_type(t)) return;
+    const int col = key_column(g, k);
+    if (!column_owned(g, col)) return;
+    for (int dir = 0; dir < 2; ++dir) {
+        const bool in = dir == 0 ? (col < 2 * g.range) : (col >= g.nx - 2 * g.range);
+        if (!in) continue;
+        const int q = atomicAdd(&snd.count[dir], 1);
+        if (q < snd.capacity) {
+            pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], t, p.id[i]);
+            (dir == 0 ? haloSrc0 : haloSrc1)[q] = i;
+        } else atomicOr(&snd.count[2], 2);
+    }
+}
+// second exchange: PressureP of the halo particles, in the order they were packed
+__global__ void k_pack_scalar(int count, const int *__restrict__ src, const int *__restrict__ where, const double *__restrict__ a,
+                              double *__restrict__ buf)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < count) buf[q] = a[where[src[q]]];
+}
+__global__ void k_unpack_scalar(int base, int count, const int *__restrict__ where, const double *__restrict__ buf, double *__restrict__ a)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < count) a[where[base + q]] = buf[q];
+}
+// replicated solids: the slab that owns a solid particle BY POSITION computes its PressureP / its
+// fluid-coupled velocity update; everybody else contributes zeros to an all-reduce (exact).
+__global__ void k_solid_collect_P(int n, Particles p, GridDesc g, Solid sol, const double *__restrict__ P, double *__restrict__ solP)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const int k = p.key[q];
+    if (k >= g.ncells || !is_structure_type(p.type[q]) || !column_owned(g, key_column(g, k))) return;
+    solP[p.id[q] - sol.sb] = P[q];
+}
+__global__ void k_solid_spread_P(int n, Particles p, GridDesc g, Solid sol, const double *__restrict__ solP, double *__restrict__ P)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    if (p.key[q] >= g.ncells || !is_structure_type(p.type[q])) return;
+    P[q] = solP[p.id[q] - sol.sb];
+}
+// solbuf = [vx vy vz fx fy fz] planes of ns doubles, summed over slabs (one owner, others zero)
+__global__ void k_solid_apply_update(Solid sol, const double *__restrict__ solbuf)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= sol.ns) return;
+    const size_t ns = sol.ns;
+    sol.vx[s] = solbuf[s]; sol.vy[s] = solbuf[ns + s]; sol.vz[s] = solbuf[2 * ns + s];
+    sol.fx[s] = solbuf[3 * ns + s]; sol.fy[s] = solbuf[4 * ns + s]; sol.fz[s] = solbuf[5 * ns + s];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -258,14 +402,14 @@ __global__ void k_scatter_index(int n, const int *__restrict__ key, const int *_
 // K4: permute the SoA into bucket order; inside a bucket particles are ordered by original id, which
 // makes the layout (and therefore every floating-point sum) independent of atomic arrival order.
 __global__ void k_permute(int n, Particles src, Particles dst, const int *__restrict__ cellStart,
-                          const int *__restrict__ tmpIdx, GridDesc g)
+                          const int *__restrict__ tmpIdx, GridDesc g, int *__restrict__ where)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
+    if (q >= n || q >= cellStart[g.ncells + 1]) return; // the dead bucket (last) is dropped
     int s = tmpIdx[q];
     const int k = src.key[s];
     const int b = cellStart[k], e = cellStart[k + 1];
-    if (e - b > 1) {
+    if (e - b > 1 && k < g.ncells) { // (the parked bucket is never traversed: any order will do)
         const int want = q - b;
         for (int a = b; a < e; ++a) {
             const int sa = tmpIdx[a];
@@ -275,6 +419,7 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
             if (rank == want) { s = sa; break; }
         }
     }
+    where[s] = q;
     const double x = src.x[s], y = src.y[s], z = src.z[s];
     const int t = src.type[s];
     dst.x[q] = x; dst.y[q] = y; dst.z[q] = z;
@@ -282,7 +427,7 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
     dst.type[q] = t; dst.id[q] = src.id[s]; dst.key[q] = k;
     const double icw = 1.0 / g.cellw;
     dst.pf[q] = make_float4((float)((x - g.mn[0]) * icw), (float)((y - g.mn[1]) * icw), (float)((z - g.mn[2]) * icw),
-                            __int_as_float(t));
+                            __int_as_float(real_type(t)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,162 +483,6 @@ __device__ __forceinline__ void for_each_candidate(const GridDesc &g, const int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5 "pass 1": VolStrainP, DivergenceP -> PressureP (+ DensityA, GravityCenter, PressureA when any
-// surface tension is set).  One thread per particle, all particle classes (:2320, :2349).
-template <int DIM, bool ST>
-__global__ void __launch_bounds__(128)
-k_pass1(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, double *__restrict__ P,
-        double *__restrict__ volStrain, double *__restrict__ divP, double *__restrict__ densA,
-        double *__restrict__ gcx, double *__restrict__ gcy, double *__restrict__ gcz, double *__restrict__ PA)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double xi = p.x[i], yi = p.y[i], zi = p.z[i];
-    const double vxi = p.vx[i], vyi = p.vy[i], vzi = p.vz[i];
-    const int ti = p.type[i];
-    const bool solid_i = is_structure_type(ti);
-    double nP = 0.0, dv = 0.0, nA = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
-    const double *__restrict__ VX = p.vx, *__restrict__ VY = p.vy, *__restrict__ VZ = p.vz;
-    const int *__restrict__ TY = p.type;
-    for_each_candidate<DIM>(g, cellStart, p.x, p.y, p.z, p.key[i], xi, yi, zi,
-        [&](int j, double dx, double dy, double dz, double r2) {
-            if (j == i) return;
-            if (r2 <= ph.rp2) { // :2333, :2362
-                const double r = sqrt(r2);
-                const double q = 1.0 - r * ph.irp;
-                nP += ph.cwp * (q * q);
-                const double ux = VX[j] - vxi, uy = VY[j] - vyi, uz = VZ[j] - vzi;
-                dv -= (ux * dx + uy * dy + uz * dz) / r * (ph.cdp * q);
-            }
-            if (ST && !solid_i && r2 <= ph.ra2) { // :2162, :2195
-                const double r = sqrt(r2);
-                const double qa = r * ph.ira;
-                const double ratio = ph.ratio[ti][TY[j]];
-                nA += ratio * (ph.cwa * qa * (1.0 - qa) * (1.0 - qa));
-                const double wgv = ratio * (ph.cwg * ((1.0 - qa) * (1.0 - qa))) / ph.r2g * ph.rg;
-                g0 += dx * wgv; g1 += dy * wgv; g2 += dz * wgv;
-            }
-        });
-    const double vs = nP - ph.n0p;                        // :2339
-    const double kappa = (vs < 0.0) ? 0.0 : ph.bulk[ti]; // :2112-2113
-    double pr = -ph.lambda[ti] * dv;                      // :2388
-    if (vs > 0.0) pr += kappa * vs;                       // :2389-2391
-    P[i] = pr; volStrain[i] = vs; divP[i] = dv;
-    if (ST) {
-        const double da = solid_i ? 0.0 : nA;
-        densA[i] = da;
-        gcx[i] = solid_i ? 0.0 : g0; gcy[i] = solid_i ? 0.0 : g1; gcz[i] = solid_i ? 0.0 : g2;
-        double pa = ph.cofa[ti] * (da - ph.n0a) / ph.l0; // :2219
-        if (ph.n0a <= da) pa = 0.0;
-        PA[i] = pa;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K6 "pass 2": force sums + gravity + explicit integration.
-//   fluid/wall i : pressure (:2397-2424), attractive pressure (:2228-2258), diffuse interface
-//                  (:2268-2311), viscosity (:2483-2521)
-//   solid i      : fluid->solid interface force (:2442-2472)
-//   then gravity (:2922-2935), v += F/m dt (:2943-2955), fluid a += F/m, x += v dt (:1897-1906).
-// New x/v go to the `out` arrays (the inputs are still being read by neighbouring threads).
-template <int DIM, bool ST>
-__global__ void __launch_bounds__(128)
-k_pass2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, const double *__restrict__ P,
-        const double *__restrict__ PA, const double *__restrict__ gcx, const double *__restrict__ gcy,
-        const double *__restrict__ gcz, double *__restrict__ ox, double *__restrict__ oy, double *__restrict__ oz,
-        double *__restrict__ ovx, double *__restrict__ ovy, double *__restrict__ ovz, double *__restrict__ fx,
-        double *__restrict__ fy, double *__restrict__ fz, double *__restrict__ ax, double *__restrict__ ay,
-        double *__restrict__ az, Solid sol)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double xi = p.x[i], yi = p.y[i], zi = p.z[i];
-    const double vxi = p.vx[i], vyi = p.vy[i], vzi = p.vz[i];
-    const int ti = p.type[i];
-    const bool solid_i = is_structure_type(ti);
-    const double Pi = P[i];
-    double F0 = 0.0, F1 = 0.0, F2 = 0.0;
-    const double *__restrict__ VX = p.vx, *__restrict__ VY = p.vy, *__restrict__ VZ = p.vz;
-    const int *__restrict__ TY = p.type;
-    double PAi = 0.0, gi0 = 0.0, gi1 = 0.0, gi2 = 0.0, ai = 0.0;
-    if (ST) { PAi = PA[i]; gi0 = gcx[i]; gi1 = gcy[i]; gi2 = gcz[i]; ai = ph.cofa[ti] * ph.cofk * ph.cofk; }
-    const double gscale = ph.vol / ph.l0;
-    for_each_candidate<DIM>(g, cellStart, p.x, p.y, p.z, p.key[i], xi, yi, zi,
-        [&](int j, double dx, double dy, double dz, double r2) {
-            if (j == i) return;
-            if (solid_i) {
-                if (r2 < ph.rp2) { // :2455
-                    const int tj = TY[j];
-                    if (is_structure_type(tj)) return; // :2447
-                    const double r = sqrt(r2);
-                    const double c = (Pi + P[j]) * (ph.cdp * (1.0 - r * ph.irp)) / r * ph.vol;
-                    F0 += c * dx; F1 += c * dy; F2 += c * dz;
-                }
-                return;
-            }
-            const bool inP = r2 < ph.rp2, inV = r2 < ph.rv2; // :2410, :2496 (strict)
-            if (inP || inV) {
-                const double r = sqrt(r2);
-                const double rinv = 1.0 / r;
-                double c = 0.0;
-                if (inP) c = (Pi + P[j]) * (ph.cdp * (1.0 - r * ph.irp)) * rinv * ph.vol;
-                if (inV) {
-                    const double ux = VX[j] - vxi, uy = VY[j] - vyi, uz = VZ[j] - vzi;
-                    const double ue = (ux * dx + uy * dy + uz * dz) * rinv;
-                    const double dwij = -(ph.cdv * (1.0 - r * ph.irv));
-                    c += ph.viscpair[ti][TY[j]] * ue * dwij * rinv * rinv;
-                }
-                F0 += c * dx; F1 += c * dy; F2 += c * dz;
-            }
-            if (ST && r2 < ph.ra2) { // :2243, :2285 (RadiusG == RadiusA)
-                const int tj = TY[j];
-                const double r = sqrt(r2);
-                const double rinv = 1.0 / r;
-                const double qa = r * ph.ira;
-                const double rij = ph.ratio[ti][tj], rji = ph.ratio[tj][ti];
-                const double dwa = ph.cwa * (1.0 - qa) * (1.0 - 3.0 * qa) * ph.ira; // dwadr :308
-                const double ca = (PAi * (rij * dwa) + PA[j] * (rji * dwa)) * rinv * ph.vol;
-                double A0 = ca * dx, A1 = ca * dy, A2 = ca * dz;
-                const double wgv = ph.cwg * ((1.0 - qa) * (1.0 - qa));
-                const double wij = rij * wgv, wji = rji * wgv;
-                const double aj = ai; // Q6: CofA[Property[iP]] for both (:2270, :2275)
-                const double gj0 = gcx[j], gj1 = gcy[j], gj2 = gcz[j];
-                const double s = gscale * ph.rg / ph.r2g;
-                A0 -= (aj * gj0 * wji - ai * gi0 * wij) * s;
-                A1 -= (aj * gj1 * wji - ai * gi1 * wij) * s;
-                A2 -= (aj * gj2 * wji - ai * gi2 * wij) * s;
-                const double dwg = ph.cdg * (1.0 - qa);
-                const double dwij = rij * dwg, dwji = rji * dwg;
-                const double gr = (aj * gj0 * dwji - ai * gi0 * dwij) * dx + (aj * gj1 * dwji - ai * gi1 * dwij) * dy +
-                                  (aj * gj2 * dwji - ai * gi2 * dwij) * dz;
-                const double cg = gr * rinv * s;
-                A0 -= cg * dx; A1 -= cg * dy; A2 -= cg * dz;
-                F0 += A0; F1 += A1; F2 += A2;
-            }
-        });
-    // gravity + explicit integration in the reference's operand order (explicitly rounded, so a
-    // particle whose force sum is exact -- e.g. a solid far from any fluid -- moves bit-identically)
-    const double m = ph.mass[ti];
-    double nx = xi, ny = yi, nz = zi, nvx = vxi, nvy = vyi, nvz = vzi;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    if (!is_wall_type(ti)) { // gravity on fluid and solid (:2922-2935)
-        F0 = __dadd_rn(F0, __dmul_rn(m, ph.g[0])); F1 = __dadd_rn(F1, __dmul_rn(m, ph.g[1])); F2 = __dadd_rn(F2, __dmul_rn(m, ph.g[2]));
-        nvx = __dadd_rn(vxi, __dmul_rn(__ddiv_rn(F0, m), ph.dt)); // :2944-2954
-        nvy = __dadd_rn(vyi, __dmul_rn(__ddiv_rn(F1, m), ph.dt));
-        nvz = __dadd_rn(vzi, __dmul_rn(__ddiv_rn(F2, m), ph.dt));
-        if (!solid_i) { // :1897-1906
-            a0 = __ddiv_rn(F0, m); a1 = __ddiv_rn(F1, m); a2 = __ddiv_rn(F2, m);
-            nx = __dadd_rn(xi, __dmul_rn(nvx, ph.dt)); ny = __dadd_rn(yi, __dmul_rn(nvy, ph.dt)); nz = __dadd_rn(zi, __dmul_rn(nvz, ph.dt));
-        } else {
-            const int s = p.id[i] - sol.sb;
-            sol.vx[s] = nvx; sol.vy[s] = nvy; sol.vz[s] = nvz;
-            sol.fx[s] = F0; sol.fy[s] = F1; sol.fz[s] = F2;
-        }
-    }
-    ox[i] = nx; oy[i] = ny; oz[i] = nz; ovx[i] = nvx; ovy[i] = nvy; ovz[i] = nvz;
-    fx[i] = F0; fy[i] = F1; fz[i] = F2; ax[i] = a0; ay[i] = a1; az[i] = a2;
-}
-
 // ------------------------------------------------------------------------------------------------
 // neighbour SETS with the reference's bit-exact predicate (calculateNeighbor :1759-1772 and
 // calculateInitialNeighbor :1601-1616).  MODE 0 = count, 1 = fill (+ sort row ascending).
@@ -511,6 +500,8 @@ k_neighbors_exact(int n, const double *__restrict__ X, const double *__restrict_
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (structure_only && !is_structure_type(type[i])) return;
+    // slab mode: rows are produced by the slab that owns the particle's column (never for ghosts)
+    if (key[i] >= g.ncells || (type[i] & kGhost) || !column_owned(g, key_column(g, key[i]))) return;
     const double xi = X[i], yi = Y[i], zi = Z[i];
     const int row = id[i] - row_base;
     int cnt = 0;
@@ -779,14 +770,26 @@ __global__ void k_solid_pairs(Solid so, double W0, double W1, double W2, double 
 
 // ------------------------------------------------------------------------------------------------
 // upload / download helpers (AoS original order <-> sorted SoA)
-__global__ void k_upload_split(int n, const int *__restrict__ type, const double *__restrict__ x3,
+// host arrays (global, original order AoS) -> the slots this context holds; ids == nullptr: all, in order
+__global__ void k_upload_split(int n, const int *__restrict__ ids, const int *__restrict__ type, const double *__restrict__ x3,
                                const double *__restrict__ v3, Particles p)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    p.x[i] = x3[3 * (size_t)i]; p.y[i] = x3[3 * (size_t)i + 1]; p.z[i] = x3[3 * (size_t)i + 2];
-    p.vx[i] = v3[3 * (size_t)i]; p.vy[i] = v3[3 * (size_t)i + 1]; p.vz[i] = v3[3 * (size_t)i + 2];
-    p.type[i] = type[i]; p.id[i] = i; p.key[i] = 0;
+    const int id = ids ? ids[i] : i;
+    const size_t o = 3 * (size_t)id;
+    p.x[i] = x3[o]; p.y[i] = x3[o + 1]; p.z[i] = x3[o + 2];
+    p.vx[i] = v3[o]; p.vy[i] = v3[o + 1]; p.vz[i] = v3[o + 2];
+    p.type[i] = type[id]; p.id[i] = id; p.key[i] = 0;
+}
+// the solids in their reference configuration as a particle set (for the initial-list build)
+__global__ void k_solid_reference_particles(Solid so, Particles p)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= so.ns) return;
+    p.x[s] = so.x0[s]; p.y[s] = so.y0[s]; p.z[s] = so.z0[s];
+    p.vx[s] = 0.0; p.vy[s] = 0.0; p.vz[s] = 0.0;
+    p.type[s] = so.type[s]; p.id[s] = so.sb + s; p.key[s] = 0;
 }
 __global__ void k_solid_upload(Solid so, const int *__restrict__ type, const double *__restrict__ x3,
                                const double *__restrict__ x03, const double *__restrict__ v3)
@@ -831,24 +834,50 @@ __global__ void k_restore_by_id(int n, const int *__restrict__ id, const double 
     x[q] = sx[i]; y[q] = sy[i]; z[q] = sz[i];
 }
 // sorted SoA vec3 -> original-order AoS
-__global__ void k_gather_vec3(int n, const int *__restrict__ id, const double *__restrict__ a, const double *__restrict__ b,
-                              const double *__restrict__ c, double *__restrict__ out3)
+// ownership mask of the sorted slots (slab mode: ghosts, parked solids and solids owned by another
+// slab's columns are not reported by this slab)
+__global__ void k_owned_mask(int n, Particles p, GridDesc g, int solids_too, int *__restrict__ mask)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
+    const int k = p.key[q], t = p.type[q];
+    bool own = !(t & kGhost);
+    if (g.slab) {
+        if (is_structure_type(t)) own = own && solids_too;
+        else own = own && k < g.ncells && column_owned(g, key_column(g, k));
+    }
+    mask[q] = own ? 1 : 0;
+}
+__global__ void k_global_keys(int n, Particles p, GridDesc g, int *__restrict__ out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) out[q] = p.key[q] < g.ncells ? global_key(g, p.key[q]) : -1;
+}
+__global__ void k_real_types(int n, Particles p, int *__restrict__ out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) out[q] = real_type(p.type[q]);
+}
+__global__ void k_gather_vec3(int n, const int *__restrict__ id, const int *__restrict__ mask, const double *__restrict__ a,
+                              const double *__restrict__ b, const double *__restrict__ c, double *__restrict__ out3)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n || !mask[q]) return;
     const size_t o = 3 * (size_t)id[q];
     out3[o] = a[q]; out3[o + 1] = b[q]; out3[o + 2] = c[q];
 }
-__global__ void k_gather_scalar(int n, const int *__restrict__ id, const double *__restrict__ a, double *__restrict__ out)
+__global__ void k_gather_scalar(int n, const int *__restrict__ id, const int *__restrict__ mask, const double *__restrict__ a,
+                                double *__restrict__ out)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
+    if (q >= n || !mask[q]) return;
     out[id[q]] = a[q];
 }
-__global__ void k_gather_int(int n, const int *__restrict__ id, const int *__restrict__ a, int *__restrict__ out)
+__global__ void k_gather_int(int n, const int *__restrict__ id, const int *__restrict__ mask, const int *__restrict__ a,
+                             int *__restrict__ out)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
+    if (q >= n || !mask[q]) return;
     out[id[q]] = a[q];
 }
 // solid arrays -> original-order AoS (overrides the stale sorted copies)

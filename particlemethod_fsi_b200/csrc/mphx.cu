@@ -41,8 +41,17 @@ struct Ctx {
     mphx_constants c;
     int device = 0;
     cudaStream_t stream = nullptr;
-    int n = 0, nf = 0, ns = 0, nw = 0;
+    int n = 0;        // particle slots currently held (slab mode: owned + ghosts + all solids; changes every step)
+    int n_global = 0; // particles of the whole case (= n without slabs)
+    int cap = 0;      // allocated slots
+    int nf = 0, ns = 0, nw = 0; // class counts of the whole case
     int ranges[6];
+    // slab mode (multi-GPU): see slab.inc
+    bool slab = false;
+    int rank = 0, nranks = 1, col_lo = 0, col_hi = 0, msg_cap = 0;
+    int ghost_base[2] = {0, 0}, ghost_cnt[2] = {0, 0}, halo_cnt[2] = {0, 0};
+    int *where = nullptr, *haloSrc[2] = {nullptr, nullptr}, *d_err = nullptr;
+    bool external_stream = false;
     bool uploaded = false, inited = false, surface_tension = false;
     double time = 0.0;
     double wall_center[kTypeCount][3];
@@ -61,11 +70,9 @@ struct Ctx {
     Solid sol{};
     double *d_inv_density = nullptr;
     double cw_tl = 0.0; // weight() prefactor (1.0/Swp)*(1.0/RP^d), src/main.cpp:291/293
-    double *d_x0_orig = nullptr; // InitialPosition, original order AoS (for re-upload / debugging)
     double *stage3a = nullptr, *stage3b = nullptr, *stage1 = nullptr, *stage9 = nullptr; // AoS staging (lazy)
-    int *stagei = nullptr;
+    int *stagei = nullptr, *mask = nullptr, *tmpi = nullptr;
     bool buckets_valid = false;
-    int sweep_version = 2; // MPHX_SWEEP=1 selects the simple one-phase sweeps (A/B debugging only)
     int sweep_batch = 12;  // stencil columns per filter/drain batch (3D) // cellStart / bx,by,bz describe the positions currently held
     std::vector<void *> allocs;
 
@@ -155,6 +162,7 @@ static int setup_constants(Ctx *c)
     g.range = k.stencil_range;
     g.cellw = k.cell_width;
     for (int d = 0; d < 3; ++d) { g.mn[d] = p.domain_min[d]; g.W[d] = k.domain_width[d]; }
+    g.slab = 0; g.nxg = g.nx; g.xoff = 0; g.mn0g = p.domain_min[0];
     const double cutoff = k.max_radius + 0.1 * p.particle_spacing; // MaxRadius+MARGIN (:116,:1765)
     rc = build_stencil(g, cutoff);
     if (rc) { set_last_error("stencil too large (radius ratio too big)"); return rc; }
@@ -200,10 +208,10 @@ static int setup_constants(Ctx *c)
 }
 
 // ---- bucket rebuild: K1 key/count, K2 scan, K3 scatter, K4 permute -------------------------------
-static int rebuild_buckets(Ctx *c, bool prestep_motion)
+static int stage_prestep(Ctx *c, bool prestep_motion, SlabSend snd)
 {
     const int n = c->n;
-    CK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * (size_t)c->grid.ncells, c->stream));
+    CK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)c->grid.ncells + 2), c->stream));
     WallMotion wm;
     std::memset(&wm, 0, sizeof(wm));
     wm.dt = c->p.dt;
@@ -216,21 +224,47 @@ static int rebuild_buckets(Ctx *c, bool prestep_motion)
                 wm.omega[t][d] = c->p.wall_omega[t][d];
                 for (int e = 0; e < 3; ++e) wm.R[t][d][e] = c->c.wall_rotation[t][d][e];
             }
-    LAUNCH(c, k_prestep, nblk(n), kBlock, n, c->S, c->sol, c->grid, wm, prestep_motion ? 1 : 0, c->cellCount, c->slot);
+    if (n > 0)
+        LAUNCH(c, k_prestep, nblk(n), kBlock, n, c->S, c->sol, c->grid, wm, prestep_motion ? 1 : 0, c->cellCount, c->slot, snd);
     if (prestep_motion) // :3066-3070 (host mirror of the wall centres)
         for (int t = 4; t < kTypeCount; ++t)
             for (int d = 0; d < 3; ++d) c->wall_center[t][d] += c->p.wall_velocity[t][d] * c->p.dt;
-    const int nc = c->grid.ncells;
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+// K2 scan, K3 scatter, K4 permute over the c->n slots keyed so far; afterwards c->n = live slots
+static int stage_sort(Ctx *c)
+{
+    const int n = c->n;
+    const int nc = c->grid.ncells + 2; // + parked + dead buckets
     LAUNCH(c, k_scan_reduce, c->scan_blocks, kScanThreads, c->cellCount, nc, c->blockSums);
     LAUNCH(c, k_scan_top, 1, kScanThreads, c->blockSums, c->scan_blocks);
     LAUNCH(c, k_scan_apply, c->scan_blocks, kScanThreads, c->cellCount, nc, c->blockSums, c->cellStart);
-    LAUNCH(c, k_scatter_index, nblk(n), kBlock, n, c->S.key, c->slot, c->cellStart, c->tmpIdx);
-    LAUNCH(c, k_permute, nblk(n), kBlock, n, c->S, c->T, c->cellStart, c->tmpIdx, c->grid);
+    if (n > 0) {
+        LAUNCH(c, k_scatter_index, nblk(n), kBlock, n, c->S.key, c->slot, c->cellStart, c->tmpIdx);
+        LAUNCH(c, k_permute, nblk(n), kBlock, n, c->S, c->T, c->cellStart, c->tmpIdx, c->grid, c->where);
+    }
     std::swap(c->S, c->T);
     c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
     c->buckets_valid = true;
+    if (c->slab) { // ghosts of the last step and emigrants sit in the dead bucket: drop them
+        int keep = 0;
+        CK(cudaMemcpyAsync(&keep, c->cellStart + c->grid.ncells + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->n = keep;
+    }
     CK(cudaGetLastError());
     return MPHX_OK;
+}
+
+static int rebuild_buckets(Ctx *c, bool prestep_motion)
+{
+    if (c->slab) { set_last_error("slab contexts are stepped through the mphx_slab_* calls"); return MPHX_ERR_INVALID; }
+    SlabSend none{};
+    int rc = stage_prestep(c, prestep_motion, none);
+    if (rc) return rc;
+    return stage_sort(c);
 }
 
 // squared cut-off (bucket units) of the sweep's fp32 filter: the exact cut-off plus a margin that
@@ -251,13 +285,7 @@ static int run_pass1(Ctx *c)
 {
     const int n = c->n;
     const mphx_constants &k = c->c;
-    if (c->sweep_version == 1) {
-#define P1(D, ST) LAUNCH(c, (k_pass1<D, ST>), nblk(n), kBlock, n, c->S, c->cellStart, c->grid, c->phys, c->P, c->volStrain, \
-                         c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA)
-        if (c->p.dim == 3) { if (c->surface_tension) P1(3, true); else P1(3, false); }
-        else               { if (c->surface_tension) P1(2, true); else P1(2, false); }
-#undef P1
-    } else {
+    {
         const float f2 = filter_radius2(c, c->surface_tension ? std::max(k.radius_p, k.radius_a) : k.radius_p);
         const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
 #define P1(D, ST) LAUNCH(c, (k_pass1_v2<D, ST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
@@ -270,25 +298,18 @@ static int run_pass1(Ctx *c)
     return MPHX_OK;
 }
 
-static int run_pass2(Ctx *c)
+static int run_pass2(Ctx *c, double *solbuf = nullptr)
 {
     const int n = c->n;
     const mphx_constants &k = c->c;
-    if (c->sweep_version == 1) {
-#define P2(D, ST) LAUNCH(c, (k_pass2<D, ST>), nblk(n), kBlock, n, c->S, c->cellStart, c->grid, c->phys, c->P, c->PA, c->gcx, \
-                         c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, c->fy, c->fz, c->ax,  \
-                         c->ay, c->az, c->sol)
-        if (c->p.dim == 3) { if (c->surface_tension) P2(3, true); else P2(3, false); }
-        else               { if (c->surface_tension) P2(2, true); else P2(2, false); }
-#undef P2
-    } else {
+    {
         double rmax = std::max(k.radius_p, k.radius_v);
         if (c->surface_tension) rmax = std::max(rmax, k.radius_a);
         const float f2 = filter_radius2(c, rmax);
         const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
 #define P2(D, ST) LAUNCH(c, (k_pass2_v2<D, ST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
                          batch, c->P, c->PA, c->gcx, c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, \
-                         c->fy, c->fz, c->ax, c->ay, c->az, c->sol)
+                         c->fy, c->fz, c->ax, c->ay, c->az, c->sol, solbuf)
         if (c->p.dim == 3) { if (c->surface_tension) P2(3, true); else P2(3, false); }
         else               { if (c->surface_tension) P2(2, true); else P2(2, false); }
 #undef P2
@@ -413,35 +434,66 @@ static int exact_lists(Ctx *c, bool structure_only, bool xy_only, int row_base, 
     return MPHX_OK;
 }
 
-static int init_solid(Ctx *c, const double *d_x03_orig)
+static int init_solid(Ctx *c)
 {
     if (c->ns <= 0) return MPHX_OK;
-    const int n = c->n, ns = c->ns;
+    const int ns = c->ns;
     int rc;
-    // buckets over InitialPosition: temporarily load x0 into the position arrays.  S is still in
-    // original order here (id == index; no rebuild has happened since the first upload).
-    double *sx = nullptr, *sy = nullptr, *sz = nullptr;
-    CK(cudaMalloc(&sx, sizeof(double) * n)); CK(cudaMalloc(&sy, sizeof(double) * n)); CK(cudaMalloc(&sz, sizeof(double) * n));
-    CK(cudaMemcpyAsync(sx, c->S.x, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaMemcpyAsync(sy, c->S.y, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaMemcpyAsync(sz, c->S.z, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->stream));
-    LAUNCH(c, k_split_vec3, nblk(n), kBlock, n, d_x03_orig, c->S.x, c->S.y, c->S.z);
-    // solids read their position from the solid arrays in k_prestep: point them at x0 for this build
-    Solid tmp = c->sol;
-    tmp.x = c->sol.x0; tmp.y = c->sol.y0; tmp.z = c->sol.z0;
-    Solid keep = c->sol;
-    c->sol = tmp;
+    // calculateInitialNeighbor (:1497-1644): buckets over InitialPosition, structure particles only.
+    // Built on a temporary particle set (the solids in their reference configuration) with the
+    // GLOBAL periodic grid, so the lists are complete on every slab of a multi-GPU run.
+    Ctx saved = *c; // shallow: pointers / descriptors swapped out below are restored from here
+    {
+        GridDesc &g = c->grid;
+        const mphx_constants &k = c->c;
+        g.slab = 0; g.nx = k.cell_count[0]; g.nxg = g.nx; g.xoff = 0; g.mn[0] = c->p.domain_min[0];
+        g.ncells = k.cell_counts;
+    }
+    Particles A{}, B{};
+    std::vector<void *> tmp;
+    auto talloc = [&](auto **ptr, size_t count) -> int {
+        void *q = nullptr;
+        if (cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(**ptr)) != cudaSuccess) return MPHX_ERR_NOMEM;
+        tmp.push_back(q);
+        *ptr = (std::remove_reference_t<decltype(**ptr)> *)q;
+        return 0;
+    };
+    auto tfree = [&]() { for (void *q : tmp) cudaFree(q); };
+    int e = 0;
+    for (Particles *p : {&A, &B}) {
+        e |= talloc(&p->x, ns); e |= talloc(&p->y, ns); e |= talloc(&p->z, ns);
+        e |= talloc(&p->vx, ns); e |= talloc(&p->vy, ns); e |= talloc(&p->vz, ns);
+        e |= talloc(&p->type, ns); e |= talloc(&p->id, ns); e |= talloc(&p->key, ns); e |= talloc(&p->pf, ns);
+    }
+    const size_t ncg = (size_t)c->grid.ncells;
+    const int sb_blocks = (int)((ncg + 2 + kScanChunk - 1) / kScanChunk);
+    e |= talloc(&c->cellCount, ncg + 2); e |= talloc(&c->cellStart, ncg + 3); e |= talloc(&c->blockSums, (size_t)sb_blocks + 1);
+    e |= talloc(&c->slot, ns); e |= talloc(&c->tmpIdx, ns); e |= talloc(&c->where, ns);
+    if (e) { tfree(); *c = saved; return MPHX_ERR_NOMEM; }
+    c->scan_blocks = sb_blocks;
+    c->S = A; c->T = B; c->n = ns; c->slab = false;
+    LAUNCH(c, k_solid_reference_particles, nblk(ns), kBlock, c->sol, c->S);
+    // k_prestep reads a solid's position from the solid arrays: point them at the reference positions
+    c->sol.x = saved.sol.x0; c->sol.y = saved.sol.y0; c->sol.z = saved.sol.z0;
     rc = rebuild_buckets(c, false);
-    c->sol = keep;
-    if (rc) return rc;
+    c->sol = saved.sol;
+    if (rc) { tfree(); *c = saved; return rc; }
     std::vector<long long> off;
     int *d_ids = nullptr;
     long long total = 0;
     rc = exact_lists(c, true, c->p.dim == 2, c->sol.sb, ns, off, &d_ids, &total);
-    if (rc) return rc;
+    if (rc) { tfree(); *c = saved; return rc; }
     std::vector<int> ids((size_t)std::max<long long>(total, 1));
-    CK(cudaMemcpy(ids.data(), d_ids, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost));
-    cudaFree(d_ids);
+    {
+        cudaError_t ce = cudaMemcpy(ids.data(), d_ids, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost);
+        cudaFree(d_ids);
+        const long long launches = c->launches;
+        tfree();
+        *c = saved; // back to the real particle set / grid
+        c->launches = launches;
+        if (ce != cudaSuccess) { set_last_error("copying the initial lists failed"); return MPHX_ERR_CUDA; }
+    }
+    if (rc) return rc;
     if (total > 0x7fffffffLL) return MPHX_ERR_UNSUPPORTED;
     std::vector<int> off32((size_t)ns + 1);
     for (int s = 0; s <= ns; ++s) off32[s] = (int)off[s];
@@ -453,7 +505,8 @@ static int init_solid(Ctx *c, const double *d_x03_orig)
         CK(cudaMemcpy(hx0.data(), c->sol.x0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(hy0.data(), c->sol.y0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(hz0.data(), c->sol.z0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
-        const GridDesc &g = c->grid;
+        GridDesc g = c->grid; // global bucket coordinates (the context's own grid may be one slab)
+        g.nx = c->c.cell_count[0]; g.mn[0] = c->p.domain_min[0];
         auto coord = [](double x, double mn, double cw, int n) {
             int v = ((int)std::floor((x - mn) / cw)) % n;
             return (v % n + n) % n;
@@ -493,7 +546,7 @@ static int init_solid(Ctx *c, const double *d_x03_orig)
         for (int s = 0; s < ns; ++s)
             for (int k = off32[s]; k < off32[s + 1]; ++k) rnbr[fill[ids[k]]++] = s;
     }
-    int e = 0;
+    e = 0;
     e |= c->alloc(&c->sol.off, (size_t)ns + 1); e |= c->alloc(&c->sol.nbr, (size_t)total);
     e |= c->alloc(&c->sol.roff, (size_t)ns + 1); e |= c->alloc(&c->sol.rnbr, (size_t)total);
     {
@@ -537,11 +590,8 @@ static int init_solid(Ctx *c, const double *d_x03_orig)
     else
         LAUNCH(c, k_solid_normalizer<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, c->cw_tl);
     CK(cudaGetLastError());
-    // restore the current positions (the arrays are now in x0-bucket order): gather through the ids
-    LAUNCH(c, k_restore_by_id, nblk(n), kBlock, n, c->S.id, sx, sy, sz, c->S.x, c->S.y, c->S.z);
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
-    cudaFree(sx); cudaFree(sy); cudaFree(sz);
     return MPHX_OK;
 }
 
@@ -627,7 +677,6 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
         return MPHX_ERR_CUDA;
     }
     c->timing = std::getenv("MPHX_TIMING") != nullptr;
-    if (const char *e = std::getenv("MPHX_SWEEP")) c->sweep_version = std::atoi(e) == 1 ? 1 : 2;
     if (const char *e = std::getenv("MPHX_SWEEP_BATCH")) c->sweep_batch = std::max(1, std::atoi(e));
     for (int k = 0; k < 2; ++k) cudaEventCreate(&c->tev[k]);
     *out = reinterpret_cast<mphx_ctx *>(c);
@@ -643,7 +692,7 @@ void mphx_destroy(mphx_ctx *ctx)
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) if (c->tev[k]) cudaEventDestroy(c->tev[k]);
     for (void *q : c->allocs) cudaFree(q);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->stream && !c->external_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -652,7 +701,8 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
 {
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || n <= 0 || !property || !position || !initial_position || !velocity) return MPHX_ERR_INVALID;
-    if (c->uploaded && n != c->n) return MPHX_ERR_INVALID; // re-upload must keep the particle count
+    if (c->uploaded && n != c->n_global) return MPHX_ERR_INVALID; // re-upload must keep the particle count
+    if (c->uploaded && c->slab) { set_last_error("re-upload is not supported on a slab context"); return MPHX_ERR_UNSUPPORTED; }
     CK(cudaSetDevice(c->device));
     for (int i = 0; i < n; ++i)
         if (property[i] < 0 || property[i] >= kTypeCount) { set_last_error("particle type outside 0..5"); return MPHX_ERR_INVALID; }
@@ -666,28 +716,50 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
             const int k = t < 2 ? 0 : t < 4 ? 1 : 2;
             if (k != cls) { set_last_error("particle classes are not contiguous in file order"); return MPHX_ERR_UNSUPPORTED; }
         }
+    // slab mode: this context keeps the fluid/wall particles of its own columns and ALL solids
+    std::vector<int> ids;
+    if (c->slab) {
+        const GridDesc &g = c->grid;
+        for (int i = 0; i < n; ++i) {
+            bool keep = property[i] >= 2 && property[i] < 4;
+            if (!keep) {
+                int cx = ((int)std::floor((position[3 * (size_t)i] - g.mn0g) / g.cellw)) % g.nxg; // :1671
+                cx = (cx % g.nxg + g.nxg) % g.nxg;
+                cx -= g.xoff;
+                if (cx < 0) cx += g.nxg; else if (cx >= g.nxg) cx -= g.nxg;
+                keep = cx >= g.range && cx < g.nx - g.range;
+            }
+            if (keep) ids.push_back(i);
+        }
+    }
+    const int nloc = c->slab ? (int)ids.size() : n;
     const bool first = !c->uploaded;
     if (first) {
-        c->n = n;
+        c->n_global = n;
+        c->n = nloc;
+        if (!c->slab) c->cap = n;
+        if (nloc > c->cap) { set_last_error("slab capacity too small for the initial particle set"); return MPHX_ERR_NOMEM; }
+        const size_t cap = (size_t)c->cap;
         std::memcpy(c->ranges, r, sizeof(r));
         c->nf = r[0] >= 0 ? r[1] - r[0] : 0;
         c->ns = r[2] >= 0 ? r[3] - r[2] : 0;
         c->nw = r[4] >= 0 ? r[5] - r[4] : 0;
         int e = 0;
-        e |= alloc_particles(c, &c->S, n);
-        e |= alloc_particles(c, &c->T, n);
-        e |= c->alloc(&c->cellCount, (size_t)c->grid.ncells);
-        e |= c->alloc(&c->cellStart, (size_t)c->grid.ncells + 1);
-        c->scan_blocks = (int)(((long long)c->grid.ncells + kScanChunk - 1) / kScanChunk);
+        e |= alloc_particles(c, &c->S, cap);
+        e |= alloc_particles(c, &c->T, cap);
+        e |= c->alloc(&c->cellCount, (size_t)c->grid.ncells + 2);
+        e |= c->alloc(&c->cellStart, (size_t)c->grid.ncells + 3);
+        c->scan_blocks = (int)(((long long)c->grid.ncells + 2 + kScanChunk - 1) / kScanChunk);
         e |= c->alloc(&c->blockSums, (size_t)c->scan_blocks + 1);
-        e |= c->alloc(&c->slot, n); e |= c->alloc(&c->tmpIdx, n);
-        e |= c->alloc(&c->P, n); e |= c->alloc(&c->volStrain, n); e |= c->alloc(&c->divP, n);
-        e |= c->alloc(&c->fx, n); e |= c->alloc(&c->fy, n); e |= c->alloc(&c->fz, n);
-        e |= c->alloc(&c->ax, n); e |= c->alloc(&c->ay, n); e |= c->alloc(&c->az, n);
-        e |= c->alloc(&c->densA, n); e |= c->alloc(&c->gcx, n); e |= c->alloc(&c->gcy, n);
-        e |= c->alloc(&c->gcz, n); e |= c->alloc(&c->PA, n);
+        e |= c->alloc(&c->slot, cap); e |= c->alloc(&c->tmpIdx, cap); e |= c->alloc(&c->where, cap);
+        e |= c->alloc(&c->P, cap); e |= c->alloc(&c->volStrain, cap); e |= c->alloc(&c->divP, cap);
+        e |= c->alloc(&c->fx, cap); e |= c->alloc(&c->fy, cap); e |= c->alloc(&c->fz, cap);
+        e |= c->alloc(&c->ax, cap); e |= c->alloc(&c->ay, cap); e |= c->alloc(&c->az, cap);
+        e |= c->alloc(&c->densA, cap); e |= c->alloc(&c->gcx, cap); e |= c->alloc(&c->gcy, cap);
+        e |= c->alloc(&c->gcz, cap); e |= c->alloc(&c->PA, cap);
         e |= c->alloc(&c->d_inv_density, kTypeCount);
-        e |= c->alloc(&c->d_x0_orig, (size_t)3 * n);
+        e |= c->alloc(&c->d_err, 4);
+        if (c->slab) { e |= c->alloc(&c->haloSrc[0], (size_t)c->msg_cap); e |= c->alloc(&c->haloSrc[1], (size_t)c->msg_cap); }
         Solid &so = c->sol;
         so.ns = c->ns; so.sb = c->ns > 0 ? r[2] : 0;
         const size_t ns = (size_t)c->ns;
@@ -699,27 +771,36 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         e |= c->alloc(&so.type, ns);
         if (e) return MPHX_ERR_NOMEM;
         CK(cudaMemcpy(c->d_inv_density, c->phys.inv_density, sizeof(double) * kTypeCount, cudaMemcpyHostToDevice));
+        CK(cudaMemsetAsync(c->d_err, 0, sizeof(int) * 4, c->stream));
         double *zs[] = {c->P, c->volStrain, c->divP, c->fx, c->fy, c->fz, c->ax, c->ay, c->az, c->densA, c->gcx, c->gcy, c->gcz, c->PA};
-        for (double *q : zs) CK(cudaMemsetAsync(q, 0, sizeof(double) * n, c->stream));
+        for (double *q : zs) CK(cudaMemsetAsync(q, 0, sizeof(double) * cap, c->stream));
         if (ns > 0)
             for (double **q : st) CK(cudaMemsetAsync(*q, 0, sizeof(double) * 9 * ns, c->stream));
     }
-    // stage AoS host arrays, split to SoA on the device
-    int *d_t = nullptr;
-    double *d_x = nullptr, *d_v = nullptr;
+    // stage the host arrays (global, original order), split to SoA on the device
+    int *d_t = nullptr, *d_ids = nullptr;
+    double *d_x = nullptr, *d_v = nullptr, *d_x0 = nullptr;
     CK(cudaMalloc(&d_t, sizeof(int) * n));
     CK(cudaMalloc(&d_x, sizeof(double) * 3 * (size_t)n));
     CK(cudaMalloc(&d_v, sizeof(double) * 3 * (size_t)n));
+    CK(cudaMalloc(&d_x0, sizeof(double) * 3 * (size_t)n));
     CK(cudaMemcpyAsync(d_t, property, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_x, position, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(d_v, velocity, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_x0_orig, initial_position, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(c, k_upload_split, nblk(n), kBlock, n, d_t, d_x, d_v, c->S);
-    if (c->ns > 0) LAUNCH(c, k_solid_upload, nblk(c->ns), kBlock, c->sol, d_t, d_x, c->d_x0_orig, d_v);
+    CK(cudaMemcpyAsync(d_x0, initial_position, sizeof(double) * 3 * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (c->slab) {
+        CK(cudaMalloc(&d_ids, sizeof(int) * (size_t)std::max(nloc, 1)));
+        CK(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * (size_t)nloc, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (nloc > 0) LAUNCH(c, k_upload_split, nblk(nloc), kBlock, nloc, d_ids, d_t, d_x, d_v, c->S);
+    if (c->ns > 0) LAUNCH(c, k_solid_upload, nblk(c->ns), kBlock, c->sol, d_t, d_x, d_x0, d_v);
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
-    cudaFree(d_t); cudaFree(d_x); cudaFree(d_v);
+    cudaFree(d_t); cudaFree(d_x); cudaFree(d_v); cudaFree(d_x0);
+    if (d_ids) cudaFree(d_ids);
+    c->n = nloc;
     c->uploaded = true;
+    c->buckets_valid = false;
     if (!first && c->inited) {
         // state replaced on an initialised context: rebuild the buckets (no wall motion / wrap)
         int rc = rebuild_buckets(c, false);
@@ -735,7 +816,7 @@ int mphx_upload_state(mphx_ctx *ctx, const double *position, const double *veloc
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !c->inited || !position || !velocity) return MPHX_ERR_INVALID;
     CK(cudaSetDevice(c->device));
-    const size_t N = (size_t)c->n;
+    const size_t N = (size_t)c->n_global;
     if (!c->stage3a && c->alloc(&c->stage3a, 3 * N)) return MPHX_ERR_NOMEM;
     if (!c->stage3b && c->alloc(&c->stage3b, 3 * N)) return MPHX_ERR_NOMEM;
     CK(cudaMemcpyAsync(c->stage3a, position, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
@@ -753,11 +834,13 @@ int mphx_init(mphx_ctx *ctx)
     if (c->inited) return MPHX_OK;
     CK(cudaSetDevice(c->device));
     int rc;
-    if ((rc = init_solid(c, c->d_x0_orig))) return rc; // calculateInitialNeighbor, Lame, Normalizer
+    if ((rc = init_solid(c))) return rc; // calculateInitialNeighbor, Lame, Normalizer
     // first calculateNeighbor + density sums on the initial positions (:565-568): gives
     // NeighborCount / PressureP for the `output.vtk` written before the loop (:572)
-    if ((rc = rebuild_buckets(c, false))) return rc;
-    if ((rc = run_pass1(c))) return rc;
+    if (!c->slab) { // (a slab needs its neighbours' halos first: done by the first mphx_slab_* step)
+        if ((rc = rebuild_buckets(c, false))) return rc;
+        if ((rc = run_pass1(c))) return rc;
+    }
     CK(cudaStreamSynchronize(c->stream));
     c->inited = true;
     return MPHX_OK;
@@ -847,34 +930,44 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !v || !c->uploaded) return MPHX_ERR_INVALID;
     CK(cudaSetDevice(c->device));
+    // Arrays are in ORIGINAL particle order and sized for the whole case.  A slab context fills the
+    // entries of the particles it owns (solids: slab 0 only) and zeros elsewhere, so the caller can
+    // combine the slabs with a plain sum.
     const int n = c->n, ns = c->ns;
-    const size_t N = (size_t)n;
+    const size_t N = (size_t)c->n_global;
     if (!c->stage3a && c->alloc(&c->stage3a, 3 * N)) return MPHX_ERR_NOMEM;
     if (!c->stage1 && c->alloc(&c->stage1, N)) return MPHX_ERR_NOMEM;
     if (!c->stagei && c->alloc(&c->stagei, N)) return MPHX_ERR_NOMEM;
+    if (!c->mask && c->alloc(&c->mask, (size_t)c->cap)) return MPHX_ERR_NOMEM;
+    if (!c->tmpi && c->alloc(&c->tmpi, (size_t)c->cap)) return MPHX_ERR_NOMEM;
     double *d3 = c->stage3a, *d1 = c->stage1, *d9 = c->stage9;
     int *di = c->stagei;
     const Particles &S = c->S;
     const Solid &so = c->sol;
+    const bool report_solids = !c->slab || c->rank == 0;
+    if (n > 0) LAUNCH(c, k_owned_mask, nblk(n), kBlock, n, S, c->grid, report_solids ? 1 : 0, c->mask);
     int rc = MPHX_OK;
     auto vec3 = [&](double *host, const double *a, const double *b, const double *cc, const double *sa, const double *sb_, const double *sc) -> int {
         if (!host) return MPHX_OK;
-        LAUNCH(c, k_gather_vec3, nblk(n), kBlock, n, S.id, a, b, cc, d3);
-        if (ns > 0 && sa) LAUNCH(c, k_solid_vec3_to_orig, nblk(ns), kBlock, so, sa, sb_, sc, d3);
+        if (c->slab) CK(cudaMemsetAsync(d3, 0, sizeof(double) * 3 * N, c->stream));
+        if (n > 0) LAUNCH(c, k_gather_vec3, nblk(n), kBlock, n, S.id, c->mask, a, b, cc, d3);
+        if (ns > 0 && sa && report_solids) LAUNCH(c, k_solid_vec3_to_orig, nblk(ns), kBlock, so, sa, sb_, sc, d3);
         CK(cudaMemcpyAsync(host, d3, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
     };
     auto scal = [&](double *host, const double *a) -> int {
         if (!host) return MPHX_OK;
-        LAUNCH(c, k_gather_scalar, nblk(n), kBlock, n, S.id, a, d1);
+        if (c->slab) CK(cudaMemsetAsync(d1, 0, sizeof(double) * N, c->stream));
+        if (n > 0) LAUNCH(c, k_gather_scalar, nblk(n), kBlock, n, S.id, c->mask, a, d1);
         CK(cudaMemcpyAsync(host, d1, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
     };
     auto ints = [&](int *host, const int *a) -> int {
         if (!host) return MPHX_OK;
-        LAUNCH(c, k_gather_int, nblk(n), kBlock, n, S.id, a, di);
+        if (c->slab) CK(cudaMemsetAsync(di, 0, sizeof(int) * N, c->stream));
+        if (n > 0) LAUNCH(c, k_gather_int, nblk(n), kBlock, n, S.id, c->mask, a, di);
         CK(cudaMemcpyAsync(host, di, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
@@ -886,7 +979,7 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
             d9 = c->stage9;
         }
         CK(cudaMemsetAsync(d9, 0, sizeof(double) * 9 * N, c->stream));
-        if (ns > 0) LAUNCH(c, k_solid_tensor_to_orig, nblk(ns), kBlock, so, M, d9);
+        if (ns > 0 && report_solids) LAUNCH(c, k_solid_tensor_to_orig, nblk(ns), kBlock, so, M, d9);
         CK(cudaMemcpyAsync(host, d9, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
@@ -894,13 +987,16 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     auto solid_scal = [&](double *host, const double *a) -> int {
         if (!host) return MPHX_OK;
         CK(cudaMemsetAsync(d1, 0, sizeof(double) * N, c->stream));
-        if (ns > 0) LAUNCH(c, k_solid_scalar_to_orig, nblk(ns), kBlock, so, a, d1);
+        if (ns > 0 && report_solids) LAUNCH(c, k_solid_scalar_to_orig, nblk(ns), kBlock, so, a, d1);
         CK(cudaMemcpyAsync(host, d1, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
     };
     do {
-        if ((rc = ints(v->property, S.type))) break;
+        if (v->property) {
+            if (n > 0) LAUNCH(c, k_real_types, nblk(n), kBlock, n, S, c->tmpi);
+            if ((rc = ints(v->property, c->tmpi))) break;
+        }
         if ((rc = vec3(v->position, S.x, S.y, S.z, so.x, so.y, so.z))) break;
         if ((rc = vec3(v->velocity, S.vx, S.vy, S.vz, so.vx, so.vy, so.vz))) break;
         if ((rc = vec3(v->force, c->fx, c->fy, c->fz, so.fx, so.fy, so.fz))) break;
@@ -911,18 +1007,24 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         if ((rc = scal(v->density_a, c->densA))) break;
         if ((rc = vec3(v->gravity_center, c->gcx, c->gcy, c->gcz, nullptr, nullptr, nullptr))) break;
         if ((rc = scal(v->pressure_a, c->PA))) break;
-        if ((rc = ints(v->cell_index, S.key))) break;
+        if (v->cell_index) {
+            if (n > 0) LAUNCH(c, k_global_keys, nblk(n), kBlock, n, S, c->grid, c->tmpi);
+            if ((rc = ints(v->cell_index, c->tmpi))) break;
+        }
         if (v->neighbor_count) {
             if (!c->inited) { rc = MPHX_ERR_INVALID; break; }
-            if (!c->buckets_valid && (rc = rebuild_buckets(c, false))) break;
+            if (!c->buckets_valid) {
+                if (c->slab) { rc = MPHX_ERR_INVALID; break; }
+                if ((rc = rebuild_buckets(c, false))) break;
+            }
             std::vector<long long> off;
             long long total = 0;
-            if ((rc = exact_lists(c, false, false, 0, n, off, nullptr, &total))) break;
-            for (int i = 0; i < n; ++i) v->neighbor_count[i] = (int)(off[i + 1] - off[i]);
+            if ((rc = exact_lists(c, false, false, 0, (int)N, off, nullptr, &total))) break;
+            for (size_t i = 0; i < N; ++i) v->neighbor_count[i] = (int)(off[i + 1] - off[i]);
         }
         if (v->initial_structure_neighbor_count) {
             CK(cudaMemsetAsync(di, 0, sizeof(int) * N, c->stream));
-            if (ns > 0 && so.off) LAUNCH(c, k_solid_rowlen_to_orig, nblk(ns), kBlock, so, di);
+            if (ns > 0 && so.off && report_solids) LAUNCH(c, k_solid_rowlen_to_orig, nblk(ns), kBlock, so, di);
             CK(cudaMemcpyAsync(v->initial_structure_neighbor_count, di, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
         }
@@ -945,9 +1047,10 @@ int mphx_debug_neighbors(mphx_ctx *ctx, long long *offsets, int *ids, long long 
     std::vector<long long> off;
     long long total = 0;
     int *d_ids = nullptr;
-    int rc = exact_lists(c, false, false, 0, c->n, off, ids ? &d_ids : nullptr, &total);
+    if (!c->buckets_valid) return MPHX_ERR_INVALID;
+    int rc = exact_lists(c, false, false, 0, c->n_global, off, ids ? &d_ids : nullptr, &total);
     if (rc) return rc;
-    std::memcpy(offsets, off.data(), sizeof(long long) * ((size_t)c->n + 1));
+    std::memcpy(offsets, off.data(), sizeof(long long) * ((size_t)c->n_global + 1));
     if (ids) {
         if (cap < total) { cudaFree(d_ids); return MPHX_ERR_OVERFLOW; }
         CK(cudaMemcpy(ids, d_ids, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost));
@@ -961,7 +1064,7 @@ int mphx_debug_initial_structure_neighbors(mphx_ctx *ctx, long long *offsets, in
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !c->inited || !offsets) return MPHX_ERR_INVALID;
     CK(cudaSetDevice(c->device));
-    const int n = c->n, ns = c->ns, sb = c->sol.sb;
+    const int n = c->n_global, ns = c->ns, sb = c->sol.sb;
     std::vector<int> off32((size_t)ns + 1, 0);
     if (ns > 0) CK(cudaMemcpy(off32.data(), c->sol.off, sizeof(int) * ((size_t)ns + 1), cudaMemcpyDeviceToHost));
     for (int i = 0; i <= n; ++i) {
@@ -999,5 +1102,7 @@ double mphx_algorithmic_bytes_per_step(const mphx_ctx *ctx)
     const int nsub = (int)(c->p.dt / c->p.elastic_dt + 0.5);
     return 368.0 * c->nf + 260.0 * c->nw + (344.0 + 384.0 * nsub) * c->ns;
 }
+
+#include "slab.inc"
 
 } // extern "C"

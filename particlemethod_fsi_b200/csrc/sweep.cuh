@@ -176,16 +176,19 @@ k_pass1_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     for (int e = threadIdx.x; e < g.nsten; e += blockDim.x) { sm.sdx[e] = g.sdx[e]; sm.sdy[e] = g.sdy[e]; sm.sh[e] = g.sh[e]; }
     __syncthreads();
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i0 < n;
-    const int i = active ? i0 : n - 1;
+    const int i = i0 < n ? i0 : n - 1;
     const double vxi = p.vx[i], vyi = p.vy[i], vzi = p.vz[i];
-    const int ti = p.type[i];
+    const int tflag = p.type[i], ti = real_type(tflag), keyi = p.key[i];
     const bool solid_i = is_structure_type(ti);
+    // slab mode: ghosts and parked solids are only ever neighbours; a solid is evaluated by the slab
+    // that owns its current column
+    bool active = i0 < n && keyi < g.ncells && !(tflag & kGhost);
+    if (g.slab && solid_i && active) active = column_owned(g, key_column(g, keyi));
     const double rp2 = ph.rp2, irp = ph.irp, ra2 = ph.ra2, ira = ph.ira;
     double nP = 0.0, dv = 0.0, nA = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0; // nP, dv without their constant factors
     const double *__restrict__ VX = p.vx, *__restrict__ VY = p.vy, *__restrict__ VZ = p.vz;
     const float4 *__restrict__ PF = p.pf;
-    sweep<DIM>(sm, g, cellStart, p.pf, p.x, p.y, p.z, i, active, p.key[i], filt2, batch,
+    sweep<DIM>(sm, g, cellStart, p.pf, p.x, p.y, p.z, i, active, active ? keyi : 0, filt2, batch,
         [&](int j, double dx, double dy, double dz, double r2) {
             if (r2 <= rp2) { // :2333, :2362
                 const double rinv = rsqrt(r2);
@@ -231,7 +234,8 @@ k_pass2_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
            const double *__restrict__ gcy, const double *__restrict__ gcz, double *__restrict__ ox,
            double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ovx, double *__restrict__ ovy,
            double *__restrict__ ovz, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
-           double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az, Solid sol)
+           double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az, Solid sol,
+           double *__restrict__ solbuf)
 {
     __shared__ SweepShared sm;
     __shared__ double s_visc[kTypeCount][kTypeCount];
@@ -242,12 +246,13 @@ k_pass2_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
         s_visc[e / kTypeCount][e % kTypeCount] = -ph.viscpair[e / kTypeCount][e % kTypeCount] * ph.cdv;
     __syncthreads();
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i0 < n;
-    const int i = active ? i0 : n - 1;
+    const int i = i0 < n ? i0 : n - 1;
     const double xi = p.x[i], yi = p.y[i], zi = p.z[i];
     const double vxi = p.vx[i], vyi = p.vy[i], vzi = p.vz[i];
-    const int ti = p.type[i];
+    const int tflag = p.type[i], ti = real_type(tflag), keyi = p.key[i];
     const bool solid_i = is_structure_type(ti);
+    bool active = i0 < n && keyi < g.ncells && !(tflag & kGhost);
+    if (g.slab && solid_i && active) active = column_owned(g, key_column(g, keyi));
     const double Pi = P[i];
     const double rp2 = ph.rp2, irp = ph.irp, rv2 = ph.rv2, irv = ph.irv;
     const double cpv = ph.cdp * ph.vol; // dwp/dr prefactor times particle volume
@@ -258,7 +263,7 @@ k_pass2_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     double PAi = 0.0, gi0 = 0.0, gi1 = 0.0, gi2 = 0.0, ai = 0.0;
     if (ST) { PAi = PA[i]; gi0 = gcx[i]; gi1 = gcy[i]; gi2 = gcz[i]; ai = ph.cofa[ti] * ph.cofk * ph.cofk; }
     const double gscale = ph.vol / ph.l0;
-    sweep<DIM>(sm, g, cellStart, p.pf, p.x, p.y, p.z, i, active, p.key[i], filt2, batch,
+    sweep<DIM>(sm, g, cellStart, p.pf, p.x, p.y, p.z, i, active, active ? keyi : 0, filt2, batch,
         [&](int j, double dx, double dy, double dz, double r2) {
             if (solid_i) {
                 if (r2 < rp2) { // :2455
@@ -310,7 +315,12 @@ k_pass2_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
                 F0 += A0; F1 += A1; F2 += A2;
             }
         });
-    if (!active) return;
+    if (i0 >= n) return;
+    if (!active) { // ghost / parked / not-owned solid: carried through unchanged (dropped or refreshed next step)
+        ox[i] = xi; oy[i] = yi; oz[i] = zi; ovx[i] = vxi; ovy[i] = vyi; ovz[i] = vzi;
+        fx[i] = 0.0; fy[i] = 0.0; fz[i] = 0.0; ax[i] = 0.0; ay[i] = 0.0; az[i] = 0.0;
+        return;
+    }
     // gravity + explicit integration in the reference's operand order (explicitly rounded)
     const double m = ph.mass[ti];
     double nx = xi, ny = yi, nz = zi, nvx = vxi, nvy = vyi, nvz = vzi;
@@ -325,8 +335,14 @@ k_pass2_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
             nx = __dadd_rn(xi, __dmul_rn(nvx, ph.dt)); ny = __dadd_rn(yi, __dmul_rn(nvy, ph.dt)); nz = __dadd_rn(zi, __dmul_rn(nvz, ph.dt));
         } else {
             const int s = p.id[i] - sol.sb;
-            sol.vx[s] = nvx; sol.vy[s] = nvy; sol.vz[s] = nvz;
-            sol.fx[s] = F0; sol.fy[s] = F1; sol.fz[s] = F2;
+            if (solbuf) { // slab mode: published through an all-reduce (all other slabs add zeros)
+                const size_t ns = sol.ns;
+                solbuf[s] = nvx; solbuf[ns + s] = nvy; solbuf[2 * ns + s] = nvz;
+                solbuf[3 * ns + s] = F0; solbuf[4 * ns + s] = F1; solbuf[5 * ns + s] = F2;
+            } else {
+                sol.vx[s] = nvx; sol.vy[s] = nvy; sol.vz[s] = nvz;
+                sol.fx[s] = F0; sol.fy[s] = F1; sol.fz[s] = F2;
+            }
         }
     }
     ox[i] = nx; oy[i] = ny; oz[i] = nz; ovx[i] = nvx; ovy[i] = nvy; ovz[i] = nvz;

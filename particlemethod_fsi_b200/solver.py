@@ -72,6 +72,15 @@ def _load():
     L.mphx_launch_count.restype = C.c_longlong
     L.mphx_algorithmic_bytes_per_step.argtypes = [vp]
     L.mphx_algorithmic_bytes_per_step.restype = C.c_double
+    L.mphx_set_stream.argtypes = [vp, vp]
+    L.mphx_slab_configure.argtypes = [vp] + [C.c_int] * 6
+    L.mphx_slab_begin.argtypes = [vp, vp, vp, vp]
+    L.mphx_slab_append.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
+    L.mphx_slab_pack_halo.argtypes = [vp, vp, vp, vp]
+    L.mphx_slab_build_pass1.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
+    L.mphx_slab_pass2.argtypes = [vp, vp, vp, vp, vp]
+    L.mphx_slab_finish.argtypes = [vp, vp]
+    L.mphx_slab_info.argtypes = [vp, C.POINTER(C.c_int * 4)]
     return L
 
 
