@@ -843,7 +843,9 @@ __global__ void k_owned_mask(int n, Particles p, GridDesc g, int solids_too, int
     const int k = p.key[q], t = p.type[q];
     bool own = !(t & kGhost);
     if (g.slab) {
-        if (is_structure_type(t)) own = own && solids_too;
+        // solids are replicated: solids_too 0 = never, 1 = always (one reporting slab), 2 = the slab
+        // that owns the particle's current column (bucket-related fields)
+        if (is_structure_type(t) && solids_too != 2) own = own && solids_too;
         else own = own && k < g.ncells && column_owned(g, key_column(g, k));
     }
     mask[q] = own ? 1 : 0;

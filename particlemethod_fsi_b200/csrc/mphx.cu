@@ -71,7 +71,7 @@ struct Ctx {
     double *d_inv_density = nullptr;
     double cw_tl = 0.0; // weight() prefactor (1.0/Swp)*(1.0/RP^d), src/main.cpp:291/293
     double *stage3a = nullptr, *stage3b = nullptr, *stage1 = nullptr, *stage9 = nullptr; // AoS staging (lazy)
-    int *stagei = nullptr, *mask = nullptr, *tmpi = nullptr;
+    int *stagei = nullptr, *mask = nullptr, *mask2 = nullptr, *tmpi = nullptr;
     bool buckets_valid = false;
     int sweep_batch = 12;  // stencil columns per filter/drain batch (3D) // cellStart / bx,by,bz describe the positions currently held
     std::vector<void *> allocs;
@@ -98,8 +98,11 @@ struct Ctx {
 
 #define LAUNCH(ctx, kernel, grid, block, ...)                                                      \
     do {                                                                                           \
-        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                 \
-        ++(ctx)->launches;                                                                         \
+        const int grid_ = (grid);                                                                  \
+        if (grid_ > 0) { /* an empty slab launches nothing */                                      \
+            kernel<<<grid_, (block), 0, (ctx)->stream>>>(__VA_ARGS__);                              \
+            ++(ctx)->launches;                                                                     \
+        }                                                                                          \
     } while (0)
 
 static int alloc_particles(Ctx *c, Particles *p, size_t n)
@@ -939,13 +942,18 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     if (!c->stage1 && c->alloc(&c->stage1, N)) return MPHX_ERR_NOMEM;
     if (!c->stagei && c->alloc(&c->stagei, N)) return MPHX_ERR_NOMEM;
     if (!c->mask && c->alloc(&c->mask, (size_t)c->cap)) return MPHX_ERR_NOMEM;
+    if (!c->mask2 && c->alloc(&c->mask2, (size_t)c->cap)) return MPHX_ERR_NOMEM;
     if (!c->tmpi && c->alloc(&c->tmpi, (size_t)c->cap)) return MPHX_ERR_NOMEM;
     double *d3 = c->stage3a, *d1 = c->stage1, *d9 = c->stage9;
     int *di = c->stagei;
     const Particles &S = c->S;
     const Solid &so = c->sol;
     const bool report_solids = !c->slab || c->rank == 0;
+    // mask: per-particle state (solids: one reporting slab, values come from the replicated solid arrays);
+    // mask2: fields evaluated per bucket sweep (PressureP, VolStrainP, CellIndex, ...), reported for a solid
+    // by the slab that owns its current column
     if (n > 0) LAUNCH(c, k_owned_mask, nblk(n), kBlock, n, S, c->grid, report_solids ? 1 : 0, c->mask);
+    if (n > 0) LAUNCH(c, k_owned_mask, nblk(n), kBlock, n, S, c->grid, 2, c->mask2);
     int rc = MPHX_OK;
     auto vec3 = [&](double *host, const double *a, const double *b, const double *cc, const double *sa, const double *sb_, const double *sc) -> int {
         if (!host) return MPHX_OK;
@@ -959,15 +967,15 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     auto scal = [&](double *host, const double *a) -> int {
         if (!host) return MPHX_OK;
         if (c->slab) CK(cudaMemsetAsync(d1, 0, sizeof(double) * N, c->stream));
-        if (n > 0) LAUNCH(c, k_gather_scalar, nblk(n), kBlock, n, S.id, c->mask, a, d1);
+        if (n > 0) LAUNCH(c, k_gather_scalar, nblk(n), kBlock, n, S.id, c->mask2, a, d1);
         CK(cudaMemcpyAsync(host, d1, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
     };
-    auto ints = [&](int *host, const int *a) -> int {
+    auto ints = [&](int *host, const int *a, const int *msk) -> int {
         if (!host) return MPHX_OK;
         if (c->slab) CK(cudaMemsetAsync(di, 0, sizeof(int) * N, c->stream));
-        if (n > 0) LAUNCH(c, k_gather_int, nblk(n), kBlock, n, S.id, c->mask, a, di);
+        if (n > 0) LAUNCH(c, k_gather_int, nblk(n), kBlock, n, S.id, msk, a, di);
         CK(cudaMemcpyAsync(host, di, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
@@ -995,7 +1003,7 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     do {
         if (v->property) {
             if (n > 0) LAUNCH(c, k_real_types, nblk(n), kBlock, n, S, c->tmpi);
-            if ((rc = ints(v->property, c->tmpi))) break;
+            if ((rc = ints(v->property, c->tmpi, c->mask))) break;
         }
         if ((rc = vec3(v->position, S.x, S.y, S.z, so.x, so.y, so.z))) break;
         if ((rc = vec3(v->velocity, S.vx, S.vy, S.vz, so.vx, so.vy, so.vz))) break;
@@ -1009,7 +1017,7 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         if ((rc = scal(v->pressure_a, c->PA))) break;
         if (v->cell_index) {
             if (n > 0) LAUNCH(c, k_global_keys, nblk(n), kBlock, n, S, c->grid, c->tmpi);
-            if ((rc = ints(v->cell_index, c->tmpi))) break;
+            if ((rc = ints(v->cell_index, c->tmpi, c->mask2))) break;
         }
         if (v->neighbor_count) {
             if (!c->inited) { rc = MPHX_ERR_INVALID; break; }
