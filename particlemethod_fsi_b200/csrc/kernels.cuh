@@ -67,11 +67,20 @@ struct WallMotion {
     double center[kTypeCount][3], vel[kTypeCount][3], omega[kTypeCount][3], R[kTypeCount][3][3];
 };
 
+struct __align__(32) PfPair { float2 x, y, z; int2 t; };
+struct __align__(32) Rec { double a, b, c, d; };
+
 // cell-sorted particle arrays
 struct Particles {
     double *x, *y, *z, *vx, *vy, *vz;
     int *type, *id, *key;
-    float4 *pf; // (position - DomainMin)/CellWidth in fp32 + type bits: input of the sweep's fp32 filter
+    // (position - DomainMin)/CellWidth in fp32 + type, PAIR-interleaved (particles 2k, 2k+1 share one
+    // 32-byte record): input of the sweep's packed-fp32 filter.  Padded by two pairs.
+    PfPair *pf;
+    // 32-byte gather records of the sorted particles (what a NEIGHBOUR's thread reads per pair, one
+    // 256-bit load each): ra[q] = (x, y, z, vx);  rb[q] = (vy, vz, PressureP, type bits).
+    // Written by the permute (PressureP by pass 1); one buffer shared by both ping-pong sets.
+    Rec *ra, *rb;
 };
 
 // total-Lagrangian solid, static order (solid-local index s = original id - sb)
@@ -275,10 +284,14 @@ __global__ void k_pack_scalar(int count, const int *__restrict__ src, const int 
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q < count) buf[q] = a[where[src[q]]];
 }
-__global__ void k_unpack_scalar(int base, int count, const int *__restrict__ where, const double *__restrict__ buf, double *__restrict__ a)
+__global__ void k_unpack_scalar(int base, int count, const int *__restrict__ where, const double *__restrict__ buf, double *__restrict__ a,
+                                Rec *__restrict__ rb)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < count) a[where[base + q]] = buf[q];
+    if (q >= count) return;
+    const int w = where[base + q];
+    a[w] = buf[q];
+    rb[w].c = buf[q]; // PressureP slot of the gather record
 }
 // replicated solids: the slab that owns a solid particle BY POSITION computes its PressureP / its
 // fluid-coupled velocity update; everybody else contributes zeros to an all-reduce (exact).
@@ -295,7 +308,9 @@ __global__ void k_solid_spread_P(int n, Particles p, GridDesc g, Solid sol, cons
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     if (p.key[q] >= g.ncells || !is_structure_type(p.type[q])) return;
-    P[q] = solP[p.id[q] - sol.sb];
+    const double v = solP[p.id[q] - sol.sb];
+    P[q] = v;
+    p.rb[q].c = v;
 }
 // solbuf = [vx vy vz fx fy fz] planes of ns doubles, summed over slabs (one owner, others zero)
 __global__ void k_solid_apply_update(Solid sol, const double *__restrict__ solbuf)
@@ -423,11 +438,18 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
     const double x = src.x[s], y = src.y[s], z = src.z[s];
     const int t = src.type[s];
     dst.x[q] = x; dst.y[q] = y; dst.z[q] = z;
-    dst.vx[q] = src.vx[s]; dst.vy[q] = src.vy[s]; dst.vz[q] = src.vz[s];
     dst.type[q] = t; dst.id[q] = src.id[s]; dst.key[q] = k;
     const double icw = 1.0 / g.cellw;
-    dst.pf[q] = make_float4((float)((x - g.mn[0]) * icw), (float)((y - g.mn[1]) * icw), (float)((z - g.mn[2]) * icw),
-                            __int_as_float(real_type(t)));
+    float *pfw = reinterpret_cast<float *>(dst.pf + (q >> 1)) + (q & 1); // x0 x1 y0 y1 z0 z1 t0 t1
+    pfw[0] = (float)((x - g.mn[0]) * icw); pfw[2] = (float)((y - g.mn[1]) * icw); pfw[4] = (float)((z - g.mn[2]) * icw);
+    pfw[6] = __int_as_float(real_type(t));
+    const double vx = src.vx[s], vy = src.vy[s], vz = src.vz[s];
+    dst.vx[q] = vx; dst.vy[q] = vy; dst.vz[q] = vz;
+    Rec ra, rb;
+    ra.a = x; ra.b = y; ra.c = z; ra.d = vx;
+    rb.a = vy; rb.b = vz; rb.c = 0.0; rb.d = __longlong_as_double((long long)real_type(t));
+    dst.ra[q] = ra;
+    dst.rb[q] = rb;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -73,7 +73,9 @@ struct Ctx {
     double *stage3a = nullptr, *stage3b = nullptr, *stage1 = nullptr, *stage9 = nullptr; // AoS staging (lazy)
     int *stagei = nullptr, *mask = nullptr, *mask2 = nullptr, *tmpi = nullptr;
     bool buckets_valid = false;
-    int sweep_batch = 12;  // stencil columns per filter/drain batch (3D) // cellStart / bx,by,bz describe the positions currently held
+    int sweep_batch = 12;  // stencil columns per filter/drain batch (3D)
+    PairList pl{};         // pass 1 -> pass 2 neighbour list (nbr == nullptr: disabled, pass 2 sweeps again)
+    int list_cap = -1;     // list slots per particle (-1: default by dimension, 0: no list)
     std::vector<void *> allocs;
 
     // phase timers (src/main.cpp:695-700 split)
@@ -111,7 +113,15 @@ static int alloc_particles(Ctx *c, Particles *p, size_t n)
     rc |= c->alloc(&p->x, n); rc |= c->alloc(&p->y, n); rc |= c->alloc(&p->z, n);
     rc |= c->alloc(&p->vx, n); rc |= c->alloc(&p->vy, n); rc |= c->alloc(&p->vz, n);
     rc |= c->alloc(&p->type, n); rc |= c->alloc(&p->id, n); rc |= c->alloc(&p->key, n);
-    rc |= c->alloc(&p->pf, n);
+    rc |= c->alloc(&p->pf, n / 2 + 4);
+    return rc ? MPHX_ERR_NOMEM : MPHX_OK;
+}
+// the gather records: one buffer serves both ping-pong sets (the permute reads SoA, writes records)
+static int alloc_records(Ctx *c, Particles *a, Particles *b, size_t n)
+{
+    int rc = 0;
+    rc |= c->alloc(&a->ra, n); rc |= c->alloc(&a->rb, n);
+    b->ra = a->ra; b->rb = a->rb;
     return rc ? MPHX_ERR_NOMEM : MPHX_OK;
 }
 
@@ -284,17 +294,34 @@ static float filter_radius2(const Ctx *c, double rmax)
     return (float)(R * R + margin) * (1.0f + 1e-6f);
 }
 
+static float sweep_filter2(const Ctx *c)
+{
+    // the filter covers every kernel radius of BOTH passes: they share one candidate list
+    const mphx_constants &k = c->c;
+    double rmax = std::max(k.radius_p, k.radius_v);
+    if (c->surface_tension) rmax = std::max(rmax, k.radius_a);
+    return filter_radius2(c, rmax);
+}
+
 static int run_pass1(Ctx *c)
 {
     const int n = c->n;
-    const mphx_constants &k = c->c;
     {
-        const float f2 = filter_radius2(c, c->surface_tension ? std::max(k.radius_p, k.radius_a) : k.radius_p);
+        const float f2 = sweep_filter2(c);
         const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
-#define P1(D, ST) LAUNCH(c, (k_pass1_v2<D, ST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
-                         batch, c->P, c->volStrain, c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA)
-        if (c->p.dim == 3) { if (c->surface_tension) P1(3, true); else P1(3, false); }
-        else               { if (c->surface_tension) P1(2, true); else P1(2, false); }
+        if (c->pl.nbr) { // K5a: candidate list of this step
+            CK(cudaMemsetAsync(c->pl.flags, 0, sizeof(int), c->stream));
+            if (c->p.dim == 3) LAUNCH(c, k_filter<3>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
+            else               LAUNCH(c, k_filter<2>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
+        }
+#define P1(D, ST, LIST) LAUNCH(c, (k_pass1_v3<D, ST, LIST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
+                         batch, c->P, c->volStrain, c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA, c->pl)
+#define P1D(ST, LIST) do { if (c->p.dim == 3) P1(3, ST, LIST); else P1(2, ST, LIST); } while (0)
+        if (c->pl.nbr) { // list traversal, then the fused sweep for particles whose list overflowed (normally none)
+            if (c->surface_tension) P1D(true, true); else P1D(false, true);
+        }
+        if (c->surface_tension) P1D(true, false); else P1D(false, false);
+#undef P1D
 #undef P1
     }
     CK(cudaGetLastError());
@@ -306,15 +333,17 @@ static int run_pass2(Ctx *c, double *solbuf = nullptr)
     const int n = c->n;
     const mphx_constants &k = c->c;
     {
-        double rmax = std::max(k.radius_p, k.radius_v);
-        if (c->surface_tension) rmax = std::max(rmax, k.radius_a);
-        const float f2 = filter_radius2(c, rmax);
+        const float f2 = sweep_filter2(c);
         const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
-#define P2(D, ST) LAUNCH(c, (k_pass2_v2<D, ST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
+#define P2(D, ST, LIST) LAUNCH(c, (k_pass2_v3<D, ST, LIST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
                          batch, c->P, c->PA, c->gcx, c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, \
-                         c->fy, c->fz, c->ax, c->ay, c->az, c->sol, solbuf)
-        if (c->p.dim == 3) { if (c->surface_tension) P2(3, true); else P2(3, false); }
-        else               { if (c->surface_tension) P2(2, true); else P2(2, false); }
+                         c->fy, c->fz, c->ax, c->ay, c->az, c->sol, solbuf, c->pl)
+#define P2D(ST, LIST) do { if (c->p.dim == 3) P2(3, ST, LIST); else P2(2, ST, LIST); } while (0)
+        if (c->pl.nbr) { // list traversal, then the sweep variant for particles whose list overflowed (normally none)
+            if (c->surface_tension) P2D(true, true); else P2D(false, true);
+        }
+        if (c->surface_tension) P2D(true, false); else P2D(false, false);
+#undef P2D
 #undef P2
     }
     // S keeps type/id/key of this step's order and takes the integrated x,v; T keeps the pre-step
@@ -466,8 +495,10 @@ static int init_solid(Ctx *c)
     for (Particles *p : {&A, &B}) {
         e |= talloc(&p->x, ns); e |= talloc(&p->y, ns); e |= talloc(&p->z, ns);
         e |= talloc(&p->vx, ns); e |= talloc(&p->vy, ns); e |= talloc(&p->vz, ns);
-        e |= talloc(&p->type, ns); e |= talloc(&p->id, ns); e |= talloc(&p->key, ns); e |= talloc(&p->pf, ns);
+        e |= talloc(&p->type, ns); e |= talloc(&p->id, ns); e |= talloc(&p->key, ns); e |= talloc(&p->pf, (size_t)ns / 2 + 4);
     }
+    e |= talloc(&A.ra, (size_t)ns); e |= talloc(&A.rb, (size_t)ns);
+    B.ra = A.ra; B.rb = A.rb;
     const size_t ncg = (size_t)c->grid.ncells;
     const int sb_blocks = (int)((ncg + 2 + kScanChunk - 1) / kScanChunk);
     e |= talloc(&c->cellCount, ncg + 2); e |= talloc(&c->cellStart, ncg + 3); e |= talloc(&c->blockSums, (size_t)sb_blocks + 1);
@@ -681,6 +712,7 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
     }
     c->timing = std::getenv("MPHX_TIMING") != nullptr;
     if (const char *e = std::getenv("MPHX_SWEEP_BATCH")) c->sweep_batch = std::max(1, std::atoi(e));
+    if (const char *e = std::getenv("MPHX_LIST_CAP")) c->list_cap = std::max(0, std::atoi(e)); // 0: pass 2 sweeps again
     for (int k = 0; k < 2; ++k) cudaEventCreate(&c->tev[k]);
     *out = reinterpret_cast<mphx_ctx *>(c);
     return MPHX_OK;
@@ -750,6 +782,18 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         int e = 0;
         e |= alloc_particles(c, &c->S, cap);
         e |= alloc_particles(c, &c->T, cap);
+        e |= alloc_records(c, &c->S, &c->T, cap);
+        {
+            int L = c->list_cap;
+            if (L < 0) L = c->p.dim == 3 ? 128 : 48;
+            c->pl = PairList{};
+            if (L > 0) {
+                e |= c->alloc(&c->pl.nbr, ((size_t)L + 1) * cap); // + the parking row of overflowed lists
+                e |= c->alloc(&c->pl.count, cap);
+                e |= c->alloc(&c->pl.flags, 4);
+                c->pl.cap = (int)cap; c->pl.L = L;
+            }
+        }
         e |= c->alloc(&c->cellCount, (size_t)c->grid.ncells + 2);
         e |= c->alloc(&c->cellStart, (size_t)c->grid.ncells + 3);
         c->scan_blocks = (int)(((long long)c->grid.ncells + 2 + kScanChunk - 1) / kScanChunk);

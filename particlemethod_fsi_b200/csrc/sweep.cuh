@@ -1,18 +1,27 @@
-// sweep.cuh -- the two stencil sweeps of the explicit step (K5 "pass 1", K6 "pass 2"), version 2.
+// sweep.cuh -- the two stencil sweeps of the explicit step (K5 "pass 1", K6 "pass 2"), version 3.
 //
-// One thread per particle (cell-sorted order), two phases per batch of stencil columns:
+// Pass 1 (one thread per particle, cell-sorted order) walks the particle's stencil in batches of
+// columns, two phases per batch:
 //
 //   phase A (FP32 / integer pipes): walk the contiguous particle runs of the stencil columns and
 //       test every candidate with a CONSERVATIVE single-precision distance filter on `pf` (position
 //       in bucket units, one 16-byte load per candidate); survivors are pushed to a per-thread
 //       queue in shared memory (slot-major layout: bank = lane, conflict-free).
-//   phase B (FP64 pipe): drain the queue: exact double-precision separation, exact cut-off test,
-//       kernel weights and the pair terms.  All lanes of a warp drain together, so the FP64 work
-//       runs (nearly) divergence-free instead of being scattered over the candidate loop.
+//   phase B (FP64 pipe): drain the queue: exact double-precision separation from the 32-byte gather
+//       records (x,y,z,vx | vy,vz,P,type), exact cut-off test, kernel weights and the pair terms.
+//       All lanes of a warp drain together, so the FP64 work runs (nearly) divergence-free.
 //
 // The filter only has to be a superset of the exact predicate: the float coordinates carry an
 // error <= 2 ulp_f32(max bucket coordinate) each, which the host turns into a margin on the
 // squared cut-off (see filter_radius2 in mphx.cu).  Physics is decided in phase B in fp64.
+// (A particle always passes its own filter test; phase B rejects j == i.)
+//
+// Normal operation splits the work differently (the fused sweep above remains as the fall-back):
+// k_filter runs phase A alone for all particles at full occupancy and writes the survivors into a
+// per-step ELL candidate list (entry k of particle i at nbr[k*cap + i]: coalesced); pass 1 and pass 2
+// run in the same step on the same positions, so both just traverse that list (phase B only, FP64
+// pipe).  Particles whose list overflowed (count > L) are finished by the fused-sweep variants of
+// pass 1 / pass 2 (second launches that exit at once when there is no overflow).
 //
 // The reference procedures these kernels replace are listed at the top of kernels.cuh.
 #pragma once
@@ -21,88 +30,172 @@
 namespace mphx {
 
 constexpr int kSweepThreads = 128;
-constexpr int kQueueCap = 40; // queue slots per thread (16-byte aligned rows of 128 uint)
+constexpr int kQueueCap = 40; // queue slots per thread (rows of 128 uint); one spare row absorbs masked stores
 
 struct SweepShared {
-    unsigned q[kQueueCap][kSweepThreads];
+    unsigned q[kQueueCap + 1][kSweepThreads];
     int sdx[kMaxStencil], sdy[kMaxStencil], sh[kMaxStencil];
+    int dlo[kMaxStencil], dhi[kMaxStencil]; // bucket offsets of a column's run ends relative to the own key
 };
 
-// Walks the stencil of particle i in batches of `batch` columns; calls hit(j, dx, dy, dz, r2) in
-// phase B for every candidate that passed the fp32 filter (never for j == i).  dx,dy,dz,r2 are the
-// exact fp64 separation (minimum image) of j from i.
+__device__ __forceinline__ void load_stencil(SweepShared &sm, const GridDesc &g)
+{
+    for (int e = threadIdx.x; e < g.nsten; e += blockDim.x) {
+        const int dx = g.sdx[e], dy = g.sdy[e], h = g.sh[e];
+        sm.sdx[e] = dx; sm.sdy[e] = dy; sm.sh[e] = h;
+        const int d = (g.dim == 3) ? (dx * g.ny + dy) * g.nz : dx * g.ny;
+        sm.dlo[e] = d - h;
+        sm.dhi[e] = d + h + 1;
+    }
+}
+
+// 1/sqrt(a) for a > 0: hardware seed (MUFU.RSQ64H) + two Newton steps (error ~1 ulp).
+__device__ __forceinline__ double rsqrt_nr(double a)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double h = 0.5 * a;
+    double e = fma(-h * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-h * y, y, 0.5);
+    return fma(y, e, y);
+}
+
+// 256-bit loads (LDG.E.256 on sm_100a): one request per 32-byte record.
+__device__ __forceinline__ Rec ld_rec_nc(const Rec *p)
+{
+    Rec r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    return r;
+}
+// coherent variant: pass 1 reads (vy, vz) from records whose PressureP slot other threads are writing
+__device__ __forceinline__ Rec ld_rec(const Rec *p)
+{
+    Rec r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ PfPair ld_pf_nc(const PfPair *p)
+{
+    unsigned v0, v1, v2, v3, v4, v5, v6, v7;
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3), "=r"(v4), "=r"(v5), "=r"(v6), "=r"(v7)
+        : "l"(p));
+    PfPair r;
+    r.x = make_float2(__uint_as_float(v0), __uint_as_float(v1));
+    r.y = make_float2(__uint_as_float(v2), __uint_as_float(v3));
+    r.z = make_float2(__uint_as_float(v4), __uint_as_float(v5));
+    r.t = make_int2((int)v6, (int)v7);
+    return r;
+}
+
+struct Bucket3 { int cx, cy, cr, nr; };
+template <int DIM> __device__ __forceinline__ Bucket3 split_key(const GridDesc &g, int key)
+{
+    Bucket3 b;
+    if (DIM == 3) { b.cr = key % g.nz; const int t = key / g.nz; b.cy = t % g.ny; b.cx = t / g.ny; b.nr = g.nz; }
+    else { b.cr = key % g.ny; b.cx = key / g.ny; b.cy = 0; b.nr = g.ny; }
+    return b;
+}
+// does any part of the stencil of this bucket cross the periodic box?
+template <int DIM> __device__ __forceinline__ bool stencil_wraps(const GridDesc &g, const Bucket3 &b)
+{
+    const int R = g.range;
+    bool w = (b.cx - R < 0) || (b.cx + R >= g.nx) || (b.cr - R < 0) || (b.cr + R >= b.nr);
+    if (DIM == 3) w = w || (b.cy - R < 0) || (b.cy + R >= g.ny);
+    return w;
+}
+
+struct MinImage {
+    double W0, W1, W2, h0, h1, h2;
+    __device__ __forceinline__ explicit MinImage(const GridDesc &g)
+        : W0(g.W[0]), W1(g.W[1]), W2(g.W[2]), h0(0.5 * g.W[0]), h1(0.5 * g.W[1]), h2(0.5 * g.W[2]) {}
+    __device__ __forceinline__ void apply(double &dx, double &dy, double &dz) const
+    {
+        dx = dx > h0 ? dx - W0 : (dx < -h0 ? dx + W0 : dx);
+        dy = dy > h1 ? dy - W1 : (dy < -h1 ? dy + W1 : dy);
+        dz = dz > h2 ? dz - W2 : (dz < -h2 ? dz + W2 : dz);
+    }
+};
+
+// Walks the stencil of particle i in batches of `batch` columns; calls hit(j, dx, dy, dz, r2, vxj) in
+// phase B for every candidate that passed the fp32 filter (INCLUDING j == i, which the caller
+// rejects).  dx,dy,dz,r2 are the exact fp64 separation (minimum image) of j from i; vxj rides along
+// in the same 32-byte gather record.
+//
+// Phase A works on PAIRS of candidates: the filter coordinates are stored pair-interleaved
+// (PfPair = x0 x1 y0 y1 z0 z1 t0 t1, one 256-bit load), so the three subtractions and the three
+// multiply-adds of the distance test are Blackwell's packed f32x2 instructions (FADD2/FMUL2/FFMA2:
+// two candidates per issue slot).  Pushes are branch-free: the candidate index is always stored at
+// the queue top and the top only advances when the test passed.
 template <int DIM, class Hit>
 __device__ __forceinline__ void sweep(SweepShared &sm, const GridDesc &g, const int *__restrict__ cellStart,
-                                      const float4 *__restrict__ pf, const double *__restrict__ X,
-                                      const double *__restrict__ Y, const double *__restrict__ Z, int i, bool active,
-                                      int key, float filt2, int batch, Hit &&hit)
+                                      const PfPair *__restrict__ pf, const Rec *__restrict__ ra, int i, bool active,
+                                      int key, double xi, double yi, double zi, float filt2, int batch, Hit &&hit)
 {
     const int tid = threadIdx.x;
-    double xi = 0.0, yi = 0.0, zi = 0.0;
     float fxi = 0.f, fyi = 0.f, fzi = 0.f;
     if (active) {
-        xi = X[i]; yi = Y[i]; zi = Z[i];
-        const float4 f = pf[i];
-        fxi = f.x; fyi = f.y; fzi = f.z;
+        const float *f = reinterpret_cast<const float *>(pf + (i >> 1)) + (i & 1);
+        fxi = f[0]; fyi = f[2]; fzi = f[4];
     }
-    int cx, cy, cr, nr;
-    if (DIM == 3) { cr = key % g.nz; const int t = key / g.nz; cy = t % g.ny; cx = t / g.ny; nr = g.nz; }
-    else { cr = key % g.ny; cx = key / g.ny; cy = 0; nr = g.ny; }
-    // does any part of this particle's stencil cross the periodic box?  (rare: then phase B applies
-    // the minimum image explicitly; decided per warp so the branch is uniform)
-    const int R = g.range;
-    bool wraps = (cx - R < 0) || (cx + R >= g.nx) || (cr - R < 0) || (cr + R >= nr);
-    if (DIM == 3) wraps = wraps || (cy - R < 0) || (cy + R >= g.ny);
+    const Bucket3 b = split_key<DIM>(g, key);
+    const int cx = b.cx, cy = b.cy, cr = b.cr, nr = b.nr;
+    const bool wraps = stencil_wraps<DIM>(g, b);
     const bool warp_wraps = __any_sync(0xffffffffu, active && wraps);
-    const double W0 = g.W[0], W1 = g.W[1], W2 = g.W[2];
-    const double hW0 = 0.5 * W0, hW1 = 0.5 * W1, hW2 = 0.5 * W2;
+    const MinImage mi(g);
 
-    int cnt = 0;
+    unsigned *const q0 = &sm.q[0][tid];
+    unsigned *qp = q0; // queue top
+    auto queued = [&]() { return (int)(qp - q0) / kSweepThreads; };
     auto drain = [&]() {
-        // two queue entries per trip: both position loads are issued before either is used
+        const int cnt = queued();
+        // two queue entries per trip: both record loads are issued before either is used
         for (int s = 0; s < cnt; s += 2) {
             const bool two = s + 1 < cnt;
-            const int j0 = (int)sm.q[s][tid];
-            const int j1 = two ? (int)sm.q[s + 1][tid] : j0;
-            double dx0 = X[j0] - xi, dy0 = Y[j0] - yi, dz0 = Z[j0] - zi;
-            double dx1 = X[j1] - xi, dy1 = Y[j1] - yi, dz1 = Z[j1] - zi;
-            if (warp_wraps) {
-                dx0 = dx0 > hW0 ? dx0 - W0 : (dx0 < -hW0 ? dx0 + W0 : dx0);
-                dy0 = dy0 > hW1 ? dy0 - W1 : (dy0 < -hW1 ? dy0 + W1 : dy0);
-                dz0 = dz0 > hW2 ? dz0 - W2 : (dz0 < -hW2 ? dz0 + W2 : dz0);
-                dx1 = dx1 > hW0 ? dx1 - W0 : (dx1 < -hW0 ? dx1 + W0 : dx1);
-                dy1 = dy1 > hW1 ? dy1 - W1 : (dy1 < -hW1 ? dy1 + W1 : dy1);
-                dz1 = dz1 > hW2 ? dz1 - W2 : (dz1 < -hW2 ? dz1 + W2 : dz1);
-            }
-            hit(j0, dx0, dy0, dz0, dx0 * dx0 + dy0 * dy0 + dz0 * dz0);
-            if (two) hit(j1, dx1, dy1, dz1, dx1 * dx1 + dy1 * dy1 + dz1 * dz1);
+            const int j0 = (int)q0[s * kSweepThreads];
+            const int j1 = two ? (int)q0[(s + 1) * kSweepThreads] : j0;
+            const Rec a0 = ld_rec_nc(ra + j0);
+            const Rec a1 = ld_rec_nc(ra + j1);
+            double dx0 = a0.a - xi, dy0 = a0.b - yi, dz0 = a0.c - zi;
+            double dx1 = a1.a - xi, dy1 = a1.b - yi, dz1 = a1.c - zi;
+            if (warp_wraps) { mi.apply(dx0, dy0, dz0); mi.apply(dx1, dy1, dz1); }
+            hit(j0, dx0, dy0, dz0, dx0 * dx0 + dy0 * dy0 + dz0 * dz0, a0.d);
+            if (two) hit(j1, dx1, dy1, dz1, dx1 * dx1 + dy1 * dy1 + dz1 * dz1, a1.d);
         }
-        cnt = 0;
+        qp = q0;
     };
 
-    // phase A over one contiguous run [jb, je) of candidates, four loads in flight at a time.
-    // The caller guarantees room in the queue for the whole run.
+    // phase A over one contiguous run [jb, je) of candidates (the caller guarantees queue room for
+    // je - jb + 1 entries).  Pairs (2k, 2k+1) are loaded whole; the elements outside [jb, je) are
+    // masked by the range test.  Two pair loads are in flight per trip (pf is padded by two pairs).
     auto scan_run = [&](int jb, int je, float fx, float fy, float fz) {
-        for (int j = jb; j < je; j += 4) {
-            const float4 far = make_float4(1e18f, 1e18f, 1e18f, 0.f);
-            const float4 f0 = __ldg(&pf[j]);
-            const float4 f1 = (j + 1 < je) ? __ldg(&pf[j + 1]) : far;
-            const float4 f2 = (j + 2 < je) ? __ldg(&pf[j + 2]) : far;
-            const float4 f3 = (j + 3 < je) ? __ldg(&pf[j + 3]) : far;
-#define MPHX_TEST(f, jj)                                                                           \
+        const float2 nx = make_float2(-fx, -fx), ny = make_float2(-fy, -fy), nz = make_float2(-fz, -fz);
+        const int len = je - jb, lenm1 = len - 1;
+        int j0 = jb & ~1;
+        int t = j0 - jb; // -1 or 0: position of the pair's first element in the run
+        const PfPair *pp = pf + (j0 >> 1);
+        for (; t < len; t += 4, j0 += 4, pp += 2) {
+            const PfPair fa = ld_pf_nc(pp), fb = ld_pf_nc(pp + 1);
+#define MPHX_TEST2(f, tt, jj)                                                                      \
     {                                                                                              \
-        const float ddx = f.x - fx, ddy = f.y - fy, ddz = f.z - fz;                                \
-        const float d2 = ddx * ddx + ddy * ddy + ddz * ddz;                                        \
-        if (d2 <= filt2 && (jj) != i) { sm.q[cnt][tid] = (unsigned)(jj); ++cnt; }                  \
+        const float2 ddx = __fadd2_rn(f.x, nx), ddy = __fadd2_rn(f.y, ny), ddz = __fadd2_rn(f.z, nz); \
+        float2 d2 = __fmul2_rn(ddx, ddx);                                                          \
+        d2 = __ffma2_rn(ddy, ddy, d2);                                                             \
+        d2 = __ffma2_rn(ddz, ddz, d2);                                                             \
+        const bool ok0 = (unsigned)(tt) < (unsigned)len && d2.x <= filt2;                          \
+        const bool ok1 = (tt) < lenm1 && d2.y <= filt2;                                            \
+        *qp = (unsigned)(jj); qp += ok0 ? kSweepThreads : 0;                                       \
+        *qp = (unsigned)(jj) + 1u; qp += ok1 ? kSweepThreads : 0;                                  \
     }
-            MPHX_TEST(f0, j) MPHX_TEST(f1, j + 1) MPHX_TEST(f2, j + 2) MPHX_TEST(f3, j + 3)
-#undef MPHX_TEST
+            MPHX_TEST2(fa, t, j0) MPHX_TEST2(fb, t + 2, j0 + 2)
+#undef MPHX_TEST2
         }
     };
     auto scan_checked = [&](int jb, int je, float fx, float fy, float fz) {
         while (jb < je) { // make room first; a run longer than the queue is scanned in pieces
-            const int room = kQueueCap - cnt;
-            if (room == 0) { drain(); continue; }
+            const int room = kQueueCap - queued();
+            if (room < 2) { drain(); continue; }
             const int jm = (je - jb <= room) ? je : jb + room;
             scan_run(jb, jm, fx, fy, fz);
             jb = jm;
@@ -115,17 +208,11 @@ __device__ __forceinline__ void sweep(SweepShared &sm, const GridDesc &g, const 
         if (active && !wraps) {
             // fast path (stencil inside the box): one run per column, bounds of the next column are
             // fetched while the current run is scanned
-            auto bounds = [&](int e, int &jb, int &je) {
-                const int base = (DIM == 3) ? ((cx + sm.sdx[e]) * g.ny + cy + sm.sdy[e]) * g.nz : (cx + sm.sdx[e]) * g.ny;
-                const int h = sm.sh[e];
-                jb = cellStart[base + cr - h];
-                je = cellStart[base + cr + h + 1];
-            };
-            int jbn, jen;
-            bounds(e0, jbn, jen);
+            const int *cs = cellStart + key;
+            int jbn = cs[sm.dlo[e0]], jen = cs[sm.dhi[e0]];
             for (int e = e0; e < e1; ++e) {
                 const int jb = jbn, je = jen;
-                if (e + 1 < e1) bounds(e + 1, jbn, jen);
+                if (e + 1 < e1) { jbn = cs[sm.dlo[e + 1]]; jen = cs[sm.dhi[e + 1]]; }
                 scan_checked(jb, je, fxi, fyi, fzi);
             }
         } else if (active) {
@@ -148,14 +235,14 @@ __device__ __forceinline__ void sweep(SweepShared &sm, const GridDesc &g, const 
                 // in-range part, then the wrapped images
 #pragma unroll 1
                 for (int seg = 0; seg < 3; ++seg) {
-                    int a, b;
+                    int a, bb;
                     float shf = 0.f;
-                    if (seg == 0) { a = lo < 0 ? 0 : lo; b = hi >= nr ? nr - 1 : hi; }
-                    else if (seg == 1) { if (lo >= 0) continue; a = lo + nr; b = nr - 1; shf = (float)nr; }
-                    else { if (hi < nr) break; a = 0; b = hi - nr; shf = -(float)nr; }
+                    if (seg == 0) { a = lo < 0 ? 0 : lo; bb = hi >= nr ? nr - 1 : hi; }
+                    else if (seg == 1) { if (lo >= 0) continue; a = lo + nr; bb = nr - 1; shf = (float)nr; }
+                    else { if (hi < nr) break; a = 0; bb = hi - nr; shf = -(float)nr; }
                     const float fyy = (DIM == 2) ? fy + shf : fy;
                     const float fzz = (DIM == 3) ? fz + shf : fz;
-                    scan_checked(cellStart[base + a], cellStart[base + b + 1], fx, fyy, fzz);
+                    scan_checked(cellStart[base + a], cellStart[base + bb + 1], fx, fyy, fzz);
                 }
             }
         }
@@ -163,20 +250,145 @@ __device__ __forceinline__ void sweep(SweepShared &sm, const GridDesc &g, const 
     }
 }
 
+// Candidate list of one step: written by k_filter, traversed by pass 1 and pass 2 (same step, same
+// positions).  It holds the survivors of the conservative fp32 filter (a superset of every exact
+// cut-off test, possibly including the particle itself); the physics kernels apply the exact fp64
+// tests.  ELL layout: entry k of particle i at nbr[k*cap + i] (coalesced across a warp).
+struct PairList {
+    int *nbr;    // [L + 1][cap]; row L is a parking row for the stores of overflowed lists
+    int *count;  // [cap] entries of particle i; L + 1 = overflowed (that particle is swept instead)
+    int *flags;  // [0] != 0: some list overflowed in this step
+    int cap, L;
+};
+
+// K5a "filter": phase A alone, for every particle at once.  No fp64, no shared-memory queue, few
+// registers: the kernel runs at full occupancy, which hides the latency of the candidate loads.
+// Candidates are tested in pairs with the packed f32x2 instructions (see sweep()).
+template <int DIM>
+__global__ void __launch_bounds__(kSweepThreads)
+k_filter(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, float filt2, PairList pl)
+{
+    __shared__ int s_dlo[kMaxStencil], s_dhi[kMaxStencil], s_sdx[kMaxStencil], s_sdy[kMaxStencil], s_sh[kMaxStencil];
+    for (int e = threadIdx.x; e < g.nsten; e += blockDim.x) {
+        const int dx = g.sdx[e], dy = g.sdy[e], h = g.sh[e];
+        const int d = (DIM == 3) ? (dx * g.ny + dy) * g.nz : dx * g.ny;
+        s_dlo[e] = d - h; s_dhi[e] = d + h + 1; s_sdx[e] = dx; s_sdy[e] = dy; s_sh[e] = h;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int tflag = p.type[i], keyi = p.key[i];
+    bool active = keyi < g.ncells && !(tflag & kGhost);
+    if (g.slab && is_structure_type(tflag) && active) active = column_owned(g, key_column(g, keyi));
+    if (!active) { pl.count[i] = 0; return; }
+    const PfPair *__restrict__ pf = p.pf;
+    const float *fo = reinterpret_cast<const float *>(pf + (i >> 1)) + (i & 1);
+    const float fxi = fo[0], fyi = fo[2], fzi = fo[4];
+    const Bucket3 b = split_key<DIM>(g, keyi);
+    const bool wraps = stencil_wraps<DIM>(g, b);
+    const size_t stride0 = (size_t)pl.cap;
+    size_t stride = stride0;
+    int *lp = pl.nbr + i;
+    int *const lpark = pl.nbr + (size_t)pl.L * stride0 + i;
+    int *const lp0 = lp;
+    bool over = false;
+
+    auto scan_run = [&](int jb, int je, float fx, float fy, float fz) {
+        const int len = je - jb, lenm1 = len - 1;
+        if (len <= 0) return;
+        // room for the whole run (+ the masked partner of an unaligned first pair)?  If not, the list
+        // overflows: keep scanning into the parking row so that control flow stays simple.
+        if (!over && (long long)(lp - lp0) + (long long)(len + 1) * (long long)stride0 > (long long)pl.L * (long long)stride0) {
+            over = true; lp = lpark; stride = 0;
+        }
+        const float2 nx = make_float2(-fx, -fx), ny = make_float2(-fy, -fy), nz = make_float2(-fz, -fz);
+        int j0 = jb & ~1;
+        int t = j0 - jb; // -1 or 0: position of the pair's first element in the run
+        const PfPair *pp = pf + (j0 >> 1);
+        for (; t < len; t += 4, j0 += 4, pp += 2) {
+            const PfPair fa = ld_pf_nc(pp), fb = ld_pf_nc(pp + 1);
+#define MPHX_TEST2(f, tt, jj)                                                                      \
+    {                                                                                              \
+        const float2 ddx = __fadd2_rn(f.x, nx), ddy = __fadd2_rn(f.y, ny), ddz = __fadd2_rn(f.z, nz); \
+        float2 d2 = __fmul2_rn(ddx, ddx);                                                          \
+        d2 = __ffma2_rn(ddy, ddy, d2);                                                             \
+        d2 = __ffma2_rn(ddz, ddz, d2);                                                             \
+        if ((unsigned)(tt) < (unsigned)len && d2.x <= filt2) { *lp = (jj); lp += stride; }         \
+        if ((tt) < lenm1 && d2.y <= filt2) { *lp = (jj) + 1; lp += stride; }                       \
+    }
+            MPHX_TEST2(fa, t, j0) MPHX_TEST2(fb, t + 2, j0 + 2)
+#undef MPHX_TEST2
+        }
+    };
+
+    const int nsten = g.nsten;
+    if (!wraps) {
+        // stencil inside the box: one run per column; the bounds of the next column are fetched
+        // while the current run is scanned
+        const int *cs = cellStart + keyi;
+        int jbn = cs[s_dlo[0]], jen = cs[s_dhi[0]];
+        for (int e = 0; e < nsten; ++e) {
+            const int jb = jbn, je = jen;
+            if (e + 1 < nsten) { jbn = cs[s_dlo[e + 1]]; jen = cs[s_dhi[e + 1]]; }
+            scan_run(jb, je, fxi, fyi, fzi);
+        }
+    } else {
+        const int cx = b.cx, cy = b.cy, cr = b.cr, nr = b.nr;
+        for (int e = 0; e < nsten; ++e) {
+            int ccx = cx + s_sdx[e];
+            float fx = fxi, fy = fyi, fz = fzi;
+            if (ccx < 0) { ccx += g.nx; fx += (float)g.nx; }
+            else if (ccx >= g.nx) { ccx -= g.nx; fx -= (float)g.nx; }
+            int base;
+            if (DIM == 3) {
+                int ccy = cy + s_sdy[e];
+                if (ccy < 0) { ccy += g.ny; fy += (float)g.ny; }
+                else if (ccy >= g.ny) { ccy -= g.ny; fy -= (float)g.ny; }
+                base = (ccx * g.ny + ccy) * g.nz;
+            } else {
+                base = ccx * g.ny;
+            }
+            const int h = s_sh[e];
+            const int lo = cr - h, hi = cr + h;
+#pragma unroll 1
+            for (int seg = 0; seg < 3; ++seg) { // in-range part, then the wrapped images
+                int a, bb;
+                float shf = 0.f;
+                if (seg == 0) { a = lo < 0 ? 0 : lo; bb = hi >= nr ? nr - 1 : hi; }
+                else if (seg == 1) { if (lo >= 0) continue; a = lo + nr; bb = nr - 1; shf = (float)nr; }
+                else { if (hi < nr) break; a = 0; bb = hi - nr; shf = -(float)nr; }
+                const float fyy = (DIM == 2) ? fy + shf : fy;
+                const float fzz = (DIM == 3) ? fz + shf : fz;
+                scan_run(cellStart[base + a], cellStart[base + bb + 1], fx, fyy, fzz);
+            }
+        }
+    }
+    if (over) { pl.count[i] = pl.L + 1; atomicOr(pl.flags, 1); }
+    else pl.count[i] = (int)((lp - lp0) / (long long)stride0);
+}
+
 // K5 "pass 1": VolStrainP, DivergenceP -> PressureP (+ DensityA, GravityCenter, PressureA when any
 // surface tension is set).  All particle classes (:2320, :2349).
-template <int DIM, bool ST>
+//   LIST = true : candidates come from k_filter's list; particles whose list overflowed are skipped.
+//   LIST = false: fused stencil sweep (phase A + phase B); with pl.count set only the overflowed
+//                 particles are processed (the block exits at once if it has none), else all.
+template <int DIM, bool ST, bool LIST>
 __global__ void __launch_bounds__(kSweepThreads)
-k_pass1_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
+k_pass1_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
            double *__restrict__ P, double *__restrict__ volStrain, double *__restrict__ divP,
            double *__restrict__ densA, double *__restrict__ gcx, double *__restrict__ gcy, double *__restrict__ gcz,
-           double *__restrict__ PA)
+           double *__restrict__ PA, PairList pl)
 {
-    __shared__ SweepShared sm;
-    for (int e = threadIdx.x; e < g.nsten; e += blockDim.x) { sm.sdx[e] = g.sdx[e]; sm.sdy[e] = g.sdy[e]; sm.sh[e] = g.sh[e]; }
-    __syncthreads();
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = i0 < n ? i0 : n - 1;
+    int mycount = 0;
+    bool mine = i0 < n;
+    if (pl.count) {
+        mycount = pl.count[i];
+        mine = mine && (LIST ? mycount <= pl.L : mycount > pl.L);
+        if (!LIST && !__syncthreads_or(mine ? 1 : 0)) return; // no overflowed particle in this block
+    }
+    const double xi = p.x[i], yi = p.y[i], zi = p.z[i];
     const double vxi = p.vx[i], vyi = p.vy[i], vzi = p.vz[i];
     const int tflag = p.type[i], ti = real_type(tflag), keyi = p.key[i];
     const bool solid_i = is_structure_type(ti);
@@ -186,28 +398,67 @@ k_pass1_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     if (g.slab && solid_i && active) active = column_owned(g, key_column(g, keyi));
     const double rp2 = ph.rp2, irp = ph.irp, ra2 = ph.ra2, ira = ph.ira;
     double nP = 0.0, dv = 0.0, nA = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0; // nP, dv without their constant factors
-    const double *__restrict__ VX = p.vx, *__restrict__ VY = p.vy, *__restrict__ VZ = p.vz;
-    const float4 *__restrict__ PF = p.pf;
-    sweep<DIM>(sm, g, cellStart, p.pf, p.x, p.y, p.z, i, active, active ? keyi : 0, filt2, batch,
-        [&](int j, double dx, double dy, double dz, double r2) {
-            if (r2 <= rp2) { // :2333, :2362
-                const double rinv = rsqrt(r2);
-                const double r = r2 * rinv;
-                const double q = 1.0 - r * irp;
-                nP += q * q;
-                const double ux = VX[j] - vxi, uy = VY[j] - vyi, uz = VZ[j] - vzi;
-                dv -= (ux * dx + uy * dy + uz * dz) * rinv * q;
-            }
-            if (ST && !solid_i && r2 <= ra2) { // :2162, :2195
-                const double r = sqrt(r2);
-                const double qa = r * ira;
-                const double ratio = ph.ratio[ti][__float_as_int(PF[j].w)];
-                nA += ratio * (ph.cwa * qa * (1.0 - qa) * (1.0 - qa));
-                const double wgv = ratio * (ph.cwg * ((1.0 - qa) * (1.0 - qa))) / ph.r2g * ph.rg;
-                g0 += dx * wgv; g1 += dy * wgv; g2 += dz * wgv;
-            }
-        });
-    if (!active) return;
+    const Rec *__restrict__ RA = p.ra;
+    const Rec *__restrict__ RB = p.rb;
+    // pair terms; rb = (vy, vz, -, type bits) of j
+    auto pair = [&](int j, double dx, double dy, double dz, double r2, double vxj, const Rec rb) {
+        const bool other = j != i;
+        if (other && r2 <= rp2) { // :2333, :2362
+            const double rinv = rsqrt_nr(r2);
+            const double q = 1.0 - (r2 * rinv) * irp;
+            nP += q * q;
+            const double ux = vxj - vxi, uy = rb.a - vyi, uz = rb.b - vzi;
+            dv -= (ux * dx + uy * dy + uz * dz) * rinv * q;
+        }
+        if (ST && other && !solid_i && r2 <= ra2) { // :2162, :2195
+            const double r = sqrt(r2);
+            const double qa = r * ira;
+            const double ratio = ph.ratio[ti][(int)__double_as_longlong(rb.d)];
+            nA += ratio * (ph.cwa * qa * (1.0 - qa) * (1.0 - qa));
+            const double wgv = ratio * (ph.cwg * ((1.0 - qa) * (1.0 - qa))) / ph.r2g * ph.rg;
+            g0 += dx * wgv; g1 += dy * wgv; g2 += dz * wgv;
+        }
+    };
+    if (LIST) {
+        const Bucket3 b = split_key<DIM>(g, active ? keyi : 0);
+        const bool warp_wraps = __any_sync(0xffffffffu, active && mine && stencil_wraps<DIM>(g, b));
+        const MinImage mi(g);
+        const int cnt = (active && mine) ? mycount : 0;
+        const int *lp = pl.nbr + i;
+        const size_t ls = (size_t)pl.cap;
+        int k = 0;
+        int j0 = 0, j1 = 0;
+        if (cnt > 0) j0 = __ldcs(lp);
+        if (cnt > 1) j1 = __ldcs(lp + ls);
+        for (; k + 1 < cnt; k += 2) { // two pairs per trip; the next two list entries are fetched first
+            const int a_j = j0, b_j = j1;
+            if (k + 2 < cnt) j0 = __ldcs(lp + (size_t)(k + 2) * ls);
+            if (k + 3 < cnt) j1 = __ldcs(lp + (size_t)(k + 3) * ls);
+            const Rec a0 = ld_rec_nc(RA + a_j), a1 = ld_rec_nc(RA + b_j);
+            const Rec c0 = ld_rec(RB + a_j), c1 = ld_rec(RB + b_j);
+            double dx0 = a0.a - xi, dy0 = a0.b - yi, dz0 = a0.c - zi;
+            double dx1 = a1.a - xi, dy1 = a1.b - yi, dz1 = a1.c - zi;
+            if (warp_wraps) { mi.apply(dx0, dy0, dz0); mi.apply(dx1, dy1, dz1); }
+            pair(a_j, dx0, dy0, dz0, dx0 * dx0 + dy0 * dy0 + dz0 * dz0, a0.d, c0);
+            pair(b_j, dx1, dy1, dz1, dx1 * dx1 + dy1 * dy1 + dz1 * dz1, a1.d, c1);
+        }
+        if (k < cnt) {
+            const Rec a0 = ld_rec_nc(RA + j0), c0 = ld_rec(RB + j0);
+            double dx0 = a0.a - xi, dy0 = a0.b - yi, dz0 = a0.c - zi;
+            if (warp_wraps) mi.apply(dx0, dy0, dz0);
+            pair(j0, dx0, dy0, dz0, dx0 * dx0 + dy0 * dy0 + dz0 * dz0, a0.d, c0);
+        }
+    } else {
+        __shared__ SweepShared sm;
+        load_stencil(sm, g);
+        __syncthreads();
+        const bool go = active && mine;
+        sweep<DIM>(sm, g, cellStart, p.pf, p.ra, i, go, go ? keyi : 0, xi, yi, zi, filt2, batch,
+            [&](int j, double dx, double dy, double dz, double r2, double vxj) {
+                if (r2 <= rp2 || (ST && r2 <= ra2)) pair(j, dx, dy, dz, r2, vxj, ld_rec(RB + j));
+            });
+    }
+    if (!mine || !active) return;
     nP *= ph.cwp;
     dv *= ph.cdp;
     const double vs = nP - ph.n0p;                        // :2339
@@ -215,6 +466,7 @@ k_pass1_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     double pr = -ph.lambda[ti] * dv;                      // :2388
     if (vs > 0.0) pr += kappa * vs;                       // :2389-2391
     P[i] = pr; volStrain[i] = vs; divP[i] = dv;
+    p.rb[i].c = pr; // the gather record pass 2 reads
     if (ST) {
         const double da = solid_i ? 0.0 : nA;
         densA[i] = da;
@@ -225,28 +477,37 @@ k_pass1_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     }
 }
 
-// K6 "pass 2": force sums + gravity + explicit integration (see k_pass2 in kernels.cuh for the
-// line-by-line citations; the arithmetic per pair is the same, only the traversal differs).
-template <int DIM, bool ST>
+// K6 "pass 2": force sums (PressureP :2394-2425, PressureA :2225-2259, DiffuseInterface :2265-2312,
+// ViscosityV :2480-2522, InterfaceForce :2439-2473) + gravity :2917 + explicit integration
+// (:2938-2956, :1892-1907).
+//   LIST = true : neighbours come from pass 1's list; particles whose list overflowed are skipped.
+//   LIST = false: stencil sweep; with pl.count set only the overflowed particles are processed
+//                 (and the block exits at once if it has none), otherwise all particles.
+template <int DIM, bool ST, bool LIST>
 __global__ void __launch_bounds__(kSweepThreads)
-k_pass2_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
+k_pass2_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
            const double *__restrict__ P, const double *__restrict__ PA, const double *__restrict__ gcx,
            const double *__restrict__ gcy, const double *__restrict__ gcz, double *__restrict__ ox,
            double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ovx, double *__restrict__ ovy,
            double *__restrict__ ovz, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
            double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az, Solid sol,
-           double *__restrict__ solbuf)
+           double *__restrict__ solbuf, PairList pl)
 {
-    __shared__ SweepShared sm;
     __shared__ double s_visc[kTypeCount][kTypeCount];
-    for (int e = threadIdx.x; e < g.nsten; e += blockDim.x) { sm.sdx[e] = g.sdx[e]; sm.sdy[e] = g.sdy[e]; sm.sh[e] = g.sh[e]; }
     // pair viscosity table with the constant factors of the viscous term folded in:
     // c_d mu_ij V * (-cdv)   (:2505-2512, dwij = -dwvdr)
     for (int e = threadIdx.x; e < kTypeCount * kTypeCount; e += blockDim.x)
         s_visc[e / kTypeCount][e % kTypeCount] = -ph.viscpair[e / kTypeCount][e % kTypeCount] * ph.cdv;
-    __syncthreads();
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = i0 < n ? i0 : n - 1;
+    int mycount = 0;
+    bool mine = i0 < n;
+    if (pl.count) {
+        mycount = pl.count[i];
+        mine = mine && (LIST ? mycount <= pl.L : mycount > pl.L);
+        if (!LIST && !__syncthreads_or(mine ? 1 : 0)) return; // no overflowed particle in this block
+    }
+    __syncthreads();
     const double xi = p.x[i], yi = p.y[i], zi = p.z[i];
     const double vxi = p.vx[i], vyi = p.vy[i], vzi = p.vz[i];
     const int tflag = p.type[i], ti = real_type(tflag), keyi = p.key[i];
@@ -255,67 +516,105 @@ k_pass2_v2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     if (g.slab && solid_i && active) active = column_owned(g, key_column(g, keyi));
     const double Pi = P[i];
     const double rp2 = ph.rp2, irp = ph.irp, rv2 = ph.rv2, irv = ph.irv;
+    const double rpv2 = rp2 > rv2 ? rp2 : rv2;
     const double cpv = ph.cdp * ph.vol; // dwp/dr prefactor times particle volume
     double F0 = 0.0, F1 = 0.0, F2 = 0.0;
-    const double *__restrict__ VX = p.vx, *__restrict__ VY = p.vy, *__restrict__ VZ = p.vz;
-    const float4 *__restrict__ PF = p.pf;
+    const Rec *__restrict__ RA = p.ra;
+    const Rec *__restrict__ RB = p.rb;
     const double *visc_row = s_visc[ti];
     double PAi = 0.0, gi0 = 0.0, gi1 = 0.0, gi2 = 0.0, ai = 0.0;
     if (ST) { PAi = PA[i]; gi0 = gcx[i]; gi1 = gcy[i]; gi2 = gcz[i]; ai = ph.cofa[ti] * ph.cofk * ph.cofk; }
     const double gscale = ph.vol / ph.l0;
-    sweep<DIM>(sm, g, cellStart, p.pf, p.x, p.y, p.z, i, active, active ? keyi : 0, filt2, batch,
-        [&](int j, double dx, double dy, double dz, double r2) {
-            if (solid_i) {
-                if (r2 < rp2) { // :2455
-                    const int tj = __float_as_int(PF[j].w);
-                    if (!is_structure_type(tj)) { // :2447
-                        const double rinv = rsqrt(r2);
-                        const double c = (Pi + P[j]) * (1.0 - r2 * rinv * irp) * rinv * cpv;
-                        F0 += c * dx; F1 += c * dy; F2 += c * dz;
-                    }
-                }
-                return;
+    // pair terms; rb = (vy, vz, PressureP, type bits) of j
+    auto pair = [&](int j, double dx, double dy, double dz, double r2, double vxj, const Rec rb) {
+        if (j == i) return;
+        const int tj = (int)__double_as_longlong(rb.d);
+        if (solid_i) {
+            if (r2 < rp2 && !is_structure_type(tj)) { // :2455, :2447
+                const double rinv = rsqrt_nr(r2);
+                const double cc = (Pi + rb.c) * (1.0 - r2 * rinv * irp) * rinv * cpv;
+                F0 += cc * dx; F1 += cc * dy; F2 += cc * dz;
             }
+            return;
+        }
+        if (r2 < rpv2) {
             const bool inP = r2 < rp2, inV = r2 < rv2; // :2410, :2496 (strict)
-            if (inP || inV) {
-                const double rinv = rsqrt(r2);
-                const double r = r2 * rinv;
-                double c = 0.0;
-                if (inP) c = (Pi + P[j]) * (1.0 - r * irp) * rinv * cpv;
-                if (inV) {
-                    const double ux = VX[j] - vxi, uy = VY[j] - vyi, uz = VZ[j] - vzi;
-                    const double ue = (ux * dx + uy * dy + uz * dz) * rinv;
-                    c += visc_row[__float_as_int(PF[j].w)] * ue * (1.0 - r * irv) * (rinv * rinv);
-                }
-                F0 += c * dx; F1 += c * dy; F2 += c * dz;
+            const double rinv = rsqrt_nr(r2);
+            const double r = r2 * rinv;
+            double cc = 0.0;
+            if (inP) cc = (Pi + rb.c) * (1.0 - r * irp) * rinv * cpv;
+            if (inV) {
+                const double ux = vxj - vxi, uy = rb.a - vyi, uz = rb.b - vzi;
+                const double ue = (ux * dx + uy * dy + uz * dz) * rinv;
+                cc += visc_row[tj] * ue * (1.0 - r * irv) * (rinv * rinv);
             }
-            if (ST && r2 < ph.ra2) { // :2243, :2285 (RadiusG == RadiusA)
-                const int tj = __float_as_int(PF[j].w);
-                const double r = sqrt(r2);
-                const double rinv = 1.0 / r;
-                const double qa = r * ph.ira;
-                const double rij = ph.ratio[ti][tj], rji = ph.ratio[tj][ti];
-                const double dwa = ph.cwa * (1.0 - qa) * (1.0 - 3.0 * qa) * ph.ira; // dwadr :308
-                const double ca = (PAi * (rij * dwa) + PA[j] * (rji * dwa)) * rinv * ph.vol;
-                double A0 = ca * dx, A1 = ca * dy, A2 = ca * dz;
-                const double wgv = ph.cwg * ((1.0 - qa) * (1.0 - qa));
-                const double wij = rij * wgv, wji = rji * wgv;
-                const double aj = ai; // Q6: CofA[Property[iP]] for both (:2270, :2275)
-                const double gj0 = gcx[j], gj1 = gcy[j], gj2 = gcz[j];
-                const double s = gscale * ph.rg / ph.r2g;
-                A0 -= (aj * gj0 * wji - ai * gi0 * wij) * s;
-                A1 -= (aj * gj1 * wji - ai * gi1 * wij) * s;
-                A2 -= (aj * gj2 * wji - ai * gi2 * wij) * s;
-                const double dwg = ph.cdg * (1.0 - qa);
-                const double dwij = rij * dwg, dwji = rji * dwg;
-                const double gr = (aj * gj0 * dwji - ai * gi0 * dwij) * dx + (aj * gj1 * dwji - ai * gi1 * dwij) * dy +
-                                  (aj * gj2 * dwji - ai * gi2 * dwij) * dz;
-                const double cg = gr * rinv * s;
-                A0 -= cg * dx; A1 -= cg * dy; A2 -= cg * dz;
-                F0 += A0; F1 += A1; F2 += A2;
-            }
-        });
-    if (i0 >= n) return;
+            F0 += cc * dx; F1 += cc * dy; F2 += cc * dz;
+        }
+        if (ST && r2 < ph.ra2) { // :2243, :2285 (RadiusG == RadiusA)
+            const double r = sqrt(r2);
+            const double rinv = 1.0 / r;
+            const double qa = r * ph.ira;
+            const double rij = ph.ratio[ti][tj], rji = ph.ratio[tj][ti];
+            const double dwa = ph.cwa * (1.0 - qa) * (1.0 - 3.0 * qa) * ph.ira; // dwadr :308
+            const double ca = (PAi * (rij * dwa) + PA[j] * (rji * dwa)) * rinv * ph.vol;
+            double A0 = ca * dx, A1 = ca * dy, A2 = ca * dz;
+            const double wgv = ph.cwg * ((1.0 - qa) * (1.0 - qa));
+            const double wij = rij * wgv, wji = rji * wgv;
+            const double aj = ai; // Q6: CofA[Property[iP]] for both (:2270, :2275)
+            const double gj0 = gcx[j], gj1 = gcy[j], gj2 = gcz[j];
+            const double s = gscale * ph.rg / ph.r2g;
+            A0 -= (aj * gj0 * wji - ai * gi0 * wij) * s;
+            A1 -= (aj * gj1 * wji - ai * gi1 * wij) * s;
+            A2 -= (aj * gj2 * wji - ai * gi2 * wij) * s;
+            const double dwg = ph.cdg * (1.0 - qa);
+            const double dwij = rij * dwg, dwji = rji * dwg;
+            const double gr = (aj * gj0 * dwji - ai * gi0 * dwij) * dx + (aj * gj1 * dwji - ai * gi1 * dwij) * dy +
+                              (aj * gj2 * dwji - ai * gi2 * dwij) * dz;
+            const double cg = gr * rinv * s;
+            A0 -= cg * dx; A1 -= cg * dy; A2 -= cg * dz;
+            F0 += A0; F1 += A1; F2 += A2;
+        }
+    };
+    if (LIST) {
+        const Bucket3 b = split_key<DIM>(g, active ? keyi : 0);
+        const bool warp_wraps = __any_sync(0xffffffffu, active && mine && stencil_wraps<DIM>(g, b));
+        const MinImage mi(g);
+        const int cnt = (active && mine) ? mycount : 0;
+        const int *lp = pl.nbr + i;
+        const size_t ls = (size_t)pl.cap;
+        int k = 0;
+        int j0 = 0, j1 = 0;
+        if (cnt > 0) j0 = __ldcs(lp);
+        if (cnt > 1) j1 = __ldcs(lp + ls);
+        for (; k + 1 < cnt; k += 2) { // two pairs per trip; the next two list entries are fetched first
+            const int a_j = j0, b_j = j1;
+            if (k + 2 < cnt) j0 = __ldcs(lp + (size_t)(k + 2) * ls);
+            if (k + 3 < cnt) j1 = __ldcs(lp + (size_t)(k + 3) * ls);
+            const Rec a0 = ld_rec_nc(RA + a_j), a1 = ld_rec_nc(RA + b_j);
+            const Rec c0 = ld_rec_nc(RB + a_j), c1 = ld_rec_nc(RB + b_j);
+            double dx0 = a0.a - xi, dy0 = a0.b - yi, dz0 = a0.c - zi;
+            double dx1 = a1.a - xi, dy1 = a1.b - yi, dz1 = a1.c - zi;
+            if (warp_wraps) { mi.apply(dx0, dy0, dz0); mi.apply(dx1, dy1, dz1); }
+            pair(a_j, dx0, dy0, dz0, dx0 * dx0 + dy0 * dy0 + dz0 * dz0, a0.d, c0);
+            pair(b_j, dx1, dy1, dz1, dx1 * dx1 + dy1 * dy1 + dz1 * dz1, a1.d, c1);
+        }
+        if (k < cnt) {
+            const Rec a0 = ld_rec_nc(RA + j0), c0 = ld_rec_nc(RB + j0);
+            double dx0 = a0.a - xi, dy0 = a0.b - yi, dz0 = a0.c - zi;
+            if (warp_wraps) mi.apply(dx0, dy0, dz0);
+            pair(j0, dx0, dy0, dz0, dx0 * dx0 + dy0 * dy0 + dz0 * dz0, a0.d, c0);
+        }
+    } else {
+        __shared__ SweepShared sm;
+        load_stencil(sm, g);
+        __syncthreads();
+        const bool go = active && mine;
+        sweep<DIM>(sm, g, cellStart, p.pf, p.ra, i, go, go ? keyi : 0, xi, yi, zi, filt2, batch,
+            [&](int j, double dx, double dy, double dz, double r2, double vxj) {
+                pair(j, dx, dy, dz, r2, vxj, ld_rec_nc(RB + j));
+            });
+    }
+    if (!mine) return;
     if (!active) { // ghost / parked / not-owned solid: carried through unchanged (dropped or refreshed next step)
         ox[i] = xi; oy[i] = yi; oz[i] = zi; ovx[i] = vxi; ovy[i] = vyi; ovz[i] = vzi;
         fx[i] = 0.0; fy[i] = 0.0; fz[i] = 0.0; ax[i] = 0.0; ay[i] = 0.0; az[i] = 0.0;
