@@ -67,15 +67,16 @@ struct WallMotion {
     double center[kTypeCount][3], vel[kTypeCount][3], omega[kTypeCount][3], R[kTypeCount][3][3];
 };
 
-struct __align__(32) PfPair { float2 x, y, z; int2 t; };
+struct __align__(8) PfPair { float2 x, y, z; }; // 24 bytes: x0 x1 y0 y1 z0 z1
 struct __align__(32) Rec { double a, b, c, d; };
 
 // cell-sorted particle arrays
 struct Particles {
     double *x, *y, *z, *vx, *vy, *vz;
     int *type, *id, *key;
-    // (position - DomainMin)/CellWidth in fp32 + type, PAIR-interleaved (particles 2k, 2k+1 share one
-    // 32-byte record): input of the sweep's packed-fp32 filter.  Padded by two pairs.
+    // (position - DomainMin)/CellWidth in fp32, PAIR-interleaved (particles 2k, 2k+1 share one
+    // 24-byte record x0 x1 y0 y1 z0 z1): input of the packed-fp32 filter.  Padded by two pairs.
+    // (The filter is bound by the bytes the L1 returns to registers, so the record carries nothing else.)
     PfPair *pf;
     // 32-byte gather records of the sorted particles (what a NEIGHBOUR's thread reads per pair, one
     // 256-bit load each): ra[q] = (x, y, z, vx);  rb[q] = (vy, vz, PressureP, type bits).
@@ -440,9 +441,8 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
     dst.x[q] = x; dst.y[q] = y; dst.z[q] = z;
     dst.type[q] = t; dst.id[q] = src.id[s]; dst.key[q] = k;
     const double icw = 1.0 / g.cellw;
-    float *pfw = reinterpret_cast<float *>(dst.pf + (q >> 1)) + (q & 1); // x0 x1 y0 y1 z0 z1 t0 t1
+    float *pfw = reinterpret_cast<float *>(dst.pf + (q >> 1)) + (q & 1); // x0 x1 y0 y1 z0 z1
     pfw[0] = (float)((x - g.mn[0]) * icw); pfw[2] = (float)((y - g.mn[1]) * icw); pfw[4] = (float)((z - g.mn[2]) * icw);
-    pfw[6] = __int_as_float(real_type(t));
     const double vx = src.vx[s], vy = src.vy[s], vz = src.vz[s];
     dst.vx[q] = vx; dst.vy[q] = vy; dst.vz[q] = vz;
     Rec ra, rb;

@@ -787,6 +787,7 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
             int L = c->list_cap;
             if (L < 0) L = c->p.dim == 3 ? 128 : 48;
             c->pl = PairList{};
+            while (L > 0 && ((size_t)L + 1) * cap >= 0xffffffffull) L /= 2; // k_filter addresses the list with 32-bit offsets
             if (L > 0) {
                 e |= c->alloc(&c->pl.nbr, ((size_t)L + 1) * cap); // + the parking row of overflowed lists
                 e |= c->alloc(&c->pl.count, cap);

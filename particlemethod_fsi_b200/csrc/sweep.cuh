@@ -30,6 +30,16 @@
 namespace mphx {
 
 constexpr int kSweepThreads = 128;
+// minimum resident blocks per SM the register allocation of each kernel is tuned for
+#ifndef MPHX_FILTER_MINB
+#define MPHX_FILTER_MINB 10
+#endif
+#ifndef MPHX_P1_MINB
+#define MPHX_P1_MINB 8
+#endif
+#ifndef MPHX_P2_MINB
+#define MPHX_P2_MINB 6
+#endif
 constexpr int kQueueCap = 40; // queue slots per thread (rows of 128 uint); one spare row absorbs masked stores
 
 struct SweepShared {
@@ -68,24 +78,20 @@ __device__ __forceinline__ Rec ld_rec_nc(const Rec *p)
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
     return r;
 }
-// coherent variant: pass 1 reads (vy, vz) from records whose PressureP slot other threads are writing
-__device__ __forceinline__ Rec ld_rec(const Rec *p)
+// coherent variants: pass 1 reads (vy, vz) from records whose PressureP slot other threads are writing.
+// FULL = false fetches only the first half (vy, vz); c, d are then unspecified.
+template <bool FULL> __device__ __forceinline__ Rec ld_rec(const Rec *p)
 {
     Rec r;
-    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    if (FULL) asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    else { asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(r.a), "=d"(r.b) : "l"(p)); r.c = 0.0; r.d = 0.0; }
     return r;
 }
 __device__ __forceinline__ PfPair ld_pf_nc(const PfPair *p)
 {
-    unsigned v0, v1, v2, v3, v4, v5, v6, v7;
-    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-        : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3), "=r"(v4), "=r"(v5), "=r"(v6), "=r"(v7)
-        : "l"(p));
+    const float2 *q = reinterpret_cast<const float2 *>(p);
     PfPair r;
-    r.x = make_float2(__uint_as_float(v0), __uint_as_float(v1));
-    r.y = make_float2(__uint_as_float(v2), __uint_as_float(v3));
-    r.z = make_float2(__uint_as_float(v4), __uint_as_float(v5));
-    r.t = make_int2((int)v6, (int)v7);
+    r.x = __ldg(q); r.y = __ldg(q + 1); r.z = __ldg(q + 2);
     return r;
 }
 
@@ -265,7 +271,7 @@ struct PairList {
 // registers: the kernel runs at full occupancy, which hides the latency of the candidate loads.
 // Candidates are tested in pairs with the packed f32x2 instructions (see sweep()).
 template <int DIM>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, MPHX_FILTER_MINB)
 k_filter(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, float filt2, PairList pl)
 {
     __shared__ int s_dlo[kMaxStencil], s_dhi[kMaxStencil], s_sdx[kMaxStencil], s_sdy[kMaxStencil], s_sh[kMaxStencil];
@@ -286,38 +292,40 @@ k_filter(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, floa
     const float fxi = fo[0], fyi = fo[2], fzi = fo[4];
     const Bucket3 b = split_key<DIM>(g, keyi);
     const bool wraps = stencil_wraps<DIM>(g, b);
-    const size_t stride0 = (size_t)pl.cap;
-    size_t stride = stride0;
-    int *lp = pl.nbr + i;
-    int *const lpark = pl.nbr + (size_t)pl.L * stride0 + i;
-    int *const lp0 = lp;
-    bool over = false;
+    // list top as a 32-bit element offset into nbr (host guarantees (L+1)*cap < 2^32); a push past
+    // row L-1 lands on the parking row (offset `park`) and stays there: no capacity branch.
+    int *__restrict__ nbr = pl.nbr;
+    unsigned stride = (unsigned)pl.cap;
+    unsigned park = (unsigned)pl.L * stride + (unsigned)i;
+    float filt = filt2;
+    // keep the loop invariants in registers (the compiler otherwise re-reads them from the constant
+    // bank under every predicated push)
+    asm volatile("" : "+l"(nbr), "+r"(stride), "+r"(park), "+f"(filt));
+    unsigned off = (unsigned)i;
 
     auto scan_run = [&](int jb, int je, float fx, float fy, float fz) {
         const int len = je - jb, lenm1 = len - 1;
-        if (len <= 0) return;
-        // room for the whole run (+ the masked partner of an unaligned first pair)?  If not, the list
-        // overflows: keep scanning into the parking row so that control flow stays simple.
-        if (!over && (long long)(lp - lp0) + (long long)(len + 1) * (long long)stride0 > (long long)pl.L * (long long)stride0) {
-            over = true; lp = lpark; stride = 0;
-        }
         const float2 nx = make_float2(-fx, -fx), ny = make_float2(-fy, -fy), nz = make_float2(-fz, -fz);
         int j0 = jb & ~1;
         int t = j0 - jb; // -1 or 0: position of the pair's first element in the run
         const PfPair *pp = pf + (j0 >> 1);
         for (; t < len; t += 4, j0 += 4, pp += 2) {
-            const PfPair fa = ld_pf_nc(pp), fb = ld_pf_nc(pp + 1);
+            const PfPair fa = ld_pf_nc(pp);
+            PfPair fb = fa;
+            if (t + 2 < len) fb = ld_pf_nc(pp + 1); // (its tests are masked by the range check otherwise)
+#define MPHX_PUSH(ok, jj) if (ok) { nbr[off] = (jj); off = min(off + stride, park); }
 #define MPHX_TEST2(f, tt, jj)                                                                      \
     {                                                                                              \
         const float2 ddx = __fadd2_rn(f.x, nx), ddy = __fadd2_rn(f.y, ny), ddz = __fadd2_rn(f.z, nz); \
         float2 d2 = __fmul2_rn(ddx, ddx);                                                          \
         d2 = __ffma2_rn(ddy, ddy, d2);                                                             \
         d2 = __ffma2_rn(ddz, ddz, d2);                                                             \
-        if ((unsigned)(tt) < (unsigned)len && d2.x <= filt2) { *lp = (jj); lp += stride; }         \
-        if ((tt) < lenm1 && d2.y <= filt2) { *lp = (jj) + 1; lp += stride; }                       \
+        MPHX_PUSH((unsigned)(tt) < (unsigned)len && d2.x <= filt, (jj))                            \
+        MPHX_PUSH((tt) < lenm1 && d2.y <= filt, (jj) + 1)                                          \
     }
             MPHX_TEST2(fa, t, j0) MPHX_TEST2(fb, t + 2, j0 + 2)
 #undef MPHX_TEST2
+#undef MPHX_PUSH
         }
     };
 
@@ -325,11 +333,11 @@ k_filter(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, floa
     if (!wraps) {
         // stencil inside the box: one run per column; the bounds of the next column are fetched
         // while the current run is scanned
-        const int *cs = cellStart + keyi;
-        int jbn = cs[s_dlo[0]], jen = cs[s_dhi[0]];
+        int jbn = __ldg(cellStart + (keyi + s_dlo[0])), jen = __ldg(cellStart + (keyi + s_dhi[0]));
         for (int e = 0; e < nsten; ++e) {
             const int jb = jbn, je = jen;
-            if (e + 1 < nsten) { jbn = cs[s_dlo[e + 1]]; jen = cs[s_dhi[e + 1]]; }
+            const int en = (e + 1 < nsten) ? e + 1 : e; // (the last trip re-reads its own bounds: no branch)
+            jbn = __ldg(cellStart + (keyi + s_dlo[en])); jen = __ldg(cellStart + (keyi + s_dhi[en]));
             scan_run(jb, je, fxi, fyi, fzi);
         }
     } else {
@@ -363,8 +371,8 @@ k_filter(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, floa
             }
         }
     }
-    if (over) { pl.count[i] = pl.L + 1; atomicOr(pl.flags, 1); }
-    else pl.count[i] = (int)((lp - lp0) / (long long)stride0);
+    if (off == park) { pl.count[i] = pl.L + 1; atomicOr(pl.flags, 1); } // (a list of exactly L entries counts as overflowed)
+    else pl.count[i] = (int)((off - (unsigned)i) / stride);
 }
 
 // K5 "pass 1": VolStrainP, DivergenceP -> PressureP (+ DensityA, GravityCenter, PressureA when any
@@ -373,12 +381,13 @@ k_filter(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, floa
 //   LIST = false: fused stencil sweep (phase A + phase B); with pl.count set only the overflowed
 //                 particles are processed (the block exits at once if it has none), else all.
 template <int DIM, bool ST, bool LIST>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, LIST ? MPHX_P1_MINB : 1)
 k_pass1_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
            double *__restrict__ P, double *__restrict__ volStrain, double *__restrict__ divP,
            double *__restrict__ densA, double *__restrict__ gcx, double *__restrict__ gcy, double *__restrict__ gcz,
            double *__restrict__ PA, PairList pl)
 {
+    if (!LIST && pl.count && *reinterpret_cast<volatile const int *>(pl.flags) == 0) return; // no list overflowed in this step
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = i0 < n ? i0 : n - 1;
     int mycount = 0;
@@ -435,7 +444,7 @@ k_pass1_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
             if (k + 2 < cnt) j0 = __ldcs(lp + (size_t)(k + 2) * ls);
             if (k + 3 < cnt) j1 = __ldcs(lp + (size_t)(k + 3) * ls);
             const Rec a0 = ld_rec_nc(RA + a_j), a1 = ld_rec_nc(RA + b_j);
-            const Rec c0 = ld_rec(RB + a_j), c1 = ld_rec(RB + b_j);
+            const Rec c0 = ld_rec<ST>(RB + a_j), c1 = ld_rec<ST>(RB + b_j);
             double dx0 = a0.a - xi, dy0 = a0.b - yi, dz0 = a0.c - zi;
             double dx1 = a1.a - xi, dy1 = a1.b - yi, dz1 = a1.c - zi;
             if (warp_wraps) { mi.apply(dx0, dy0, dz0); mi.apply(dx1, dy1, dz1); }
@@ -443,7 +452,7 @@ k_pass1_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
             pair(b_j, dx1, dy1, dz1, dx1 * dx1 + dy1 * dy1 + dz1 * dz1, a1.d, c1);
         }
         if (k < cnt) {
-            const Rec a0 = ld_rec_nc(RA + j0), c0 = ld_rec(RB + j0);
+            const Rec a0 = ld_rec_nc(RA + j0), c0 = ld_rec<ST>(RB + j0);
             double dx0 = a0.a - xi, dy0 = a0.b - yi, dz0 = a0.c - zi;
             if (warp_wraps) mi.apply(dx0, dy0, dz0);
             pair(j0, dx0, dy0, dz0, dx0 * dx0 + dy0 * dy0 + dz0 * dz0, a0.d, c0);
@@ -455,7 +464,7 @@ k_pass1_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
         const bool go = active && mine;
         sweep<DIM>(sm, g, cellStart, p.pf, p.ra, i, go, go ? keyi : 0, xi, yi, zi, filt2, batch,
             [&](int j, double dx, double dy, double dz, double r2, double vxj) {
-                if (r2 <= rp2 || (ST && r2 <= ra2)) pair(j, dx, dy, dz, r2, vxj, ld_rec(RB + j));
+                if (r2 <= rp2 || (ST && r2 <= ra2)) pair(j, dx, dy, dz, r2, vxj, ld_rec<ST>(RB + j));
             });
     }
     if (!mine || !active) return;
@@ -484,7 +493,7 @@ k_pass1_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
 //   LIST = false: stencil sweep; with pl.count set only the overflowed particles are processed
 //                 (and the block exits at once if it has none), otherwise all particles.
 template <int DIM, bool ST, bool LIST>
-__global__ void __launch_bounds__(kSweepThreads)
+__global__ void __launch_bounds__(kSweepThreads, LIST ? MPHX_P2_MINB : 1)
 k_pass2_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
            const double *__restrict__ P, const double *__restrict__ PA, const double *__restrict__ gcx,
            const double *__restrict__ gcy, const double *__restrict__ gcz, double *__restrict__ ox,
@@ -498,6 +507,7 @@ k_pass2_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     // c_d mu_ij V * (-cdv)   (:2505-2512, dwij = -dwvdr)
     for (int e = threadIdx.x; e < kTypeCount * kTypeCount; e += blockDim.x)
         s_visc[e / kTypeCount][e % kTypeCount] = -ph.viscpair[e / kTypeCount][e % kTypeCount] * ph.cdv;
+    if (!LIST && pl.count && *reinterpret_cast<volatile const int *>(pl.flags) == 0) return; // no list overflowed in this step
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = i0 < n ? i0 : n - 1;
     int mycount = 0;

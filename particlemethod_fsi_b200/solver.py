@@ -13,7 +13,7 @@ import numpy as np
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmphx.so")
+LIB_PATH = os.environ.get("MPHX_LIB") or os.path.join(_HERE, "libmphx.so")   # MPHX_LIB: developer override (kernel variants)
 
 
 class MphxError(RuntimeError):

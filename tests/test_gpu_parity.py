@@ -261,3 +261,24 @@ def test_error_paths():
     p.domain_max[0] = p.domain_min[0] + 3 * p.particle_spacing   # narrower than the stencil
     with pytest.raises(solver.MphxError):
         Solver(p)
+
+
+@pytest.mark.parametrize("cap", ["0", "12"])
+@pytest.mark.parametrize("name", ["tiny2d", "fsi3d_mini"])
+def test_candidate_list_fallbacks_agree(name, cap, monkeypatch):
+    """MPHX_LIST_CAP=0: no candidate list (both passes are fused sweeps); =12: every 3D list and most 2D
+    lists overflow, so the overflow fall-back kernels do the work.  All traverse the candidates in the
+    same order as the list kernels; only the compiler's FMA contraction differs between the kernel
+    instantiations, so the results agree to a few ulp (1e-13 relative)."""
+    case = getattr(cases, name)()
+    ref = Solver.from_case(case)
+    ref.step(12, sync=True)
+    a = ref.download("position", "velocity", "pressure_p", "force")
+    ref.close()
+    monkeypatch.setenv("MPHX_LIST_CAP", cap)
+    s = Solver.from_case(case)
+    s.step(12, sync=True)
+    b = s.download("position", "velocity", "pressure_p", "force")
+    s.close()
+    for f in a:
+        assert rel_err(b[f], a[f]) <= 1e-13, (name, cap, f, rel_err(b[f], a[f]))
