@@ -191,6 +191,16 @@ int mphx_set_time(mphx_ctx *ctx, double time);
 /* replaces `acc update host` (src/main.cpp:987-989); un-permutes to original particle order */
 int mphx_download(mphx_ctx *ctx, const mphx_host_views *views);
 
+/* compact per-context I/O (no reference counterpart: the reference keeps one host copy of everything).
+ * A single context owns every particle; a slab context owns the fluid/wall particles of its columns and
+ * reports ALL of the replicated solids.  Rows come in the context's current slot order.
+ * mphx_upload_owned takes the rows of the LAST mphx_download_owned back (same ids in the same order,
+ * values possibly modified; no step in between).  In slab mode every rank must be given the same solid
+ * rows.  Buffers: ids[capacity], position/velocity[capacity][3]; page-locked memory makes the copies
+ * asynchronous to the host. */
+int mphx_download_owned(mphx_ctx *ctx, int capacity, int *ids, double *position, double *velocity, int *count);
+int mphx_upload_owned(mphx_ctx *ctx, int count, const int *ids, const double *position, const double *velocity);
+
 /* ---- parity / debug ------------------------------------------------------------------------------ */
 /* The neighbour SETS of calculateNeighbor (src/main.cpp:1730-1810) with its bit-exact predicate,
  * as CSR in original particle ids, each row sorted ascending.  offsets has N+1 entries.

@@ -100,6 +100,7 @@ EXPORTS = [
     "mphx_compute_constants",
     "mphx_create", "mphx_destroy", "mphx_upload", "mphx_upload_state", "mphx_init", "mphx_get_constants",
     "mphx_step", "mphx_step_fluid_only", "mphx_sync", "mphx_time", "mphx_set_time", "mphx_download",
+    "mphx_download_owned", "mphx_upload_owned",
     "mphx_debug_neighbors", "mphx_debug_initial_structure_neighbors",
     "mphx_timed_steps", "mphx_set_timing", "mphx_get_timers", "mphx_launch_count", "mphx_algorithmic_bytes_per_step",
     "mphx_set_stream", "mphx_slab_configure", "mphx_slab_begin", "mphx_slab_append", "mphx_slab_pack_halo",

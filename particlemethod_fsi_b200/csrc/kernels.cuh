@@ -872,6 +872,40 @@ __global__ void k_owned_mask(int n, Particles p, GridDesc g, int solids_too, int
     }
     mask[q] = own ? 1 : 0;
 }
+// compact state of the masked slots: out row r = scan[q] for mask[q] != 0; solids report the solid arrays
+__global__ void k_compact_owned(int n, Particles p, Solid sol, const int *__restrict__ mask, const int *__restrict__ scan,
+                                int *__restrict__ slot_of_row, int *__restrict__ ids, double *__restrict__ x3, double *__restrict__ v3)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n || !mask[q]) return;
+    const int r = scan[q];
+    const int id = p.id[q];
+    double x = p.x[q], y = p.y[q], z = p.z[q], vx = p.vx[q], vy = p.vy[q], vz = p.vz[q];
+    if (is_structure_type(p.type[q])) {
+        const int s = id - sol.sb;
+        x = sol.x[s]; y = sol.y[s]; z = sol.z[s]; vx = sol.vx[s]; vy = sol.vy[s]; vz = sol.vz[s];
+    }
+    slot_of_row[r] = q;
+    ids[r] = id;
+    const size_t o = 3 * (size_t)r;
+    x3[o] = x; x3[o + 1] = y; x3[o + 2] = z; v3[o] = vx; v3[o + 1] = vy; v3[o + 2] = vz;
+}
+// the inverse: rows (in the order of the last k_compact_owned) back into their slots; err |= 1 on an id mismatch
+__global__ void k_scatter_owned(int count, Particles p, Solid sol, const int *__restrict__ slot_of_row, const int *__restrict__ ids,
+                                const double *__restrict__ x3, const double *__restrict__ v3, int *__restrict__ err)
+{
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= count) return;
+    const int q = slot_of_row[r];
+    if (p.id[q] != ids[r]) { atomicOr(err, 1); return; }
+    const size_t o = 3 * (size_t)r;
+    const double x = x3[o], y = x3[o + 1], z = x3[o + 2], vx = v3[o], vy = v3[o + 1], vz = v3[o + 2];
+    p.x[q] = x; p.y[q] = y; p.z[q] = z; p.vx[q] = vx; p.vy[q] = vy; p.vz[q] = vz;
+    if (is_structure_type(p.type[q])) {
+        const int s = ids[r] - sol.sb;
+        sol.x[s] = x; sol.y[s] = y; sol.z[s] = z; sol.vx[s] = vx; sol.vy[s] = vy; sol.vz[s] = vz;
+    }
+}
 __global__ void k_global_keys(int n, Particles p, GridDesc g, int *__restrict__ out)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;

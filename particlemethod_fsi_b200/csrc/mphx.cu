@@ -72,6 +72,11 @@ struct Ctx {
     double cw_tl = 0.0; // weight() prefactor (1.0/Swp)*(1.0/RP^d), src/main.cpp:291/293
     double *stage3a = nullptr, *stage3b = nullptr, *stage1 = nullptr, *stage9 = nullptr; // AoS staging (lazy)
     int *stagei = nullptr, *mask = nullptr, *mask2 = nullptr, *tmpi = nullptr;
+    // compact owned-particle I/O (mphx_download_owned / mphx_upload_owned)
+    int *own_scan = nullptr, *own_sums = nullptr, *own_slot = nullptr, *own_ids = nullptr;
+    double *own_x = nullptr, *own_v = nullptr;
+    int own_blocks = 0, own_count = -1;
+    long long own_epoch = -1; // steps_done at the last mphx_download_owned
     bool buckets_valid = false;
     int sweep_batch = 12;  // stencil columns per filter/drain batch (3D)
     PairList pl{};         // pass 1 -> pass 2 neighbour list (nbr == nullptr: disabled, pass 2 sweeps again)
@@ -1090,6 +1095,78 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     } while (0);
     if (rc == MPHX_OK) { CK(cudaGetLastError()); }
     return rc;
+}
+
+// ---- compact I/O of the particles a context owns ------------------------------------------------------
+// (single context: every particle; slab context: the fluid/wall particles of its columns plus ALL of the
+// replicated solids).  Rows come in the context's current slot order; mphx_upload_owned takes the rows of
+// the last mphx_download_owned back (same order, possibly modified values) -- the per-step host<->device
+// path of a distributed caller, moving 1/nranks of the state per rank.
+static int owned_prepare(Ctx *c)
+{
+    const size_t cap = (size_t)c->cap;
+    if (!c->mask && c->alloc(&c->mask, cap)) return MPHX_ERR_NOMEM;
+    if (!c->own_scan) {
+        c->own_blocks = (int)((cap + 1 + kScanChunk - 1) / kScanChunk);
+        int e = 0;
+        e |= c->alloc(&c->own_scan, cap + 2); e |= c->alloc(&c->own_sums, (size_t)c->own_blocks + 1);
+        e |= c->alloc(&c->own_slot, cap); e |= c->alloc(&c->own_ids, cap);
+        e |= c->alloc(&c->own_x, 3 * cap); e |= c->alloc(&c->own_v, 3 * cap);
+        if (e) return MPHX_ERR_NOMEM;
+    }
+    return MPHX_OK;
+}
+
+int mphx_download_owned(mphx_ctx *ctx, int capacity, int *ids, double *position, double *velocity, int *count)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->inited || !ids || !position || !velocity || !count) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    int rc = owned_prepare(c);
+    if (rc) return rc;
+    const int n = c->n;
+    LAUNCH(c, k_owned_mask, nblk(n), kBlock, n, c->S, c->grid, 1, c->mask);
+    const int nb = (int)(((long long)n + kScanChunk - 1) / kScanChunk);
+    LAUNCH(c, k_scan_reduce, nb, kScanThreads, c->mask, n, c->own_sums);
+    LAUNCH(c, k_scan_top, 1, kScanThreads, c->own_sums, nb);
+    LAUNCH(c, k_scan_apply, nb, kScanThreads, c->mask, n, c->own_sums, c->own_scan);
+    int total = 0;
+    CK(cudaMemcpyAsync(&total, c->own_scan + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    LAUNCH(c, k_compact_owned, nblk(n), kBlock, n, c->S, c->sol, c->mask, c->own_scan, c->own_slot, c->own_ids, c->own_x, c->own_v);
+    CK(cudaStreamSynchronize(c->stream));
+    *count = total;
+    if (total > capacity) { set_last_error("mphx_download_owned: capacity too small"); return MPHX_ERR_OVERFLOW; }
+    CK(cudaMemcpyAsync(ids, c->own_ids, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(position, c->own_x, sizeof(double) * 3 * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(velocity, c->own_v, sizeof(double) * 3 * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->own_count = total;
+    c->own_epoch = c->steps_done;
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+int mphx_upload_owned(mphx_ctx *ctx, int count, const int *ids, const double *position, const double *velocity)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->inited || !ids || !position || !velocity) return MPHX_ERR_INVALID;
+    if (c->own_epoch != c->steps_done || count != c->own_count) {
+        set_last_error("mphx_upload_owned: rows must be those of the last mphx_download_owned (no step in between)");
+        return MPHX_ERR_INVALID;
+    }
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->own_ids, ids, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->own_x, position, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->own_v, velocity, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+    LAUNCH(c, k_scatter_owned, nblk(count), kBlock, count, c->S, c->sol, c->own_slot, c->own_ids, c->own_x, c->own_v, c->d_err);
+    int err = 0;
+    CK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (err) { set_last_error("mphx_upload_owned: ids do not match the rows of the last download"); return MPHX_ERR_INVALID; }
+    c->buckets_valid = false;
+    CK(cudaGetLastError());
+    return MPHX_OK;
 }
 
 int mphx_debug_neighbors(mphx_ctx *ctx, long long *offsets, int *ids, long long cap)

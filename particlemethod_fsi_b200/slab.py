@@ -398,25 +398,29 @@ def bench_main(args, METRIC, UNIT, WORKLOAD, peaks, ClockSampler, cpu_reference_
     held = torch.tensor([float(info["held"])], dtype=torch.float64, device=device)
     dist.all_reduce(held, op=dist.ReduceOp.MAX)
 
-    # end to end through the C-ABI with HOST buffers, every step: mphx_upload_state (Position+Velocity of
-    # the whole case from page-locked memory; each slab picks the particles it holds), one slab step,
-    # mphx_download of the owned particles into page-locked memory.  Copies are inside the timed region.
-    full = s.download("position", "velocity")
-    hx = torch.from_numpy(full["position"]).pin_memory()
-    hv = torch.from_numpy(full["velocity"]).pin_memory()
-    ox = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-    ov = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-    ke = max(1, min(K, args.e2e_steps))
+    # end to end through the C-ABI with HOST buffers, every step: mphx_upload_owned (ids, Position, Velocity
+    # of the particles this rank owns + the replicated solids, from page-locked memory), one slab step,
+    # mphx_download_owned back into page-locked memory.  Copies are inside the timed region; every rank
+    # moves its own share over its own PCIe link.
     ctx0 = s.slabs[0].ctx
+    rows_cap = s.info()[0]["capacity"]
+    hid = torch.empty(rows_cap, dtype=torch.int32).pin_memory()
+    hx = torch.empty((rows_cap, 3), dtype=torch.float64).pin_memory()
+    hv = torch.empty((rows_cap, 3), dtype=torch.float64).pin_memory()
+    ke = max(1, min(K, args.e2e_steps))
+    nrow = C.c_int()
+
+    def fetch():
+        s.slabs[0]._ck("mphx_download_owned", s.lib.mphx_download_owned(
+            ctx0, rows_cap, C.c_void_p(hid.data_ptr()), C.c_void_p(hx.data_ptr()), C.c_void_p(hv.data_ptr()), C.byref(nrow)))
 
     def e2e_step():
-        s.slabs[0]._ck("mphx_upload_state", s.lib.mphx_upload_state(ctx0, C.c_void_p(hx.data_ptr()), C.c_void_p(hv.data_ptr())))
+        s.slabs[0]._ck("mphx_upload_owned", s.lib.mphx_upload_owned(
+            ctx0, nrow.value, C.c_void_p(hid.data_ptr()), C.c_void_p(hx.data_ptr()), C.c_void_p(hv.data_ptr())))
         s.step(1)
-        views = abi.HostViews()
-        views.position = C.cast(ox.data_ptr(), C.POINTER(C.c_double))
-        views.velocity = C.cast(ov.data_ptr(), C.POINTER(C.c_double))
-        s.slabs[0]._ck("mphx_download", s.lib.mphx_download(ctx0, C.byref(views)))
+        fetch()
 
+    fetch()
     e2e_step()
     tr.barrier()
     torch.cuda.synchronize()
@@ -425,6 +429,9 @@ def bench_main(args, METRIC, UNIT, WORKLOAD, peaks, ClockSampler, cpu_reference_
         e2e_step()
     torch.cuda.synchronize()
     te = tr.allreduce_max_float(time.perf_counter() - t0, device)
+    rt = torch.tensor([float(nrow.value)], dtype=torch.float64, device=device)
+    dist.all_reduce(rt)
+    rows_total = rt.item()
     s.close()
     if rank == 0:
         pk, pk_kind = peaks()
@@ -439,10 +446,10 @@ def bench_main(args, METRIC, UNIT, WORKLOAD, peaks, ClockSampler, cpu_reference_
                            "cache": "inputs larger than L2", "parallelism": f"{world} x-slabs (ring), halo + migration over NCCL",
                            "partition_columns": s.partition, "max_slots_held": int(held.item())},
                 "clocks": clocks,
-                "e2e": {"value": n * ke / te, "unit": UNIT, "h2d_bytes_per_step": 48 * n, "d2h_bytes_per_step": 48 * n,
-                        "steps": ke, "ms_per_step": 1e3 * te / ke,
-                        "path": "per rank: mphx_upload_state (whole-case Position+Velocity, pinned) + slab step + mphx_download "
-                                "(owned particles, pinned); bytes are per rank"},
+                "e2e": {"value": n * ke / te, "unit": UNIT, "h2d_bytes_per_step": int(rows_total) * 52,
+                        "d2h_bytes_per_step": int(rows_total) * 52, "steps": ke, "ms_per_step": 1e3 * te / ke,
+                        "path": "per rank: mphx_upload_owned + slab step + mphx_download_owned (ids+Position+Velocity of the owned "
+                                "particles and the replicated solids, pinned host buffers); bytes summed over ranks"},
                 "gpu_launches": int(lt.item()),
                 "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": agg, "peak": pk["hbm_gbs"] * world,
                              "unit": "GB/s", "frac": agg / (pk["hbm_gbs"] * world), "traffic": None,

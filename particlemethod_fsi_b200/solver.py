@@ -63,6 +63,8 @@ def _load():
     L.mphx_time.restype = C.c_double
     L.mphx_set_time.argtypes = [vp, C.c_double]
     L.mphx_download.argtypes = [vp, C.POINTER(abi.HostViews)]
+    L.mphx_download_owned.argtypes = [vp, C.c_int, vp, vp, vp, ip]
+    L.mphx_upload_owned.argtypes = [vp, C.c_int, vp, vp, vp]
     L.mphx_debug_neighbors.argtypes = [vp, vp, vp, C.c_longlong]
     L.mphx_debug_initial_structure_neighbors.argtypes = [vp, vp, vp, C.c_longlong]
     L.mphx_timed_steps.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
@@ -166,6 +168,11 @@ def device_count() -> int:
     return lib.mphx_device_count()
 
 
+def _addr(a):
+    """host address of a numpy array or a torch (pinned) tensor"""
+    return C.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data)
+
+
 # ---- the solver context ---------------------------------------------------------------------------
 VTK_FIELDS = ("property", "position", "velocity", "force", "acceleration", "stress", "strain",
               "neighbor_count", "initial_structure_neighbor_count")
@@ -225,6 +232,17 @@ class Solver:
             _shape, is_int = abi.VIEW_FIELDS[nm]
             setattr(hv, nm, C.cast(ptr, C.POINTER(C.c_int if is_int else C.c_double)))
         _ck("mphx_download", lib.mphx_download(self._ctx, C.byref(hv)))
+
+    def download_owned(self, ids, position, velocity) -> int:
+        """compact (ids, Position, Velocity) of the particles this context owns into caller arrays
+        (numpy, or anything with .ctypes.data / an int address); returns the row count"""
+        n = C.c_int()
+        cap = int(ids.shape[0])
+        _ck("mphx_download_owned", lib.mphx_download_owned(self._ctx, cap, _addr(ids), _addr(position), _addr(velocity), C.byref(n)))
+        return n.value
+
+    def upload_owned(self, count: int, ids, position, velocity):
+        _ck("mphx_upload_owned", lib.mphx_upload_owned(self._ctx, count, _addr(ids), _addr(position), _addr(velocity)))
 
     def init(self):
         _ck("mphx_init", lib.mphx_init(self._ctx))

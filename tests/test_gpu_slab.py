@@ -73,3 +73,53 @@ def test_flow_through_the_periodic_seam():
     # the reference's Mod-based minimum image: 1e-12, not bit-equal
     # (PressureP of a force-free drifting block is round-off around zero: compare the kinematics)
     _compare(sub, 2, [1, 30, 200], exact=False, fields=("position", "velocity", "cell_index", "property"))
+
+
+def test_compact_owned_io_round_trip():
+    """mphx_download_owned / mphx_upload_owned: rows of every slab together are the whole case (+ the
+    replicated solids once per slab); taking them back unchanged and stepping equals plain stepping."""
+    import ctypes as C
+    case = cases.fsi3d_mini()
+    ref = Solver.from_case(case)
+    ring = slab.SlabSolver(case, slab.LocalRing(3))
+    ref.step(3, sync=True)
+    ring.step(3)
+    ns = case.counts()[1]
+    seen = np.zeros(case.n, dtype=np.int64)
+    want = ref.download("position", "velocity")
+    bufs = []
+    for s in ring.slabs:
+        cap = ring.info()[s.rank]["capacity"]
+        ids = np.empty(cap, dtype=np.int32)
+        x = np.empty((cap, 3))
+        v = np.empty((cap, 3))
+        n = C.c_int()
+        s._ck("mphx_download_owned", ring.lib.mphx_download_owned(s.ctx, cap, ids.ctypes.data, x.ctypes.data, v.ctypes.data, C.byref(n)))
+        m = n.value
+        np.add.at(seen, ids[:m], 1)
+        assert np.array_equal(x[:m], want["position"][ids[:m]])
+        assert np.array_equal(v[:m], want["velocity"][ids[:m]])
+        bufs.append((s, m, ids, x, v))
+    solid = (case.property >= 2) & (case.property < 4)
+    assert np.all(seen[~solid] == 1) and np.all(seen[solid] == 3) and int(solid.sum()) == ns
+    for s, m, ids, x, v in bufs:
+        s._ck("mphx_upload_owned", ring.lib.mphx_upload_owned(s.ctx, m, ids.ctypes.data, x.ctypes.data, v.ctypes.data))
+    ref.step(4, sync=True)
+    ring.step(4)
+    a, b = ref.download("position", "velocity"), ring.download("position", "velocity")
+    assert np.array_equal(a["position"], b["position"]) and np.array_equal(a["velocity"], b["velocity"])
+    # a stale upload (a step happened since the download) is refused
+    s, m, ids, x, v = bufs[0]
+    assert ring.lib.mphx_upload_owned(s.ctx, m, ids.ctypes.data, x.ctypes.data, v.ctypes.data) != 0
+    # single context: owned = everything; modified rows are taken over
+    ids = np.empty(case.n, dtype=np.int32)
+    x = np.empty((case.n, 3))
+    v = np.empty((case.n, 3))
+    m = ref.download_owned(ids, x, v)
+    assert m == case.n and np.array_equal(np.sort(ids), np.arange(case.n))
+    v[:, 1] += 0.25
+    ref.upload_owned(m, ids, x, v)
+    got = ref.download("velocity")["velocity"]
+    assert np.array_equal(got[ids], v)
+    ref.close()
+    ring.close()
