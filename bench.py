@@ -13,10 +13,11 @@ sub-steps, integration) over all particles.
   e2e        the same metric through the C-ABI with HOST buffers: every step copies Position and
              Velocity host->device from page-locked memory (mphx_upload_state), steps once, and
              reads Position and Velocity back (mphx_download); copies are inside the timed region.
-  roofline   dominant kernel (stencil sweep "pass 2"): algorithmic HBM bytes per launch (SURVEY 8(d):
-             108 B/fluid, 60 B wall/solid ... see DESIGN.md) / average launch duration measured
-             live with CUDA events, against MEASURED_PEAKS.json hbm_gbs.  The sweeps are FP64-pipe
-             bound; the FP64 fraction is reported beside it as fp64_frac.
+  roofline   dominant kernel (normally pass 2 over the candidate list): algorithmic HBM bytes per
+             launch (108 B/fluid, 60 B wall/solid ... see DESIGN.md) / average launch
+             duration measured live with CUDA events on the library's stream, against
+             MEASURED_PEAKS.json hbm_gbs.  The sweeps are not HBM bound; the ncu facts that say what
+             binds them (FP64 pipe, issue slots, L1 data pipe) ride along under roofline.ncu.
   cpu_baseline  the reference's own CPU build (oracle/_ref, all host threads) on a bounded sample.
 
 --impl reference times the reference's CPU implementation (oracle/_ref when built, else the oracle
@@ -205,38 +206,46 @@ def run_mphx(args):
     ms = s.timed_steps(K)
     clocks = sampler.stop()
     phase = s.timers_ms()
+    kms = s.kernel_timers_ms()          # [rebuild, k_filter, pass 1 (list), pass 2 (list), solid sub-steps]
     s.set_timing(False)
     launches = s.launch_count - l0
     value = n * K / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     pk, pk_kind = peaks()
-    # algorithmic bytes per launch of pass 2: R x 24, v 24, type 4, P 8; W x 24, v 24
-    # = 108 B per fluid particle; wall/solid particles read the same 60 B and write nothing that
-    # the model counts.
-    pass2_bytes = 108.0 * nf + 60.0 * (nw + ns)
-    pass1_bytes = 60.0 * n
-    dom = 2 if phase[2] >= phase[1] else 1
-    dom_ms = phase[dom] / K
-    dom_bytes = pass2_bytes if dom == 2 else pass1_bytes
+    # algorithmic HBM bytes per launch:
+    #   pass 2: R x 24, v 24, type 4, P 8; W x 24, v 24 = 108 B per fluid particle; wall/solid particles
+    #           read the same 60 B and write nothing the model counts;
+    #   pass 1: R x 24, v 24, type 4; W PressureP 8 = 60 B per particle.  The model has no separate filter
+    #           kernel: k_filter reads the positions it tests (24 B + type 4 per particle).
+    cand = [("k_filter<3>", kms[1] / K, 28.0 * n),
+            ("k_pass1_v3<3,false,true>", kms[2] / K, 60.0 * n),
+            ("k_pass2_v3<3,false,true>", kms[3] / K, 108.0 * nf + 60.0 * (nw + ns))]
+    dom_name, dom_ms, dom_bytes = max(cand, key=lambda c: c[1])
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = None
-    tf = os.path.join(ROOT, "profiles", "pass2_dram_bytes_per_launch.json")
+    traffic, ncu_facts = None, None
+    tf = os.path.join(ROOT, "profiles", "sweep_ncu_facts.json")
     if os.path.exists(tf):
         try:
-            traffic = json.load(open(tf)).get("dram_bytes_per_launch")
+            facts = json.load(open(tf))
+            ncu_facts = facts.get(dom_name)
+            traffic = ncu_facts.get("dram_bytes_per_launch") if ncu_facts else None
         except Exception:
             traffic = None
     step_bytes = s.algorithmic_bytes_per_step
-    roofline = {"bound": "hbm", "kernel": "k_pass2<3,false>" if dom == 2 else "k_pass1<3,false>",
-                "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
-                "traffic": traffic, "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)",
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic,
+                "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs)",
                 "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
+                "kernel_ms_per_step": {"bucket_rebuild": kms[0] / K, "k_filter": kms[1] / K, "pass1_list": kms[2] / K,
+                                       "pass2_list": kms[3] / K, "solid_substeps": kms[4] / K},
                 "phase_ms_per_step": {"bucket_rebuild": phase[0] / K, "pass1": phase[1] / K, "pass2": phase[2] / K,
                                       "solid_substeps": phase[3] / K},
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes * K / (ms * 1e-3) / 1e9,
                                "frac": step_bytes * K / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
-                "note": "the stencil sweeps are FP64-pipe bound, not HBM bound (SURVEY 8(d)); see DESIGN.md"}
+                "ncu": ncu_facts,
+                "note": "the sweeps are bound by the FP64 pipe, instruction issue and the L1 data pipe, not by HBM "
+                        "(ncu facts under profiles/; DESIGN.md section 3)"}
 
     # ---- end to end through the C-ABI with host buffers ------------------------------------------------
     hx = torch.empty((n, 3), dtype=torch.float64).pin_memory()

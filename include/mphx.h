@@ -220,6 +220,9 @@ int mphx_set_timing(mphx_ctx *ctx, int on);
  * src/main.cpp:611), [1] pass 1, [2] pass 2, [3] solid sub-steps ([1]+[2]+[3] = its "explicit
  * calculation" timer, :669) */
 int mphx_get_timers(mphx_ctx *ctx, double ms[4]);
+/* the same split by kernel group: [0] bucket rebuild, [1] candidate filter (k_filter), [2] pass 1 over the
+ * candidate list, [3] pass 2 over the candidate list (+ integration), [4] solid sub-steps */
+int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5]);
 /* number of kernel launches issued by mphx_step since mphx_create (for bench.py gpu_launches) */
 long long mphx_launch_count(const mphx_ctx *ctx);
 /* algorithmic HBM bytes of one step for the resident case (SURVEY.md 8(d) model):

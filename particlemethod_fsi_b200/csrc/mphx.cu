@@ -16,6 +16,7 @@
 
 #include "kernels.cuh"
 #include "sweep.cuh"
+#include "sweep_pair.cuh"
 #include "mphx.h"
 #include "mphx_internal.h"
 
@@ -81,12 +82,13 @@ struct Ctx {
     int sweep_batch = 12;  // stencil columns per filter/drain batch (3D)
     PairList pl{};         // pass 1 -> pass 2 neighbour list (nbr == nullptr: disabled, pass 2 sweeps again)
     int list_cap = -1;     // list slots per particle (-1: default by dimension, 0: no list)
+    bool filter2 = true;   // build the lists two particles per thread (k_filter2, sweep_pair.cuh)
     std::vector<void *> allocs;
 
     // phase timers (src/main.cpp:695-700 split)
     bool timing = false;
     std::vector<cudaEvent_t> ev;
-    double ms[4] = {0, 0, 0, 0};
+    double ms[5] = {0, 0, 0, 0, 0}; // rebuild, filter, pass 1, pass 2, solid sub-steps
     cudaEvent_t tev[2] = {nullptr, nullptr};
 
     template <class Tp> int alloc(Tp **ptr, size_t count)
@@ -308,7 +310,8 @@ static float sweep_filter2(const Ctx *c)
     return filter_radius2(c, rmax);
 }
 
-static int run_pass1(Ctx *c)
+static void timer_mark(Ctx *c);
+static int run_pass1(Ctx *c, bool timed = false)
 {
     const int n = c->n;
     {
@@ -316,9 +319,16 @@ static int run_pass1(Ctx *c)
         const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
         if (c->pl.nbr) { // K5a: candidate list of this step
             CK(cudaMemsetAsync(c->pl.flags, 0, sizeof(int), c->stream));
-            if (c->p.dim == 3) LAUNCH(c, k_filter<3>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
-            else               LAUNCH(c, k_filter<2>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
+            const int npairs = (n + 1) / 2;
+            if (c->filter2) {
+                if (c->p.dim == 3) LAUNCH(c, k_filter2<3>, nblk(npairs, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
+                else               LAUNCH(c, k_filter2<2>, nblk(npairs, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
+            } else {
+                if (c->p.dim == 3) LAUNCH(c, k_filter<3>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
+                else               LAUNCH(c, k_filter<2>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
+            }
         }
+        if (timed) timer_mark(c);
 #define P1(D, ST, LIST) LAUNCH(c, (k_pass1_v3<D, ST, LIST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
                          batch, c->P, c->volStrain, c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA, c->pl)
 #define P1D(ST, LIST) do { if (c->p.dim == 3) P1(3, ST, LIST); else P1(2, ST, LIST); } while (0)
@@ -395,9 +405,10 @@ static void timer_resolve(Ctx *c)
 {
     if (c->ev.empty()) return;
     cudaStreamSynchronize(c->stream);
-    // events come in groups of 5 per step: start, after rebuild, after pass 1, after pass 2, after solid
-    for (size_t i = 0; i + 4 < c->ev.size(); i += 5)
-        for (int k = 0; k < 4; ++k) {
+    // events come in groups of 6 per step: start, after rebuild, after the filter, after pass 1, after
+    // pass 2, after the solid sub-steps
+    for (size_t i = 0; i + 5 < c->ev.size(); i += 6)
+        for (int k = 0; k < 5; ++k) {
             float a = 0;
             cudaEventElapsedTime(&a, c->ev[i + k], c->ev[i + k + 1]);
             c->ms[k] += a;
@@ -412,7 +423,7 @@ static int one_step(Ctx *c, bool fluid_only)
     timer_mark(c);
     if ((rc = rebuild_buckets(c, true))) return rc; // calculateWall, PeriodicBoundary, resets, calculateNeighbor
     timer_mark(c);
-    if ((rc = run_pass1(c))) return rc;             // DensityA..DivergenceP, coefficients, PressureP/A
+    if ((rc = run_pass1(c, true))) return rc;       // filter; DensityA..DivergenceP, coefficients, PressureP/A
     timer_mark(c);
     if ((rc = run_pass2(c))) return rc;             // force sums, gravity, interface, acceleration, convection
     timer_mark(c);
@@ -422,7 +433,7 @@ static int one_step(Ctx *c, bool fluid_only)
         ++c->steps_done;
     }
     timer_mark(c);
-    if (c->ev.size() >= 5000) timer_resolve(c);
+    if (c->ev.size() >= 6000) timer_resolve(c);
     return MPHX_OK;
 }
 
@@ -717,7 +728,8 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
     }
     c->timing = std::getenv("MPHX_TIMING") != nullptr;
     if (const char *e = std::getenv("MPHX_SWEEP_BATCH")) c->sweep_batch = std::max(1, std::atoi(e));
-    if (const char *e = std::getenv("MPHX_LIST_CAP")) c->list_cap = std::max(0, std::atoi(e)); // 0: pass 2 sweeps again
+    if (const char *e = std::getenv("MPHX_LIST_CAP")) c->list_cap = std::max(0, std::atoi(e)); // 0: no list, fused sweeps
+    if (const char *e = std::getenv("MPHX_FILTER2")) c->filter2 = std::atoi(e) != 0;           // 0: one particle per thread
     for (int k = 0; k < 2; ++k) cudaEventCreate(&c->tev[k]);
     *out = reinterpret_cast<mphx_ctx *>(c);
     return MPHX_OK;
@@ -946,7 +958,7 @@ int mphx_set_timing(mphx_ctx *ctx, int on)
     cudaSetDevice(c->device);
     timer_resolve(c);
     c->timing = on != 0;
-    if (on) for (int k = 0; k < 4; ++k) c->ms[k] = 0.0;
+    if (on) for (int k = 0; k < 5; ++k) c->ms[k] = 0.0;
     return MPHX_OK;
 }
 
@@ -1219,7 +1231,17 @@ int mphx_get_timers(mphx_ctx *ctx, double ms[4])
     if (!c || !ms) return MPHX_ERR_INVALID;
     cudaSetDevice(c->device);
     timer_resolve(c);
-    for (int i = 0; i < 4; ++i) ms[i] = c->ms[i];
+    ms[0] = c->ms[0]; ms[1] = c->ms[1] + c->ms[2]; ms[2] = c->ms[3]; ms[3] = c->ms[4];
+    return MPHX_OK;
+}
+
+int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5])
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !ms) return MPHX_ERR_INVALID;
+    cudaSetDevice(c->device);
+    timer_resolve(c);
+    for (int i = 0; i < 5; ++i) ms[i] = c->ms[i];
     return MPHX_OK;
 }
 

@@ -70,6 +70,7 @@ def _load():
     L.mphx_timed_steps.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     L.mphx_set_timing.argtypes = [vp, C.c_int]
     L.mphx_get_timers.argtypes = [vp, C.POINTER(C.c_double * 4)]
+    L.mphx_get_kernel_timers.argtypes = [vp, C.POINTER(C.c_double * 5)]
     L.mphx_launch_count.argtypes = [vp]
     L.mphx_launch_count.restype = C.c_longlong
     L.mphx_algorithmic_bytes_per_step.argtypes = [vp]
@@ -312,6 +313,12 @@ class Solver:
     def timers_ms(self):
         ms = (C.c_double * 4)()
         _ck("mphx_get_timers", lib.mphx_get_timers(self._ctx, C.byref(ms)))
+        return list(ms)
+
+    def kernel_timers_ms(self):
+        """[bucket rebuild, candidate filter, pass 1, pass 2, solid sub-steps] accumulated device ms"""
+        ms = (C.c_double * 5)()
+        _ck("mphx_get_kernel_timers", lib.mphx_get_kernel_timers(self._ctx, C.byref(ms)))
         return list(ms)
 
     @property
