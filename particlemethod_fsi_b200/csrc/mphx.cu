@@ -329,7 +329,10 @@ static int run_pass1(Ctx *c, bool timed = false)
             }
         }
         if (timed) timer_mark(c);
-#define P1(D, ST, LIST) LAUNCH(c, (k_pass1_v3<D, ST, LIST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
+        // fused-sweep fall-backs: a small persistent grid when they only have to look at the overflow flag
+        const int vblocks = nblk(n, kSweepThreads);
+#define SWEEP_GRID(LIST) ((LIST) || !c->pl.nbr ? vblocks : std::min(vblocks, 4 * 148))
+#define P1(D, ST, LIST) LAUNCH(c, (k_pass1_v3<D, ST, LIST>), SWEEP_GRID(LIST), kSweepThreads, vblocks, n, c->S, c->cellStart, c->grid, c->phys, f2, \
                          batch, c->P, c->volStrain, c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA, c->pl)
 #define P1D(ST, LIST) do { if (c->p.dim == 3) P1(3, ST, LIST); else P1(2, ST, LIST); } while (0)
         if (c->pl.nbr) { // list traversal, then the fused sweep for particles whose list overflowed (normally none)
@@ -350,7 +353,8 @@ static int run_pass2(Ctx *c, double *solbuf = nullptr)
     {
         const float f2 = sweep_filter2(c);
         const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
-#define P2(D, ST, LIST) LAUNCH(c, (k_pass2_v3<D, ST, LIST>), nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, c->phys, f2, \
+        const int vblocks = nblk(n, kSweepThreads);
+#define P2(D, ST, LIST) LAUNCH(c, (k_pass2_v3<D, ST, LIST>), SWEEP_GRID(LIST), kSweepThreads, vblocks, n, c->S, c->cellStart, c->grid, c->phys, f2, \
                          batch, c->P, c->PA, c->gcx, c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, \
                          c->fy, c->fz, c->ax, c->ay, c->az, c->sol, solbuf, c->pl)
 #define P2D(ST, LIST) do { if (c->p.dim == 3) P2(3, ST, LIST); else P2(2, ST, LIST); } while (0)

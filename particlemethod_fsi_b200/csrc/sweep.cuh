@@ -381,14 +381,13 @@ k_filter(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, floa
 //   LIST = false: fused stencil sweep (phase A + phase B); with pl.count set only the overflowed
 //                 particles are processed (the block exits at once if it has none), else all.
 template <int DIM, bool ST, bool LIST>
-__global__ void __launch_bounds__(kSweepThreads, LIST ? MPHX_P1_MINB : 1)
-k_pass1_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
+__device__ __forceinline__ void
+pass1_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, const GridDesc &g, const Phys &ph, float filt2, int batch,
            double *__restrict__ P, double *__restrict__ volStrain, double *__restrict__ divP,
            double *__restrict__ densA, double *__restrict__ gcx, double *__restrict__ gcy, double *__restrict__ gcz,
            double *__restrict__ PA, PairList pl)
 {
-    if (!LIST && pl.count && *reinterpret_cast<volatile const int *>(pl.flags) == 0) return; // no list overflowed in this step
-    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i0 = vblock * blockDim.x + threadIdx.x;
     const int i = i0 < n ? i0 : n - 1;
     int mycount = 0;
     bool mine = i0 < n;
@@ -486,6 +485,26 @@ k_pass1_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     }
 }
 
+// kernel wrappers.  The list variants run one block per 128 particles.  The fused-sweep variants are
+// normally fall-backs that find nothing to do: they are launched as a small persistent grid that first
+// reads the step's overflow flag and otherwise loops over the virtual blocks.
+template <int DIM, bool ST, bool LIST>
+__global__ void __launch_bounds__(kSweepThreads, LIST ? MPHX_P1_MINB : 1)
+k_pass1_v3(int vblocks, int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
+           double *__restrict__ P, double *__restrict__ volStrain, double *__restrict__ divP, double *__restrict__ densA,
+           double *__restrict__ gcx, double *__restrict__ gcy, double *__restrict__ gcz, double *__restrict__ PA, PairList pl)
+{
+    if constexpr (LIST) {
+        pass1_block<DIM, ST, true>(blockIdx.x, n, p, cellStart, g, ph, filt2, batch, P, volStrain, divP, densA, gcx, gcy, gcz, PA, pl);
+    } else {
+        if (pl.count && *reinterpret_cast<volatile const int *>(pl.flags) == 0) return; // no list overflowed in this step
+        for (int vb = blockIdx.x; vb < vblocks; vb += gridDim.x) {
+            pass1_block<DIM, ST, false>(vb, n, p, cellStart, g, ph, filt2, batch, P, volStrain, divP, densA, gcx, gcy, gcz, PA, pl);
+            __syncthreads(); // the shared-memory queue is reused by the next virtual block
+        }
+    }
+}
+
 // K6 "pass 2": force sums (PressureP :2394-2425, PressureA :2225-2259, DiffuseInterface :2265-2312,
 // ViscosityV :2480-2522, InterfaceForce :2439-2473) + gravity :2917 + explicit integration
 // (:2938-2956, :1892-1907).
@@ -493,8 +512,8 @@ k_pass1_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
 //   LIST = false: stencil sweep; with pl.count set only the overflowed particles are processed
 //                 (and the block exits at once if it has none), otherwise all particles.
 template <int DIM, bool ST, bool LIST>
-__global__ void __launch_bounds__(kSweepThreads, LIST ? MPHX_P2_MINB : 1)
-k_pass2_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
+__device__ __forceinline__ void
+pass2_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, const GridDesc &g, const Phys &ph, float filt2, int batch,
            const double *__restrict__ P, const double *__restrict__ PA, const double *__restrict__ gcx,
            const double *__restrict__ gcy, const double *__restrict__ gcz, double *__restrict__ ox,
            double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ovx, double *__restrict__ ovy,
@@ -507,8 +526,7 @@ k_pass2_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     // c_d mu_ij V * (-cdv)   (:2505-2512, dwij = -dwvdr)
     for (int e = threadIdx.x; e < kTypeCount * kTypeCount; e += blockDim.x)
         s_visc[e / kTypeCount][e % kTypeCount] = -ph.viscpair[e / kTypeCount][e % kTypeCount] * ph.cdv;
-    if (!LIST && pl.count && *reinterpret_cast<volatile const int *>(pl.flags) == 0) return; // no list overflowed in this step
-    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i0 = vblock * blockDim.x + threadIdx.x;
     const int i = i0 < n ? i0 : n - 1;
     int mycount = 0;
     bool mine = i0 < n;
@@ -656,6 +674,29 @@ k_pass2_v3(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Ph
     }
     ox[i] = nx; oy[i] = ny; oz[i] = nz; ovx[i] = nvx; ovy[i] = nvy; ovz[i] = nvz;
     fx[i] = F0; fy[i] = F1; fz[i] = F2; ax[i] = a0; ay[i] = a1; az[i] = a2;
+}
+
+template <int DIM, bool ST, bool LIST>
+__global__ void __launch_bounds__(kSweepThreads, LIST ? MPHX_P2_MINB : 1)
+k_pass2_v3(int vblocks, int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
+           const double *__restrict__ P, const double *__restrict__ PA, const double *__restrict__ gcx,
+           const double *__restrict__ gcy, const double *__restrict__ gcz, double *__restrict__ ox,
+           double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ovx, double *__restrict__ ovy,
+           double *__restrict__ ovz, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
+           double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az, Solid sol,
+           double *__restrict__ solbuf, PairList pl)
+{
+    if constexpr (LIST) {
+        pass2_block<DIM, ST, true>(blockIdx.x, n, p, cellStart, g, ph, filt2, batch, P, PA, gcx, gcy, gcz, ox, oy, oz, ovx, ovy, ovz, fx, fy,
+                                   fz, ax, ay, az, sol, solbuf, pl);
+    } else {
+        if (pl.count && *reinterpret_cast<volatile const int *>(pl.flags) == 0) return; // no list overflowed in this step
+        for (int vb = blockIdx.x; vb < vblocks; vb += gridDim.x) {
+            pass2_block<DIM, ST, false>(vb, n, p, cellStart, g, ph, filt2, batch, P, PA, gcx, gcy, gcz, ox, oy, oz, ovx, ovy, ovz, fx, fy,
+                                        fz, ax, ay, az, sol, solbuf, pl);
+            __syncthreads();
+        }
+    }
 }
 
 } // namespace mphx
