@@ -320,9 +320,12 @@ static int run_pass1(Ctx *c, bool timed = false)
         if (c->pl.nbr) { // K5a: candidate list of this step
             CK(cudaMemsetAsync(c->pl.flags, 0, sizeof(int), c->stream));
             const int npairs = (n + 1) / 2;
-            if (c->filter2) {
-                if (c->p.dim == 3) LAUNCH(c, k_filter2<3>, nblk(npairs, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
-                else               LAUNCH(c, k_filter2<2>, nblk(npairs, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
+            const bool big = ((size_t)c->pl.L + 1) * (size_t)c->pl.cap >= 0xffffffffull;
+            if (c->filter2 || big) {
+#define F2(D, B) LAUNCH(c, (k_filter2<D, B>), nblk(npairs, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl)
+                if (c->p.dim == 3) { if (big) F2(3, true); else F2(3, false); }
+                else               { if (big) F2(2, true); else F2(2, false); }
+#undef F2
             } else {
                 if (c->p.dim == 3) LAUNCH(c, k_filter<3>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
                 else               LAUNCH(c, k_filter<2>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
@@ -349,7 +352,6 @@ static int run_pass1(Ctx *c, bool timed = false)
 static int run_pass2(Ctx *c, double *solbuf = nullptr)
 {
     const int n = c->n;
-    const mphx_constants &k = c->c;
     {
         const float f2 = sweep_filter2(c);
         const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
@@ -808,7 +810,6 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
             int L = c->list_cap;
             if (L < 0) L = c->p.dim == 3 ? 128 : 48;
             c->pl = PairList{};
-            while (L > 0 && ((size_t)L + 1) * cap >= 0xffffffffull) L /= 2; // k_filter addresses the list with 32-bit offsets
             if (L > 0) {
                 e |= c->alloc(&c->pl.nbr, ((size_t)L + 1) * cap); // + the parking row of overflowed lists
                 e |= c->alloc(&c->pl.count, cap);

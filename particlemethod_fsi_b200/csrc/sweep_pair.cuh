@@ -12,6 +12,8 @@
 // (Tried and rejected on B200, see DESIGN.md: one SHARED list per pair and two particles per thread in
 // the physics kernels -- register pressure and the longer lists cost more than the saved gathers.)
 #pragma once
+#include <type_traits>
+
 #include "sweep.cuh"
 
 namespace mphx {
@@ -30,10 +32,12 @@ __device__ __forceinline__ bool particle_active(const GridDesc &g, int i, int n,
 }
 
 // K5a, two particles per thread; same outputs as k_filter (one list per particle).
-template <int DIM>
+// BIG: the list has 2^32 or more slots (e.g. 10^8 particles on one GPU): 64-bit offsets.
+template <int DIM, bool BIG>
 __global__ void __launch_bounds__(kSweepThreads, MPHX_FILTER2_MINB)
 k_filter2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, float filt2, PairList pl)
 {
+    using off_t = typename std::conditional<BIG, unsigned long long, unsigned>::type;
     __shared__ int s_dlo[kMaxStencil], s_dhi[kMaxStencil], s_sdx[kMaxStencil], s_sdy[kMaxStencil], s_sh[kMaxStencil];
     for (int e = threadIdx.x; e < g.nsten; e += blockDim.x) {
         const int dx = g.sdx[e], dy = g.sdy[e], h = g.sh[e];
@@ -54,11 +58,13 @@ k_filter2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, flo
     const bool wrapA = stencil_wraps<DIM>(g, bA), wrapB = stencil_wraps<DIM>(g, bB);
 
     int *__restrict__ nbr = pl.nbr;
-    unsigned stride = (unsigned)pl.cap;
-    unsigned parkA = (unsigned)pl.L * stride + (unsigned)ia; // (particle 2t+1: parkA + 1)
+    off_t stride = (off_t)pl.cap;
+    off_t parkA = (off_t)pl.L * stride + (off_t)ia; // (particle 2t+1: parkA + 1)
     float filt = filt2;
-    asm volatile("" : "+l"(nbr), "+r"(stride), "+r"(parkA), "+f"(filt)); // keep the loop invariants in registers
-    unsigned offA = (unsigned)ia, offB = (unsigned)ia + 1u;
+    // keep the loop invariants in registers
+    if constexpr (BIG) asm volatile("" : "+l"(nbr), "+l"(stride), "+l"(parkA), "+f"(filt));
+    else asm volatile("" : "+l"(nbr), "+r"(stride), "+r"(parkA), "+f"(filt));
+    off_t offA = (off_t)ia, offB = (off_t)ia + 1u;
 
     // one contiguous run [jb, je) of candidates against particle A (filter radius^2 fA; negative = masked)
     // and particle B (fB)
@@ -78,9 +84,9 @@ k_filter2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, flo
             da = __ffma2_rn(az2, az2, da); db = __ffma2_rn(bz2, bz2, db);
             const bool in0 = (unsigned)tt < (unsigned)len, in1 = tt < lenm1;
             if (in0 && da.x <= fA) { nbr[offA] = j0; offA = min(offA + stride, parkA); }
-            if (in0 && db.x <= fB) { nbr[offB] = j0; offB = min(offB + stride, parkA + 1u); }
+            if (in0 && db.x <= fB) { nbr[offB] = j0; offB = min(offB + stride, parkA + (off_t)1); }
             if (in1 && da.y <= fA) { nbr[offA] = j0 + 1; offA = min(offA + stride, parkA); }
-            if (in1 && db.y <= fB) { nbr[offB] = j0 + 1; offB = min(offB + stride, parkA + 1u); }
+            if (in1 && db.y <= fB) { nbr[offB] = j0 + 1; offB = min(offB + stride, parkA + (off_t)1); }
         }
     };
     // the stencil of ONE particle (general path: periodic images handled per column segment)
@@ -145,11 +151,11 @@ k_filter2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, flo
     // (a list of exactly L entries counts as overflowed)
     if (!actA) pl.count[ia] = 0;
     else if (offA == parkA) { pl.count[ia] = pl.L + 1; atomicOr(pl.flags, 1); }
-    else pl.count[ia] = (int)((offA - (unsigned)ia) / stride);
+    else pl.count[ia] = (int)((offA - (off_t)ia) / stride);
     if (ib < n) {
         if (!actB) pl.count[ib] = 0;
-        else if (offB == parkA + 1u) { pl.count[ib] = pl.L + 1; atomicOr(pl.flags, 1); }
-        else pl.count[ib] = (int)((offB - (unsigned)ib) / stride);
+        else if (offB == parkA + (off_t)1) { pl.count[ib] = pl.L + 1; atomicOr(pl.flags, 1); }
+        else pl.count[ib] = (int)((offB - (off_t)ib) / stride);
     }
 }
 
