@@ -42,6 +42,7 @@ sys.path.insert(0, ROOT)
 METRIC = "particle_steps_per_sec"
 UNIT = "particle-steps/s"
 WORKLOAD = "3D dam break on elastic plate, synthetic 10M particles (BASELINE.json configs[3])"
+WORKLOAD_100M = "3D FSI scaling case, synthetic 100M particles (BASELINE.json configs[4])"
 
 
 def peaks():
@@ -300,6 +301,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "mphx" else args.warmup
+    global WORKLOAD
+    if args.particles >= 5.0e7:
+        WORKLOAD = WORKLOAD_100M
+    elif abs(args.particles - 1.0e7) > 1.0e6:
+        WORKLOAD = "3D dam break on elastic plate, synthetic %.3gM particles (BASELINE.json configs[3] geometry)" % (args.particles / 1e6)
     if args.impl == "reference":
         run_reference(args)
     else:
