@@ -52,6 +52,7 @@ struct Ctx {
     int rank = 0, nranks = 1, col_lo = 0, col_hi = 0, msg_cap = 0;
     int ghost_base[2] = {0, 0}, ghost_cnt[2] = {0, 0}, halo_cnt[2] = {0, 0};
     int *where = nullptr, *haloSrc[2] = {nullptr, nullptr}, *d_err = nullptr;
+    int slab_err[4] = {0, 0, 0, 0}; // host copy of d_err, refreshed by stage_sort
     bool external_stream = false;
     bool uploaded = false, inited = false, surface_tension = false;
     double time = 0.0;
@@ -269,8 +270,10 @@ static int stage_sort(Ctx *c)
     c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
     c->buckets_valid = true;
     if (c->slab) { // ghosts of the last step and emigrants sit in the dead bucket: drop them
+        // (one synchronisation: the live slot count and the exchange error flags come back together)
         int keep = 0;
         CK(cudaMemcpyAsync(&keep, c->cellStart + c->grid.ncells + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaMemcpyAsync(c->slab_err, c->d_err, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         c->n = keep;
     }

@@ -265,16 +265,19 @@ class SlabSolver:
     def _ptr(self, t):
         return C.c_void_p(t.data_ptr())
 
-    def _host_counts(self, what):
-        """(to_left, to_right) of every local slab + the error flags packed by the kernels"""
-        out = []
-        for s in self.slabs:
-            c = s.counts.cpu().numpy()
+    def _counts(self, what):
+        """Own (to_left, to_right) and received (from_left, from_right) counts of every local slab with ONE
+        device->host read per slab: the neighbours' counts are exchanged device-side first."""
+        recv = self.tr.exchange_counts([s.counts for s in self.slabs])
+        sent, got = [], []
+        for s, r in zip(self.slabs, recv):
+            c = self.torch.cat([s.counts[:3], r.to(s.counts.dtype)]).cpu().numpy()
             if c[2]:
                 raise RuntimeError(f"slab {s.rank}: {what}: exchange error flags {int(c[2])} "
                                    "(1: a particle crossed more than one halo width in a step, 2: message buffer too small)")
-            out.append((int(c[0]), int(c[1])))
-        return out
+            sent.append((int(c[0]), int(c[1])))
+            got.append((int(c[3]), int(c[4])))
+        return sent, got
 
     def step(self, nsteps: int = 1):
         lib, tr, ck = self.lib, self.tr, self.slabs[0]._ck
@@ -282,8 +285,7 @@ class SlabSolver:
             # A: pre-step + migration
             for s in self.slabs:
                 ck("mphx_slab_begin", lib.mphx_slab_begin(s.ctx, self._ptr(s.send[0]), self._ptr(s.send[1]), self._ptr(s.counts)))
-            sent = self._host_counts("migration")
-            got = [tuple(int(v) for v in c.cpu().numpy()) for c in tr.exchange_counts([s.counts for s in self.slabs])]
+            sent, got = self._counts("migration")
             tr.exchange([(s.send[0], sent[i][0], s.send[1], sent[i][1], s.recv[0], got[i][0], s.recv[1], got[i][1], MSG_DOUBLES)
                          for i, s in enumerate(self.slabs)])
             for i, s in enumerate(self.slabs):
@@ -291,8 +293,7 @@ class SlabSolver:
             # B: halo
             for s in self.slabs:
                 ck("mphx_slab_pack_halo", lib.mphx_slab_pack_halo(s.ctx, self._ptr(s.send[0]), self._ptr(s.send[1]), self._ptr(s.counts)))
-            sent = self._host_counts("halo")
-            got = [tuple(int(v) for v in c.cpu().numpy()) for c in tr.exchange_counts([s.counts for s in self.slabs])]
+            sent, got = self._counts("halo")
             tr.exchange([(s.send[0], sent[i][0], s.send[1], sent[i][1], s.recv[0], got[i][0], s.recv[1], got[i][1], MSG_DOUBLES)
                          for i, s in enumerate(self.slabs)])
             for i, s in enumerate(self.slabs):
