@@ -40,6 +40,10 @@ constexpr int kSweepThreads = 128;
 #ifndef MPHX_P2_MINB
 #define MPHX_P2_MINB 6
 #endif
+// straight-line (masked) pair bodies in pass 1 / pass 2 instead of branches
+#ifndef MPHX_BRANCHFREE
+#define MPHX_BRANCHFREE 1
+#endif
 constexpr int kQueueCap = 40; // queue slots per thread (rows of 128 uint); one spare row absorbs masked stores
 
 struct SweepShared {
@@ -411,6 +415,18 @@ pass1_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
     // pair terms; rb = (vy, vz, -, type bits) of j
     auto pair = [&](int j, double dx, double dy, double dz, double r2, double vxj, const Rec rb) {
         const bool other = j != i;
+#if MPHX_BRANCHFREE
+        { // straight-line form: a masked pair contributes exact zeros, and the FP64 chains of the two
+          // pairs of a trip can be interleaved by the scheduler (no reconvergence regions in between)
+            const bool in = other && r2 <= rp2; // :2333, :2362
+            const double r2s = in ? r2 : 1.0;
+            const double rinv = rsqrt_nr(r2s);
+            const double q = in ? 1.0 - (r2s * rinv) * irp : 0.0;
+            nP += q * q;
+            const double ux = vxj - vxi, uy = rb.a - vyi, uz = rb.b - vzi;
+            dv -= (ux * dx + uy * dy + uz * dz) * rinv * q;
+        }
+#else
         if (other && r2 <= rp2) { // :2333, :2362
             const double rinv = rsqrt_nr(r2);
             const double q = 1.0 - (r2 * rinv) * irp;
@@ -418,6 +434,7 @@ pass1_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
             const double ux = vxj - vxi, uy = rb.a - vyi, uz = rb.b - vzi;
             dv -= (ux * dx + uy * dy + uz * dz) * rinv * q;
         }
+#endif
         if (ST && other && !solid_i && r2 <= ra2) { // :2162, :2195
             const double r = sqrt(r2);
             const double qa = r * ira;
@@ -555,16 +572,34 @@ pass2_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
     const double gscale = ph.vol / ph.l0;
     // pair terms; rb = (vy, vz, PressureP, type bits) of j
     auto pair = [&](int j, double dx, double dy, double dz, double r2, double vxj, const Rec rb) {
+#if !MPHX_BRANCHFREE
         if (j == i) return;
+#endif
+        const bool other = j != i;
         const int tj = (int)__double_as_longlong(rb.d);
         if (solid_i) {
-            if (r2 < rp2 && !is_structure_type(tj)) { // :2455, :2447
+            if (other && r2 < rp2 && !is_structure_type(tj)) { // :2455, :2447
                 const double rinv = rsqrt_nr(r2);
                 const double cc = (Pi + rb.c) * (1.0 - r2 * rinv * irp) * rinv * cpv;
                 F0 += cc * dx; F1 += cc * dy; F2 += cc * dz;
             }
             return;
         }
+#if MPHX_BRANCHFREE
+        { // straight-line form (see pass 1): masked terms are exact zeros
+            const bool inP = other && r2 < rp2, inV = other && r2 < rv2; // :2410, :2496 (strict)
+            const double r2s = (inP || inV) ? r2 : 1.0;
+            const double rinv = rsqrt_nr(r2s);
+            const double r = r2s * rinv;
+            const double cP = (Pi + rb.c) * (1.0 - r * irp) * rinv * cpv;
+            const double ux = vxj - vxi, uy = rb.a - vyi, uz = rb.b - vzi;
+            const double ue = (ux * dx + uy * dy + uz * dz) * rinv;
+            const double cV = visc_row[tj] * ue * (1.0 - r * irv) * (rinv * rinv);
+            double cc = inP ? cP : 0.0;
+            cc += inV ? cV : 0.0;
+            F0 += cc * dx; F1 += cc * dy; F2 += cc * dz;
+        }
+#else
         if (r2 < rpv2) {
             const bool inP = r2 < rp2, inV = r2 < rv2; // :2410, :2496 (strict)
             const double rinv = rsqrt_nr(r2);
@@ -578,7 +613,8 @@ pass2_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
             }
             F0 += cc * dx; F1 += cc * dy; F2 += cc * dz;
         }
-        if (ST && r2 < ph.ra2) { // :2243, :2285 (RadiusG == RadiusA)
+#endif
+        if (ST && other && r2 < ph.ra2) { // :2243, :2285 (RadiusG == RadiusA)
             const double r = sqrt(r2);
             const double rinv = 1.0 / r;
             const double qa = r * ph.ira;
