@@ -10,5 +10,5 @@ CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --e2e-steps 1"
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu1.log 2>&1
 $CMD > gpurun_out/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_pass -s 8 -c 2 -o gpurun_out/${TAG}_sweeps $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k_filter2|k_pass._v3" -s 15 -c 5 -o gpurun_out/${TAG}_sweeps $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest.log; cat gpurun_out/${TAG}_bench.json; tail -2 gpurun_out/${TAG}_bench.err
