@@ -96,7 +96,7 @@ struct Solid {
     // The sub-step kernels read the lists in ELL layout (entry kk of row s at [kk*ns + s]: coalesced
     // across the threads of a warp) together with static per-pair data of the reference
     // configuration computed once: x0_ij and weight(x0_ij).
-    int *len, *rlen;                 // row lengths
+    int *len, *rlen, *rsplit;        // row lengths; rsplit = number of transposed entries of rows j < s
     int *enbr, *ernbr;               // ELL neighbour ids (own rows / transposed rows)
     double *d0x, *d0y, *d0z, *w;     // own rows
     double *rd0x, *rd0y, *rd0z, *rw; // transposed: x0_js as row j computes it
@@ -639,14 +639,16 @@ __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double 
     const double ui[3] = {so.ux[s], so.uy[s], DIMS == 3 ? so.uz[s] : 0.0};
     double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     const int len = so.len[s];
+    // (unrolled so that the loads of four list entries are in flight together; the sum order is unchanged)
+#pragma unroll 4
     for (int kk = 0; kk < len; ++kk) {
         const size_t k = (size_t)kk * ns + s;
-        const int j = so.enbr[k];
-        const double d0[3] = {so.d0x[k], so.d0y[k], DIMS == 3 ? so.d0z[k] : 0.0};
+        const int j = __ldg(&so.enbr[k]);
+        const double d0[3] = {__ldg(&so.d0x[k]), __ldg(&so.d0y[k]), DIMS == 3 ? __ldg(&so.d0z[k]) : 0.0};
         const double uj[3] = {so.ux[j], so.uy[j], DIMS == 3 ? so.uz[j] : 0.0};
         double d[3];
         for (int a = 0; a < DIMS; ++a) d[a] = add(d0[a], sub(uj[a], ui[a])); // :2716
-        const double w = so.w[k];
+        const double w = __ldg(&so.w[k]);
         for (int a = 0; a < DIMS; ++a)
             for (int b = 0; b < DIMS; ++b) G[a][b] = add(G[a][b], mul(mul(w, d[a]), d0[b])); // :2726
     }
@@ -703,8 +705,8 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
     double v[3] = {so.vx[s], so.vy[s], so.vz[s]};
     auto scattered_from = [&](int kk, int j) { // row j lists s:  v_s -= invRho_s * (w P_j x0_js) * dt
         const size_t k = (size_t)kk * ns + s;
-        const double d0[3] = {so.rd0x[k], so.rd0y[k], DIMS == 3 ? so.rd0z[k] : 0.0};
-        const double w = so.rw[k];
+        const double d0[3] = {__ldg(&so.rd0x[k]), __ldg(&so.rd0y[k]), DIMS == 3 ? __ldg(&so.rd0z[k]) : 0.0};
+        const double w = __ldg(&so.rw[k]);
         for (int a = 0; a < DIMS; ++a) {
             double f = 0.0;
             for (int b = 0; b < DIMS; ++b) f = add(f, mul(MPHX_T(so.Pk, a, b, j, ns), d0[b]));
@@ -712,22 +714,19 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
             v[a] = sub(v[a], mul(mul(ir, f), edt)); // :2885
         }
     };
-    int kr = 0;
-    const int rlen = so.rlen[s];
-    for (; kr < rlen; ++kr) {
-        const int j = so.ernbr[(size_t)kr * ns + s];
-        if (j >= s) break;
-        scattered_from(kr, j);
-    }
+    const int rlen = so.rlen[s], rsplit = so.rsplit[s]; // transposed entries [0, rsplit) are rows j < s
+#pragma unroll 4
+    for (int kr = 0; kr < rsplit; ++kr) scattered_from(kr, __ldg(&so.ernbr[(size_t)kr * ns + s]));
     {
         double Pi[3][3];
         for (int a = 0; a < 3; ++a)
             for (int b = 0; b < 3; ++b) Pi[a][b] = (a < DIMS && b < DIMS) ? MPHX_T(so.Pk, a, b, s, ns) : 0.0;
         const int len = so.len[s];
+#pragma unroll 4
         for (int kk = 0; kk < len; ++kk) { // own row: v_s += invRho_s * (w P_s x0_sj) * dt
             const size_t q = (size_t)kk * ns + s;
-            const double d0[3] = {so.d0x[q], so.d0y[q], DIMS == 3 ? so.d0z[q] : 0.0};
-            const double w = so.w[q];
+            const double d0[3] = {__ldg(&so.d0x[q]), __ldg(&so.d0y[q]), DIMS == 3 ? __ldg(&so.d0z[q]) : 0.0};
+            const double w = __ldg(&so.w[q]);
             for (int a = 0; a < DIMS; ++a) {
                 double f = 0.0;
                 for (int b = 0; b < DIMS; ++b) f = add(f, mul(Pi[a][b], d0[b]));
@@ -736,7 +735,8 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
             }
         }
     }
-    for (; kr < rlen; ++kr) scattered_from(kr, so.ernbr[(size_t)kr * ns + s]);
+#pragma unroll 4
+    for (int kr = rsplit; kr < rlen; ++kr) scattered_from(kr, __ldg(&so.ernbr[(size_t)kr * ns + s]));
     double x[3] = {so.x[s], so.y[s], so.z[s]};
     // Acceleration of solids is 0 (:2892): v += 0*dt leaves v unchanged
     if (module != 0) {
@@ -778,6 +778,7 @@ __global__ void k_solid_pairs(Solid so, double W0, double W1, double W2, double 
     }
     so.len[s] = kk;
     kk = 0;
+    int split = 0;
     for (int c = so.roff[s]; c < so.roff[s + 1]; ++c, ++kk) {
         const int j = so.rnbr[c]; // row j lists s: x0_js = Mod(x0_s - x0_j ...) as row j computes it
         const size_t k = (size_t)kk * ns + s;
@@ -786,8 +787,10 @@ __global__ void k_solid_pairs(Solid so, double W0, double W1, double W2, double 
         so.ernbr[k] = j;
         so.rd0x[k] = a; so.rd0y[k] = b; so.rd0z[k] = cc;
         so.rw[k] = tl_weight<DIMS>(a, b, cc, radius, cw);
+        if (j < s) split = kk + 1; // (rows ascending: the entries of rows j < s come first)
     }
     so.rlen[s] = kk;
+    so.rsplit[s] = split;
 }
 
 // ------------------------------------------------------------------------------------------------

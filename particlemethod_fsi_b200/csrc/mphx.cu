@@ -619,7 +619,7 @@ static int init_solid(Ctx *c)
         double **pr[] = {&c->sol.rd0x, &c->sol.rd0y, &c->sol.rd0z, &c->sol.rw};
         for (double **q : pr) e |= c->alloc(q, (size_t)rmaxlen * ns);
         e |= c->alloc(&c->sol.enbr, (size_t)maxlen * ns); e |= c->alloc(&c->sol.ernbr, (size_t)rmaxlen * ns);
-        e |= c->alloc(&c->sol.len, (size_t)ns); e |= c->alloc(&c->sol.rlen, (size_t)ns);
+        e |= c->alloc(&c->sol.len, (size_t)ns); e |= c->alloc(&c->sol.rlen, (size_t)ns); e |= c->alloc(&c->sol.rsplit, (size_t)ns);
     }
     if (e) return MPHX_ERR_NOMEM;
     CK(cudaMemcpy(c->sol.off, off32.data(), sizeof(int) * ((size_t)ns + 1), cudaMemcpyHostToDevice));
