@@ -97,6 +97,7 @@ struct Solid {
     // across the threads of a warp) together with static per-pair data of the reference
     // configuration computed once: x0_ij and weight(x0_ij).
     int *len, *rlen, *rsplit;        // row lengths; rsplit = number of transposed entries of rows j < s
+    int *slot;                       // sorted slot of solid s in the current bucket order (written by the permute)
     int *enbr, *ernbr;               // ELL neighbour ids (own rows / transposed rows)
     double *d0x, *d0y, *d0z, *w;     // own rows
     double *rd0x, *rd0y, *rd0z, *rw; // transposed: x0_js as row j computes it
@@ -175,12 +176,17 @@ __device__ __forceinline__ void pack_particle(double *dst, double x, double y, d
     dst[6] = __longlong_as_double(((long long)real_type(type) << 32) | (long long)(unsigned)id);
 }
 
+// `only` != nullptr: the listed slots (the solids, handled later than the rest so that their sub-steps can
+// overlap the start of the next step); skip_solids: everything but the solids.
 __global__ void k_prestep(int n, Particles p, Solid sol, GridDesc g, WallMotion wm, int do_wrap,
-                          int *__restrict__ cellCount, int *__restrict__ slot, SlabSend snd)
+                          int *__restrict__ cellCount, int *__restrict__ slot, SlabSend snd, const int *__restrict__ only,
+                          int skip_solids)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t0 >= n) return;
+    const int i = only ? only[t0] : t0;
     const int t = p.type[i];
+    if (skip_solids && is_structure_type(t) && !(t & kGhost)) return;
     if (t & kGhost) { // last step's halo copy
         const int k = g.ncells + 1;
         p.key[i] = k;
@@ -418,7 +424,8 @@ __global__ void k_scatter_index(int n, const int *__restrict__ key, const int *_
 // K4: permute the SoA into bucket order; inside a bucket particles are ordered by original id, which
 // makes the layout (and therefore every floating-point sum) independent of atomic arrival order.
 __global__ void k_permute(int n, Particles src, Particles dst, const int *__restrict__ cellStart,
-                          const int *__restrict__ tmpIdx, GridDesc g, int *__restrict__ where)
+                          const int *__restrict__ tmpIdx, GridDesc g, int *__restrict__ where, int *__restrict__ solid_slot,
+                          int solid_base)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n || q >= cellStart[g.ncells + 1]) return; // the dead bucket (last) is dropped
@@ -438,6 +445,7 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
     where[s] = q;
     const double x = src.x[s], y = src.y[s], z = src.z[s];
     const int t = src.type[s];
+    if (solid_slot && is_structure_type(t) && !(t & kGhost)) solid_slot[src.id[s] - solid_base] = q; // sorted slot of each solid
     dst.x[q] = x; dst.y[q] = y; dst.z[q] = z;
     dst.type[q] = t; dst.id[q] = src.id[s]; dst.key[q] = k;
     const double icw = 1.0 / g.cellw;
@@ -797,7 +805,7 @@ __global__ void k_solid_pairs(Solid so, double W0, double W1, double W2, double 
 // upload / download helpers (AoS original order <-> sorted SoA)
 // host arrays (global, original order AoS) -> the slots this context holds; ids == nullptr: all, in order
 __global__ void k_upload_split(int n, const int *__restrict__ ids, const int *__restrict__ type, const double *__restrict__ x3,
-                               const double *__restrict__ v3, Particles p)
+                               const double *__restrict__ v3, Particles p, int *__restrict__ solid_slot, int solid_base)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -806,6 +814,7 @@ __global__ void k_upload_split(int n, const int *__restrict__ ids, const int *__
     p.x[i] = x3[o]; p.y[i] = x3[o + 1]; p.z[i] = x3[o + 2];
     p.vx[i] = v3[o]; p.vy[i] = v3[o + 1]; p.vz[i] = v3[o + 2];
     p.type[i] = type[id]; p.id[i] = id; p.key[i] = 0;
+    if (solid_slot && is_structure_type(type[id])) solid_slot[id - solid_base] = i;
 }
 // the solids in their reference configuration as a particle set (for the initial-list build)
 __global__ void k_solid_reference_particles(Solid so, Particles p)

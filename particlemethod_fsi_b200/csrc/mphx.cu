@@ -84,6 +84,14 @@ struct Ctx {
     PairList pl{};         // pass 1 -> pass 2 neighbour list (nbr == nullptr: disabled, pass 2 sweeps again)
     int list_cap = -1;     // list slots per particle (-1: default by dimension, 0: no list)
     bool filter2 = true;   // build the lists two particles per thread (k_filter2, sweep_pair.cuh)
+    // the solid sub-steps only need the solids' share of pass 2: they run on a second stream while the
+    // fluid's share (FP64 / issue bound; the sub-steps are HBM bound) is still being computed
+    bool overlap_solid = true;
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_solid_ready = nullptr, ev_solid_done = nullptr;
+    bool solids_pending = false;  // sub-steps enqueued on `side`, not yet joined by the main stream
+    WallMotion held_wm{};         // arguments of the deferred solid share of the pre-step
+    int held_wrap = 0;
     std::vector<void *> allocs;
 
     // phase timers (src/main.cpp:695-700 split)
@@ -106,6 +114,14 @@ struct Ctx {
     }
 };
 
+#define LAUNCH_ON(ctx, strm, kernel, grid, block, ...)                                             \
+    do {                                                                                           \
+        const int grid_ = (grid);                                                                  \
+        if (grid_ > 0) {                                                                           \
+            kernel<<<grid_, (block), 0, (strm)>>>(__VA_ARGS__);                                     \
+            ++(ctx)->launches;                                                                     \
+        }                                                                                          \
+    } while (0)
 #define LAUNCH(ctx, kernel, grid, block, ...)                                                      \
     do {                                                                                           \
         const int grid_ = (grid);                                                                  \
@@ -228,6 +244,18 @@ static int setup_constants(Ctx *c)
     return MPHX_OK;
 }
 
+// The solid sub-steps run on a second stream and are joined as late as possible: they overlap the fluid's
+// share of pass 2 (single context) and the pre-step / migration / halo phases of the next step.
+static bool defer_solids(const Ctx *c) { return c->overlap_solid && c->ns > 0 && c->side != nullptr && c->pl.nbr != nullptr; }
+static int join_solids(Ctx *c)
+{
+    if (c->solids_pending) {
+        CK(cudaStreamWaitEvent(c->stream, c->ev_solid_done, 0));
+        c->solids_pending = false;
+    }
+    return MPHX_OK;
+}
+
 // ---- bucket rebuild: K1 key/count, K2 scan, K3 scatter, K4 permute -------------------------------
 static int stage_prestep(Ctx *c, bool prestep_motion, SlabSend snd)
 {
@@ -246,7 +274,9 @@ static int stage_prestep(Ctx *c, bool prestep_motion, SlabSend snd)
                 for (int e = 0; e < 3; ++e) wm.R[t][d][e] = c->c.wall_rotation[t][d][e];
             }
     if (n > 0)
-        LAUNCH(c, k_prestep, nblk(n), kBlock, n, c->S, c->sol, c->grid, wm, prestep_motion ? 1 : 0, c->cellCount, c->slot, snd);
+        LAUNCH(c, k_prestep, nblk(n), kBlock, n, c->S, c->sol, c->grid, wm, prestep_motion ? 1 : 0, c->cellCount, c->slot, snd,
+               (const int *)nullptr, defer_solids(c) ? 1 : 0);
+    c->held_wm = wm; c->held_wrap = prestep_motion ? 1 : 0;
     if (prestep_motion) // :3066-3070 (host mirror of the wall centres)
         for (int t = 4; t < kTypeCount; ++t)
             for (int d = 0; d < 3; ++d) c->wall_center[t][d] += c->p.wall_velocity[t][d] * c->p.dt;
@@ -258,13 +288,20 @@ static int stage_prestep(Ctx *c, bool prestep_motion, SlabSend snd)
 static int stage_sort(Ctx *c)
 {
     const int n = c->n;
+    if (defer_solids(c)) { // the solids' share of the pre-step, once their sub-steps have finished
+        int rc = join_solids(c);
+        if (rc) return rc;
+        SlabSend none{};
+        LAUNCH(c, k_prestep, nblk(c->ns), kBlock, c->ns, c->S, c->sol, c->grid, c->held_wm, c->held_wrap, c->cellCount, c->slot, none,
+               (const int *)c->sol.slot, 0);
+    }
     const int nc = c->grid.ncells + 2; // + parked + dead buckets
     LAUNCH(c, k_scan_reduce, c->scan_blocks, kScanThreads, c->cellCount, nc, c->blockSums);
     LAUNCH(c, k_scan_top, 1, kScanThreads, c->blockSums, c->scan_blocks);
     LAUNCH(c, k_scan_apply, c->scan_blocks, kScanThreads, c->cellCount, nc, c->blockSums, c->cellStart);
     if (n > 0) {
         LAUNCH(c, k_scatter_index, nblk(n), kBlock, n, c->S.key, c->slot, c->cellStart, c->tmpIdx);
-        LAUNCH(c, k_permute, nblk(n), kBlock, n, c->S, c->T, c->cellStart, c->tmpIdx, c->grid, c->where);
+        LAUNCH(c, k_permute, nblk(n), kBlock, n, c->S, c->T, c->cellStart, c->tmpIdx, c->grid, c->where, c->sol.slot, c->sol.sb);
     }
     std::swap(c->S, c->T);
     c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
@@ -352,6 +389,9 @@ static int run_pass1(Ctx *c, bool timed = false)
     return MPHX_OK;
 }
 
+// single context with solids and a candidate list: pass 2 is split so that the sub-steps can overlap it
+static bool solid_split(const Ctx *c) { return defer_solids(c) && !c->slab; }
+
 static int run_pass2(Ctx *c, double *solbuf = nullptr)
 {
     const int n = c->n;
@@ -359,14 +399,27 @@ static int run_pass2(Ctx *c, double *solbuf = nullptr)
         const float f2 = sweep_filter2(c);
         const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
         const int vblocks = nblk(n, kSweepThreads);
-#define P2(D, ST, LIST) LAUNCH(c, (k_pass2_v3<D, ST, LIST>), SWEEP_GRID(LIST), kSweepThreads, vblocks, n, c->S, c->cellStart, c->grid, c->phys, f2, \
-                         batch, c->P, c->PA, c->gcx, c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, \
-                         c->fy, c->fz, c->ax, c->ay, c->az, c->sol, solbuf, c->pl)
-#define P2D(ST, LIST) do { if (c->p.dim == 3) P2(3, ST, LIST); else P2(2, ST, LIST); } while (0)
-        if (c->pl.nbr) { // list traversal, then the sweep variant for particles whose list overflowed (normally none)
-            if (c->surface_tension) P2D(true, true); else P2D(false, true);
+#define P2(D, ST, LIST, GRID, SUB) LAUNCH(c, (k_pass2_v3<D, ST, LIST>), GRID, kSweepThreads, vblocks, n, c->S, c->cellStart, c->grid, \
+                         c->phys, f2, batch, c->P, c->PA, c->gcx, c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, \
+                         c->fy, c->fz, c->ax, c->ay, c->az, c->sol, solbuf, c->pl, SUB)
+#define P2D(ST, LIST, GRID, SUB) do { if (c->p.dim == 3) P2(3, ST, LIST, GRID, SUB); else P2(2, ST, LIST, GRID, SUB); } while (0)
+#define P2ALL(GRIDL, SUB) do { \
+        if (c->pl.nbr) { /* list traversal, then the sweep variant for particles whose list overflowed (normally none) */ \
+            if (c->surface_tension) P2D(true, true, GRIDL, SUB); else P2D(false, true, GRIDL, SUB); \
+        } \
+        if (c->surface_tension) P2D(true, false, SWEEP_GRID(false), SUB); else P2D(false, false, SWEEP_GRID(false), SUB); \
+    } while (0)
+        if (solid_split(c)) {
+            // the solids' share first (a few blocks), so that the sub-steps can start; then everything else
+            const Subset solids{c->sol.slot, c->ns, 0}, rest{nullptr, 0, 1};
+            P2ALL(nblk(c->ns, kSweepThreads), solids);
+            CK(cudaEventRecord(c->ev_solid_ready, c->stream));
+            P2ALL(vblocks, rest);
+        } else {
+            const Subset all{nullptr, 0, 0};
+            P2ALL(vblocks, all);
         }
-        if (c->surface_tension) P2D(true, false); else P2D(false, false);
+#undef P2ALL
 #undef P2D
 #undef P2
     }
@@ -379,7 +432,7 @@ static int run_pass2(Ctx *c, double *solbuf = nullptr)
     return MPHX_OK;
 }
 
-static int run_solid_substeps(Ctx *c)
+static int run_solid_substeps(Ctx *c, cudaStream_t strm)
 {
     if (c->ns <= 0) return MPHX_OK;
     const int substeps = (int)(c->p.dt / c->p.elastic_dt + 0.5); // :653
@@ -389,12 +442,12 @@ static int run_solid_substeps(Ctx *c)
     const int dbl = (c->p.ref_compat & MPHX_COMPAT_DOUBLE_UPDATE) ? 1 : 0;
     for (int s = 0; s < substeps; ++s) {
         if (c->p.dim == 3) {
-            LAUNCH(c, k_solid_pass1<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw);
-            LAUNCH(c, k_solid_pass2<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw,
+            LAUNCH_ON(c, strm, k_solid_pass1<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw);
+            LAUNCH_ON(c, strm, k_solid_pass2<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw,
                    c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);
         } else {
-            LAUNCH(c, k_solid_pass1<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw);
-            LAUNCH(c, k_solid_pass2<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw,
+            LAUNCH_ON(c, strm, k_solid_pass1<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw);
+            LAUNCH_ON(c, strm, k_solid_pass2<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw,
                    c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);
         }
     }
@@ -437,7 +490,12 @@ static int one_step(Ctx *c, bool fluid_only)
     if ((rc = run_pass2(c))) return rc;             // force sums, gravity, interface, acceleration, convection
     timer_mark(c);
     if (!fluid_only) {
-        if ((rc = run_solid_substeps(c))) return rc;
+        if (solid_split(c)) { // sub-steps on the second stream: joined by the next bucket sort (or by any reader)
+            CK(cudaStreamWaitEvent(c->side, c->ev_solid_ready, 0));
+            if ((rc = run_solid_substeps(c, c->side))) return rc;
+            CK(cudaEventRecord(c->ev_solid_done, c->side));
+            c->solids_pending = true;
+        } else if ((rc = run_solid_substeps(c, c->stream))) return rc;
         c->time += c->p.dt; // :685
         ++c->steps_done;
     }
@@ -530,10 +588,11 @@ static int init_solid(Ctx *c)
     e |= talloc(&c->slot, ns); e |= talloc(&c->tmpIdx, ns); e |= talloc(&c->where, ns);
     if (e) { tfree(); *c = saved; return MPHX_ERR_NOMEM; }
     c->scan_blocks = sb_blocks;
-    c->S = A; c->T = B; c->n = ns; c->slab = false;
+    c->S = A; c->T = B; c->n = ns; c->slab = false; c->overlap_solid = false; // (restored with the rest of the context)
     LAUNCH(c, k_solid_reference_particles, nblk(ns), kBlock, c->sol, c->S);
     // k_prestep reads a solid's position from the solid arrays: point them at the reference positions
     c->sol.x = saved.sol.x0; c->sol.y = saved.sol.y0; c->sol.z = saved.sol.z0;
+    c->sol.slot = nullptr; // (the permute of this temporary set must not overwrite the solids' real slots)
     rc = rebuild_buckets(c, false);
     c->sol = saved.sol;
     if (rc) { tfree(); *c = saved; return rc; }
@@ -740,6 +799,15 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
     if (const char *e = std::getenv("MPHX_LIST_CAP")) c->list_cap = std::max(0, std::atoi(e)); // 0: no list, fused sweeps
     if (const char *e = std::getenv("MPHX_FILTER2")) c->filter2 = std::atoi(e) != 0;           // 0: one particle per thread
     for (int k = 0; k < 2; ++k) cudaEventCreate(&c->tev[k]);
+    if (const char *e = std::getenv("MPHX_OVERLAP_SOLID")) c->overlap_solid = std::atoi(e) != 0;
+    {   // highest priority: the few blocks of a sub-step kernel must get SM slots as pass-2 blocks retire,
+        // not after the whole pass-2 grid has been issued
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, hi) != cudaSuccess) c->side = nullptr;
+    }
+    cudaEventCreateWithFlags(&c->ev_solid_ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_solid_done, cudaEventDisableTiming);
     *out = reinterpret_cast<mphx_ctx *>(c);
     return MPHX_OK;
 }
@@ -752,6 +820,9 @@ void mphx_destroy(mphx_ctx *ctx)
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) if (c->tev[k]) cudaEventDestroy(c->tev[k]);
+    if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+    if (c->ev_solid_ready) cudaEventDestroy(c->ev_solid_ready);
+    if (c->ev_solid_done) cudaEventDestroy(c->ev_solid_done);
     for (void *q : c->allocs) cudaFree(q);
     if (c->stream && !c->external_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -765,6 +836,7 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
     if (c->uploaded && n != c->n_global) return MPHX_ERR_INVALID; // re-upload must keep the particle count
     if (c->uploaded && c->slab) { set_last_error("re-upload is not supported on a slab context"); return MPHX_ERR_UNSUPPORTED; }
     CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
     for (int i = 0; i < n; ++i)
         if (property[i] < 0 || property[i] >= kTypeCount) { set_last_error("particle type outside 0..5"); return MPHX_ERR_INVALID; }
     int r[6];
@@ -841,7 +913,7 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         for (double **q : sv) e |= c->alloc(q, ns);
         double **st[] = {&so.Linv, &so.Fm, &so.E, &so.S, &so.Pk};
         for (double **q : st) e |= c->alloc(q, 9 * ns);
-        e |= c->alloc(&so.type, ns);
+        e |= c->alloc(&so.type, ns); e |= c->alloc(&so.slot, ns);
         if (e) return MPHX_ERR_NOMEM;
         CK(cudaMemcpy(c->d_inv_density, c->phys.inv_density, sizeof(double) * kTypeCount, cudaMemcpyHostToDevice));
         CK(cudaMemsetAsync(c->d_err, 0, sizeof(int) * 4, c->stream));
@@ -865,7 +937,7 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         CK(cudaMalloc(&d_ids, sizeof(int) * (size_t)std::max(nloc, 1)));
         CK(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * (size_t)nloc, cudaMemcpyHostToDevice, c->stream));
     }
-    if (nloc > 0) LAUNCH(c, k_upload_split, nblk(nloc), kBlock, nloc, d_ids, d_t, d_x, d_v, c->S);
+    if (nloc > 0) LAUNCH(c, k_upload_split, nblk(nloc), kBlock, nloc, d_ids, d_t, d_x, d_v, c->S, c->sol.slot, c->sol.sb);
     if (c->ns > 0) LAUNCH(c, k_solid_upload, nblk(c->ns), kBlock, c->sol, d_t, d_x, d_x0, d_v);
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
@@ -889,6 +961,7 @@ int mphx_upload_state(mphx_ctx *ctx, const double *position, const double *veloc
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !c->inited || !position || !velocity) return MPHX_ERR_INVALID;
     CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
     const size_t N = (size_t)c->n_global;
     if (!c->stage3a && c->alloc(&c->stage3a, 3 * N)) return MPHX_ERR_NOMEM;
     if (!c->stage3b && c->alloc(&c->stage3b, 3 * N)) return MPHX_ERR_NOMEM;
@@ -950,6 +1023,7 @@ int mphx_timed_steps(mphx_ctx *ctx, int nsteps, double *elapsed_ms)
         int rc = one_step(c, false);
         if (rc) return rc;
     }
+    { int jrc = join_solids(c); if (jrc) return jrc; } // the timed region ends when the last sub-steps have finished
     CK(cudaEventRecord(c->tev[1], c->stream));
     CK(cudaEventSynchronize(c->tev[1]));
     float ms = 0.f;
@@ -983,6 +1057,7 @@ int mphx_sync(mphx_ctx *ctx)
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c) return MPHX_ERR_INVALID;
     CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
     return MPHX_OK;
@@ -1003,6 +1078,7 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !v || !c->uploaded) return MPHX_ERR_INVALID;
     CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
     // Arrays are in ORIGINAL particle order and sized for the whole case.  A slab context fills the
     // entries of the particles it owns (solids: slab 0 only) and zeros elsewhere, so the caller can
     // combine the slabs with a plain sum.
@@ -1142,6 +1218,7 @@ int mphx_download_owned(mphx_ctx *ctx, int capacity, int *ids, double *position,
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !c->inited || !ids || !position || !velocity || !count) return MPHX_ERR_INVALID;
     CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
     int rc = owned_prepare(c);
     if (rc) return rc;
     const int n = c->n;
@@ -1175,6 +1252,7 @@ int mphx_upload_owned(mphx_ctx *ctx, int count, const int *ids, const double *po
         return MPHX_ERR_INVALID;
     }
     CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
     CK(cudaMemcpyAsync(c->own_ids, ids, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->own_x, position, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->own_v, velocity, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, c->stream));

@@ -260,6 +260,14 @@ __device__ __forceinline__ void sweep(SweepShared &sm, const GridDesc &g, const 
     }
 }
 
+// Restriction of a pass-2 launch: only the sorted slots listed (the solids), or everything but the solids.
+// Lets the solid sub-steps start -- on a second stream -- as soon as the solids' share of pass 2 is done.
+struct Subset {
+    const int *slots; // nullptr: thread t handles particle t
+    int count;
+    int skip_solids;
+};
+
 // Candidate list of one step: written by k_filter, traversed by pass 1 and pass 2 (same step, same
 // positions).  It holds the survivors of the conservative fp32 filter (a superset of every exact
 // cut-off test, possibly including the particle itself); the physics kernels apply the exact fp64
@@ -536,17 +544,20 @@ pass2_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
            double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ovx, double *__restrict__ ovy,
            double *__restrict__ ovz, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
            double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az, Solid sol,
-           double *__restrict__ solbuf, PairList pl)
+           double *__restrict__ solbuf, PairList pl, Subset sub)
 {
     __shared__ double s_visc[kTypeCount][kTypeCount];
     // pair viscosity table with the constant factors of the viscous term folded in:
     // c_d mu_ij V * (-cdv)   (:2505-2512, dwij = -dwvdr)
     for (int e = threadIdx.x; e < kTypeCount * kTypeCount; e += blockDim.x)
         s_visc[e / kTypeCount][e % kTypeCount] = -ph.viscpair[e / kTypeCount][e % kTypeCount] * ph.cdv;
-    const int i0 = vblock * blockDim.x + threadIdx.x;
+    const int t0 = vblock * blockDim.x + threadIdx.x;
+    const int i0 = sub.slots ? (t0 < sub.count ? sub.slots[t0] : n) : t0; // (a listed subset, or particle t0)
     const int i = i0 < n ? i0 : n - 1;
+    const int tflag = p.type[i], ti = real_type(tflag), keyi = p.key[i];
+    const bool solid_i = is_structure_type(ti);
     int mycount = 0;
-    bool mine = i0 < n;
+    bool mine = i0 < n && !(sub.skip_solids && solid_i);
     if (pl.count) {
         mycount = pl.count[i];
         mine = mine && (LIST ? mycount <= pl.L : mycount > pl.L);
@@ -555,8 +566,6 @@ pass2_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
     __syncthreads();
     const double xi = p.x[i], yi = p.y[i], zi = p.z[i];
     const double vxi = p.vx[i], vyi = p.vy[i], vzi = p.vz[i];
-    const int tflag = p.type[i], ti = real_type(tflag), keyi = p.key[i];
-    const bool solid_i = is_structure_type(ti);
     bool active = i0 < n && keyi < g.ncells && !(tflag & kGhost);
     if (g.slab && solid_i && active) active = column_owned(g, key_column(g, keyi));
     const double Pi = P[i];
@@ -720,16 +729,16 @@ k_pass2_v3(int vblocks, int n, Particles p, const int *__restrict__ cellStart, G
            double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ovx, double *__restrict__ ovy,
            double *__restrict__ ovz, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
            double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az, Solid sol,
-           double *__restrict__ solbuf, PairList pl)
+           double *__restrict__ solbuf, PairList pl, Subset sub)
 {
     if constexpr (LIST) {
         pass2_block<DIM, ST, true>(blockIdx.x, n, p, cellStart, g, ph, filt2, batch, P, PA, gcx, gcy, gcz, ox, oy, oz, ovx, ovy, ovz, fx, fy,
-                                   fz, ax, ay, az, sol, solbuf, pl);
+                                   fz, ax, ay, az, sol, solbuf, pl, sub);
     } else {
         if (pl.count && *reinterpret_cast<volatile const int *>(pl.flags) == 0) return; // no list overflowed in this step
         for (int vb = blockIdx.x; vb < vblocks; vb += gridDim.x) {
             pass2_block<DIM, ST, false>(vb, n, p, cellStart, g, ph, filt2, batch, P, PA, gcx, gcy, gcz, ox, oy, oz, ovx, ovy, ovz, fx, fy,
-                                        fz, ax, ay, az, sol, solbuf, pl);
+                                        fz, ax, ay, az, sol, solbuf, pl, sub);
             __syncthreads();
         }
     }
