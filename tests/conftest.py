@@ -16,7 +16,8 @@ def pytest_configure(config):
 
 def _ensure_built():
     so = os.path.join(ROOT, "particlemethod_fsi_b200", "libmphx.so")
-    if not os.path.exists(so):
+    exe = os.path.join(ROOT, "particlemethod_fsi_b200", "Mph_Elastic_Explicit")
+    if not (os.path.exists(so) and os.path.exists(exe)):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "particlemethod_fsi_b200", "csrc")])
     if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
         subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
