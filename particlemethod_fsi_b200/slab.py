@@ -255,6 +255,9 @@ class SlabSolver:
             solver._ck("mphx_init", self.lib.mphx_init(s.ctx))
             self.slabs.append(s)
         self._per_col = per_col
+        # host mirror of the wall centres (src/main.cpp:3066-3070: advanced every step), carried across rebalance()
+        self._wall_center = [[case.params.wall_center[t][d] for d in range(3)] for t in range(abi.TYPE_COUNT)]
+        self._msg_capacity_arg, self._capacity_arg = None, capacity
 
     def close(self):
         for s in self.slabs:
@@ -316,6 +319,41 @@ class SlabSolver:
             # E: solid sub-steps
             for s in self.slabs:
                 ck("mphx_slab_finish", lib.mphx_slab_finish(s.ctx, self._ptr(s.solbuf)))
+            p = self.case.params
+            for t in range(4, abi.TYPE_COUNT):
+                for d in range(3):
+                    self._wall_center[t][d] += p.wall_velocity[t][d] * p.dt
+
+    def imbalance(self) -> float:
+        """largest / mean number of particle slots held by a slab (1.0 = perfectly balanced)"""
+        held = [i["held"] for i in self.info()]
+        if isinstance(self.tr, DistTransport) and self.tr.world > 1:
+            t = self.torch.tensor([float(held[0])], dtype=self.torch.float64, device=self.device)
+            mx = self.tr.allreduce_max_float(float(held[0]), self.device)
+            self.tr.allreduce_sum([t])
+            return mx / (t.item() / self.tr.world)
+        return max(held) / (sum(held) / len(held))
+
+    def rebalance(self):
+        """Re-cut the slabs on the CURRENT particle distribution (a dam break empties some
+        slabs and fills others).  The state is gathered through the hosts and the slab contexts are rebuilt
+        from it: a coarse operation meant for every few hundred steps.  The continuation is bit-identical
+        (same in-bucket order, same sums); Time and the wall centres carry over."""
+        from . import cases
+        full = self.download("position", "velocity")
+        case = self.case
+        p = case.params.copy()
+        p.time0 = self.time
+        for t in range(abi.TYPE_COUNT):
+            for d in range(3):
+                p.wall_center[t][d] = self._wall_center[t][d]
+        new_case = cases.Case(case.name, p, case.rc, case.property, full["position"], case.initial_position, full["velocity"],
+                              getattr(case, "cuboids", []))
+        tr, device, cap = self.tr, self.device, self._capacity_arg
+        old = self.partition
+        self.close()
+        self.__init__(new_case, tr, device=device, capacity=cap)
+        return old, self.partition
 
     def sync(self):
         self.torch.cuda.synchronize(self.device)
