@@ -450,7 +450,14 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
     dst.type[q] = t; dst.id[q] = src.id[s]; dst.key[q] = k;
     const double icw = 1.0 / g.cellw;
     float *pfw = reinterpret_cast<float *>(dst.pf + (q >> 1)) + (q & 1); // x0 x1 y0 y1 z0 z1
-    pfw[0] = (float)((x - g.mn[0]) * icw); pfw[2] = (float)((y - g.mn[1]) * icw); pfw[4] = (float)((z - g.mn[2]) * icw);
+    // filter coordinates in bucket units, consistent with the (periodically wrapped) bucket index: a
+    // position that has not been wrapped into the box yet (input of the very first bucket build, which
+    // the reference does before its first calculatePeriodicBoundary) is filtered at its image in the box
+    double fx = (x - g.mn[0]) * icw, fy = (y - g.mn[1]) * icw, fz = (z - g.mn[2]) * icw;
+    if (!g.slab) fx = fx < 0.0 ? fx + g.nx : (fx >= g.nx ? fx - g.nx : fx);
+    fy = fy < 0.0 ? fy + g.ny : (fy >= g.ny ? fy - g.ny : fy);
+    fz = fz < 0.0 ? fz + g.nz : (fz >= g.nz ? fz - g.nz : fz);
+    pfw[0] = (float)fx; pfw[2] = (float)fy; pfw[4] = (float)fz;
     const double vx = src.vx[s], vy = src.vy[s], vz = src.vz[s];
     dst.vx[q] = vx; dst.vy[q] = vy; dst.vz[q] = vz;
     Rec ra, rb;
