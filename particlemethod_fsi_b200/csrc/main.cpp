@@ -10,12 +10,18 @@
 // here they are the optional 7th/8th arguments or MPHX_DIM / MPHX_MODULE (defaults: 2, bar -- the
 // shipped configuration).  `nthreads` is accepted and ignored (there is no CPU path).
 #include <chrono>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mphx.h"
@@ -41,6 +47,60 @@ static void die(const char *what, int rc)
     log_printf("mphx: %s failed: %s (%s)\n", what, mphx_strerror(rc), mphx_last_error());
     exit(1);
 }
+
+// the .prof / .vtk text is formatted and written by a background thread from a snapshot of
+// the downloaded arrays while the GPU keeps stepping (at 10^7 particles the ASCII writers of the reference,
+// src/main.cpp:957-1189, take far longer than a step).  One job may wait while one is being written; a
+// third output request blocks the main loop (bounded memory).  Same writer functions, same bytes, same
+// file order.  MPHX_SYNC_IO=1 writes in the main thread instead.
+class Writer {
+  public:
+    explicit Writer(bool async) : async_(async) { if (async_) th_ = std::thread([this] { run(); }); }
+    ~Writer() { finish(); }
+    void submit(std::function<void()> job)
+    {
+        if (!async_) { job(); return; }
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [this] { return q_.size() < 1; });
+        q_.push_back(std::move(job));
+        cv_.notify_all();
+    }
+    void finish()
+    {
+        if (!async_ || !th_.joinable()) return;
+        { std::lock_guard<std::mutex> lk(m_); done_ = true; }
+        cv_.notify_all();
+        th_.join();
+    }
+
+  private:
+    void run()
+    {
+        for (;;) {
+            std::function<void()> job;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [this] { return done_ || !q_.empty(); });
+                if (q_.empty()) return;
+                job = std::move(q_.front());
+                q_.pop_front();
+                cv_.notify_all();
+            }
+            job();
+        }
+    }
+    bool async_, done_ = false;
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> q_;
+};
+
+// a snapshot of everything one output file needs (the writer thread owns it)
+struct Snapshot {
+    std::vector<int> property, nbc, inbc;
+    std::vector<double> position, velocity, force, accel, stress, strain;
+};
 
 static int parse_module(const char *s)
 {
@@ -104,25 +164,39 @@ int main(int argc, char *argv[])
     mphx_set_timing(ctx, 1);
 
     const size_t N = (size_t)n;
-    std::vector<double> force(3 * N), accel(3 * N), stress(9 * N), strain(9 * N);
-    std::vector<int> nbc(N), inbc(N);
-    auto download_state = [&]() {
+    Writer writer(!(getenv("MPHX_SYNC_IO") && atoi(getenv("MPHX_SYNC_IO")) != 0));
+    auto write_prof = [&](const std::string &fn, double time) { // state BEFORE the step (Q8)
+        auto snap = std::make_shared<Snapshot>();
+        snap->position.resize(3 * N); snap->velocity.resize(3 * N);
         mphx_host_views v;
         memset(&v, 0, sizeof(v));
-        v.position = position;
-        v.velocity = velocity;
+        v.position = snap->position.data();
+        v.velocity = snap->velocity.data();
         int e = mphx_download(ctx, &v);
         if (e) die("mphx_download", e);
+        writer.submit([=, &p]() {
+            int e2 = mphx_write_prof_file(fn.c_str(), time, &p, n, property, snap->position.data(), initial_position, snap->velocity.data());
+            if (e2) die("writeProfFile", e2);
+        });
     };
-    auto write_vtk = [&](const char *fn) {
+    auto write_vtk = [&](const std::string &fn) {
+        auto snap = std::make_shared<Snapshot>();
+        snap->property.resize(N); snap->nbc.resize(N); snap->inbc.resize(N);
+        snap->position.resize(3 * N); snap->velocity.resize(3 * N); snap->force.resize(3 * N); snap->accel.resize(3 * N);
+        snap->stress.resize(9 * N); snap->strain.resize(9 * N);
         mphx_host_views v;
         memset(&v, 0, sizeof(v));
-        v.property = property; v.position = position; v.velocity = velocity;
-        v.force = force.data(); v.acceleration = accel.data(); v.stress = stress.data(); v.strain = strain.data();
-        v.neighbor_count = nbc.data(); v.initial_structure_neighbor_count = inbc.data();
+        v.property = snap->property.data(); v.position = snap->position.data(); v.velocity = snap->velocity.data();
+        v.force = snap->force.data(); v.acceleration = snap->accel.data(); v.stress = snap->stress.data(); v.strain = snap->strain.data();
+        v.neighbor_count = snap->nbc.data(); v.initial_structure_neighbor_count = snap->inbc.data();
         int e = mphx_download(ctx, &v);
         if (e) die("mphx_download", e);
-        if ((e = mphx_write_vtk_file(fn, n, initial_position, &v))) die("writeVtkFile", e);
+        writer.submit([=]() {
+            mphx_host_views w = v; // (the pointers stay valid: the snapshot lives as long as this job)
+            (void)snap;
+            int e2 = mphx_write_vtk_file(fn.c_str(), n, initial_position, &w);
+            if (e2) die("writeVtkFile", e2);
+        });
     };
     write_vtk("output.vtk"); // :572
     {
@@ -140,9 +214,7 @@ int main(int argc, char *argv[])
         if (Time + 1.0e-5 * Dt >= OutputNext) { // :583-589
             char filename[2048];
             snprintf(filename, sizeof(filename), proffilename.c_str(), iStep);
-            download_state();
-            if ((rc = mphx_write_prof_file(filename, Time, &p, n, property, position, initial_position, velocity)))
-                die("writeProfFile", rc);
+            write_prof(filename, Time);
             log_printf("@ Prof Output Time : %e\n", Time);
             OutputNext += rc_.output_interval;
         }
@@ -162,6 +234,7 @@ int main(int argc, char *argv[])
         iStep++;
     }
     if ((rc = mphx_sync(ctx))) die("mphx_sync", rc);
+    writer.finish(); // every output file is complete before the timers are logged
     {
         double t1 = now(); sStep += t1 - tFrom;
         double ms[4] = {0, 0, 0, 0};

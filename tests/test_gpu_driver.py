@@ -28,8 +28,9 @@ def _numbers(txt):
     return np.array(out)
 
 
+@pytest.mark.parametrize("sync_io", ["0", "1"])   # background writer thread (default) / writes in the main thread
 @pytest.mark.parametrize("name,dim,module", [("tiny2d", "2", "dam"), ("tiny3d", "3", "dam")])
-def test_driver_outputs_match_reference_cli(name, dim, module, tmp_path):
+def test_driver_outputs_match_reference_cli(name, dim, module, sync_io, tmp_path):
     c = getattr(cases, name)()
     c.rc.end_time = 3.5 * c.params.dt
     c.rc.output_interval = 2.0 * c.params.dt
@@ -37,7 +38,7 @@ def test_driver_outputs_match_reference_cli(name, dim, module, tmp_path):
     cases.write_grid_file(str(tmp_path / "c.grid"), c)
     cases.write_data_file(str(tmp_path / "t.data"), c.params, c.rc)
     r = subprocess.run([EXE, "t.data", "c.grid", "t%03d.prof", "t%03d.vtk", "t.log", "4", dim, module],
-                       cwd=tmp_path, capture_output=True, text=True)
+                       cwd=tmp_path, capture_output=True, text=True, env=dict(os.environ, MPHX_SYNC_IO=sync_io), timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     produced = sorted(f for f in os.listdir(tmp_path) if f.endswith((".prof", ".vtk")))
     assert produced == ["output.vtk", "t000.prof", "t000.vtk", "t002.prof", "t003.vtk"]   # quirk Q8 naming
