@@ -207,10 +207,20 @@ def run_mphx(args):
     ms = s.timed_steps(K)
     clocks = sampler.stop()
     phase = s.timers_ms()
-    kms = s.kernel_timers_ms()          # [rebuild, k_filter, pass 1 (list), pass 2 (list), solid sub-steps]
     s.set_timing(False)
     launches = s.launch_count - l0
     value = n * K / (ms * 1e-3)
+    # per-kernel durations for the roofline: a few more steps with the solid sub-steps serialised on the
+    # main stream (in the timed region above they overlap pass 2 on a second stream, so an event pair around
+    # pass 2 would time both)
+    KK = max(3, min(K, 5))
+    s.set_overlap(False)
+    s.step(1, sync=True)
+    s.set_timing(True)
+    s.step(KK, sync=True)
+    kms = [t * K / KK for t in s.kernel_timers_ms()]   # [rebuild, k_filter, pass 1, pass 2, solid]; scaled to K steps
+    s.set_timing(False)
+    s.set_overlap(True)
 
     # ---- roofline of the dominant kernel -----------------------------------------------------------
     pk, pk_kind = peaks()
@@ -246,7 +256,8 @@ def run_mphx(args):
                                "frac": step_bytes * K / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
                 "ncu": ncu_facts,
                 "note": "the sweeps are bound by the FP64 pipe, instruction issue and the L1 data pipe, not by HBM "
-                        "(ncu facts under profiles/; DESIGN.md section 3)"}
+                        "(ncu facts under profiles/; DESIGN.md section 3).  kernel_ms_per_step: isolated kernels (solid "
+                        "sub-steps serialised); phase_ms_per_step: the timed region, where the sub-steps overlap pass 2"}
 
     # ---- end to end through the C-ABI with host buffers ------------------------------------------------
     hx = torch.empty((n, 3), dtype=torch.float64).pin_memory()

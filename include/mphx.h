@@ -223,6 +223,9 @@ int mphx_get_timers(mphx_ctx *ctx, double ms[4]);
 /* the same split by kernel group: [0] bucket rebuild, [1] candidate filter (k_filter), [2] pass 1 over the
  * candidate list, [3] pass 2 over the candidate list (+ integration), [4] solid sub-steps */
 int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5]);
+/* the solid sub-steps normally run on a second stream, overlapping pass 2 and the start of the next step;
+ * on = 0 serialises them on the context's stream (isolated per-kernel timings), on = 1 restores the default */
+int mphx_set_overlap(mphx_ctx *ctx, int on);
 /* number of kernel launches issued by mphx_step since mphx_create (for bench.py gpu_launches) */
 long long mphx_launch_count(const mphx_ctx *ctx);
 /* algorithmic HBM bytes of one step for the resident case (SURVEY.md 8(d) model):

@@ -1331,6 +1331,16 @@ int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5])
     return MPHX_OK;
 }
 
+int mphx_set_overlap(mphx_ctx *ctx, int on)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
+    c->overlap_solid = on != 0;
+    return MPHX_OK;
+}
+
 long long mphx_launch_count(const mphx_ctx *ctx) { return ctx ? reinterpret_cast<const Ctx *>(ctx)->launches : 0; }
 
 double mphx_algorithmic_bytes_per_step(const mphx_ctx *ctx)

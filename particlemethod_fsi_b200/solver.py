@@ -71,6 +71,7 @@ def _load():
     L.mphx_set_timing.argtypes = [vp, C.c_int]
     L.mphx_get_timers.argtypes = [vp, C.POINTER(C.c_double * 4)]
     L.mphx_get_kernel_timers.argtypes = [vp, C.POINTER(C.c_double * 5)]
+    L.mphx_set_overlap.argtypes = [vp, C.c_int]
     L.mphx_launch_count.argtypes = [vp]
     L.mphx_launch_count.restype = C.c_longlong
     L.mphx_algorithmic_bytes_per_step.argtypes = [vp]
@@ -314,6 +315,10 @@ class Solver:
         ms = (C.c_double * 4)()
         _ck("mphx_get_timers", lib.mphx_get_timers(self._ctx, C.byref(ms)))
         return list(ms)
+
+    def set_overlap(self, on: bool):
+        """solid sub-steps on the second stream (default) or serialised on the context's stream"""
+        _ck("mphx_set_overlap", lib.mphx_set_overlap(self._ctx, 1 if on else 0))
 
     def kernel_timers_ms(self):
         """[bucket rebuild, candidate filter, pass 1, pass 2, solid sub-steps] accumulated device ms"""
