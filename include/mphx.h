@@ -226,6 +226,9 @@ int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5]);
 /* the solid sub-steps normally run on a second stream, overlapping pass 2 and the start of the next step;
  * on = 0 serialises them on the context's stream (isolated per-kernel timings), on = 1 restores the default */
 int mphx_set_overlap(mphx_ctx *ctx, int on);
+/* make the context's stream wait (device-side, no host synchronisation) for everything the library has
+ * enqueued on its internal second stream: call before recording an end-of-region event on that stream */
+int mphx_join(mphx_ctx *ctx);
 /* number of kernel launches issued by mphx_step since mphx_create (for bench.py gpu_launches) */
 long long mphx_launch_count(const mphx_ctx *ctx);
 /* algorithmic HBM bytes of one step for the resident case (SURVEY.md 8(d) model):

@@ -102,7 +102,7 @@ EXPORTS = [
     "mphx_step", "mphx_step_fluid_only", "mphx_sync", "mphx_time", "mphx_set_time", "mphx_download",
     "mphx_download_owned", "mphx_upload_owned",
     "mphx_debug_neighbors", "mphx_debug_initial_structure_neighbors",
-    "mphx_timed_steps", "mphx_set_timing", "mphx_get_timers", "mphx_get_kernel_timers", "mphx_set_overlap", "mphx_launch_count", "mphx_algorithmic_bytes_per_step",
+    "mphx_timed_steps", "mphx_set_timing", "mphx_get_timers", "mphx_get_kernel_timers", "mphx_set_overlap", "mphx_join", "mphx_launch_count", "mphx_algorithmic_bytes_per_step",
     "mphx_set_stream", "mphx_slab_configure", "mphx_slab_begin", "mphx_slab_append", "mphx_slab_pack_halo",
     "mphx_slab_build_pass1", "mphx_slab_pass2", "mphx_slab_finish", "mphx_slab_info",
 ]

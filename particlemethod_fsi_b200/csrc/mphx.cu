@@ -1341,6 +1341,14 @@ int mphx_set_overlap(mphx_ctx *ctx, int on)
     return MPHX_OK;
 }
 
+int mphx_join(mphx_ctx *ctx)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    return join_solids(c);
+}
+
 long long mphx_launch_count(const mphx_ctx *ctx) { return ctx ? reinterpret_cast<const Ctx *>(ctx)->launches : 0; }
 
 double mphx_algorithmic_bytes_per_step(const mphx_ctx *ctx)

@@ -72,6 +72,7 @@ def _load():
     L.mphx_get_timers.argtypes = [vp, C.POINTER(C.c_double * 4)]
     L.mphx_get_kernel_timers.argtypes = [vp, C.POINTER(C.c_double * 5)]
     L.mphx_set_overlap.argtypes = [vp, C.c_int]
+    L.mphx_join.argtypes = [vp]
     L.mphx_launch_count.argtypes = [vp]
     L.mphx_launch_count.restype = C.c_longlong
     L.mphx_algorithmic_bytes_per_step.argtypes = [vp]
