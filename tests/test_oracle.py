@@ -103,3 +103,71 @@ def test_oracle_surface_tension_path_runs_and_is_symmetric_free():
     assert np.isfinite(o.get("Force")).all()
     assert np.abs(o.get("PressureA")).max() > 0
     o.close()
+
+
+def _through_the_file(c, tmp_path):
+    """write the case as the reference reads it (%e: 7 digits) and take the parsed values back, so that the
+    oracle starts from exactly what the reference parsed"""
+    cases.write_grid_file(str(tmp_path / "c.grid"), c)
+    cases.write_data_file(str(tmp_path / "c.data"), c.params, c.rc)
+    _t, _h, t, x, x0, v = cases.read_grid_file(str(tmp_path / "c.grid"))
+    return cases.Case(c.name, c.params, c.rc, t, x, x0, v)
+
+
+def _jitter(c, amp, seed=12345):
+    rng = np.random.default_rng(seed)
+    fl = c.property < 2
+    d = rng.uniform(-amp, amp, size=(int(fl.sum()), 3)) * c.params.particle_spacing
+    if c.params.dim == 2:
+        d[:, 2] = 0.0
+    c.position[fl] += d
+    return c
+
+
+def _variants():
+    a = _jitter(cases.tiny2d(), 0.8)                     # several particles per bucket, empty buckets
+    b = _jitter(cases.tiny3d(), 0.8)
+    st = _jitter(cases.tiny2d(), 0.3)                    # surface tension + asymmetric wetting (zero in all shipped data)
+    st.params.surface_tension[0] = st.params.surface_tension[1] = 0.072
+    st.params.interaction_ratio[1][4] = 0.6
+    mw = cases.tiny2d()                                  # moving, rotating wall (Wall6 line of the .data file)
+    mw.params.wall_velocity[4][0] = 0.5
+    mw.params.wall_omega[4][2] = 2.0
+    mw.params.wall_center[4][0] = 0.05
+    return [("jitter2d", a, "2d_dam"), ("jitter3d", b, "3d_dam"), ("surface_tension", st, "2d_dam"), ("moving_wall", mw, "2d_dam")]
+
+
+@pytest.mark.skipif(not REF_PRESENT, reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("which", [0, 1, 2, 3])
+def test_oracle_vs_live_reference_off_the_lattice(which, tmp_path):
+    """the regimes the GPU parity tests rely on beyond the lattice-born cases: irregular bucket occupancy,
+    surface tension switched on, a moving wall -- oracle and reference library stage by stage, bit for bit"""
+    from oracle.refharness import RefHarness
+    name, c, variant = _variants()[which]
+    c = _through_the_file(c, tmp_path)
+    h = RefHarness(variant, str(tmp_path / "c.data"), str(tmp_path / "c.grid"), nthreads=2)
+    h.init()
+    o = Oracle.from_case(c)
+    o.init()
+    for f in ("NeighborCount", "VolStrainP", "DensityA"):
+        assert np.array_equal(h.get(f), o.get(f)), (name, "init", f)
+    if which < 2:
+        assert np.bincount(o.cell_of_particle()).max() >= 2
+    stages = ["calculateWall", "calculatePeriodicBoundary", "resetForce", "resetAccel", "calculateNeighbor",
+              "calculateDensityA", "calculateGravityCenter", "calculateDensityP", "calculateDivergenceP",
+              "calculatePhysicalCoefficients", "calculatePressureP", "calculatePressureA",
+              "calculateDiffuseInterface", "calculateViscosityV", "calculateGravity", "calculateInterfaceForce",
+              "calculateAcceleration", "calculateConvection", "calculateElasticDeformationVector",
+              "calculateStress", "calculateStressForce", "updateElasticPosition"]
+    watch = ["Position", "Velocity", "Force", "Acceleration", "PressureP", "VolStrainP", "DivergenceP", "DensityA",
+             "GravityCenter", "PressureA", "NeighborCount", "Neighbor", "DeformGradient", "Strain", "Stress"]
+    for step in range(3):
+        for st in stages:
+            h.call(st)
+            o.call(st)
+            for f in watch:
+                assert np.array_equal(h.get(f), o.get(f)), (name, step, st, f)
+    if which == 2:
+        assert np.abs(o.get("PressureA")).max() > 0
+    h.close()
+    o.close()
