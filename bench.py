@@ -307,7 +307,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mphx", choices=["mphx", "reference"])
     ap.add_argument("--particles", type=float, default=1.0e7)
-    ap.add_argument("--ref-particles", type=float, default=2.0e5, help="sample size of the CPU reference arm")
+    ap.add_argument("--ref-particles", type=float, default=1.0e6, help="sample size of the CPU reference arm (10-30 s of host work)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
