@@ -190,7 +190,8 @@ class _Slab:
         from .solver import _ck
         self._ck = _ck
         _ck("mphx_create", lib.mphx_create(C.byref(self.ctx), C.byref(case_params), device.index or 0))
-        _ck("mphx_set_stream", lib.mphx_set_stream(self.ctx, C.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+        stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0  # (cpu: protocol tests)
+        _ck("mphx_set_stream", lib.mphx_set_stream(self.ctx, C.c_void_p(stream)))
         _ck("mphx_slab_configure", lib.mphx_slab_configure(self.ctx, rank, world, cols[0], cols[1], capacity, msg_cap))
         f64 = dict(dtype=torch.float64, device=device)
         self.send = [torch.zeros(MSG_DOUBLES * msg_cap, **f64) for _ in range(2)]
@@ -213,11 +214,12 @@ class SlabSolver:
     """The explicit step on `world` x-slabs.  With a DistTransport every process holds one slab
     (rank = torch.distributed rank); with a LocalRing this object holds them all."""
 
-    def __init__(self, case, transport, device=None, capacity: int | None = None, msg_capacity: int | None = None):
+    def __init__(self, case, transport, device=None, capacity: int | None = None, msg_capacity: int | None = None, lib=None):
         import torch
         from . import solver
         self.torch = torch
-        self.lib = solver.lib
+        self.lib = lib if lib is not None else solver.lib   # (lib: a stand-in with the mphx_slab_* contract, for the
+        #                                                      CPU tests of this orchestration; never a compute path)
         self.tr = transport
         self.case = case
         self.n = case.n
@@ -349,10 +351,10 @@ class SlabSolver:
                 p.wall_center[t][d] = self._wall_center[t][d]
         new_case = cases.Case(case.name, p, case.rc, case.property, full["position"], case.initial_position, full["velocity"],
                               getattr(case, "cuboids", []))
-        tr, device, cap = self.tr, self.device, self._capacity_arg
+        tr, device, cap, lib = self.tr, self.device, self._capacity_arg, self.lib
         old = self.partition
         self.close()
-        self.__init__(new_case, tr, device=device, capacity=cap)
+        self.__init__(new_case, tr, device=device, capacity=cap, lib=lib)
         return old, self.partition
 
     def join(self):
@@ -361,7 +363,8 @@ class SlabSolver:
             s._ck("mphx_join", self.lib.mphx_join(s.ctx))
 
     def sync(self):
-        self.torch.cuda.synchronize(self.device)
+        if self.device.type == "cuda":
+            self.torch.cuda.synchronize(self.device)
 
     def info(self):
         out = []
