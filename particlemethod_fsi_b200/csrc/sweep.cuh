@@ -1,27 +1,25 @@
-// sweep.cuh -- the two stencil sweeps of the explicit step (K5 "pass 1", K6 "pass 2"), version 3.
+// sweep.cuh -- pass 1 (K5) and pass 2 (K6) of the explicit step, and the one-particle candidate filter.
 //
-// Pass 1 (one thread per particle, cell-sorted order) walks the particle's stencil in batches of
-// columns, two phases per batch:
+// Normal operation (see also sweep_pair.cuh):
+//   k_filter2 / k_filter  test every candidate of a particle's stencil with a CONSERVATIVE single-precision
+//       distance filter on `pf` (positions in bucket units, pair-interleaved 24-byte records, packed f32x2
+//       arithmetic) and write the survivors into a per-step ELL candidate list (entry k of particle i at
+//       nbr[k*cap + i]: coalesced).  No fp64, no shared-memory queue, few registers: full occupancy.
+//   k_pass1_v3<.., LIST=true>, k_pass2_v3<.., LIST=true>  traverse that list -- both passes run in the same
+//       step on the same positions -- two entries per trip: exact double-precision separation from the
+//       32-byte gather records (x,y,z,vx | vy,vz,P,type; one 256-bit load each), the reference's exact
+//       cut-off tests, kernel weights and pair terms as straight-line (masked) code.
 //
-//   phase A (FP32 / integer pipes): walk the contiguous particle runs of the stencil columns and
-//       test every candidate with a CONSERVATIVE single-precision distance filter on `pf` (position
-//       in bucket units, one 16-byte load per candidate); survivors are pushed to a per-thread
-//       queue in shared memory (slot-major layout: bank = lane, conflict-free).
-//   phase B (FP64 pipe): drain the queue: exact double-precision separation from the 32-byte gather
-//       records (x,y,z,vx | vy,vz,P,type), exact cut-off test, kernel weights and the pair terms.
-//       All lanes of a warp drain together, so the FP64 work runs (nearly) divergence-free.
+// The filter only has to be a superset of the exact predicates: the float coordinates carry an error
+// <= 2 ulp_f32(max bucket coordinate) each, which the host turns into a margin on the squared cut-off
+// (filter_radius2 in mphx.cu).  Physics is decided in fp64.  (A particle always passes its own filter
+// test; the passes reject j == i.)
 //
-// The filter only has to be a superset of the exact predicate: the float coordinates carry an
-// error <= 2 ulp_f32(max bucket coordinate) each, which the host turns into a margin on the
-// squared cut-off (see filter_radius2 in mphx.cu).  Physics is decided in phase B in fp64.
-// (A particle always passes its own filter test; phase B rejects j == i.)
-//
-// Normal operation splits the work differently (the fused sweep above remains as the fall-back):
-// k_filter runs phase A alone for all particles at full occupancy and writes the survivors into a
-// per-step ELL candidate list (entry k of particle i at nbr[k*cap + i]: coalesced); pass 1 and pass 2
-// run in the same step on the same positions, so both just traverse that list (phase B only, FP64
-// pipe).  Particles whose list overflowed (count > L) are finished by the fused-sweep variants of
-// pass 1 / pass 2 (second launches that exit at once when there is no overflow).
+// Fall-back (LIST=false): the FUSED sweep -- one thread per particle walks its stencil in batches of
+// columns, phase A (the same filter, survivors pushed to a per-thread queue in shared memory: slot-major
+// layout, bank = lane, conflict-free) and phase B (drain the queue: the same pair terms) per batch.  It
+// finishes the particles whose list overflowed (count > L) and serves MPHX_LIST_CAP=0; with a list it is
+// launched as a small persistent grid that returns at once when the step's overflow flag is clear.
 //
 // The reference procedures these kernels replace are listed at the top of kernels.cuh.
 #pragma once
