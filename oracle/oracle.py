@@ -17,8 +17,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 _VEC = {"Position", "InitialPosition", "Velocity", "Force", "Acceleration", "GravityCenter"}
-_TEN = {"Normalizer", "DeformGradient", "Strain", "Stress"}
-_SCAL = {"Mass", "DensityA", "PressureA", "VolStrainP", "DivergenceP", "PressureP", "Mu", "Lambda",
+_TEN = {"Normalizer", "DeformGradient", "Strain", "Stress", "VirialStressAtParticle"}
+_SCAL = {"Mass", "DensityA", "PressureA", "VolStrainP", "DivergenceP", "PressureP", "Mu", "Lambda", "VirialPressureAtParticle",
          "Kappa", "LambdaLames", "MuLames"}
 _INT = {"Property", "NeighborCount", "InitialStructureNeighborCount"}
 

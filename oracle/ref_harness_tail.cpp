@@ -227,6 +227,8 @@ void *ref_ptr(const char *name)
     if (s == "DeformGradient") return DeformGradient;
     if (s == "Strain") return Strain;
     if (s == "Stress") return Stress;
+    if (s == "VirialStressAtParticle") return VirialStressAtParticle;
+    if (s == "VirialPressureAtParticle") return VirialPressureAtParticle;
     if (s == "DomainMin") return DomainMin;
     if (s == "DomainMax") return DomainMax;
     if (s == "DomainWidth") return DomainWidth;

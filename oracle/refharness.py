@@ -21,8 +21,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 
 _VEC = {"Position", "InitialPosition", "Velocity", "Force", "Acceleration", "GravityCenter"}
-_TEN = {"Normalizer", "DeformGradient", "Strain", "Stress"}
-_SCAL = {"Mass", "DensityA", "PressureA", "VolStrainP", "DivergenceP", "PressureP", "Mu", "Lambda",
+_TEN = {"Normalizer", "DeformGradient", "Strain", "Stress", "VirialStressAtParticle"}
+_SCAL = {"Mass", "DensityA", "PressureA", "VolStrainP", "DivergenceP", "PressureP", "Mu", "Lambda", "VirialPressureAtParticle",
          "Kappa", "LambdaLames", "MuLames"}
 _INT = {"Property", "NeighborCount", "InitialStructureNeighborCount"}
 _TYPE6 = {"CofA", "Density", "BulkModulus", "BulkViscosity", "ShearViscosity", "SurfaceTension",

@@ -171,3 +171,28 @@ def test_oracle_vs_live_reference_off_the_lattice(which, tmp_path):
         assert np.abs(o.get("PressureA")).max() > 0
     h.close()
     o.close()
+
+
+@pytest.mark.skipif(not REF_PRESENT, reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("which", [0, 1, 2])
+def test_oracle_virial_stress_vs_live_reference(which, tmp_path):
+    """calculateVirialStressAtParticle (src/main.cpp:3077-3318): the per-output-step
+    diagnostic, restated in the oracle ahead of its CUDA kernel -- bit for bit against the reference
+    library after a few steps, incl. the surface-tension terms"""
+    from oracle.refharness import RefHarness
+    name, c, variant = _variants()[which]
+    c = _through_the_file(c, tmp_path)
+    h = RefHarness(variant, str(tmp_path / "c.data"), str(tmp_path / "c.grid"), nthreads=2)
+    h.init()
+    o = Oracle.from_case(c)
+    o.init()
+    h.step(3)
+    o.step(3)
+    h.call("calculateVirialStressAtParticle")
+    o.call("calculateVirialStressAtParticle")
+    for f in ("VirialStressAtParticle", "VirialPressureAtParticle"):
+        a, b = h.get(f), o.get(f)
+        assert np.array_equal(a, b), (name, f, float(np.abs(a - b).max()))
+    assert np.abs(o.get("VirialStressAtParticle")).max() > 0
+    h.close()
+    o.close()
