@@ -454,14 +454,18 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
     // position that has not been wrapped into the box yet (input of the very first bucket build, which
     // the reference does before its first calculatePeriodicBoundary) is filtered at its image in the box
     double fx = (x - g.mn[0]) * icw, fy = (y - g.mn[1]) * icw, fz = (z - g.mn[2]) * icw;
+    double xr = x; // x as a NEIGHBOUR's thread sees it (the gather record)
     if (!g.slab) fx = fx < 0.0 ? fx + g.nx : (fx >= g.nx ? fx - g.nx : fx);
+    else if (fx < 0.0) { fx += g.nxg; xr = x + g.W[0]; }          // slab mode: a replicated solid keeps its global x; seen
+    else if (fx >= (double)g.nxg) { fx -= g.nxg; xr = x - g.W[0]; } // through the periodic seam it sits one box width away
+                                                                   // (ghost fluid arrives already shifted, mphx_slab_append)
     fy = fy < 0.0 ? fy + g.ny : (fy >= g.ny ? fy - g.ny : fy);
     fz = fz < 0.0 ? fz + g.nz : (fz >= g.nz ? fz - g.nz : fz);
     pfw[0] = (float)fx; pfw[2] = (float)fy; pfw[4] = (float)fz;
     const double vx = src.vx[s], vy = src.vy[s], vz = src.vz[s];
     dst.vx[q] = vx; dst.vy[q] = vy; dst.vz[q] = vz;
     Rec ra, rb;
-    ra.a = x; ra.b = y; ra.c = z; ra.d = vx;
+    ra.a = xr; ra.b = y; ra.c = z; ra.d = vx;
     rb.a = vy; rb.b = vz; rb.c = 0.0; rb.d = __longlong_as_double((long long)real_type(t));
     dst.ra[q] = ra;
     dst.rb[q] = rb;

@@ -360,7 +360,8 @@ static int run_pass1(Ctx *c, bool timed = false)
         if (c->pl.nbr) { // K5a: candidate list of this step
             CK(cudaMemsetAsync(c->pl.flags, 0, sizeof(int), c->stream));
             const int npairs = (n + 1) / 2;
-            const bool big = ((size_t)c->pl.L + 1) * (size_t)c->pl.cap >= 0xffffffffull;
+            // 32-bit offsets must hold a parked top plus one stride ((L + 1) * cap + i + cap) without wrapping
+            const bool big = ((size_t)c->pl.L + 2) * (size_t)c->pl.cap >= 0xffffffffull;
             if (c->filter2 || big) {
 #define F2(D, B) LAUNCH(c, (k_filter2<D, B>), nblk(npairs, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl)
                 if (c->p.dim == 3) { if (big) F2(3, true); else F2(3, false); }

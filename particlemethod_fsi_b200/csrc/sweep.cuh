@@ -38,6 +38,14 @@ constexpr int kSweepThreads = 128;
 #ifndef MPHX_P2_MINB
 #define MPHX_P2_MINB 6
 #endif
+// the surface-tension instantiations carry ~50 more live values per pair (DensityA, GravityCenter, the
+// diffuse-interface terms): fewer resident blocks instead of spills
+#ifndef MPHX_P1ST_MINB
+#define MPHX_P1ST_MINB 5
+#endif
+#ifndef MPHX_P2ST_MINB
+#define MPHX_P2ST_MINB 3
+#endif
 // straight-line (masked) pair bodies in pass 1 / pass 2 instead of branches
 #ifndef MPHX_BRANCHFREE
 #define MPHX_BRANCHFREE 1
@@ -512,7 +520,7 @@ pass1_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
 // normally fall-backs that find nothing to do: they are launched as a small persistent grid that first
 // reads the step's overflow flag and otherwise loops over the virtual blocks.
 template <int DIM, bool ST, bool LIST>
-__global__ void __launch_bounds__(kSweepThreads, LIST ? MPHX_P1_MINB : 1)
+__global__ void __launch_bounds__(kSweepThreads, LIST ? (ST ? MPHX_P1ST_MINB : MPHX_P1_MINB) : 1)
 k_pass1_v3(int vblocks, int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
            double *__restrict__ P, double *__restrict__ volStrain, double *__restrict__ divP, double *__restrict__ densA,
            double *__restrict__ gcx, double *__restrict__ gcy, double *__restrict__ gcz, double *__restrict__ PA, PairList pl)
@@ -720,7 +728,7 @@ pass2_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
 }
 
 template <int DIM, bool ST, bool LIST>
-__global__ void __launch_bounds__(kSweepThreads, LIST ? MPHX_P2_MINB : 1)
+__global__ void __launch_bounds__(kSweepThreads, LIST ? (ST ? MPHX_P2ST_MINB : MPHX_P2_MINB) : 1)
 k_pass2_v3(int vblocks, int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
            const double *__restrict__ P, const double *__restrict__ PA, const double *__restrict__ gcx,
            const double *__restrict__ gcy, const double *__restrict__ gcz, double *__restrict__ ox,

@@ -89,7 +89,20 @@ def _load():
     return L
 
 
-lib = _load()
+class _LazyLib:
+    """libmphx.so is mapped on first use, not on import: `bench.py --impl reference` imports
+    `cases` through this package and must not load the product library.  A missing library is still
+    a loud ImportError -- at the first call instead of at import."""
+    _L = None
+
+    def __getattr__(self, name):
+        L = _LazyLib._L
+        if L is None:
+            L = _LazyLib._L = _load()
+        return getattr(L, name)
+
+
+lib = _LazyLib()
 
 
 def _ck(what: str, rc: int):

@@ -1,59 +1,115 @@
 """Parity tests proper (-m gpu): the CUDA path through the C-ABI against the oracle on the same
-inputs, against golden vectors dumped from the reference, and size-independent properties at scale.
+inputs, against golden vectors dumped from the reference, against the live compiled reference at
+250k particles, and size-independent properties at scale.
 
 Tolerances (stated per BASELINE.json north_star: 1e-10 relative, fp64, first 100 steps):
   * buckets (CellIndex) and neighbour sets: bit-exact.
-  * per-particle fields: max|a-b| <= RTOL * max|b| with RTOL = 1e-10 (max-norm relative), plus for
-    quantities that are kappa * (sum w - N0p) -- PressureP and what it drives -- an absolute floor
-    from the cancellation in (sum w - N0p): ATOL_P = 256 eps * max(BulkModulus) * N0p.  The
-    reference's own value of these quantities changes by that much under any re-association of its
-    neighbour sum (its in-bucket order is an artefact of an unstable bitonic sort, :1686-1707).
+  * per-particle fields: max|a-b| <= RTOL * max|b| with RTOL = 1e-10 (max-norm relative).  The measured
+    max-norm error AND the per-element relative error of every comparison are written to
+    gpurun_out/parity_r02.json (committed copy: profiles/parity_r02.json).
+  * quantities that are kappa * (sum w - N0p) -- PressureP and what it drives -- additionally get an
+    absolute floor for the cancellation in (sum w - N0p): re-associating a sum of n <= 80 positive
+    kernel weights changes it by up to (n-1) eps * sum (worst case, Higham), so the reference's own
+    PressureP is only defined to ~79 eps * kappa * N0p (its in-bucket order is an artefact of an
+    unstable bitonic sort, :1686-1707).  FLOOR_C = 64 of those eps are granted, with kappa = the
+    largest BulkModulus among the particle types PRESENT in the case.
 """
+import atexit
 import hashlib
+import json
 import os
+import tempfile
 
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, rel_err
+from conftest import GOLDEN, ROOT, rel_err
 from oracle.oracle import Oracle
+from oracle import refharness
 from particlemethod_fsi_b200 import Solver, abi, cases, solver
 
 pytestmark = pytest.mark.gpu
 
 RTOL = 1.0e-10
 EPS = np.finfo(np.float64).eps
+FLOOR_C = 64
 MAP = dict(position="Position", velocity="Velocity", force="Force", acceleration="Acceleration",
            pressure_p="PressureP", vol_strain_p="VolStrainP", divergence_p="DivergenceP",
            normalizer="Normalizer", deform_gradient="DeformGradient", strain="Strain", stress="Stress",
            lambda_lames="LambdaLames", mu_lames="MuLames")
 INTS = dict(neighbor_count="NeighborCount", initial_structure_neighbor_count="InitialStructureNeighborCount")
 
+# ---- measured-error report ------------------------------------------------------------------------
+_REPORT = []
+
+
+def record(tag, field, got, ref, floor=0.0, rtol=RTOL):
+    """max-norm error, max-norm relative error and per-element relative error (over the elements that
+    carry at least 1e-6 of the field's scale) of one comparison; returns (err, scale)"""
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    if ref.size == 0:
+        return 0.0, 0.0
+    d = np.abs(got - ref)
+    scale = float(np.abs(ref).max())
+    err = float(d.max())
+    big = np.abs(ref) >= 1e-6 * scale if scale > 0 else np.zeros(ref.shape, dtype=bool)
+    elem = float((d[big] / np.abs(ref[big])).max()) if big.any() else 0.0
+    _REPORT.append(dict(case=str(tag), field=field, max_abs_err=err, scale=scale,
+                        max_norm_rel=(err / scale if scale > 0 else err), per_element_rel=elem,
+                        abs_floor=float(floor), rtol=float(rtol), bit_equal=bool(err == 0.0)))
+    return err, scale
+
+
+def _dump_report():
+    if not _REPORT:
+        return
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_r02.json"), "w") as f:
+            json.dump(dict(note="CUDA path vs oracle / live reference / goldens; max_norm_rel = max|a-b|/max|b|; per_element_rel = "
+                                "max over elements with |b_i| >= 1e-6 max|b| of |a_i-b_i|/|b_i|", rtol=RTOL, floor_c=FLOOR_C,
+                           comparisons=_REPORT), f, indent=0)
+    except OSError:
+        pass
+
+
+atexit.register(_dump_report)
+
+
+def present_types(case):
+    return sorted(int(t) for t in np.unique(case.property))
+
 
 def pressure_floor(case, k):
-    return 256 * EPS * max(case.params.bulk_modulus) * k.n0p
+    return FLOOR_C * EPS * max(case.params.bulk_modulus[t] for t in present_types(case)) * k.n0p
 
 
-def check_fields(case, s, get_ref, tag, rtol=None):
+def check_fields(case, s, get_ref, tag, rtol=None, fields=None):
     k = s.constants()
-    got = s.download(*MAP.keys(), *INTS.keys(), "cell_index")
+    names = list(fields or MAP.keys())
+    got = s.download(*names, *INTS.keys(), "cell_index")
     atol_p = pressure_floor(case, k)
     # force/acceleration floors implied by the pressure floor: |dF| <= sum_j 2 dP |dw/dr| V
     dwmax = abs(2.0 / k.radius_p / k.swp / (k.radius_p ** case.params.dim))
     atol_f = 2 * atol_p * dwmax * k.particle_volume * k.n0p_count
-    atol_a = atol_f / (min(d for d in case.params.density) * k.particle_volume)
+    atol_a = atol_f / (min(case.params.density[t] for t in present_types(case)) * k.particle_volume)
     floors = dict(pressure_p=atol_p, force=atol_f, acceleration=atol_a, velocity=atol_a * case.params.dt * 100)
-    for f, r in MAP.items():
-        ref = get_ref(r)
-        scale = float(np.abs(ref).max()) if ref.size else 0.0
-        err = float(np.abs(got[f] - ref).max()) if ref.size else 0.0
-        assert err <= (rtol or {}).get(f, RTOL) * scale + floors.get(f, 0.0), (tag, f, err, scale)
+    bad = []
+    for f in names:
+        ref = get_ref(MAP[f])
+        tol = (rtol or {}).get(f, RTOL)
+        err, scale = record(tag, f, got[f], ref, floors.get(f, 0.0), tol)
+        if not err <= tol * scale + floors.get(f, 0.0):
+            bad.append((tag, f, err, scale))
+    assert not bad, bad
     for f, r in INTS.items():
         assert np.array_equal(got[f], get_ref(r)), (tag, f)
     return got
 
 
-@pytest.mark.parametrize("name,steps", [("dam2d", [0, 1, 10, 100]), ("bar2d", [0, 1, 30]),
+@pytest.mark.parametrize("name,steps", [("dam2d", [0, 1, 10, 100]), ("bar2d", [0, 1, 30, 100]),
                                         ("fsi2d", [0, 1, 10, 100]), ("fsi3d_mini", [0, 1, 10, 100])])
 def test_cuda_path_matches_oracle(name, steps):
     case = getattr(cases, name)()
@@ -113,10 +169,10 @@ def test_dam2d_100_steps_vs_reference_golden():
     s = Solver.from_case(case)
     s.step(100, sync=True)
     got = s.download("position", "velocity", "pressure_p", "neighbor_count", "cell_index")
-    assert rel_err(got["position"], g["s100_Position"]) <= RTOL
-    assert rel_err(got["velocity"], g["s100_Velocity"]) <= RTOL
-    assert np.abs(got["pressure_p"] - g["s100_PressureP"]).max() <= RTOL * np.abs(g["s100_PressureP"]).max() + \
-        pressure_floor(case, s.constants())
+    fp = pressure_floor(case, s.constants())
+    for f, r, fl in (("position", "Position", 0.0), ("velocity", "Velocity", 0.0), ("pressure_p", "PressureP", fp)):
+        err, scale = record("dam2d_golden_100", f, got[f], g["s100_" + r], fl)
+        assert err <= RTOL * scale + fl, (f, err, scale)
     assert np.array_equal(got["neighbor_count"], g["s100_NeighborCount"])
     assert np.array_equal(got["cell_index"], g["s100_CellIndex"])
     s.close()
@@ -140,22 +196,36 @@ def test_single_step_from_reference_state_mid_trajectory():
     o.close()
 
 
-def test_surface_tension_path_matches_oracle():
-    case = cases.tiny2d()
+def _st_floors(case, k):
+    """PressureA = CofA (nA - N0a) / l0 carries the same cancellation as PressureP (see the module docstring)"""
+    cofa = max(abs(k.cof_a[t]) for t in present_types(case))
+    return dict(pressure_a=FLOOR_C * EPS * cofa * k.n0a / case.params.particle_spacing)
+
+
+@pytest.mark.parametrize("name,amp", [("tiny2d", 0.0), ("tiny3d", 0.0), ("tiny3d", 0.4)])
+def test_surface_tension_path_matches_oracle(name, amp):
+    """a10/a11/a16/a17 (DensityA, GravityCenter, PressureA, DiffuseInterface) in 2D and in 3D, on the lattice
+    and off it (several particles per bucket), with asymmetric wetting (ratio_ij != ratio_ji)"""
+    case = getattr(cases, name)()
+    if amp:
+        case = _jittered(case, amp)
     case.params.surface_tension[0] = case.params.surface_tension[1] = 0.072
-    case.params.interaction_ratio[1][4] = 0.6   # asymmetric wetting (ratio_ij != ratio_ji)
+    case.params.interaction_ratio[1][4] = 0.6
     o = Oracle.from_case(case)
     o.init()
     s = Solver.from_case(case)
     s.step(10, sync=True)
     o.step(10)
-    check_fields(case, s, o.get, "st")
+    tag = ("st", case.name)
+    check_fields(case, s, o.get, tag)
     got = s.download("density_a", "gravity_center", "pressure_a")
     fluidwall = ~((case.property >= 2) & (case.property < 4))
-    assert rel_err(got["density_a"][fluidwall], o.get("DensityA")[fluidwall]) <= RTOL
-    assert rel_err(got["gravity_center"][fluidwall], o.get("GravityCenter")[fluidwall]) <= 1e-9
     assert np.abs(o.get("PressureA")).max() > 0
-    assert rel_err(got["pressure_a"][fluidwall], o.get("PressureA")[fluidwall]) <= 1e-9
+    fl = _st_floors(case, s.constants())
+    for f, r in dict(density_a="DensityA", gravity_center="GravityCenter", pressure_a="PressureA").items():
+        ref = o.get(r)[fluidwall]
+        err, scale = record(tag, f, got[f][fluidwall], ref, fl.get(f, 0.0))
+        assert err <= RTOL * scale + fl.get(f, 0.0), (tag, f, err, scale)
     s.close()
     o.close()
 
@@ -241,6 +311,69 @@ def test_scale_properties_3d_300k():
     fl = g1["property"] < 2
     assert g1["velocity"][fl, 1].mean() < 0
     s.close()
+
+
+def _reference_or_oracle(case, nthreads=None):
+    """the live compiled reference (oracle/_ref, travels to the GPU box) when present, else the oracle"""
+    variant = refharness.variant_name(case.params.dim, "dam" if case.params.clamp_module == abi.MODULE_DAM else "bar",
+                                      nb128=case.params.dim == 3)
+    if refharness.available(variant):
+        d = tempfile.mkdtemp(prefix="mphx_ref_")
+        cases.write_grid_file(os.path.join(d, "c.grid"), case)
+        cases.write_data_file(os.path.join(d, "c.data"), case.params, case.rc)
+        so, se = os.dup(1), os.dup(2)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1), os.dup2(devnull, 2)    # the reference prints a line per unknown .data row
+        try:
+            h = refharness.RefHarness(variant, os.path.join(d, "c.data"), os.path.join(d, "c.grid"),
+                                      nthreads=nthreads or len(os.sched_getaffinity(0)))
+            h.init()
+        finally:
+            os.dup2(so, 1), os.dup2(se, 2)
+        return h, "reference"
+    o = Oracle.from_case(case, max_neighbor_count=128 if case.params.dim == 3 else 512)
+    o.init()
+    return o, "oracle"
+
+
+def _cell_of_particle(r, n):
+    ci, cp = r.view("CellIndex")[:n], r.view("CellParticle")[:n]
+    out = np.empty(n, dtype=np.int32)
+    out[cp] = ci
+    return out
+
+
+def test_fsi3d_250k_replica_matches_the_live_reference():
+    """BASELINE configs[3] (3D dam break on an elastic plate) down-scaled to 250k particles -- the
+    same generator rule, geometry, materials and sub-stepping as the 10M benchmark case -- against the
+    UNMODIFIED reference compiled from /root/reference (oracle/_ref/libref_3d_dam_nb128.so; the oracle
+    restatement where that is absent): fields at 1e-10 over 10 steps, buckets and neighbour sets bit-exact."""
+    case = cases.fsi3d_for_count(2.5e5)
+    assert 2.0e5 < case.n < 3.2e5
+    r, kind = _reference_or_oracle(case)
+    s = Solver.from_case(case)
+    done = 0
+    for target in (1, 5, 10):
+        s.step(target - done, sync=True)
+        r.step(target - done)
+        done = target
+        got = check_fields(case, s, r.get, ("fsi3d_250k_vs_" + kind, target))
+        assert np.array_equal(got["cell_index"], _cell_of_particle(r, case.n))
+    off, ids = s.neighbors()
+    cnt = r.get("NeighborCount")
+    assert np.array_equal(np.diff(off), cnt)
+    nb = r.view("Neighbor")
+    # every row as a sorted set, compared in bulk: pad to the row width with a sentinel and sort
+    width = nb.shape[1]
+    ref_rows = np.where(np.arange(width)[None, :] < cnt[:, None], nb, np.iinfo(np.int32).max)
+    ref_rows.sort(axis=1)
+    mine = np.full((case.n, width), np.iinfo(np.int32).max, dtype=np.int32)
+    rows = np.repeat(np.arange(case.n), np.diff(off))
+    cols = np.arange(ids.shape[0]) - np.repeat(off[:-1], np.diff(off))
+    mine[rows, cols] = ids
+    assert np.array_equal(mine, ref_rows)
+    s.close()
+    r.close()
 
 
 def test_error_paths():

@@ -75,6 +75,25 @@ def test_flow_through_the_periodic_seam():
     _compare(sub, 2, [1, 30, 200], exact=False, fields=("position", "velocity", "cell_index", "property"))
 
 
+def test_solid_next_to_the_periodic_seam():
+    """a replicated solid keeps its global x on every slab.  Here the plate touches the right edge
+    of the periodic box and the water the left edge, so on rank 0 the plate is a neighbour THROUGH the seam
+    (its gather record must sit one box width to the left) and on the last rank the water arrives as shifted
+    ghosts.  Ring == single context (1e-12: the +-W shift rounds differently from the Mod-based minimum image)."""
+    from particlemethod_fsi_b200 import abi
+    l0 = 2.0e-3
+    p, rc = cases.default_params(2, abi.MODULE_DAM)
+    p.elastic_dt = 2.0e-5
+    cubs = [cases.Cuboid(1, (0.0, 0.0, 0.0), (0.012, 0.03, l0), l0),
+            cases.Cuboid(2, (0.08 - 3 * l0, 0.0, 0.0), (0.08, 0.024, l0), l0),
+            cases.Cuboid(4, (0.0, -3 * l0, 0.0), (0.08, 0.0, l0), l0)]
+    case = cases._assemble("seam_solid", p, rc, l0, (0.0, -7 * l0, 0.0), (0.08, 0.06, l0), cubs)
+    assert case.counts()[1] > 0
+    fields = ("position", "velocity", "pressure_p", "force", "cell_index", "property")
+    for world in (2, 3):
+        _compare(case, world, [1, 10, 60], exact=False, fields=fields)
+
+
 def test_compact_owned_io_round_trip():
     """mphx_download_owned / mphx_upload_owned: rows of every slab together are the whole case (+ the
     replicated solids once per slab); taking them back unchanged and stepping equals plain stepping."""
