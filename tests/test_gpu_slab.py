@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 FIELDS = ("position", "velocity", "pressure_p", "force", "cell_index", "stress", "property")
 
 
-def _compare(case, world, steps, exact=True, fields=FIELDS):
+def _compare(case, world, steps, exact=True, fields=FIELDS, atol=None):
     ref = Solver.from_case(case)
     ring = slab.SlabSolver(case, slab.LocalRing(world))
     done = 0
@@ -31,7 +31,7 @@ def _compare(case, world, steps, exact=True, fields=FIELDS):
                 assert np.array_equal(a[f], b[f]), (case.name, world, target, f, float(np.abs(a[f] - b[f]).max()))
             else:
                 scale = max(float(np.abs(a[f]).max()), 1e-300)
-                assert float(np.abs(a[f] - b[f]).max()) <= 1e-12 * scale, (case.name, world, target, f)
+                assert float(np.abs(a[f] - b[f]).max()) <= 1e-12 * scale + (atol or {}).get(f, 0.0), (case.name, world, target, f)
         assert ring.time == ref.time
     info = ring.info()
     ref.close()
@@ -90,8 +90,9 @@ def test_solid_next_to_the_periodic_seam():
     case = cases._assemble("seam_solid", p, rc, l0, (0.0, -7 * l0, 0.0), (0.08, 0.06, l0), cubs)
     assert case.counts()[1] > 0
     fields = ("position", "velocity", "pressure_p", "force", "cell_index", "property")
+    # (PressureP of water at rest is rounding noise around zero, ~1e-11 for kappa = 1e4: absolute floors)
     for world in (2, 3):
-        _compare(case, world, [1, 10, 60], exact=False, fields=fields)
+        _compare(case, world, [1, 10, 60], exact=False, fields=fields, atol=dict(pressure_p=1e-9, force=1e-12))
 
 
 def test_compact_owned_io_round_trip():
