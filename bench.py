@@ -195,7 +195,7 @@ def run_mphx(args):
     case = cases.fsi3d_for_count(args.particles)
     n = case.n
     nf, ns, nw = case.counts()
-    s = pm.Solver.from_case(case, device=local)
+    s = pm.Solver.from_case(case, device=local, list_reuse=None if args.list_reuse < 0 else bool(args.list_reuse))
     K, W = args.steps, args.warmup
 
     # ---- resident-state throughput ("value") -------------------------------------------------------
@@ -278,6 +278,8 @@ def run_mphx(args):
            "steps": ke, "ms_per_step": 1e3 * te / ke,
            "path": "mphx_upload_state + mphx_step + mphx_download (pinned host buffers, wall clock)"}
     assert bool(torch.isfinite(hx).all())
+    status = s.status()
+    assert status["err"] == 0, status
     s.close()
 
     # ---- CPU baseline on the host cores (bounded sample) ---------------------------------------------
@@ -295,7 +297,11 @@ def run_mphx(args):
                        "particle_spacing": case.params.particle_spacing, "dt": case.params.dt,
                        "solid_substeps": int(case.params.dt / case.params.elastic_dt + 0.5),
                        "cache": "inputs larger than L2 (state ~%.1f GB vs 126 MB L2)" % (n * 240 / 1e9),
-                       "parallelism": "1 GPU"},
+                       "parallelism": "1 GPU",
+                       "candidate_list": {"reuse": bool(status["skin_on"]), "lists_built": status["builds"],
+                                          "steps_reusing_a_list": status["reuses"],
+                                          "note": "all steps of the run incl. warm-up and the e2e leg (every e2e step uploads a new "
+                                                  "state and therefore rebuilds)"}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)
 
@@ -310,6 +316,9 @@ def main():
     ap.add_argument("--ref-particles", type=float, default=1.0e6, help="sample size of the CPU reference arm (10-30 s of host work)")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the ring-vs-single-context check of the exchange")
+    ap.add_argument("--verify-particles", type=float, default=2.0e5)
+    ap.add_argument("--list-reuse", type=int, default=-1, help="1/0: candidate-list reuse on/off (default: the library's default, on)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "mphx" else args.warmup
     global WORKLOAD

@@ -120,6 +120,10 @@ typedef struct mphx_host_views {
     double *stress;           /* [N][3][3] */
     double *lambda_lames;     /* [N] */
     double *mu_lames;         /* [N] */
+    /* calculateVirialStressAtParticle (src/main.cpp:3077-3318), evaluated on request over the state of the
+     * last step (the reference calls it on VTK steps, :671-673) */
+    double *virial_stress;    /* [N][3][3] VirialStressAtParticle   :190 */
+    double *virial_pressure;  /* [N]       VirialPressureAtParticle :189 */
 } mphx_host_views;
 
 typedef struct mphx_ctx mphx_ctx;
@@ -235,28 +239,52 @@ long long mphx_launch_count(const mphx_ctx *ctx);
  * N_f*368 + N_w*260 + N_s*(344+384*n_sub) */
 double mphx_algorithmic_bytes_per_step(const mphx_ctx *ctx);
 
+/* ---- candidate-list reuse / health -------------------------------------------------------------------------
+ * The reference rebuilds its neighbour lists every step (its Verlet-skin variant, neighborCalculation :1472-1494, is
+ * disabled at :607-609).  Here the CANDIDATE list (a conservative superset; every pair is still tested in fp64 with
+ * the reference's cut-offs, so bucket ids, neighbour sets and all sums keep their contracts) is built with
+ * radius + skin and reused until a particle has moved skin/2 -- decided on the device, no host round trip.
+ * on = 0: rebuild every step.  skin in particle spacings (<= 0: keep the default 0.25); before mphx_upload only. */
+int mphx_set_list_reuse(mphx_ctx *ctx, int on, double skin);
+/* out[0] error flags (1 particle crossed more than a halo width, 2 message buffer too small, 4 bad arrival, 8 peer
+ * timeout, 16 slots exhausted, 32 a non-finite position appeared), [1] slots held, [2] lists built, [3] steps that
+ * reused a list, [4] steps the current list has served, [5] the current list carries the skin, [6] several solids
+ * share a bucket of the reference configuration (solid path then 1e-10 instead of bit for bit), [7] ghosts held.
+ * Synchronises the context. */
+int mphx_get_status(mphx_ctx *ctx, int out[8]);
+
 /* ---- multi-GPU: one context per x-slab (the reference has no distributed path) ---
- * Protocol per step, identical on every rank (buffers are DEVICE pointers owned by the caller;
- * "left"/"right" are the ring neighbours along x; messages hold 7 doubles per particle):
- *   mphx_slab_begin      -> emigrants packed            -> exchange -> mphx_slab_append(ghost=0)
- *   mphx_slab_pack_halo  -> halo layers packed          -> exchange -> mphx_slab_append(ghost=1)
- *   mphx_slab_build_pass1-> PressureP of halo + solids  -> exchange + all-reduce(solP)
- *   mphx_slab_pass2      -> solid (v,F) updates         -> all-reduce(solbuf)
- *   mphx_slab_finish     (solid sub-steps, Time += Dt)
- * The host side of this protocol lives in particlemethod_fsi_b200/slab.py. */
+ * The exchange lives in the library and is device-side: every context owns a mailbox that its peers write
+ * into over NVLink (peer access inside one process, CUDA IPC between processes); mphx_step on a connected slab
+ * context enqueues pre-step, votes, migration / halo, buckets, pass 1, PressureP exchange, pass 2, sub-steps
+ * without any host synchronisation.  Every rank must issue the same calls (mphx_init, mphx_step) concurrently.
+ *   mphx_slab_configure -> mphx_upload -> mphx_slab_mailbox -> (carry the handles) -> mphx_slab_connect -> mphx_init */
 int mphx_set_stream(mphx_ctx *ctx, void *cuda_stream);
+int mphx_partition_columns(const long long *hist, int ncols, int nranks, int halo, int *cuts /* nranks + 1 */);
 int mphx_slab_configure(mphx_ctx *ctx, int rank, int nranks, int col_lo, int col_hi, int capacity,
                         int msg_capacity);
-int mphx_slab_begin(mphx_ctx *ctx, double *send_left, double *send_right, int *counts);
-int mphx_slab_append(mphx_ctx *ctx, const double *from_left, int n_left, const double *from_right,
-                     int n_right, int ghost);
-int mphx_slab_pack_halo(mphx_ctx *ctx, double *send_left, double *send_right, int *counts);
-int mphx_slab_build_pass1(mphx_ctx *ctx, int n_left, int n_right, double *send_left, double *send_right,
-                          double *solP);
-int mphx_slab_pass2(mphx_ctx *ctx, const double *from_left, const double *from_right, const double *solP,
-                    double *solbuf);
-int mphx_slab_finish(mphx_ctx *ctx, const double *solbuf);
+/* ipc_handle: 64 bytes (cudaIpcMemHandle_t); any output may be NULL */
+int mphx_slab_mailbox(mphx_ctx *ctx, void *ipc_handle, void **device_ptr, long long *bytes);
+/* ipc_handles: nranks * 64 bytes or NULL; device_ptrs[r] != NULL: rank r's mailbox lives in this process;
+ * devices[r]: CUDA ordinal of rank r's GPU in this process (or NULL) */
+int mphx_slab_connect(mphx_ctx *ctx, const void *ipc_handles, void *const *device_ptrs, const int *devices);
 int mphx_slab_info(mphx_ctx *ctx, int out[4]);
+
+/* one process, N devices -- what the reference's main() needs to drive a whole box (csrc/main.cpp, MPHX_NGPU):
+ * same life cycle as a single context; devices may be NULL (0..ndev-1) and may repeat */
+typedef struct mphx_multi mphx_multi;
+int mphx_multi_create(mphx_multi **m, const mphx_params *p, int ndev, const int *devices);
+void mphx_multi_destroy(mphx_multi *m);
+int mphx_multi_count(const mphx_multi *m);
+mphx_ctx *mphx_multi_context(mphx_multi *m, int i);
+int mphx_multi_upload(mphx_multi *m, int n, const int *property, const double *position,
+                      const double *initial_position, const double *velocity);
+int mphx_multi_init(mphx_multi *m);
+int mphx_multi_step(mphx_multi *m, int nsteps);
+int mphx_multi_sync(mphx_multi *m);
+double mphx_multi_time(const mphx_multi *m);
+int mphx_multi_download(mphx_multi *m, const mphx_host_views *views);
+int mphx_multi_timed_steps(mphx_multi *m, int nsteps, double *elapsed_ms);
 
 #ifdef __cplusplus
 }

@@ -78,6 +78,7 @@ class HostViews(C.Structure):
         ("neighbor_count", _pi), ("initial_structure_neighbor_count", _pi), ("cell_index", _pi),
         ("normalizer", _pd), ("deform_gradient", _pd), ("strain", _pd), ("stress", _pd),
         ("lambda_lames", _pd), ("mu_lames", _pd),
+        ("virial_stress", _pd), ("virial_pressure", _pd),
     ]
 
 
@@ -90,6 +91,7 @@ VIEW_FIELDS = {
     "initial_structure_neighbor_count": ((), True), "cell_index": ((), True),
     "normalizer": ((3, 3), False), "deform_gradient": ((3, 3), False), "strain": ((3, 3), False),
     "stress": ((3, 3), False), "lambda_lames": ((), False), "mu_lames": ((), False),
+    "virial_stress": ((3, 3), False), "virial_pressure": ((), False),
 }
 
 # every symbol include/mphx.h declares (tests/test_abi.py parses the header and compares)
@@ -103,6 +105,8 @@ EXPORTS = [
     "mphx_download_owned", "mphx_upload_owned",
     "mphx_debug_neighbors", "mphx_debug_initial_structure_neighbors",
     "mphx_timed_steps", "mphx_set_timing", "mphx_get_timers", "mphx_get_kernel_timers", "mphx_set_overlap", "mphx_join", "mphx_launch_count", "mphx_algorithmic_bytes_per_step",
-    "mphx_set_stream", "mphx_slab_configure", "mphx_slab_begin", "mphx_slab_append", "mphx_slab_pack_halo",
-    "mphx_slab_build_pass1", "mphx_slab_pass2", "mphx_slab_finish", "mphx_slab_info",
+    "mphx_set_list_reuse", "mphx_get_status",
+    "mphx_set_stream", "mphx_partition_columns", "mphx_slab_configure", "mphx_slab_mailbox", "mphx_slab_connect", "mphx_slab_info",
+    "mphx_multi_create", "mphx_multi_destroy", "mphx_multi_count", "mphx_multi_context", "mphx_multi_upload", "mphx_multi_init",
+    "mphx_multi_step", "mphx_multi_sync", "mphx_multi_time", "mphx_multi_download", "mphx_multi_timed_steps",
 ]

@@ -25,6 +25,9 @@ constexpr int kTypeCount = 6;
 // particle type as stored on the device: the reference's Property (0..5) in the low three bits; bit 3
 // marks a ghost copy received from a neighbouring slab (never integrated, dropped every step)
 constexpr int kGhost = 8;
+// slab mode: this context evaluates the (replicated) solid -- it owned the solid's column when the current
+// candidate list was built (ownership is frozen between list builds, like the lists themselves)
+constexpr int kSolidOwned = 16;
 __host__ __device__ inline int real_type(int t) { return t & 7; }
 __host__ __device__ inline bool is_structure_type(int t) { return (t & 7) >= 2 && (t & 7) < 4; }
 __host__ __device__ inline bool is_fluid_type(int t) { return (t & 7) >= 0 && (t & 7) < 2; }
@@ -45,6 +48,37 @@ struct GridDesc {
     double mn[3], W[3], cellw;
     // stencil columns.  3D: (dx,dy) with half-length sh along z.  2D: dx with half-length sh along y.
     signed char sdx[kMaxStencil], sdy[kMaxStencil], sh[kMaxStencil];
+};
+
+// sticky error flags of a context (Ctl::err)
+enum { kErrLost = 1,      // a particle crossed more than one halo width in a step
+       kErrMsgFull = 2,   // exchange message buffer too small
+       kErrArrival = 4,   // a received particle does not belong where it was sent
+       kErrTimeout = 8,   // a peer's flag did not arrive (exchange wait timed out)
+       kErrCapacity = 16, // particle slots exhausted
+       kErrNaN = 32 };    // a non-finite position came out of the integration
+
+// Device-resident control block of one context.  Everything the step decides -- how many slots are held,
+// whether this step rebuilds the buckets and the candidate list or reuses them, the exchange counts -- lives
+// here, so a step is a fixed sequence of kernel launches with no device->host read-back.
+struct Ctl {
+    int n;          // particle slots currently held (slab mode: owned + ghosts + all solids)
+    int rebuild;    // this step: 1 = rebuild buckets + candidate list, 0 = reuse them
+    int force;      // host request: rebuild at the next step (first step, uploads)
+    int need;       // local reasons to rebuild this step (slab mode: OR-ed over the ranks)
+    int age;        // steps the current list has served
+    int last_age;   // steps the previous list served
+    int probe;      // builds since the skin was last tried
+    int skin_on;    // the current list carries the Verlet skin
+    unsigned maxdisp2; // float bits: max |x - anchor|^2 over the particles this context moves, this step
+    float filt2;    // squared filter radius (bucket units) of the list being built
+    int err;        // kErr* bits
+    int builds, reuses; // statistics
+    int n_own_sol;  // slab mode: solids this context evaluates (list own_sol)
+    int mig_cnt[2];   // emigrants packed for the left / right neighbour (this step)
+    int halo_cnt[2];  // halo particles packed for left / right (current list)
+    int ghost_base[2], ghost_cnt[2]; // pre-permute slots of the ghosts received from left / right (current list)
+    unsigned push_done[8]; // block counters of the push kernels
 };
 
 struct Phys {
@@ -159,16 +193,111 @@ __device__ __forceinline__ double minimg(double d, double W)
 }
 
 // ------------------------------------------------------------------------------------------------
-// K0/K1: pre-step.  wall kinematics (t<0.2), periodic wrap, bucket key, per-bucket count + slot.
-// Solids take their state from the solid arrays (they are integrated there).
-// Slab mode: ghosts of the previous step die; fluid/wall particles whose column left the owned
-// range are packed for the neighbouring slab (migration) and die here.
-struct SlabSend {
-    double *buf[2]; // [0] to the left neighbour, [1] to the right; 7 doubles per particle (AoS)
-    int *count;     // count[0], count[1]  (+ count[2] = error flags)
-    int capacity;   // particles per buffer
+// Exchange between slabs (multi-GPU).  Every context owns one MAILBOX allocation that its ring
+// neighbours (particles, PressureP) and all ranks (replicated solids, rebuild votes) write into with
+// plain stores over NVLink -- peer memory mapped either directly (one process, several devices) or through
+// CUDA IPC (one process per device).  A message is complete when its flag carries the step's epoch;
+// receivers spin on the flag inside a one-warp kernel, so no count or flag ever travels through a host.
+constexpr int kMaxRanks = 16;
+constexpr int kMsgDoubles = 7; // x y z vx vy vz (type << 32 | id)
+struct Mailbox {               // pointers into ONE context's mailbox (the layout is the same on every rank)
+    unsigned long long *vote;  // [nranks] (epoch << 1 | need) : rebuild votes
+    unsigned long long *fmig, *fhalo, *fp; // [2] each: from the left / right neighbour
+    unsigned long long *fsolP, *fsolV;     // [nranks]
+    int *cnt_mig, *cnt_halo;   // [2] each
+    double *mig[2], *halo[2];  // [7 * msg_cap]
+    double *p[2];              // [msg_cap]  PressureP of the halo copies
+    double *solP, *solV;       // [ns], [3 * ns]  replicated solids: PressureP and the coupled velocity
 };
-constexpr int kMsgDoubles = 7;
+struct Peers {                 // the mailboxes a context writes into
+    int nranks, rank;
+    Mailbox left, right;       // ring neighbours
+    double *solP[kMaxRanks], *solV[kMaxRanks];
+    unsigned long long *fsolP[kMaxRanks], *fsolV[kMaxRanks], *vote[kMaxRanks];
+};
+
+__device__ __forceinline__ unsigned long long ld_flag(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_flag(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kWaitTimeoutNs = 4000000000ull; // a missing peer becomes an error flag, never a hang
+
+// wait until flags[0..nflags) carry this step's epoch (SHIFT = 1: the flag also carries a vote bit, the
+// OR of the votes goes to ctl->need)
+// (the epoch is a kernel argument, not device state: the waits of the solid sub-steps run on a second stream
+// while the context's stream may already be enqueuing the next step)
+template <int SHIFT>
+__global__ void k_wait(Ctl *ctl, unsigned long long epoch, const unsigned long long *flags, int nflags)
+{
+    const int lane = threadIdx.x;
+    const unsigned long long want = epoch;
+    unsigned long long v = want << SHIFT;
+    if (lane < nflags) {
+        const unsigned long long t0 = global_ns();
+        for (;;) {
+            v = ld_flag(flags + lane);
+            if ((v >> SHIFT) >= want) break;
+            if (global_ns() - t0 > kWaitTimeoutNs) { atomicOr(&ctl->err, kErrTimeout); break; }
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+    if (SHIFT) {
+        const unsigned any = __ballot_sync(0xffffffffu, lane < nflags && (v & 1ull));
+        if (lane == 0 && any) ctl->need = 1;
+    }
+}
+// post this rank's rebuild vote into every rank's mailbox
+__global__ void k_vote(Ctl *ctl, unsigned long long epoch, Peers peers)
+{
+    const int r = threadIdx.x;
+    if (r < peers.nranks) st_flag(peers.vote[r] + peers.rank, (epoch << 1) | (unsigned long long)(ctl->need != 0));
+}
+// the last block of a pushing kernel publishes the message: count (optional), then the flag
+__device__ __forceinline__ void push_complete(Ctl *ctl, unsigned long long epoch, int which, int *dst_cnt, int cnt, unsigned long long *dst_flag)
+{
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned done = atomicAdd(&ctl->push_done[which], 1u);
+        if (done == gridDim.x - 1) {
+            ctl->push_done[which] = 0;
+            if (dst_cnt) *dst_cnt = cnt;
+            __threadfence_system();
+            st_flag(dst_flag, epoch);
+        }
+    }
+}
+// copy cnt * width doubles of a packed message into the neighbour's mailbox (coalesced stores over NVLink)
+__global__ void k_push(Ctl *ctl, unsigned long long epoch, int which, const double *__restrict__ src, const int *cnt_p, int width, double *dst, int *dst_cnt,
+                       unsigned long long *dst_flag)
+{
+    const int cnt = *cnt_p;
+    const long long total = (long long)cnt * width;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) dst[k] = src[k];
+    push_complete(ctl, epoch, which, dst_cnt, cnt, dst_flag);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: pre-step for every particle this context moves.  wall kinematics (t<0.2), periodic wrap, bucket key,
+// and the displacement from the position the current candidate list was built on (the rebuild criterion).
+// Solids take their state from the solid arrays (they are integrated there).  Ghosts are left alone: they
+// die (rebuild) or are refreshed by their owner (reuse).
+//   `only` != nullptr: the listed slots (the solids, handled once their sub-steps have finished);
+//   skip_solids: everything but the solids.
 __device__ __forceinline__ void pack_particle(double *dst, double x, double y, double z, double vx, double vy, double vz,
                                               int type, int id)
 {
@@ -176,100 +305,195 @@ __device__ __forceinline__ void pack_particle(double *dst, double x, double y, d
     dst[6] = __longlong_as_double(((long long)real_type(type) << 32) | (long long)(unsigned)id);
 }
 
-// `only` != nullptr: the listed slots (the solids, handled later than the rest so that their sub-steps can
-// overlap the start of the next step); skip_solids: everything but the solids.
-__global__ void k_prestep(int n, Particles p, Solid sol, GridDesc g, WallMotion wm, int do_wrap,
-                          int *__restrict__ cellCount, int *__restrict__ slot, SlabSend snd, const int *__restrict__ only,
-                          int skip_solids)
+__global__ void k_prestep(Ctl *ctl, Particles p, Solid sol, GridDesc g, WallMotion wm, int do_wrap,
+                          const double *__restrict__ ancx, const double *__restrict__ ancy, const double *__restrict__ ancz,
+                          const int *__restrict__ only, int only_count, int skip_solids)
 {
+    const int n = only ? only_count : ctl->n;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t0 >= n) return;
-    const int i = only ? only[t0] : t0;
-    const int t = p.type[i];
-    if (skip_solids && is_structure_type(t) && !(t & kGhost)) return;
-    if (t & kGhost) { // last step's halo copy
-        const int k = g.ncells + 1;
-        p.key[i] = k;
-        slot[i] = atomicAdd(&cellCount[k], 1);
-        return;
-    }
-    double x = p.x[i], y = p.y[i], z = p.z[i];
-    int s = -1;
-    if (is_structure_type(t)) {
-        s = p.id[i] - sol.sb;
-        x = sol.x[s]; y = sol.y[s]; z = sol.z[s];
-        p.vx[i] = sol.vx[s]; p.vy[i] = sol.vy[s]; p.vz[i] = sol.vz[s];
-    } else if (wm.active && is_wall_type(t)) { // :3036-3060, operand order kept (bit-exact)
-        const double r0 = __dsub_rn(x, wm.center[t][0]), r1 = __dsub_rn(y, wm.center[t][1]),
-                     r2 = __dsub_rn(z, wm.center[t][2]);
-        const double(*R)[3] = wm.R[t];
-        const double q0 = __dadd_rn(__dadd_rn(__dmul_rn(R[0][0], r0), __dmul_rn(R[0][1], r1)), __dmul_rn(R[0][2], r2));
-        const double q1 = __dadd_rn(__dadd_rn(__dmul_rn(R[1][0], r0), __dmul_rn(R[1][1], r1)), __dmul_rn(R[1][2], r2));
-        const double q2 = __dadd_rn(__dadd_rn(__dmul_rn(R[2][0], r0), __dmul_rn(R[2][1], r1)), __dmul_rn(R[2][2], r2));
-        const double *w = wm.omega[t], *V = wm.vel[t];
-        p.vx[i] = __dadd_rn(__dsub_rn(__dmul_rn(w[1], q2), __dmul_rn(w[2], q1)), V[0]);
-        p.vy[i] = __dadd_rn(__dsub_rn(__dmul_rn(w[2], q0), __dmul_rn(w[0], q2)), V[1]);
-        p.vz[i] = __dadd_rn(__dsub_rn(__dmul_rn(w[0], q1), __dmul_rn(w[1], q0)), V[2]);
-        x = __dadd_rn(__dadd_rn(q0, wm.center[t][0]), __dmul_rn(V[0], wm.dt));
-        y = __dadd_rn(__dadd_rn(q1, wm.center[t][1]), __dmul_rn(V[1], wm.dt));
-        z = __dadd_rn(__dadd_rn(q2, wm.center[t][2]), __dmul_rn(V[2], wm.dt));
-    }
-    if (do_wrap) { // :3330
-        x = __dadd_rn(mod_exact(__dsub_rn(x, g.mn0g), g.W[0]), g.mn0g);
-        y = __dadd_rn(mod_exact(__dsub_rn(y, g.mn[1]), g.W[1]), g.mn[1]);
-        z = __dadd_rn(mod_exact(__dsub_rn(z, g.mn[2]), g.W[2]), g.mn[2]);
-    }
-    p.x[i] = x; p.y[i] = y; p.z[i] = z;
-    if (s >= 0) {
-        sol.x[s] = x; sol.y[s] = y; sol.z[s] = z;
-        sol.ux[s] = minimg_exact(x, sol.x0[s], g.W[0]); // :2712, from the (wrapped) position the sub-steps start from
-        sol.uy[s] = minimg_exact(y, sol.y0[s], g.W[1]);
-        sol.uz[s] = minimg_exact(z, sol.z0[s], g.W[2]);
-    }
-    int col;
-    int k = cell_key(g, x, y, z, &col);
-    if (g.slab && s < 0 && !column_owned(g, col)) { // migrate: hand the particle to the neighbouring slab
-        const int dir = (col < g.range) ? 0 : ((col >= g.nx - g.range && col < g.nx) ? 1 : -1);
-        if (dir < 0) atomicOr(&snd.count[2], 1); // moved further than one halo width: lost
-        else {
-            const int q = atomicAdd(&snd.count[dir], 1);
-            if (q < snd.capacity) pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, x, y, z, p.vx[i], p.vy[i], p.vz[i], t, p.id[i]);
-            else atomicOr(&snd.count[2], 2);
+    float d2 = 0.f;
+    if (t0 < n) {
+        const int i = only ? only[t0] : t0;
+        const int t = p.type[i];
+        if (!(t & kGhost) && !(skip_solids && is_structure_type(t))) {
+            double x = p.x[i], y = p.y[i], z = p.z[i];
+            int s = -1;
+            if (is_structure_type(t)) {
+                s = p.id[i] - sol.sb;
+                x = sol.x[s]; y = sol.y[s]; z = sol.z[s];
+                p.vx[i] = sol.vx[s]; p.vy[i] = sol.vy[s]; p.vz[i] = sol.vz[s];
+            } else if (wm.active && is_wall_type(t)) { // :3036-3060, operand order kept (bit-exact)
+                const int tt = real_type(t);
+                const double r0 = __dsub_rn(x, wm.center[tt][0]), r1 = __dsub_rn(y, wm.center[tt][1]),
+                             r2 = __dsub_rn(z, wm.center[tt][2]);
+                const double(*R)[3] = wm.R[tt];
+                const double q0 = __dadd_rn(__dadd_rn(__dmul_rn(R[0][0], r0), __dmul_rn(R[0][1], r1)), __dmul_rn(R[0][2], r2));
+                const double q1 = __dadd_rn(__dadd_rn(__dmul_rn(R[1][0], r0), __dmul_rn(R[1][1], r1)), __dmul_rn(R[1][2], r2));
+                const double q2 = __dadd_rn(__dadd_rn(__dmul_rn(R[2][0], r0), __dmul_rn(R[2][1], r1)), __dmul_rn(R[2][2], r2));
+                const double *w = wm.omega[tt], *V = wm.vel[tt];
+                p.vx[i] = __dadd_rn(__dsub_rn(__dmul_rn(w[1], q2), __dmul_rn(w[2], q1)), V[0]);
+                p.vy[i] = __dadd_rn(__dsub_rn(__dmul_rn(w[2], q0), __dmul_rn(w[0], q2)), V[1]);
+                p.vz[i] = __dadd_rn(__dsub_rn(__dmul_rn(w[0], q1), __dmul_rn(w[1], q0)), V[2]);
+                x = __dadd_rn(__dadd_rn(q0, wm.center[tt][0]), __dmul_rn(V[0], wm.dt));
+                y = __dadd_rn(__dadd_rn(q1, wm.center[tt][1]), __dmul_rn(V[1], wm.dt));
+                z = __dadd_rn(__dadd_rn(q2, wm.center[tt][2]), __dmul_rn(V[2], wm.dt));
+            }
+            if (do_wrap) { // :3330
+                x = __dadd_rn(mod_exact(__dsub_rn(x, g.mn0g), g.W[0]), g.mn0g);
+                y = __dadd_rn(mod_exact(__dsub_rn(y, g.mn[1]), g.W[1]), g.mn[1]);
+                z = __dadd_rn(mod_exact(__dsub_rn(z, g.mn[2]), g.W[2]), g.mn[2]);
+            }
+            p.x[i] = x; p.y[i] = y; p.z[i] = z;
+            if (s >= 0) {
+                sol.x[s] = x; sol.y[s] = y; sol.z[s] = z;
+                sol.ux[s] = minimg_exact(x, sol.x0[s], g.W[0]); // :2712, from the (wrapped) position the sub-steps start from
+                sol.uy[s] = minimg_exact(y, sol.y0[s], g.W[1]);
+                sol.uz[s] = minimg_exact(z, sol.z0[s], g.W[2]);
+            }
+            p.key[i] = cell_key(g, x, y, z);
+            // (a particle that wrapped through the box shows up a box width away: conservative, it forces a rebuild)
+            const double ex = x - ancx[i], ey = y - ancy[i], ez = z - ancz[i];
+            const double e2 = ex * ex + ey * ey + ez * ez;
+            d2 = (e2 == e2) ? __double2float_ru(e2) : 3.0e38f; // NaN: rebuild (and the health flag reports it)
         }
-        k = g.ncells + 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
+    if ((threadIdx.x & 31) == 0 && d2 > 0.f) atomicMax(&ctl->maxdisp2, __float_as_uint(d2));
+}
+
+// The rebuild decision of this step, made on the device (one thread).  The list built with a skin d stays a
+// superset of every cut-off set while no particle has moved further than d/2 from its build position.
+//   * slab mode: `ctl->need` already holds the OR of all ranks' votes (k_wait<1>), so every rank decides alike;
+//   * a list that overflowed (its particles need the bucket-walking fall-back) or was built without a skin is
+//     rebuilt every step;
+//   * the skin costs candidates (all the physics kernels traverse the longer lists), so it is only kept
+//     while it pays: a list that served fewer than 2 steps switches the skin off for the following builds,
+//     every 16th build tries it again.
+struct DecideArgs {
+    int reuse_enabled; // host switch (MPHX_LIST_REUSE, moving walls, slab support)
+    float half_skin2;  // (skin / 2)^2 in metres^2
+    float filt2_plain, filt2_skin;
+};
+// local vote (before the exchange of votes in slab mode)
+__global__ void k_need(Ctl *ctl, DecideArgs a, const int *__restrict__ list_flags)
+{
+    const bool overflowed = list_flags && list_flags[0] != 0;
+    ctl->need = (ctl->force || !a.reuse_enabled || !ctl->skin_on || overflowed || __uint_as_float(ctl->maxdisp2) > a.half_skin2) ? 1 : 0;
+}
+__global__ void k_decide(Ctl *ctl, DecideArgs a, int *__restrict__ list_flags)
+{
+    const int rebuild = ctl->need ? 1 : 0;
+    ctl->rebuild = rebuild;
+    ctl->maxdisp2 = 0u;
+    ctl->mig_cnt[0] = 0; ctl->mig_cnt[1] = 0;
+    if (rebuild) {
+        ctl->last_age = ctl->age;
+        ctl->age = 1;
+        int skin = 0;
+        if (a.reuse_enabled) {
+            if (ctl->force || ctl->last_age >= 2 || ++ctl->probe >= 16) { skin = 1; ctl->probe = 0; }
+        }
+        ctl->skin_on = skin;
+        ctl->filt2 = skin ? a.filt2_skin : a.filt2_plain;
+        ctl->force = 0;
+        ctl->halo_cnt[0] = 0; ctl->halo_cnt[1] = 0;
+        ctl->ghost_cnt[0] = 0; ctl->ghost_cnt[1] = 0;
+        ctl->n_own_sol = 0;
+        ++ctl->builds;
+        if (list_flags) list_flags[0] = 0;
+    } else {
+        ++ctl->age;
+        ++ctl->reuses;
+    }
+}
+
+// K1 (rebuild steps): per-bucket count + arrival slot.  Slab mode: ghosts of the previous list die; fluid/wall
+// particles whose column left the owned range are packed for the neighbouring slab (migration) and die here.
+struct SlabSend {
+    double *buf[2]; // local staging: [0] to the left neighbour, [1] to the right; 7 doubles per particle (AoS)
+    int capacity;   // particles per buffer
+};
+__global__ void k_count(Ctl *ctl, Particles p, GridDesc g, int *__restrict__ cellCount, int *__restrict__ slot, SlabSend snd)
+{
+    if (!ctl->rebuild) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ctl->n) return;
+    const int t = p.type[i];
+    int k;
+    if (t & kGhost) k = g.ncells + 1; // last list's halo copy
+    else {
+        k = p.key[i];
+        if (g.slab && !is_structure_type(t)) {
+            if (k >= g.ncells) { atomicOr(&ctl->err, kErrLost); k = g.ncells + 1; } // moved further than one halo width: lost
+            else {
+                const int col = key_column(g, k);
+                if (!column_owned(g, col)) { // migrate: hand the particle to the neighbouring slab
+                    const int dir = (col < g.range) ? 0 : 1;
+                    const int q = atomicAdd(&ctl->mig_cnt[dir], 1);
+                    if (q < snd.capacity)
+                        pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], t, p.id[i]);
+                    else atomicOr(&ctl->err, kErrMsgFull);
+                    k = g.ncells + 1;
+                }
+            }
+        }
     }
     p.key[i] = k;
     slot[i] = atomicAdd(&cellCount[k], 1);
 }
-
-// slab mode: append particles received from a neighbour (migrants: ghost_flag 0; halo copies:
-// ghost_flag kGhost, x shifted by +-W across the periodic seam so separations need no wrap in x)
-__global__ void k_unpack_particles(int base, int count, const double *__restrict__ buf, double xshift, int ghost_flag,
-                                   Particles p, GridDesc g, int *__restrict__ cellCount, int *__restrict__ slot,
-                                   int *__restrict__ err)
+// the counts as they travel: never more than a message holds
+__global__ void k_clamp_counts(Ctl *ctl, int cap)
 {
+    if (threadIdx.x < 2) {
+        ctl->mig_cnt[threadIdx.x] = min(ctl->mig_cnt[threadIdx.x], cap);
+        ctl->halo_cnt[threadIdx.x] = min(ctl->halo_cnt[threadIdx.x], cap);
+    }
+}
+
+// slab mode, rebuild steps: append the particles received from a neighbour (migrants: ghost_flag 0; halo copies:
+// ghost_flag kGhost, x shifted by +-W across the periodic seam so separations need no wrap in x).
+// side 0 = from the left neighbour, 1 = from the right; cnt_in[2] are the received counts.
+__global__ void k_unpack_particles(Ctl *ctl, int side, const double *__restrict__ buf, const int *cnt_in, int msg_cap, int cap,
+                                   double xshift, int ghost_flag, Particles p, GridDesc g, int *__restrict__ cellCount,
+                                   int *__restrict__ slot, double *__restrict__ ancx, double *__restrict__ ancy, double *__restrict__ ancz)
+{
+    if (!ctl->rebuild) return;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= count) return;
+    const int cl = min(max(cnt_in[0], 0), msg_cap), cr = min(max(cnt_in[1], 0), msg_cap);
+    if (q >= (side ? cr : cl)) return;
+    const int i = ctl->n + (side ? cl : 0) + q;
+    if (i >= cap) { atomicOr(&ctl->err, kErrCapacity); return; }
     const double *m = buf + (size_t)kMsgDoubles * q;
-    const int i = base + q;
     const double x = m[0] + xshift, y = m[1], z = m[2];
     const long long meta = __double_as_longlong(m[6]);
     p.x[i] = x; p.y[i] = y; p.z[i] = z; p.vx[i] = m[3]; p.vy[i] = m[4]; p.vz[i] = m[5];
     p.type[i] = (int)(meta >> 32) | ghost_flag;
     p.id[i] = (int)(meta & 0xffffffffLL);
+    ancx[i] = x; ancy[i] = y; ancz[i] = z;
     int col;
     int k = cell_key(g, x, y, z, &col);
     const bool owned = column_owned(g, col);
-    if (k >= g.ncells || (ghost_flag ? owned : !owned)) { atomicOr(err, 4); k = g.ncells + 1; }
+    if (k >= g.ncells || (ghost_flag ? owned : !owned)) { atomicOr(&ctl->err, kErrArrival); k = g.ncells + 1; }
     p.key[i] = k;
     slot[i] = atomicAdd(&cellCount[k], 1);
 }
-
-// slab mode: pack the owned fluid/wall particles within one halo width of the slab faces
-__global__ void k_halo_pack(int n, Particles p, GridDesc g, SlabSend snd, int *__restrict__ haloSrc0, int *__restrict__ haloSrc1)
+__global__ void k_advance_n(Ctl *ctl, const int *cnt_in, int msg_cap, int cap, int ghost)
 {
+    if (!ctl->rebuild) return;
+    const int cl = min(max(cnt_in[0], 0), msg_cap), cr = min(max(cnt_in[1], 0), msg_cap);
+    if (cnt_in[0] > msg_cap || cnt_in[1] > msg_cap) atomicOr(&ctl->err, kErrMsgFull);
+    const int n = ctl->n;
+    if (ghost) { ctl->ghost_base[0] = n; ctl->ghost_cnt[0] = cl; ctl->ghost_base[1] = n + cl; ctl->ghost_cnt[1] = cr; }
+    ctl->n = min(n + cl + cr, cap);
+}
+
+// slab mode, rebuild steps: pack the owned fluid/wall particles within one halo width of the slab faces
+__global__ void k_halo_pack(Ctl *ctl, Particles p, GridDesc g, SlabSend snd, int *__restrict__ haloSrc0, int *__restrict__ haloSrc1)
+{
+    if (!ctl->rebuild) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= ctl->n) return;
     const int k = p.key[i], t = p.type[i];
     if (k >= g.ncells || (t & kGhost) || is_structure_type(t)) return;
     const int col = key_column(g, k);
@@ -277,60 +501,134 @@ __global__ void k_halo_pack(int n, Particles p, GridDesc g, SlabSend snd, int *_
     for (int dir = 0; dir < 2; ++dir) {
         const bool in = dir == 0 ? (col < 2 * g.range) : (col >= g.nx - 2 * g.range);
         if (!in) continue;
-        const int q = atomicAdd(&snd.count[dir], 1);
+        const int q = atomicAdd(&ctl->halo_cnt[dir], 1);
         if (q < snd.capacity) {
             pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], t, p.id[i]);
             (dir == 0 ? haloSrc0 : haloSrc1)[q] = i;
-        } else atomicOr(&snd.count[2], 2);
+        } else atomicOr(&ctl->err, kErrMsgFull);
     }
 }
-// second exchange: PressureP of the halo particles, in the order they were packed
-__global__ void k_pack_scalar(int count, const int *__restrict__ src, const int *__restrict__ where, const double *__restrict__ a,
-                              double *__restrict__ buf)
+// reuse steps: the SAME halo particles (sorted slots haloSlot, fixed when the list was built) with their current state
+__global__ void k_halo_repack(Ctl *ctl, Particles p, SlabSend snd, const int *__restrict__ haloSlot0, const int *__restrict__ haloSlot1)
 {
+    if (ctl->rebuild) return;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < count) buf[q] = a[where[src[q]]];
+    for (int dir = 0; dir < 2; ++dir) {
+        if (q >= ctl->halo_cnt[dir]) continue;
+        const int i = (dir == 0 ? haloSlot0 : haloSlot1)[q];
+        pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], p.type[i], p.id[i]);
+    }
 }
-__global__ void k_unpack_scalar(int base, int count, const int *__restrict__ where, const double *__restrict__ buf, double *__restrict__ a,
+// reuse steps: refresh the ghost slots with the state their owners sent
+__global__ void k_unpack_refresh(Ctl *ctl, int side, const double *__restrict__ buf, double xshift, Particles p, const int *__restrict__ ghostSlot)
+{
+    if (ctl->rebuild) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ctl->ghost_cnt[side]) return;
+    const double *m = buf + (size_t)kMsgDoubles * q;
+    const int i = ghostSlot[q];
+    p.x[i] = m[0] + xshift; p.y[i] = m[1]; p.z[i] = m[2]; p.vx[i] = m[3]; p.vy[i] = m[4]; p.vz[i] = m[5];
+}
+// after the permute of a rebuild step: the sorted slots of the halo particles sent / the ghosts received
+__global__ void k_slab_slots(Ctl *ctl, const int *__restrict__ where, const int *__restrict__ haloSrc0, const int *__restrict__ haloSrc1,
+                             int *__restrict__ haloSlot0, int *__restrict__ haloSlot1, int *__restrict__ ghostSlot0, int *__restrict__ ghostSlot1)
+{
+    if (!ctl->rebuild) return;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < ctl->halo_cnt[0]) haloSlot0[q] = where[haloSrc0[q]];
+    if (q < ctl->halo_cnt[1]) haloSlot1[q] = where[haloSrc1[q]];
+    if (q < ctl->ghost_cnt[0]) ghostSlot0[q] = where[ctl->ghost_base[0] + q];
+    if (q < ctl->ghost_cnt[1]) ghostSlot1[q] = where[ctl->ghost_base[1] + q];
+}
+// second exchange: PressureP of the halo particles, in the order they were packed, straight into the neighbour's mailbox
+__global__ void k_push_scalar(Ctl *ctl, unsigned long long epoch, int which, int dir, const int *__restrict__ haloSlot, const double *__restrict__ a, double *dst,
+                              unsigned long long *dst_flag)
+{
+    const int cnt = ctl->halo_cnt[dir];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) dst[q] = a[haloSlot[q]];
+    push_complete(ctl, epoch, which, nullptr, 0, dst_flag);
+}
+__global__ void k_unpack_scalar(Ctl *ctl, int side, const int *__restrict__ ghostSlot, const double *__restrict__ buf, double *__restrict__ a,
                                 Rec *__restrict__ rb)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= count) return;
-    const int w = where[base + q];
+    if (q >= ctl->ghost_cnt[side]) return;
+    const int w = ghostSlot[q];
     a[w] = buf[q];
     rb[w].c = buf[q]; // PressureP slot of the gather record
 }
-// replicated solids: the slab that owns a solid particle BY POSITION computes its PressureP / its
-// fluid-coupled velocity update; everybody else contributes zeros to an all-reduce (exact).
-__global__ void k_solid_collect_P(int n, Particles p, GridDesc g, Solid sol, const double *__restrict__ P, double *__restrict__ solP)
+// replicated solids: the slab that owns a solid particle (kSolidOwned: by its column when the list was built)
+// computes its PressureP / its fluid-coupled velocity update and stores them into EVERY rank's mailbox.
+__global__ void k_solid_owned_list(Ctl *ctl, Particles p, int *__restrict__ own_sol)
 {
+    if (!ctl->rebuild) return;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const int k = p.key[q];
-    if (k >= g.ncells || !is_structure_type(p.type[q]) || !column_owned(g, key_column(g, k))) return;
-    solP[p.id[q] - sol.sb] = P[q];
+    if (q >= ctl->n) return;
+    if (p.type[q] & kSolidOwned) own_sol[atomicAdd(&ctl->n_own_sol, 1)] = q;
 }
-__global__ void k_solid_spread_P(int n, Particles p, GridDesc g, Solid sol, const double *__restrict__ solP, double *__restrict__ P)
+__global__ void k_solid_publish_P(Ctl *ctl, unsigned long long epoch, int which, Particles p, Solid sol, const int *__restrict__ own_sol, const double *__restrict__ P, Peers peers)
+{
+    const int cnt = ctl->n_own_sol;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+        const int i = own_sol[q];
+        const int s = p.id[i] - sol.sb;
+        const double v = P[i];
+        for (int r = 0; r < peers.nranks; ++r) peers.solP[r][s] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(&ctl->push_done[which], 1u) == gridDim.x - 1) {
+            ctl->push_done[which] = 0;
+            __threadfence_system();
+            for (int r = 0; r < peers.nranks; ++r) st_flag(peers.fsolP[r] + peers.rank, epoch);
+        }
+    }
+}
+__global__ void k_solid_spread_P(Ctl *ctl, Particles p, GridDesc g, Solid sol, const double *__restrict__ solP, double *__restrict__ P)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    if (p.key[q] >= g.ncells || !is_structure_type(p.type[q])) return;
+    if (q >= ctl->n) return;
+    if (p.key[q] >= g.ncells || !is_structure_type(p.type[q]) || (p.type[q] & kGhost)) return;
     const double v = solP[p.id[q] - sol.sb];
     P[q] = v;
     p.rb[q].c = v;
 }
-// solbuf = [vx vy vz fx fy fz] planes of ns doubles, summed over slabs (one owner, others zero)
-__global__ void k_solid_apply_update(Solid sol, const double *__restrict__ solbuf)
+// the owner's coupled velocities (pass 2 wrote them into its solid arrays) -> every rank's mailbox
+__global__ void k_solid_publish_V(Ctl *ctl, unsigned long long epoch, int which, Particles p, Solid sol, const int *__restrict__ own_sol, Peers peers)
+{
+    const int cnt = ctl->n_own_sol;
+    const size_t ns = sol.ns;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+        const int s = p.id[own_sol[q]] - sol.sb;
+        const double vx = sol.vx[s], vy = sol.vy[s], vz = sol.vz[s];
+        for (int r = 0; r < peers.nranks; ++r) {
+            double *d = peers.solV[r];
+            d[s] = vx; d[ns + s] = vy; d[2 * ns + s] = vz;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(&ctl->push_done[which], 1u) == gridDim.x - 1) {
+            ctl->push_done[which] = 0;
+            __threadfence_system();
+            for (int r = 0; r < peers.nranks; ++r) st_flag(peers.fsolV[r] + peers.rank, epoch);
+        }
+    }
+}
+__global__ void k_solid_apply_update(Solid sol, const double *__restrict__ solV)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= sol.ns) return;
     const size_t ns = sol.ns;
-    sol.vx[s] = solbuf[s]; sol.vy[s] = solbuf[ns + s]; sol.vz[s] = solbuf[2 * ns + s];
-    sol.fx[s] = solbuf[3 * ns + s]; sol.fy[s] = solbuf[4 * ns + s]; sol.fz[s] = solbuf[5 * ns + s];
+    sol.vx[s] = solV[s]; sol.vy[s] = solV[ns + s]; sol.vz[s] = solV[2 * ns + s];
 }
 
 // ------------------------------------------------------------------------------------------------
-// K2: exclusive scan of the bucket counts (three small kernels; int32)
+// K2: exclusive scan of the bucket counts (three small kernels; int32), rebuild steps only
 constexpr int kScanThreads = 1024;
 constexpr int kScanItems = 4; // per thread
 constexpr int kScanChunk = kScanThreads * kScanItems;
@@ -364,8 +662,10 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int *total)
     return r;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const int *__restrict__ in, int n, int *__restrict__ blockSums)
+// `gate` != nullptr: the kernel only works in rebuild steps (gate->rebuild)
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const Ctl *gate, const int *__restrict__ in, int n, int *__restrict__ blockSums)
 {
+    if (gate && !gate->rebuild) return;
     __shared__ int total;
     const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
     int s = 0;
@@ -375,8 +675,9 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const int *__restr
     block_exclusive_scan(s, &total);
     if (threadIdx.x == 0) blockSums[blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(kScanThreads) k_scan_top(int *__restrict__ blockSums, int nb)
+__global__ void __launch_bounds__(kScanThreads) k_scan_top(const Ctl *gate, int *__restrict__ blockSums, int nb)
 {
+    if (gate && !gate->rebuild) return;
     __shared__ int total;
     __shared__ int carry;
     if (threadIdx.x == 0) carry = 0;
@@ -392,9 +693,11 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_top(int *__restrict__ blo
         __syncthreads();
     }
 }
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const int *__restrict__ in, int n, const int *__restrict__ blockPrefix,
-                                                             int *__restrict__ out /* n+1 */)
+// `clear`: zero the counts once they are scanned (the bucket counters are all-zero outside a rebuild)
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const Ctl *gate, int *__restrict__ in, int n, const int *__restrict__ blockPrefix,
+                                                             int *__restrict__ out /* n+1 */, int clear)
 {
+    if (gate && !gate->rebuild) return;
     __shared__ int total;
     const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
     int v[kScanItems], s = 0;
@@ -406,50 +709,60 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const int *__restri
     int ex = block_exclusive_scan(s, &total) + blockPrefix[blockIdx.x];
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
-        if (base + k < n) out[base + k] = ex;
+        if (base + k < n) { out[base + k] = ex; if (clear) in[base + k] = 0; }
         ex += v[k];
         if (base + k == n - 1) out[n] = ex;
     }
 }
 
 // K3: provisional bucket order (arrival order inside a bucket is arbitrary -> fixed up in K4)
-__global__ void k_scatter_index(int n, const int *__restrict__ key, const int *__restrict__ slot,
+__global__ void k_scatter_index(const Ctl *ctl, const int *__restrict__ key, const int *__restrict__ slot,
                                 const int *__restrict__ cellStart, int *__restrict__ tmpIdx)
 {
+    if (!ctl->rebuild) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= ctl->n) return;
     tmpIdx[cellStart[key[i]] + slot[i]] = i;
 }
 
-// K4: permute the SoA into bucket order; inside a bucket particles are ordered by original id, which
-// makes the layout (and therefore every floating-point sum) independent of atomic arrival order.
-__global__ void k_permute(int n, Particles src, Particles dst, const int *__restrict__ cellStart,
+// K4: permute the SoA into bucket order and write the gather records.  Inside a bucket particles are ordered by
+// original id, which makes the layout (and therefore every floating-point sum) independent of atomic arrival
+// order: the thread of an arrival ranks its own id among the bucket's occupants (O(m) per thread).
+// Reuse steps keep the order (identity permutation): only the state and the records move.
+__global__ void k_permute(const Ctl *ctl, Particles src, Particles dst, const int *__restrict__ cellStart,
                           const int *__restrict__ tmpIdx, GridDesc g, int *__restrict__ where, int *__restrict__ solid_slot,
-                          int solid_base)
+                          int solid_base, double *__restrict__ ancx, double *__restrict__ ancy, double *__restrict__ ancz)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n || q >= cellStart[g.ncells + 1]) return; // the dead bucket (last) is dropped
-    int s = tmpIdx[q];
+    const int rebuild = ctl->rebuild;
+    const int q0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q0 >= (rebuild ? cellStart[g.ncells + 1] : ctl->n)) return; // the dead bucket (last) is dropped
+    const int s = rebuild ? tmpIdx[q0] : q0;
     const int k = src.key[s];
-    const int b = cellStart[k], e = cellStart[k + 1];
-    if (e - b > 1 && k < g.ncells) { // (the parked bucket is never traversed: any order will do)
-        const int want = q - b;
-        for (int a = b; a < e; ++a) {
-            const int sa = tmpIdx[a];
-            const int ida = src.id[sa];
+    int q = q0;
+    if (rebuild && k < g.ncells) { // (the parked bucket is never traversed: arrival order will do)
+        const int b = cellStart[k], e = cellStart[k + 1];
+        if (e - b > 1) {
+            const int ids = src.id[s];
             int rank = 0;
-            for (int c = b; c < e; ++c) rank += (src.id[tmpIdx[c]] < ida);
-            if (rank == want) { s = sa; break; }
+            for (int c = b; c < e; ++c) rank += (src.id[tmpIdx[c]] < ids);
+            q = b + rank;
         }
     }
-    where[s] = q;
     const double x = src.x[s], y = src.y[s], z = src.z[s];
-    const int t = src.type[s];
-    if (solid_slot && is_structure_type(t) && !(t & kGhost)) solid_slot[src.id[s] - solid_base] = q; // sorted slot of each solid
+    int t = src.type[s];
+    const bool solid = is_structure_type(t) && !(t & kGhost);
+    if (rebuild) {
+        where[s] = q;
+        if (solid_slot && solid) solid_slot[src.id[s] - solid_base] = q; // sorted slot of each solid
+        if (g.slab && solid) { // the slab that owns the solid's column evaluates it until the next rebuild
+            const bool own = k < g.ncells && column_owned(g, key_column(g, k));
+            t = (t & ~kSolidOwned) | (own ? kSolidOwned : 0);
+        }
+        ancx[q] = x; ancy[q] = y; ancz[q] = z; // the positions this list is built on
+    }
     dst.x[q] = x; dst.y[q] = y; dst.z[q] = z;
     dst.type[q] = t; dst.id[q] = src.id[s]; dst.key[q] = k;
     const double icw = 1.0 / g.cellw;
-    float *pfw = reinterpret_cast<float *>(dst.pf + (q >> 1)) + (q & 1); // x0 x1 y0 y1 z0 z1
     // filter coordinates in bucket units, consistent with the (periodically wrapped) bucket index: a
     // position that has not been wrapped into the box yet (input of the very first bucket build, which
     // the reference does before its first calculatePeriodicBoundary) is filtered at its image in the box
@@ -458,10 +771,13 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
     if (!g.slab) fx = fx < 0.0 ? fx + g.nx : (fx >= g.nx ? fx - g.nx : fx);
     else if (fx < 0.0) { fx += g.nxg; xr = x + g.W[0]; }          // slab mode: a replicated solid keeps its global x; seen
     else if (fx >= (double)g.nxg) { fx -= g.nxg; xr = x - g.W[0]; } // through the periodic seam it sits one box width away
-                                                                   // (ghost fluid arrives already shifted, mphx_slab_append)
-    fy = fy < 0.0 ? fy + g.ny : (fy >= g.ny ? fy - g.ny : fy);
-    fz = fz < 0.0 ? fz + g.nz : (fz >= g.nz ? fz - g.nz : fz);
-    pfw[0] = (float)fx; pfw[2] = (float)fy; pfw[4] = (float)fz;
+                                                                   // (ghost fluid arrives already shifted)
+    if (rebuild) { // (only the filter reads pf)
+        fy = fy < 0.0 ? fy + g.ny : (fy >= g.ny ? fy - g.ny : fy);
+        fz = fz < 0.0 ? fz + g.nz : (fz >= g.nz ? fz - g.nz : fz);
+        float *pfw = reinterpret_cast<float *>(dst.pf + (q >> 1)) + (q & 1); // x0 x1 y0 y1 z0 z1
+        pfw[0] = (float)fx; pfw[2] = (float)fy; pfw[4] = (float)fz;
+    }
     const double vx = src.vx[s], vy = src.vy[s], vz = src.vz[s];
     dst.vx[q] = vx; dst.vy[q] = vy; dst.vz[q] = vz;
     Rec ra, rb;
@@ -469,6 +785,11 @@ __global__ void k_permute(int n, Particles src, Particles dst, const int *__rest
     rb.a = vy; rb.b = vz; rb.c = 0.0; rb.d = __longlong_as_double((long long)real_type(t));
     dst.ra[q] = ra;
     dst.rb[q] = rb;
+}
+// after the permute of a rebuild step: the live slots (everything but the dead bucket)
+__global__ void k_set_n(Ctl *ctl, const int *__restrict__ cellStart, int ncells)
+{
+    if (ctl->rebuild) ctl->n = cellStart[ncells + 1];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -569,6 +890,29 @@ k_neighbors_exact(int n, const double *__restrict__ X, const double *__restrict_
             dst[b + 1] = v;
         }
     }
+}
+
+// a bucket structure over an arbitrary particle set, independent of the stepping state: serves the exact
+// neighbour lists above (debug / VTK output) and the initial structure lists (once)
+__global__ void k_dbg_keycount(int n, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z, GridDesc g,
+                               int *__restrict__ key, int *__restrict__ cellCount, int *__restrict__ slot)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int k = cell_key(g, x[i], y[i], z[i]);
+    key[i] = k;
+    slot[i] = atomicAdd(&cellCount[k], 1);
+}
+__global__ void k_dbg_gather(int n, const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ z,
+                             const int *__restrict__ type, const int *__restrict__ id, const int *__restrict__ key,
+                             const int *__restrict__ slot, const int *__restrict__ cellStart, double *__restrict__ ox, double *__restrict__ oy,
+                             double *__restrict__ oz, int *__restrict__ otype, int *__restrict__ oid, int *__restrict__ okey)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int q = cellStart[key[i]] + slot[i];
+    ox[q] = x[i]; oy[q] = y[i]; oz[q] = z[i];
+    otype[q] = type[i]; oid[q] = id[i]; okey[q] = key[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -962,11 +1306,13 @@ __global__ void k_gather_int(int n, const int *__restrict__ id, const int *__res
     out[id[q]] = a[q];
 }
 // solid arrays -> original-order AoS (overrides the stale sorted copies)
+// (owner_type != nullptr: only the solids this slab evaluates -- kSolidOwned in the type of their slot)
 __global__ void k_solid_vec3_to_orig(Solid so, const double *__restrict__ a, const double *__restrict__ b,
-                                     const double *__restrict__ c, double *__restrict__ out3)
+                                     const double *__restrict__ c, double *__restrict__ out3, const int *__restrict__ owner_type)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= so.ns) return;
+    if (owner_type && !(owner_type[so.slot[s]] & kSolidOwned)) return;
     const size_t o = 3 * (size_t)(so.sb + s);
     out3[o] = a[s]; out3[o + 1] = b[s]; out3[o + 2] = c[s];
 }

@@ -9,6 +9,8 @@
 // loop).  The reference fixes dimension and clamp module at compile time (src/main.cpp:50,54-55);
 // here they are the optional 7th/8th arguments or MPHX_DIM / MPHX_MODULE (defaults: 2, bar -- the
 // shipped configuration).  `nthreads` is accepted and ignored (there is no CPU path).
+// MPHX_NGPU=N (2..16) runs the case on N devices of the box as x-slabs (mphx_multi_*: one process, the
+// slabs exchange over NVLink inside the library); MPHX_DEVICE picks the device of a single-GPU run.
 #include <chrono>
 #include <condition_variable>
 #include <cstdarg>
@@ -152,16 +154,31 @@ int main(int argc, char *argv[])
         time_t t = time(NULL);
         log_printf("start initialization at %s\n", ctime(&t));
     }
-    mphx_ctx *ctx = nullptr;
-    rc = mphx_create(&ctx, &p, getenv("MPHX_DEVICE") ? atoi(getenv("MPHX_DEVICE")) : 0);
-    if (rc) die("mphx_create", rc);
+    const int ngpu = getenv("MPHX_NGPU") ? atoi(getenv("MPHX_NGPU")) : 1;
+    mphx_ctx *ctx = nullptr;    // single context, or slab 0 of the multi-GPU run (constants, timers)
+    mphx_multi *multi = nullptr;
+    if (ngpu > 1) {
+        if ((rc = mphx_multi_create(&multi, &p, ngpu, nullptr))) die("mphx_multi_create", rc);
+        ctx = mphx_multi_context(multi, 0);
+    } else {
+        rc = mphx_create(&ctx, &p, getenv("MPHX_DEVICE") ? atoi(getenv("MPHX_DEVICE")) : 0);
+        if (rc) die("mphx_create", rc);
+    }
     mphx_constants k;
     mphx_get_constants(ctx, &k);
     log_printf("N0a = %e, count=%d\n", k.n0a, k.n0a_count); // :1258
     log_printf("N0p = %e, count=%d\n", k.n0p, k.n0p_count); // :1303
-    if ((rc = mphx_upload(ctx, n, property, position, initial_position, velocity))) die("mphx_upload", rc);
-    if ((rc = mphx_init(ctx))) die("mphx_init", rc);
+    if (multi) {
+        if ((rc = mphx_multi_upload(multi, n, property, position, initial_position, velocity))) die("mphx_multi_upload", rc);
+        if ((rc = mphx_multi_init(multi))) die("mphx_multi_init", rc);
+    } else {
+        if ((rc = mphx_upload(ctx, n, property, position, initial_position, velocity))) die("mphx_upload", rc);
+        if ((rc = mphx_init(ctx))) die("mphx_init", rc);
+    }
     mphx_set_timing(ctx, 1);
+    auto do_step = [&]() { return multi ? mphx_multi_step(multi, 1) : mphx_step(ctx, 1); };
+    auto do_sync = [&]() { return multi ? mphx_multi_sync(multi) : mphx_sync(ctx); };
+    auto do_download = [&](const mphx_host_views *v) { return multi ? mphx_multi_download(multi, v) : mphx_download(ctx, v); };
 
     const size_t N = (size_t)n;
     Writer writer(!(getenv("MPHX_SYNC_IO") && atoi(getenv("MPHX_SYNC_IO")) != 0));
@@ -172,7 +189,7 @@ int main(int argc, char *argv[])
         memset(&v, 0, sizeof(v));
         v.position = snap->position.data();
         v.velocity = snap->velocity.data();
-        int e = mphx_download(ctx, &v);
+        int e = do_download(&v);
         if (e) die("mphx_download", e);
         writer.submit([=, &p]() {
             int e2 = mphx_write_prof_file(fn.c_str(), time, &p, n, property, snap->position.data(), initial_position, snap->velocity.data());
@@ -189,7 +206,7 @@ int main(int argc, char *argv[])
         v.property = snap->property.data(); v.position = snap->position.data(); v.velocity = snap->velocity.data();
         v.force = snap->force.data(); v.acceleration = snap->accel.data(); v.stress = snap->stress.data(); v.strain = snap->strain.data();
         v.neighbor_count = snap->nbc.data(); v.initial_structure_neighbor_count = snap->inbc.data();
-        int e = mphx_download(ctx, &v);
+        int e = do_download(&v);
         if (e) die("mphx_download", e);
         writer.submit([=]() {
             mphx_host_views w = v; // (the pointers stay valid: the snapshot lives as long as this job)
@@ -219,9 +236,9 @@ int main(int argc, char *argv[])
             OutputNext += rc_.output_interval;
         }
         double t1 = now(); sOther += t1 - tFrom; tFrom = t1;
-        if ((rc = mphx_step(ctx, 1))) die("mphx_step", rc); // :596-663
+        if ((rc = do_step())) die("mphx_step", rc); // :596-663
         if (Time + 1.0e-5 * Dt >= VtkOutputNext) {          // :672-683
-            if ((rc = mphx_sync(ctx))) die("mphx_sync", rc);
+            if ((rc = do_sync())) die("mphx_sync", rc);
             t1 = now(); sStep += t1 - tFrom; tFrom = t1;
             char filename[2048];
             snprintf(filename, sizeof(filename), vtkfilename.c_str(), iStep);
@@ -233,7 +250,7 @@ int main(int argc, char *argv[])
         Time += Dt; // :685
         iStep++;
     }
-    if ((rc = mphx_sync(ctx))) die("mphx_sync", rc);
+    if ((rc = do_sync())) die("mphx_sync", rc);
     writer.finish(); // every output file is complete before the timers are logged
     {
         double t1 = now(); sStep += t1 - tFrom;
@@ -250,7 +267,7 @@ int main(int argc, char *argv[])
         log_printf("total:                   %lf [CPU sec]\n", neigh + expl + sOther);
         log_printf("total (check):           %lf [CPU sec]\n", now() - tStart);
     }
-    mphx_destroy(ctx);
+    if (multi) mphx_multi_destroy(multi); else mphx_destroy(ctx);
     mphx_free_host(property); mphx_free_host(position); mphx_free_host(initial_position); mphx_free_host(velocity);
     if (g_log) fclose(g_log);
     return 0;

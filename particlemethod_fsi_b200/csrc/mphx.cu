@@ -1,7 +1,10 @@
 // mphx.cu -- context, step orchestration and the extern-"C" layer (include/mphx.h).
 //
-// One context drives one B200.  All state lives on the device as cell-sorted SoA; the host only
-// keeps scalars (Time, wall centres) and enqueues kernels on the context's stream.
+// One context drives one B200 (or one x-slab of a multi-GPU run).  All state lives on the device as
+// cell-sorted SoA; the host only keeps scalars (Time, wall centres) and enqueues kernels on the context's
+// stream.  Everything a step decides -- rebuild or reuse of the candidate list, slot counts, exchange counts
+// -- is decided ON THE DEVICE (struct Ctl), so a step is a fixed sequence of launches without a single
+// device->host read-back; slabs exchange particles through peer-mapped mailboxes (see kernels.cuh).
 // There is no CPU fallback: every compute entry point fails with MPHX_ERR_NO_DEVICE / MPHX_ERR_CUDA
 // when no sm_100 device is usable.
 #include <algorithm>
@@ -42,19 +45,30 @@ struct Ctx {
     mphx_constants c;
     int device = 0;
     cudaStream_t stream = nullptr;
-    int n = 0;        // particle slots currently held (slab mode: owned + ghosts + all solids; changes every step)
-    int n_global = 0; // particles of the whole case (= n without slabs)
+    // Particle slots: the exact number held lives on the device (ctl->n: owned + ghosts + all solids in slab
+    // mode, changing with every rebuild); the host only knows a launch bound.
+    int nmax = 0;     // launch bound on the slots held (single context: n; slab: capacity)
+    int n_global = 0; // particles of the whole case
     int cap = 0;      // allocated slots
     int nf = 0, ns = 0, nw = 0; // class counts of the whole case
     int ranges[6];
+    Ctl *ctl = nullptr;
     // slab mode (multi-GPU): see slab.inc
-    bool slab = false;
+    bool slab = false, connected = false;
     int rank = 0, nranks = 1, col_lo = 0, col_hi = 0, msg_cap = 0;
-    int ghost_base[2] = {0, 0}, ghost_cnt[2] = {0, 0}, halo_cnt[2] = {0, 0};
-    int *where = nullptr, *haloSrc[2] = {nullptr, nullptr}, *d_err = nullptr;
-    int slab_err[4] = {0, 0, 0, 0}; // host copy of d_err, refreshed by stage_sort
+    void *mailbox = nullptr;
+    size_t mailbox_bytes = 0;
+    Mailbox mine{};
+    Peers peers{};
+    void *peer_base[kMaxRanks] = {};
+    bool peer_ipc[kMaxRanks] = {};
+    double *stage_mig[2] = {nullptr, nullptr}, *stage_halo[2] = {nullptr, nullptr};
+    int *haloSrc[2] = {nullptr, nullptr}, *haloSlot[2] = {nullptr, nullptr}, *ghostSlot[2] = {nullptr, nullptr}, *own_sol = nullptr;
+    int *where = nullptr;
     bool external_stream = false;
     bool uploaded = false, inited = false, surface_tension = false;
+    bool solid_multi_occupancy = false; // several solids share a bucket of the reference configuration (see init_solid)
+    unsigned long long epoch = 0; // exchange epoch: one per bucket stage, identical on every rank (flags carry it)
     double time = 0.0;
     double wall_center[kTypeCount][3];
     long long launches = 0;
@@ -63,12 +77,14 @@ struct Ctx {
     GridDesc grid;
     Phys phys;
     Particles S{}, T{}; // S: current cell-sorted state, T: scratch (permute target / pre-step positions)
-    double *bx = nullptr, *by = nullptr, *bz = nullptr; // positions the buckets were built from
+    double *bx = nullptr, *by = nullptr, *bz = nullptr; // positions of the last pass 1 (the reference's NeighborCount refers to them)
+    double *ancx = nullptr, *ancy = nullptr, *ancz = nullptr; // positions the current candidate list was built on
     int *cellCount = nullptr, *cellStart = nullptr, *slot = nullptr, *tmpIdx = nullptr, *blockSums = nullptr;
     int scan_blocks = 0;
     double *P = nullptr, *volStrain = nullptr, *divP = nullptr;
     double *densA = nullptr, *gcx = nullptr, *gcy = nullptr, *gcz = nullptr, *PA = nullptr;
     double *fx = nullptr, *fy = nullptr, *fz = nullptr, *ax = nullptr, *ay = nullptr, *az = nullptr;
+    double *virial = nullptr; // [10][cap]: VirialStressAtParticle (9 planes) + VirialPressureAtParticle, lazy
     Solid sol{};
     double *d_inv_density = nullptr;
     double cw_tl = 0.0; // weight() prefactor (1.0/Swp)*(1.0/RP^d), src/main.cpp:291/293
@@ -79,26 +95,30 @@ struct Ctx {
     double *own_x = nullptr, *own_v = nullptr;
     int own_blocks = 0, own_count = -1;
     long long own_epoch = -1; // steps_done at the last mphx_download_owned
-    bool buckets_valid = false;
     int sweep_batch = 12;  // stencil columns per filter/drain batch (3D)
-    PairList pl{};         // pass 1 -> pass 2 neighbour list (nbr == nullptr: disabled, pass 2 sweeps again)
+    PairList pl{};         // candidate list (nbr == nullptr: disabled, both passes walk the buckets)
     int list_cap = -1;     // list slots per particle (-1: default by dimension, 0: no list)
     bool filter2 = true;   // build the lists two particles per thread (k_filter2, sweep_pair.cuh)
+    // candidate-list reuse (internal Verlet skin): the list is built with radius + skin and serves until a
+    // particle has moved skin/2 from its build position (decided on the device, k_decide)
+    bool list_reuse = true;
+    double skin = 0.25;    // in particle spacings
     // the solid sub-steps only need the solids' share of pass 2: they run on a second stream while the
     // fluid's share (FP64 / issue bound; the sub-steps are HBM bound) is still being computed
     bool overlap_solid = true;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_solid_ready = nullptr, ev_solid_done = nullptr;
     bool solids_pending = false;  // sub-steps enqueued on `side`, not yet joined by the main stream
-    WallMotion held_wm{};         // arguments of the deferred solid share of the pre-step
-    int held_wrap = 0;
     std::vector<void *> allocs;
 
     // phase timers (src/main.cpp:695-700 split)
     bool timing = false;
-    std::vector<cudaEvent_t> ev;
+    std::vector<cudaEvent_t> ev, ev_pool;
     double ms[5] = {0, 0, 0, 0, 0}; // rebuild, filter, pass 1, pass 2, solid sub-steps
     cudaEvent_t tev[2] = {nullptr, nullptr};
+    cudaEvent_t side_ev[2] = {nullptr, nullptr}; // sub-steps on the side stream (timing)
+    std::vector<cudaEvent_t> side_marks;
+    double side_ms = 0.0;
 
     template <class Tp> int alloc(Tp **ptr, size_t count)
     {
@@ -122,14 +142,25 @@ struct Ctx {
             ++(ctx)->launches;                                                                     \
         }                                                                                          \
     } while (0)
-#define LAUNCH(ctx, kernel, grid, block, ...)                                                      \
-    do {                                                                                           \
-        const int grid_ = (grid);                                                                  \
-        if (grid_ > 0) { /* an empty slab launches nothing */                                      \
-            kernel<<<grid_, (block), 0, (ctx)->stream>>>(__VA_ARGS__);                              \
-            ++(ctx)->launches;                                                                     \
-        }                                                                                          \
-    } while (0)
+#define LAUNCH(ctx, kernel, grid, block, ...) LAUNCH_ON(ctx, (ctx)->stream, kernel, grid, block, __VA_ARGS__)
+
+// temporary device allocations of one call: freed on every exit path
+struct Scratch {
+    std::vector<void *> ptrs;
+    ~Scratch() { for (void *q : ptrs) cudaFree(q); }
+    template <class Tp> int get(Tp **ptr, size_t count)
+    {
+        void *q = nullptr;
+        if (cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(Tp)) != cudaSuccess) {
+            cudaGetLastError();
+            set_last_error("cudaMalloc (scratch) failed");
+            return MPHX_ERR_NOMEM;
+        }
+        ptrs.push_back(q);
+        *ptr = (Tp *)q;
+        return MPHX_OK;
+    }
+};
 
 static int alloc_particles(Ctx *c, Particles *p, size_t n)
 {
@@ -185,6 +216,21 @@ static int build_stencil(GridDesc &g, double cutoff)
     return MPHX_OK;
 }
 
+// largest kernel radius either pass uses: they share one candidate list
+static double sweep_radius(const Ctx *c)
+{
+    const mphx_constants &k = c->c;
+    double rmax = std::max(k.radius_p, k.radius_v);
+    if (c->surface_tension) rmax = std::max(rmax, k.radius_a);
+    return rmax;
+}
+// the Verlet skin actually used (metres): never wider than what the bucket stencil (range * CellWidth) covers
+static double skin_length(const Ctx *c)
+{
+    const double room = (double)c->grid.range * c->grid.cellw - sweep_radius(c);
+    return std::max(0.0, std::min(c->skin * c->p.particle_spacing, 0.9 * room));
+}
+
 static int setup_constants(Ctx *c)
 {
     const mphx_params &p = c->p;
@@ -200,9 +246,6 @@ static int setup_constants(Ctx *c)
     g.cellw = k.cell_width;
     for (int d = 0; d < 3; ++d) { g.mn[d] = p.domain_min[d]; g.W[d] = k.domain_width[d]; }
     g.slab = 0; g.nxg = g.nx; g.xoff = 0; g.mn0g = p.domain_min[0];
-    const double cutoff = k.max_radius + 0.1 * p.particle_spacing; // MaxRadius+MARGIN (:116,:1765)
-    rc = build_stencil(g, cutoff);
-    if (rc) { set_last_error("stencil too large (radius ratio too big)"); return rc; }
     // every traversed axis must hold the whole stencil once (otherwise the reference itself visits
     // buckets several times, :1751-1755)
     const int need = 2 * g.range + 1;
@@ -241,11 +284,16 @@ static int setup_constants(Ctx *c)
     }
     for (int d = 0; d < 3; ++d) ph.g[d] = p.gravity[d];
     c->cw_tl = (1.0 / k.swp) * (1.0 / hd(k.radius_p));
+    // the stencil must reach the reference's list cut-off MaxRadius+MARGIN (:116,:1765) and the candidate
+    // list's own radius (largest kernel radius + skin)
+    const double cutoff = std::max(k.max_radius + 0.1 * p.particle_spacing, sweep_radius(c) + skin_length(c));
+    rc = build_stencil(g, cutoff);
+    if (rc) { set_last_error("stencil too large (radius ratio too big)"); return rc; }
     return MPHX_OK;
 }
 
 // The solid sub-steps run on a second stream and are joined as late as possible: they overlap the fluid's
-// share of pass 2 (single context) and the pre-step / migration / halo phases of the next step.
+// share of pass 2 and the fluid/wall share of the next pre-step.
 static bool defer_solids(const Ctx *c) { return c->overlap_solid && c->ns > 0 && c->side != nullptr && c->pl.nbr != nullptr; }
 static int join_solids(Ctx *c)
 {
@@ -256,15 +304,90 @@ static int join_solids(Ctx *c)
     return MPHX_OK;
 }
 
-// ---- bucket rebuild: K1 key/count, K2 scan, K3 scatter, K4 permute -------------------------------
-static int stage_prestep(Ctx *c, bool prestep_motion, SlabSend snd)
+// the exact slot count (device -> host; synchronises the context's stream)
+static int read_n(Ctx *c, int *n)
 {
-    const int n = c->n;
-    CK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)c->grid.ncells + 2), c->stream));
+    CK(cudaMemcpyAsync(n, &c->ctl->n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return MPHX_OK;
+}
+static int request_rebuild(Ctx *c)
+{
+    const int one = 1;
+    CK(cudaMemcpyAsync(&c->ctl->force, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    return MPHX_OK;
+}
+
+// squared cut-off (bucket units) of the fp32 candidate filter: the exact cut-off plus a margin that
+// covers the rounding of the fp32 bucket coordinates (<= 2 ulp at the largest coordinate, per axis)
+// and of the fp32 distance arithmetic, so the filter is a superset of the fp64 predicate.
+static float filter_radius2(const Ctx *c, double rmax)
+{
+    const GridDesc &g = c->grid;
+    const double R = rmax / g.cellw;
+    const double big = (double)std::max(std::max(std::max(g.nx, g.nxg), g.ny), std::max(g.nz, 4)) + 2.0 * g.range + 2.0;
+    const double delta = std::ldexp(big, -22);           // 2 ulp_f32(big) per coordinate, both particles
+    const double margin = 2.0 * std::sqrt(3.0) * (R + 1.0) * (2.0 * delta) + 3.0 * (2.0 * delta) * (2.0 * delta) +
+                          8.0 * std::ldexp((R + 1.0) * (R + 1.0), -23) + 1e-6;
+    return (float)(R * R + margin) * (1.0f + 1e-6f);
+}
+
+static bool walls_move(const Ctx *c)
+{
+    if (c->nw <= 0 || !(c->time < 0.2)) return false; // Q7 (:3037)
+    for (int t = 4; t < kTypeCount; ++t)
+        for (int d = 0; d < 3; ++d)
+            if (c->p.wall_velocity[t][d] != 0.0 || c->p.wall_omega[t][d] != 0.0) return true;
+    return false;
+}
+
+static DecideArgs decide_args(const Ctx *c)
+{
+    DecideArgs a{};
+    const double skin = skin_length(c);
+    // moving walls travel |V| dt + |omega| r dt per step without entering the fluid's displacement bound: rebuild
+    // every step while they move (t < 0.2, Q7)
+    a.reuse_enabled = (c->list_reuse && c->pl.nbr != nullptr && skin > 0.0 && !walls_move(c)) ? 1 : 0;
+    a.half_skin2 = (float)(0.25 * skin * skin * (1.0 - 1e-6));
+    a.filt2_plain = filter_radius2(c, sweep_radius(c));
+    a.filt2_skin = filter_radius2(c, sweep_radius(c) + skin);
+    return a;
+}
+
+static void timer_mark(Ctx *c);
+
+// ---- exchange between slabs: all device-side (see kernels.cuh "Exchange between slabs") --------------------
+constexpr int kPushBlocks = 64, kPushThreads = 256;
+enum { kPushMigL = 0, kPushMigR, kPushHaloL, kPushHaloR, kPushPL, kPushPR, kPushSolP, kPushSolV };
+
+static int exchange_particles(Ctx *c, bool halo)
+{
+    // what I send "to the left" arrives in the left neighbour's mailbox as "from the right" (side 1), and vice versa
+    Ctl *ctl = c->ctl;
+    double **stage = halo ? c->stage_halo : c->stage_mig;
+    const int *cnt = halo ? ctl->halo_cnt : ctl->mig_cnt;
+    const int w0 = halo ? kPushHaloL : kPushMigL;
+    Mailbox &L = c->peers.left, &R = c->peers.right;
+    LAUNCH(c, k_push, kPushBlocks, kPushThreads, ctl, c->epoch, w0, stage[0], cnt + 0, kMsgDoubles, halo ? L.halo[1] : L.mig[1],
+           (halo ? L.cnt_halo : L.cnt_mig) + 1, (halo ? L.fhalo : L.fmig) + 1);
+    LAUNCH(c, k_push, kPushBlocks, kPushThreads, ctl, c->epoch, w0 + 1, stage[1], cnt + 1, kMsgDoubles, halo ? R.halo[0] : R.mig[0],
+           (halo ? R.cnt_halo : R.cnt_mig) + 0, (halo ? R.fhalo : R.fmig) + 0);
+    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, halo ? c->mine.fhalo : c->mine.fmig, 2);
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+// ---- bucket rebuild / refresh: K0 pre-step, decision, K1 count (+ slab exchange), K2 scan, K3 scatter, K4 permute ---
+// motion: the step's calculateWall / calculatePeriodicBoundary (false: buckets over the positions as they are)
+static int stage_build(Ctx *c, bool motion)
+{
+    Ctl *ctl = c->ctl;
+    const int nb = nblk(c->nmax);
+    ++c->epoch;
     WallMotion wm;
     std::memset(&wm, 0, sizeof(wm));
     wm.dt = c->p.dt;
-    wm.active = (prestep_motion && c->time < 0.2 && c->nw > 0) ? 1 : 0; // Q7 (:3037)
+    wm.active = (motion && c->time < 0.2 && c->nw > 0) ? 1 : 0; // Q7 (:3037)
     if (wm.active)
         for (int t = 0; t < kTypeCount; ++t)
             for (int d = 0; d < 3; ++d) {
@@ -273,136 +396,143 @@ static int stage_prestep(Ctx *c, bool prestep_motion, SlabSend snd)
                 wm.omega[t][d] = c->p.wall_omega[t][d];
                 for (int e = 0; e < 3; ++e) wm.R[t][d][e] = c->c.wall_rotation[t][d][e];
             }
-    if (n > 0)
-        LAUNCH(c, k_prestep, nblk(n), kBlock, n, c->S, c->sol, c->grid, wm, prestep_motion ? 1 : 0, c->cellCount, c->slot, snd,
-               (const int *)nullptr, defer_solids(c) ? 1 : 0);
-    c->held_wm = wm; c->held_wrap = prestep_motion ? 1 : 0;
-    if (prestep_motion) // :3066-3070 (host mirror of the wall centres)
-        for (int t = 4; t < kTypeCount; ++t)
-            for (int d = 0; d < 3; ++d) c->wall_center[t][d] += c->p.wall_velocity[t][d] * c->p.dt;
-    CK(cudaGetLastError());
-    return MPHX_OK;
-}
-
-// K2 scan, K3 scatter, K4 permute over the c->n slots keyed so far; afterwards c->n = live slots
-static int stage_sort(Ctx *c)
-{
-    const int n = c->n;
-    if (defer_solids(c)) { // the solids' share of the pre-step, once their sub-steps have finished
+    const DecideArgs da = decide_args(c); // (before the wall centres advance: walls_move looks at this step's Time)
+    const bool defer = defer_solids(c);
+    LAUNCH(c, k_prestep, nb, kBlock, ctl, c->S, c->sol, c->grid, wm, motion ? 1 : 0, c->ancx, c->ancy, c->ancz, (const int *)nullptr, 0,
+           defer ? 1 : 0);
+    if (defer) { // the solids' share, once their sub-steps have finished
         int rc = join_solids(c);
         if (rc) return rc;
-        SlabSend none{};
-        LAUNCH(c, k_prestep, nblk(c->ns), kBlock, c->ns, c->S, c->sol, c->grid, c->held_wm, c->held_wrap, c->cellCount, c->slot, none,
-               (const int *)c->sol.slot, 0);
+        LAUNCH(c, k_prestep, nblk(c->ns), kBlock, ctl, c->S, c->sol, c->grid, wm, motion ? 1 : 0, c->ancx, c->ancy, c->ancz,
+               (const int *)c->sol.slot, c->ns, 0);
+    }
+    if (motion) // :3066-3070 (host mirror of the wall centres)
+        for (int t = 4; t < kTypeCount; ++t)
+            for (int d = 0; d < 3; ++d) c->wall_center[t][d] += c->p.wall_velocity[t][d] * c->p.dt;
+    // rebuild or reuse: every rank votes, the OR decides (one context: its own vote)
+    LAUNCH(c, k_need, 1, 1, ctl, da, (const int *)c->pl.flags);
+    if (c->slab) {
+        LAUNCH(c, k_vote, 1, 32, ctl, c->epoch, c->peers);
+        LAUNCH(c, k_wait<1>, 1, 32, ctl, c->epoch, c->mine.vote, c->nranks);
+    }
+    LAUNCH(c, k_decide, 1, 1, ctl, da, c->pl.flags);
+    SlabSend snd{};
+    snd.buf[0] = c->stage_mig[0]; snd.buf[1] = c->stage_mig[1]; snd.capacity = c->msg_cap;
+    LAUNCH(c, k_count, nb, kBlock, ctl, c->S, c->grid, c->cellCount, c->slot, snd);
+    if (c->slab) {
+        int rc;
+        const int mb = nblk(c->msg_cap);
+        const double W0 = c->grid.W[0];
+        // (1) migration (rebuild steps; a reuse step sends empty messages)
+        LAUNCH(c, k_clamp_counts, 1, 32, ctl, c->msg_cap);
+        if ((rc = exchange_particles(c, false))) return rc;
+        for (int side = 0; side < 2; ++side)
+            LAUNCH(c, k_unpack_particles, mb, kBlock, ctl, side, c->mine.mig[side], c->mine.cnt_mig, c->msg_cap, c->cap, 0.0, 0, c->S, c->grid,
+                   c->cellCount, c->slot, c->ancx, c->ancy, c->ancz);
+        LAUNCH(c, k_advance_n, 1, 1, ctl, c->mine.cnt_mig, c->msg_cap, c->cap, 0);
+        // (2) halo: rebuild steps pack the particles within one halo width of the faces, reuse steps re-send the same ones
+        SlabSend hs{};
+        hs.buf[0] = c->stage_halo[0]; hs.buf[1] = c->stage_halo[1]; hs.capacity = c->msg_cap;
+        LAUNCH(c, k_halo_pack, nb, kBlock, ctl, c->S, c->grid, hs, c->haloSrc[0], c->haloSrc[1]);
+        LAUNCH(c, k_clamp_counts, 1, 32, ctl, c->msg_cap);
+        LAUNCH(c, k_halo_repack, mb, kBlock, ctl, c->S, hs, c->haloSlot[0], c->haloSlot[1]);
+        if ((rc = exchange_particles(c, true))) return rc;
+        // halo copies that crossed the periodic seam are shifted by the box width so that separations in
+        // x need no wrap inside a slab; migrants were already wrapped into the box by the sender
+        const double sh[2] = {c->rank == 0 ? -W0 : 0.0, c->rank == c->nranks - 1 ? W0 : 0.0};
+        for (int side = 0; side < 2; ++side) {
+            LAUNCH(c, k_unpack_particles, mb, kBlock, ctl, side, c->mine.halo[side], c->mine.cnt_halo, c->msg_cap, c->cap, sh[side], kGhost, c->S,
+                   c->grid, c->cellCount, c->slot, c->ancx, c->ancy, c->ancz);
+            LAUNCH(c, k_unpack_refresh, mb, kBlock, ctl, side, c->mine.halo[side], sh[side], c->S, c->ghostSlot[side]);
+        }
+        LAUNCH(c, k_advance_n, 1, 1, ctl, c->mine.cnt_halo, c->msg_cap, c->cap, 1);
     }
     const int nc = c->grid.ncells + 2; // + parked + dead buckets
-    LAUNCH(c, k_scan_reduce, c->scan_blocks, kScanThreads, c->cellCount, nc, c->blockSums);
-    LAUNCH(c, k_scan_top, 1, kScanThreads, c->blockSums, c->scan_blocks);
-    LAUNCH(c, k_scan_apply, c->scan_blocks, kScanThreads, c->cellCount, nc, c->blockSums, c->cellStart);
-    if (n > 0) {
-        LAUNCH(c, k_scatter_index, nblk(n), kBlock, n, c->S.key, c->slot, c->cellStart, c->tmpIdx);
-        LAUNCH(c, k_permute, nblk(n), kBlock, n, c->S, c->T, c->cellStart, c->tmpIdx, c->grid, c->where, c->sol.slot, c->sol.sb);
-    }
+    LAUNCH(c, k_scan_reduce, c->scan_blocks, kScanThreads, ctl, c->cellCount, nc, c->blockSums);
+    LAUNCH(c, k_scan_top, 1, kScanThreads, ctl, c->blockSums, c->scan_blocks);
+    LAUNCH(c, k_scan_apply, c->scan_blocks, kScanThreads, ctl, c->cellCount, nc, c->blockSums, c->cellStart, 1);
+    LAUNCH(c, k_scatter_index, nb, kBlock, ctl, c->S.key, c->slot, c->cellStart, c->tmpIdx);
+    LAUNCH(c, k_permute, nb, kBlock, ctl, c->S, c->T, c->cellStart, c->tmpIdx, c->grid, c->where, c->sol.slot, c->sol.sb, c->ancx, c->ancy,
+           c->ancz);
+    LAUNCH(c, k_set_n, 1, 1, ctl, c->cellStart, c->grid.ncells);
     std::swap(c->S, c->T);
     c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
-    c->buckets_valid = true;
-    if (c->slab) { // ghosts of the last step and emigrants sit in the dead bucket: drop them
-        // (one synchronisation: the live slot count and the exchange error flags come back together)
-        int keep = 0;
-        CK(cudaMemcpyAsync(&keep, c->cellStart + c->grid.ncells + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaMemcpyAsync(c->slab_err, c->d_err, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        c->n = keep;
+    if (c->slab) {
+        LAUNCH(c, k_slab_slots, nblk(c->msg_cap), kBlock, ctl, c->where, c->haloSrc[0], c->haloSrc[1], c->haloSlot[0], c->haloSlot[1],
+               c->ghostSlot[0], c->ghostSlot[1]);
+        if (c->ns > 0) LAUNCH(c, k_solid_owned_list, nb, kBlock, ctl, c->S, c->own_sol);
     }
     CK(cudaGetLastError());
     return MPHX_OK;
 }
 
-static int rebuild_buckets(Ctx *c, bool prestep_motion)
-{
-    if (c->slab) { set_last_error("slab contexts are stepped through the mphx_slab_* calls"); return MPHX_ERR_INVALID; }
-    SlabSend none{};
-    int rc = stage_prestep(c, prestep_motion, none);
-    if (rc) return rc;
-    return stage_sort(c);
-}
-
-// squared cut-off (bucket units) of the sweep's fp32 filter: the exact cut-off plus a margin that
-// covers the rounding of the fp32 bucket coordinates (<= 2 ulp at the largest coordinate, per axis)
-// and of the fp32 distance arithmetic, so the filter is a superset of the fp64 predicate.
-static float filter_radius2(const Ctx *c, double rmax)
-{
-    const GridDesc &g = c->grid;
-    const double R = rmax / g.cellw;
-    const double big = (double)std::max(std::max(g.nx, g.ny), std::max(g.nz, 4)) + 2.0 * g.range + 2.0;
-    const double delta = std::ldexp(big, -22);           // 2 ulp_f32(big) per coordinate, both particles
-    const double margin = 2.0 * std::sqrt(3.0) * (R + 1.0) * (2.0 * delta) + 3.0 * (2.0 * delta) * (2.0 * delta) +
-                          8.0 * std::ldexp((R + 1.0) * (R + 1.0), -23) + 1e-6;
-    return (float)(R * R + margin) * (1.0f + 1e-6f);
-}
-
-static float sweep_filter2(const Ctx *c)
-{
-    // the filter covers every kernel radius of BOTH passes: they share one candidate list
-    const mphx_constants &k = c->c;
-    double rmax = std::max(k.radius_p, k.radius_v);
-    if (c->surface_tension) rmax = std::max(rmax, k.radius_a);
-    return filter_radius2(c, rmax);
-}
-
-static void timer_mark(Ctx *c);
 static int run_pass1(Ctx *c, bool timed = false)
 {
-    const int n = c->n;
-    {
-        const float f2 = sweep_filter2(c);
-        const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
-        if (c->pl.nbr) { // K5a: candidate list of this step
-            CK(cudaMemsetAsync(c->pl.flags, 0, sizeof(int), c->stream));
-            const int npairs = (n + 1) / 2;
-            // 32-bit offsets must hold a parked top plus one stride ((L + 1) * cap + i + cap) without wrapping
-            const bool big = ((size_t)c->pl.L + 2) * (size_t)c->pl.cap >= 0xffffffffull;
-            if (c->filter2 || big) {
-#define F2(D, B) LAUNCH(c, (k_filter2<D, B>), nblk(npairs, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl)
-                if (c->p.dim == 3) { if (big) F2(3, true); else F2(3, false); }
-                else               { if (big) F2(2, true); else F2(2, false); }
+    Ctl *ctl = c->ctl;
+    const int nmax = c->nmax;
+    const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
+    if (c->pl.nbr) { // K5a: the candidate list (rebuild steps only: the kernel returns at once otherwise)
+        const int npairs = (nmax + 1) / 2;
+        // 32-bit offsets must hold a parked top plus one stride ((L + 1) * cap + i + cap) without wrapping
+        const bool big = ((size_t)c->pl.L + 2) * (size_t)c->pl.cap >= 0xffffffffull;
+        if (c->filter2 || big) {
+#define F2(D, B) LAUNCH(c, (k_filter2<D, B>), nblk(npairs, kSweepThreads), kSweepThreads, ctl, c->S, c->cellStart, c->grid, c->pl)
+            if (c->p.dim == 3) { if (big) F2(3, true); else F2(3, false); }
+            else               { if (big) F2(2, true); else F2(2, false); }
 #undef F2
-            } else {
-                if (c->p.dim == 3) LAUNCH(c, k_filter<3>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
-                else               LAUNCH(c, k_filter<2>, nblk(n, kSweepThreads), kSweepThreads, n, c->S, c->cellStart, c->grid, f2, c->pl);
-            }
+        } else {
+            if (c->p.dim == 3) LAUNCH(c, k_filter<3>, nblk(nmax, kSweepThreads), kSweepThreads, ctl, c->S, c->cellStart, c->grid, c->pl);
+            else               LAUNCH(c, k_filter<2>, nblk(nmax, kSweepThreads), kSweepThreads, ctl, c->S, c->cellStart, c->grid, c->pl);
         }
-        if (timed) timer_mark(c);
-        // fused-sweep fall-backs: a small persistent grid when they only have to look at the overflow flag
-        const int vblocks = nblk(n, kSweepThreads);
+    }
+    if (timed) timer_mark(c);
+    // fused-sweep fall-backs: a small persistent grid when they only have to look at the overflow flag
+    const int vblocks = nblk(nmax, kSweepThreads);
 #define SWEEP_GRID(LIST) ((LIST) || !c->pl.nbr ? vblocks : std::min(vblocks, 4 * 148))
-#define P1(D, ST, LIST) LAUNCH(c, (k_pass1_v3<D, ST, LIST>), SWEEP_GRID(LIST), kSweepThreads, vblocks, n, c->S, c->cellStart, c->grid, c->phys, f2, \
+#define P1(D, ST, LIST) LAUNCH(c, (k_pass1_v3<D, ST, LIST>), SWEEP_GRID(LIST), kSweepThreads, ctl, c->S, c->cellStart, c->grid, c->phys, \
                          batch, c->P, c->volStrain, c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA, c->pl)
 #define P1D(ST, LIST) do { if (c->p.dim == 3) P1(3, ST, LIST); else P1(2, ST, LIST); } while (0)
-        if (c->pl.nbr) { // list traversal, then the fused sweep for particles whose list overflowed (normally none)
-            if (c->surface_tension) P1D(true, true); else P1D(false, true);
-        }
-        if (c->surface_tension) P1D(true, false); else P1D(false, false);
+    if (c->pl.nbr) { // list traversal, then the fused sweep for particles whose list overflowed (normally none)
+        if (c->surface_tension) P1D(true, true); else P1D(false, true);
+    }
+    if (c->surface_tension) P1D(true, false); else P1D(false, false);
 #undef P1D
 #undef P1
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
+// slab mode, between the passes: PressureP of the halo copies (ring neighbours) and of the replicated solids (all ranks)
+static int exchange_pressure(Ctx *c)
+{
+    Ctl *ctl = c->ctl;
+    Mailbox &L = c->peers.left, &R = c->peers.right;
+    LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPL, 0, c->haloSlot[0], c->P, L.p[1], L.fp + 1);
+    LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPR, 1, c->haloSlot[1], c->P, R.p[0], R.fp + 0);
+    if (c->ns > 0) LAUNCH(c, k_solid_publish_P, kPushBlocks, kPushThreads, ctl, c->epoch, kPushSolP, c->S, c->sol, c->own_sol, c->P, c->peers);
+    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fp, 2);
+    const int mb = nblk(c->msg_cap);
+    for (int side = 0; side < 2; ++side) LAUNCH(c, k_unpack_scalar, mb, kBlock, ctl, side, c->ghostSlot[side], c->mine.p[side], c->P, c->S.rb);
+    if (c->ns > 0) {
+        LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fsolP, c->nranks);
+        LAUNCH(c, k_solid_spread_P, nblk(c->nmax), kBlock, ctl, c->S, c->grid, c->sol, c->mine.solP, c->P);
     }
     CK(cudaGetLastError());
     return MPHX_OK;
 }
 
-// single context with solids and a candidate list: pass 2 is split so that the sub-steps can overlap it
-static bool solid_split(const Ctx *c) { return defer_solids(c) && !c->slab; }
+// the solids' share of pass 2 first (a few blocks), so that the sub-steps can start on the second stream
+static bool solid_split(const Ctx *c) { return defer_solids(c); }
 
-static int run_pass2(Ctx *c, double *solbuf = nullptr)
+static int run_pass2(Ctx *c)
 {
-    const int n = c->n;
-    {
-        const float f2 = sweep_filter2(c);
-        const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
-        const int vblocks = nblk(n, kSweepThreads);
-#define P2(D, ST, LIST, GRID, SUB) LAUNCH(c, (k_pass2_v3<D, ST, LIST>), GRID, kSweepThreads, vblocks, n, c->S, c->cellStart, c->grid, \
-                         c->phys, f2, batch, c->P, c->PA, c->gcx, c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, \
-                         c->fy, c->fz, c->ax, c->ay, c->az, c->sol, solbuf, c->pl, SUB)
+    Ctl *ctl = c->ctl;
+    const int nmax = c->nmax;
+    const int batch = c->p.dim == 3 ? c->sweep_batch : c->grid.nsten;
+    const int vblocks = nblk(nmax, kSweepThreads);
+#define P2(D, ST, LIST, GRID, SUB) LAUNCH(c, (k_pass2_v3<D, ST, LIST>), GRID, kSweepThreads, ctl, c->S, c->cellStart, c->grid, \
+                         c->phys, batch, c->P, c->PA, c->gcx, c->gcy, c->gcz, c->T.x, c->T.y, c->T.z, c->T.vx, c->T.vy, c->T.vz, c->fx, \
+                         c->fy, c->fz, c->ax, c->ay, c->az, c->sol, c->pl, SUB)
 #define P2D(ST, LIST, GRID, SUB) do { if (c->p.dim == 3) P2(3, ST, LIST, GRID, SUB); else P2(2, ST, LIST, GRID, SUB); } while (0)
 #define P2ALL(GRIDL, SUB) do { \
         if (c->pl.nbr) { /* list traversal, then the sweep variant for particles whose list overflowed (normally none) */ \
@@ -410,22 +540,25 @@ static int run_pass2(Ctx *c, double *solbuf = nullptr)
         } \
         if (c->surface_tension) P2D(true, false, SWEEP_GRID(false), SUB); else P2D(false, false, SWEEP_GRID(false), SUB); \
     } while (0)
-        if (solid_split(c)) {
-            // the solids' share first (a few blocks), so that the sub-steps can start; then everything else
-            const Subset solids{c->sol.slot, c->ns, 0}, rest{nullptr, 0, 1};
-            P2ALL(nblk(c->ns, kSweepThreads), solids);
-            CK(cudaEventRecord(c->ev_solid_ready, c->stream));
-            P2ALL(vblocks, rest);
-        } else {
-            const Subset all{nullptr, 0, 0};
-            P2ALL(vblocks, all);
-        }
+    const bool split = solid_split(c);
+    if (c->ns > 0 && (split || c->slab)) {
+        const Subset solids{c->sol.slot, c->ns, 0};
+        P2ALL(nblk(c->ns, kSweepThreads), solids);
+        // slab mode: the owners' coupled velocities go to every rank's mailbox
+        if (c->slab) LAUNCH(c, k_solid_publish_V, kPushBlocks, kPushThreads, ctl, c->epoch, kPushSolV, c->S, c->sol, c->own_sol, c->peers);
+        if (split) CK(cudaEventRecord(c->ev_solid_ready, c->stream));
+        const Subset rest{nullptr, 0, 1};
+        P2ALL(vblocks, rest);
+    } else {
+        const Subset all{nullptr, 0, 0};
+        P2ALL(vblocks, all);
+    }
 #undef P2ALL
 #undef P2D
 #undef P2
-    }
+#undef SWEEP_GRID
     // S keeps type/id/key of this step's order and takes the integrated x,v; T keeps the pre-step
-    // (bucket) positions for the neighbour-count diagnostics.
+    // positions (the ones the reference's NeighborCount refers to).
     std::swap(c->S.x, c->T.x); std::swap(c->S.y, c->T.y); std::swap(c->S.z, c->T.z);
     std::swap(c->S.vx, c->T.vx); std::swap(c->S.vy, c->T.vy); std::swap(c->S.vz, c->T.vz);
     c->bx = c->T.x; c->by = c->T.y; c->bz = c->T.z;
@@ -441,6 +574,10 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
     const double cw = c->cw_tl;
     const int ns = c->ns;
     const int dbl = (c->p.ref_compat & MPHX_COMPAT_DOUBLE_UPDATE) ? 1 : 0;
+    if (c->slab) { // every rank takes the owners' coupled velocities, then runs the identical sub-steps
+        LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, c->epoch, c->mine.fsolV, c->nranks);
+        LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV);
+    }
     for (int s = 0; s < substeps; ++s) {
         if (c->p.dim == 3) {
             LAUNCH_ON(c, strm, k_solid_pass1<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw);
@@ -456,44 +593,64 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
     return MPHX_OK;
 }
 
+static cudaEvent_t timer_event(Ctx *c)
+{
+    cudaEvent_t e;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
 static void timer_mark(Ctx *c)
 {
     if (!c->timing) return;
-    cudaEvent_t e;
-    cudaEventCreate(&e);
+    cudaEvent_t e = timer_event(c);
     cudaEventRecord(e, c->stream);
     c->ev.push_back(e);
 }
 static void timer_resolve(Ctx *c)
 {
-    if (c->ev.empty()) return;
+    if (c->ev.empty() && c->side_marks.empty()) return;
     cudaStreamSynchronize(c->stream);
+    if (c->side) cudaStreamSynchronize(c->side);
     // events come in groups of 6 per step: start, after rebuild, after the filter, after pass 1, after
-    // pass 2, after the solid sub-steps
+    // pass 2, after the solid sub-steps (when those run on the context's stream)
     for (size_t i = 0; i + 5 < c->ev.size(); i += 6)
         for (int k = 0; k < 5; ++k) {
             float a = 0;
             cudaEventElapsedTime(&a, c->ev[i + k], c->ev[i + k + 1]);
             c->ms[k] += a;
         }
-    for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    // sub-steps on the second stream: their own event pairs (the reference's "explicit calculation" timer
+    // includes them, src/main.cpp:669)
+    for (size_t i = 0; i + 1 < c->side_marks.size(); i += 2) {
+        float a = 0;
+        cudaEventElapsedTime(&a, c->side_marks[i], c->side_marks[i + 1]);
+        c->ms[4] += a;
+    }
+    for (cudaEvent_t e : c->ev) c->ev_pool.push_back(e);
+    for (cudaEvent_t e : c->side_marks) c->ev_pool.push_back(e);
     c->ev.clear();
+    c->side_marks.clear();
 }
 
 static int one_step(Ctx *c, bool fluid_only)
 {
     int rc;
+    if (c->slab && !c->connected) { set_last_error("slab context is not connected to its peers (mphx_slab_connect)"); return MPHX_ERR_INVALID; }
     timer_mark(c);
-    if ((rc = rebuild_buckets(c, true))) return rc; // calculateWall, PeriodicBoundary, resets, calculateNeighbor
+    if ((rc = stage_build(c, true))) return rc;     // calculateWall, PeriodicBoundary, resets, calculateNeighbor
     timer_mark(c);
     if ((rc = run_pass1(c, true))) return rc;       // filter; DensityA..DivergenceP, coefficients, PressureP/A
+    if (c->slab && (rc = exchange_pressure(c))) return rc;
     timer_mark(c);
     if ((rc = run_pass2(c))) return rc;             // force sums, gravity, interface, acceleration, convection
     timer_mark(c);
     if (!fluid_only) {
-        if (solid_split(c)) { // sub-steps on the second stream: joined by the next bucket sort (or by any reader)
+        if (solid_split(c)) { // sub-steps on the second stream: joined by the next pre-step (or by any reader)
             CK(cudaStreamWaitEvent(c->side, c->ev_solid_ready, 0));
+            if (c->timing) { cudaEvent_t e = timer_event(c); cudaEventRecord(e, c->side); c->side_marks.push_back(e); }
             if ((rc = run_solid_substeps(c, c->side))) return rc;
+            if (c->timing) { cudaEvent_t e = timer_event(c); cudaEventRecord(e, c->side); c->side_marks.push_back(e); }
             CK(cudaEventRecord(c->ev_solid_done, c->side));
             c->solids_pending = true;
         } else if ((rc = run_solid_substeps(c, c->stream))) return rc;
@@ -505,136 +662,128 @@ static int one_step(Ctx *c, bool fluid_only)
     return MPHX_OK;
 }
 
-// ---- initial structure lists (calculateInitialNeighbor :1497-1644) + Lame + Normalizer ----------
-static int exact_lists(Ctx *c, bool structure_only, bool xy_only, int row_base, int nrows,
-                       std::vector<long long> &offsets, int **d_ids_out, long long *total_out)
+// ---- exact neighbour sets (debug / VTK NeighborCount / the initial structure lists) -----------------------
+// A private bucket structure over `n` positions (x, y, z; type, id) on `grid`, then the reference's
+// bit-exact predicate.  Independent of the stepping state (which may be several steps into a reused list).
+static int exact_lists(Ctx *c, int n, const double *x, const double *y, const double *z, const int *type, const int *id, GridDesc grid,
+                       bool structure_only, bool xy_only, int row_base, int nrows, std::vector<long long> &offsets, std::vector<int> *ids_out)
 {
-    // neighbour sets over the positions the buckets were last built from
-    const int n = c->n;
-    int *d_counts = nullptr;
-    long long *d_off = nullptr;
-    CK(cudaMalloc(&d_counts, sizeof(int) * (size_t)std::max(nrows, 1)));
+    Scratch tmp;
+    double *sx, *sy, *sz;
+    int *stype, *sid, *skey, *key, *slot, *cellCount, *cellStart, *blockSums, *d_counts;
+    const size_t nn = (size_t)std::max(n, 1), nc = (size_t)grid.ncells + 2;
+    const int sb_blocks = (int)((nc + kScanChunk - 1) / kScanChunk);
+    int e = 0;
+    e |= tmp.get(&sx, nn); e |= tmp.get(&sy, nn); e |= tmp.get(&sz, nn);
+    e |= tmp.get(&stype, nn); e |= tmp.get(&sid, nn); e |= tmp.get(&skey, nn); e |= tmp.get(&key, nn); e |= tmp.get(&slot, nn);
+    e |= tmp.get(&cellCount, nc); e |= tmp.get(&cellStart, nc + 1); e |= tmp.get(&blockSums, (size_t)sb_blocks + 1);
+    e |= tmp.get(&d_counts, (size_t)std::max(nrows, 1));
+    if (e) return MPHX_ERR_NOMEM;
+    CK(cudaMemsetAsync(cellCount, 0, sizeof(int) * nc, c->stream));
     CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)std::max(nrows, 1), c->stream));
+    LAUNCH(c, k_dbg_keycount, nblk(n), kBlock, n, x, y, z, grid, key, cellCount, slot);
+    LAUNCH(c, k_scan_reduce, sb_blocks, kScanThreads, (const Ctl *)nullptr, cellCount, (int)nc, blockSums);
+    LAUNCH(c, k_scan_top, 1, kScanThreads, (const Ctl *)nullptr, blockSums, sb_blocks);
+    LAUNCH(c, k_scan_apply, sb_blocks, kScanThreads, (const Ctl *)nullptr, cellCount, (int)nc, blockSums, cellStart, 0);
+    LAUNCH(c, k_dbg_gather, nblk(n), kBlock, n, x, y, z, type, id, key, slot, cellStart, sx, sy, sz, stype, sid, skey);
     const double cut = c->c.max_radius + 0.1 * c->p.particle_spacing;
     const double cutoff2 = cut * cut; // (MaxRadius+MARGIN)*(MaxRadius+MARGIN) :1765
-    const Particles &S = c->S;
-    if (c->p.dim == 3)
-        LAUNCH(c, (k_neighbors_exact<3, 0>), nblk(n), kBlock, n, c->bx, c->by, c->bz, S.type, S.id, S.key, c->cellStart, c->grid,
-               cutoff2, structure_only ? 1 : 0, xy_only ? 1 : 0, row_base, d_counts, (const long long *)nullptr, (int *)nullptr);
+    if (grid.dim == 3)
+        LAUNCH(c, (k_neighbors_exact<3, 0>), nblk(n), kBlock, n, sx, sy, sz, stype, sid, skey, cellStart, grid, cutoff2, structure_only ? 1 : 0,
+               xy_only ? 1 : 0, row_base, d_counts, (const long long *)nullptr, (int *)nullptr);
     else
-        LAUNCH(c, (k_neighbors_exact<2, 0>), nblk(n), kBlock, n, c->bx, c->by, c->bz, S.type, S.id, S.key, c->cellStart, c->grid,
-               cutoff2, structure_only ? 1 : 0, xy_only ? 1 : 0, row_base, d_counts, (const long long *)nullptr, (int *)nullptr);
+        LAUNCH(c, (k_neighbors_exact<2, 0>), nblk(n), kBlock, n, sx, sy, sz, stype, sid, skey, cellStart, grid, cutoff2, structure_only ? 1 : 0,
+               xy_only ? 1 : 0, row_base, d_counts, (const long long *)nullptr, (int *)nullptr);
     std::vector<int> counts((size_t)std::max(nrows, 1));
     CK(cudaMemcpyAsync(counts.data(), d_counts, sizeof(int) * (size_t)std::max(nrows, 1), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     offsets.assign((size_t)nrows + 1, 0);
     for (int r = 0; r < nrows; ++r) offsets[r + 1] = offsets[r] + counts[r];
     const long long total = offsets[nrows];
-    *total_out = total;
-    cudaFree(d_counts);
-    if (!d_ids_out) return MPHX_OK;
-    int *d_ids = nullptr;
-    CK(cudaMalloc(&d_ids, sizeof(int) * (size_t)std::max<long long>(total, 1)));
-    CK(cudaMalloc(&d_off, sizeof(long long) * ((size_t)nrows + 1)));
+    if (!ids_out) { CK(cudaGetLastError()); return MPHX_OK; }
+    int *d_ids;
+    long long *d_off;
+    if (tmp.get(&d_ids, (size_t)std::max<long long>(total, 1)) || tmp.get(&d_off, (size_t)nrows + 1)) return MPHX_ERR_NOMEM;
     CK(cudaMemcpyAsync(d_off, offsets.data(), sizeof(long long) * ((size_t)nrows + 1), cudaMemcpyHostToDevice, c->stream));
-    if (c->p.dim == 3)
-        LAUNCH(c, (k_neighbors_exact<3, 1>), nblk(n), kBlock, n, c->bx, c->by, c->bz, S.type, S.id, S.key, c->cellStart, c->grid,
-               cutoff2, structure_only ? 1 : 0, xy_only ? 1 : 0, row_base, (int *)nullptr, d_off, d_ids);
+    if (grid.dim == 3)
+        LAUNCH(c, (k_neighbors_exact<3, 1>), nblk(n), kBlock, n, sx, sy, sz, stype, sid, skey, cellStart, grid, cutoff2, structure_only ? 1 : 0,
+               xy_only ? 1 : 0, row_base, (int *)nullptr, d_off, d_ids);
     else
-        LAUNCH(c, (k_neighbors_exact<2, 1>), nblk(n), kBlock, n, c->bx, c->by, c->bz, S.type, S.id, S.key, c->cellStart, c->grid,
-               cutoff2, structure_only ? 1 : 0, xy_only ? 1 : 0, row_base, (int *)nullptr, d_off, d_ids);
+        LAUNCH(c, (k_neighbors_exact<2, 1>), nblk(n), kBlock, n, sx, sy, sz, stype, sid, skey, cellStart, grid, cutoff2, structure_only ? 1 : 0,
+               xy_only ? 1 : 0, row_base, (int *)nullptr, d_off, d_ids);
+    ids_out->assign((size_t)std::max<long long>(total, 1), 0);
+    CK(cudaMemcpyAsync(ids_out->data(), d_ids, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
-    cudaFree(d_off);
-    *d_ids_out = d_ids;
+    ids_out->resize((size_t)total);
     return MPHX_OK;
 }
+// neighbour sets of the particles this context holds, over the positions of the last pass 1
+static int exact_lists_current(Ctx *c, std::vector<long long> &offsets, std::vector<int> *ids_out)
+{
+    int n = 0, rc;
+    if ((rc = join_solids(c))) return rc;
+    if ((rc = read_n(c, &n))) return rc;
+    return exact_lists(c, n, c->bx, c->by, c->bz, c->S.type, c->S.id, c->grid, false, false, 0, c->n_global, offsets, ids_out);
+}
 
+// ---- initial structure lists (calculateInitialNeighbor :1497-1644) + Lame + Normalizer ----------
 static int init_solid(Ctx *c)
 {
     if (c->ns <= 0) return MPHX_OK;
     const int ns = c->ns;
     int rc;
-    // calculateInitialNeighbor (:1497-1644): buckets over InitialPosition, structure particles only.
-    // Built on a temporary particle set (the solids in their reference configuration) with the
+    // calculateInitialNeighbor (:1497-1644): buckets over InitialPosition, structure particles only, on the
     // GLOBAL periodic grid, so the lists are complete on every slab of a multi-GPU run.
-    Ctx saved = *c; // shallow: pointers / descriptors swapped out below are restored from here
+    GridDesc g = c->grid;
     {
-        GridDesc &g = c->grid;
         const mphx_constants &k = c->c;
-        g.slab = 0; g.nx = k.cell_count[0]; g.nxg = g.nx; g.xoff = 0; g.mn[0] = c->p.domain_min[0];
+        g.slab = 0; g.nx = k.cell_count[0]; g.nxg = g.nx; g.xoff = 0; g.mn[0] = c->p.domain_min[0]; g.mn0g = g.mn[0];
         g.ncells = k.cell_counts;
     }
-    Particles A{}, B{};
-    std::vector<void *> tmp;
-    auto talloc = [&](auto **ptr, size_t count) -> int {
-        void *q = nullptr;
-        if (cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(**ptr)) != cudaSuccess) return MPHX_ERR_NOMEM;
-        tmp.push_back(q);
-        *ptr = (std::remove_reference_t<decltype(**ptr)> *)q;
-        return 0;
-    };
-    auto tfree = [&]() { for (void *q : tmp) cudaFree(q); };
-    int e = 0;
-    for (Particles *p : {&A, &B}) {
-        e |= talloc(&p->x, ns); e |= talloc(&p->y, ns); e |= talloc(&p->z, ns);
-        e |= talloc(&p->vx, ns); e |= talloc(&p->vy, ns); e |= talloc(&p->vz, ns);
-        e |= talloc(&p->type, ns); e |= talloc(&p->id, ns); e |= talloc(&p->key, ns); e |= talloc(&p->pf, (size_t)ns / 2 + 4);
-    }
-    e |= talloc(&A.ra, (size_t)ns); e |= talloc(&A.rb, (size_t)ns);
-    B.ra = A.ra; B.rb = A.rb;
-    const size_t ncg = (size_t)c->grid.ncells;
-    const int sb_blocks = (int)((ncg + 2 + kScanChunk - 1) / kScanChunk);
-    e |= talloc(&c->cellCount, ncg + 2); e |= talloc(&c->cellStart, ncg + 3); e |= talloc(&c->blockSums, (size_t)sb_blocks + 1);
-    e |= talloc(&c->slot, ns); e |= talloc(&c->tmpIdx, ns); e |= talloc(&c->where, ns);
-    if (e) { tfree(); *c = saved; return MPHX_ERR_NOMEM; }
-    c->scan_blocks = sb_blocks;
-    c->S = A; c->T = B; c->n = ns; c->slab = false; c->overlap_solid = false; // (restored with the rest of the context)
-    LAUNCH(c, k_solid_reference_particles, nblk(ns), kBlock, c->sol, c->S);
-    // k_prestep reads a solid's position from the solid arrays: point them at the reference positions
-    c->sol.x = saved.sol.x0; c->sol.y = saved.sol.y0; c->sol.z = saved.sol.z0;
-    c->sol.slot = nullptr; // (the permute of this temporary set must not overwrite the solids' real slots)
-    rc = rebuild_buckets(c, false);
-    c->sol = saved.sol;
-    if (rc) { tfree(); *c = saved; return rc; }
     std::vector<long long> off;
-    int *d_ids = nullptr;
-    long long total = 0;
-    rc = exact_lists(c, true, c->p.dim == 2, c->sol.sb, ns, off, &d_ids, &total);
-    if (rc) { tfree(); *c = saved; return rc; }
-    std::vector<int> ids((size_t)std::max<long long>(total, 1));
+    std::vector<int> ids;
     {
-        cudaError_t ce = cudaMemcpy(ids.data(), d_ids, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost);
-        cudaFree(d_ids);
-        const long long launches = c->launches;
-        tfree();
-        *c = saved; // back to the real particle set / grid
-        c->launches = launches;
-        if (ce != cudaSuccess) { set_last_error("copying the initial lists failed"); return MPHX_ERR_CUDA; }
+        Scratch tmp;
+        int *sid;
+        if (tmp.get(&sid, (size_t)ns)) return MPHX_ERR_NOMEM;
+        std::vector<int> h((size_t)ns);
+        for (int s = 0; s < ns; ++s) h[s] = c->sol.sb + s;
+        CK(cudaMemcpyAsync(sid, h.data(), sizeof(int) * (size_t)ns, cudaMemcpyHostToDevice, c->stream));
+        rc = exact_lists(c, ns, c->sol.x0, c->sol.y0, c->sol.z0, c->sol.type, sid, g, true, c->p.dim == 2, c->sol.sb, ns, off, &ids);
+        if (rc) return rc;
     }
-    if (rc) return rc;
+    const long long total = off[ns];
     if (total > 0x7fffffffLL) return MPHX_ERR_UNSUPPORTED;
+    ids.resize((size_t)std::max<long long>(total, 1));
     std::vector<int> off32((size_t)ns + 1);
     for (int s = 0; s <= ns; ++s) off32[s] = (int)off[s];
     // Store every row in the reference's list order: buckets jCX, jCY, jCZ ascending over the
-    // stencil offsets (:1591-1620).  The reference configuration holds at most one solid particle per
-    // bucket (lattice at cell spacing); if a bucket ever holds several, ties fall back to id order.
+    // stencil offsets (:1591-1620).  The reference configuration normally holds at most one solid particle per
+    // bucket (lattice at cell spacing); if a bucket holds several, the reference orders them by its
+    // (unstable) bitonic sort -- ties fall back to id order here and the solid path is then only
+    // guaranteed to 1e-10, not bit for bit (reported through mphx_get_status).
     {
         std::vector<double> hx0(ns), hy0(ns), hz0(ns);
         CK(cudaMemcpy(hx0.data(), c->sol.x0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(hy0.data(), c->sol.y0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
         CK(cudaMemcpy(hz0.data(), c->sol.z0, sizeof(double) * ns, cudaMemcpyDeviceToHost));
-        GridDesc g = c->grid; // global bucket coordinates (the context's own grid may be one slab)
-        g.nx = c->c.cell_count[0]; g.mn[0] = c->p.domain_min[0];
         auto coord = [](double x, double mn, double cw, int n) {
             int v = ((int)std::floor((x - mn) / cw)) % n;
             return (v % n + n) % n;
         };
         std::vector<int> cx(ns), cy(ns), cz(ns);
+        std::vector<long long> cell(ns);
         for (int s = 0; s < ns; ++s) {
             cx[s] = coord(hx0[s], g.mn[0], g.cellw, g.nx);
             cy[s] = coord(hy0[s], g.mn[1], g.cellw, g.ny);
             cz[s] = g.dim == 3 ? coord(hz0[s], g.mn[2], g.cellw, g.nz) : 0;
+            cell[s] = ((long long)cx[s] * g.ny + cy[s]) * g.nz + cz[s];
+        }
+        {
+            std::vector<long long> sorted(cell);
+            std::sort(sorted.begin(), sorted.end());
+            c->solid_multi_occupancy = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
         }
         const int R = g.range, span = 2 * R + 1;
         auto off1 = [&](int cj, int ci, int n) {
@@ -665,7 +814,7 @@ static int init_solid(Ctx *c)
         for (int s = 0; s < ns; ++s)
             for (int k = off32[s]; k < off32[s + 1]; ++k) rnbr[fill[ids[k]]++] = s;
     }
-    e = 0;
+    int e = 0;
     e |= c->alloc(&c->sol.off, (size_t)ns + 1); e |= c->alloc(&c->sol.nbr, (size_t)total);
     e |= c->alloc(&c->sol.roff, (size_t)ns + 1); e |= c->alloc(&c->sol.rnbr, (size_t)total);
     {
@@ -714,12 +863,23 @@ static int init_solid(Ctx *c)
     return MPHX_OK;
 }
 
+// the half step of mphx_init: buckets, candidate list and the density sums on the initial positions (:565-568)
+static int init_enqueue(Ctx *c)
+{
+    int rc;
+    if ((rc = stage_build(c, false))) return rc;
+    return run_pass1(c);
+}
+
 } // namespace mphx
 
 using namespace mphx;
 
 // =================================================================================================
 extern "C" {
+
+static int slab_check_errors(Ctx *c, const char *where);
+static int slab_allocate(Ctx *c);
 
 int mphx_version(void) { return MPHX_VERSION; }
 
@@ -788,12 +948,22 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
     c->time = p->time0;
     for (int t = 0; t < kTypeCount; ++t)
         for (int d = 0; d < 3; ++d) c->wall_center[t][d] = p->wall_center[t][d];
+    if (const char *e = std::getenv("MPHX_LIST_REUSE")) c->list_reuse = std::atoi(e) != 0; // 0: rebuild buckets + list every step
+    if (const char *e = std::getenv("MPHX_LIST_SKIN")) c->skin = std::max(0.0, std::atof(e)); // Verlet skin in particle spacings
     int rc = setup_constants(c);
     if (rc) { delete c; return rc; }
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_last_error("cudaSetDevice/cudaStreamCreate failed");
         delete c;
         return MPHX_ERR_CUDA;
+    }
+    {
+        Ctl init{};
+        init.force = 1;
+        if (c->alloc(&c->ctl, 1) || cudaMemcpy(c->ctl, &init, sizeof(Ctl), cudaMemcpyHostToDevice) != cudaSuccess) {
+            mphx_destroy(reinterpret_cast<mphx_ctx *>(c));
+            return MPHX_ERR_NOMEM;
+        }
     }
     c->timing = std::getenv("MPHX_TIMING") != nullptr;
     if (const char *e = std::getenv("MPHX_SWEEP_BATCH")) c->sweep_batch = std::max(1, std::atoi(e));
@@ -819,7 +989,12 @@ void mphx_destroy(mphx_ctx *ctx)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->side) cudaStreamSynchronize(c->side);
     for (cudaEvent_t e : c->ev) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->side_marks) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (int r = 0; r < kMaxRanks; ++r)
+        if (c->peer_ipc[r] && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
     for (int k = 0; k < 2; ++k) if (c->tev[k]) cudaEventDestroy(c->tev[k]);
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->ev_solid_ready) cudaEventDestroy(c->ev_solid_ready);
@@ -870,8 +1045,8 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
     const bool first = !c->uploaded;
     if (first) {
         c->n_global = n;
-        c->n = nloc;
         if (!c->slab) c->cap = n;
+        c->nmax = c->cap;
         if (nloc > c->cap) { set_last_error("slab capacity too small for the initial particle set"); return MPHX_ERR_NOMEM; }
         const size_t cap = (size_t)c->cap;
         std::memcpy(c->ranges, r, sizeof(r));
@@ -904,8 +1079,7 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         e |= c->alloc(&c->densA, cap); e |= c->alloc(&c->gcx, cap); e |= c->alloc(&c->gcy, cap);
         e |= c->alloc(&c->gcz, cap); e |= c->alloc(&c->PA, cap);
         e |= c->alloc(&c->d_inv_density, kTypeCount);
-        e |= c->alloc(&c->d_err, 4);
-        if (c->slab) { e |= c->alloc(&c->haloSrc[0], (size_t)c->msg_cap); e |= c->alloc(&c->haloSrc[1], (size_t)c->msg_cap); }
+        e |= c->alloc(&c->ancx, cap); e |= c->alloc(&c->ancy, cap); e |= c->alloc(&c->ancz, cap);
         Solid &so = c->sol;
         so.ns = c->ns; so.sb = c->ns > 0 ? r[2] : 0;
         const size_t ns = (size_t)c->ns;
@@ -917,8 +1091,10 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         e |= c->alloc(&so.type, ns); e |= c->alloc(&so.slot, ns);
         if (e) return MPHX_ERR_NOMEM;
         CK(cudaMemcpy(c->d_inv_density, c->phys.inv_density, sizeof(double) * kTypeCount, cudaMemcpyHostToDevice));
-        CK(cudaMemsetAsync(c->d_err, 0, sizeof(int) * 4, c->stream));
-        double *zs[] = {c->P, c->volStrain, c->divP, c->fx, c->fy, c->fz, c->ax, c->ay, c->az, c->densA, c->gcx, c->gcy, c->gcz, c->PA};
+        CK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)c->grid.ncells + 2), c->stream)); // (all-zero outside a rebuild)
+        if (c->slab) { int src = slab_allocate(c); if (src) return src; }
+        double *zs[] = {c->P, c->volStrain, c->divP, c->fx, c->fy, c->fz, c->ax, c->ay, c->az, c->densA, c->gcx, c->gcy, c->gcz, c->PA,
+                        c->ancx, c->ancy, c->ancz};
         for (double *q : zs) CK(cudaMemsetAsync(q, 0, sizeof(double) * cap, c->stream));
         if (ns > 0)
             for (double **q : st) CK(cudaMemsetAsync(*q, 0, sizeof(double) * 9 * ns, c->stream));
@@ -944,14 +1120,11 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
     CK(cudaGetLastError());
     cudaFree(d_t); cudaFree(d_x); cudaFree(d_v); cudaFree(d_x0);
     if (d_ids) cudaFree(d_ids);
-    c->n = nloc;
+    CK(cudaMemcpy(&c->ctl->n, &nloc, sizeof(int), cudaMemcpyHostToDevice));
     c->uploaded = true;
-    c->buckets_valid = false;
-    if (!first && c->inited) {
-        // state replaced on an initialised context: rebuild the buckets (no wall motion / wrap)
-        int rc = rebuild_buckets(c, false);
-        if (rc) return rc;
-    }
+    c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
+    { int rrc = request_rebuild(c); if (rrc) return rrc; } // (state replaced: the next step rebuilds buckets and list)
+    CK(cudaStreamSynchronize(c->stream));
     return MPHX_OK;
 }
 
@@ -961,6 +1134,7 @@ int mphx_upload_state(mphx_ctx *ctx, const double *position, const double *veloc
 {
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !c->inited || !position || !velocity) return MPHX_ERR_INVALID;
+    if (c->slab) { set_last_error("mphx_upload_state: use mphx_upload_owned on a slab context"); return MPHX_ERR_UNSUPPORTED; }
     CK(cudaSetDevice(c->device));
     { int jrc = join_solids(c); if (jrc) return jrc; }
     const size_t N = (size_t)c->n_global;
@@ -968,10 +1142,10 @@ int mphx_upload_state(mphx_ctx *ctx, const double *position, const double *veloc
     if (!c->stage3b && c->alloc(&c->stage3b, 3 * N)) return MPHX_ERR_NOMEM;
     CK(cudaMemcpyAsync(c->stage3a, position, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->stage3b, velocity, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(c, k_upload_state, nblk(c->n), kBlock, c->n, c->S, c->sol, c->stage3a, c->stage3b);
-    c->buckets_valid = false;
+    LAUNCH(c, k_upload_state, nblk(c->nmax), kBlock, c->nmax, c->S, c->sol, c->stage3a, c->stage3b);
+    c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
     CK(cudaGetLastError());
-    return MPHX_OK;
+    return request_rebuild(c); // arbitrary new positions: the next step rebuilds buckets and list
 }
 
 int mphx_init(mphx_ctx *ctx)
@@ -979,18 +1153,17 @@ int mphx_init(mphx_ctx *ctx)
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || !c->uploaded) return MPHX_ERR_INVALID;
     if (c->inited) return MPHX_OK;
+    if (c->slab && !c->connected) { set_last_error("mphx_init: connect the slab to its peers first (mphx_slab_connect)"); return MPHX_ERR_INVALID; }
     CK(cudaSetDevice(c->device));
     int rc;
     if ((rc = init_solid(c))) return rc; // calculateInitialNeighbor, Lame, Normalizer
     // first calculateNeighbor + density sums on the initial positions (:565-568): gives
-    // NeighborCount / PressureP for the `output.vtk` written before the loop (:572)
-    if (!c->slab) { // (a slab needs its neighbours' halos first: done by the first mphx_slab_* step)
-        if ((rc = rebuild_buckets(c, false))) return rc;
-        if ((rc = run_pass1(c))) return rc;
-    }
+    // NeighborCount / PressureP for the `output.vtk` written before the loop (:572).
+    // (slab mode: every rank must be in this call at the same time -- the halos are exchanged)
+    if ((rc = init_enqueue(c))) return rc;
     CK(cudaStreamSynchronize(c->stream));
     c->inited = true;
-    return MPHX_OK;
+    return slab_check_errors(c, "mphx_init");
 }
 
 int mphx_get_constants(const mphx_ctx *ctx, mphx_constants *k)
@@ -1061,7 +1234,7 @@ int mphx_sync(mphx_ctx *ctx)
     { int jrc = join_solids(c); if (jrc) return jrc; }
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
-    return MPHX_OK;
+    return slab_check_errors(c, "mphx_sync");
 }
 
 double mphx_time(const mphx_ctx *ctx) { return ctx ? reinterpret_cast<const Ctx *>(ctx)->time : 0.0; }
@@ -1083,7 +1256,9 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     // Arrays are in ORIGINAL particle order and sized for the whole case.  A slab context fills the
     // entries of the particles it owns (solids: slab 0 only) and zeros elsewhere, so the caller can
     // combine the slabs with a plain sum.
-    const int n = c->n, ns = c->ns;
+    int n = 0;
+    { int nrc = read_n(c, &n); if (nrc) return nrc; }
+    const int ns = c->ns;
     const size_t N = (size_t)c->n_global;
     if (!c->stage3a && c->alloc(&c->stage3a, 3 * N)) return MPHX_ERR_NOMEM;
     if (!c->stage1 && c->alloc(&c->stage1, N)) return MPHX_ERR_NOMEM;
@@ -1102,21 +1277,23 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
     if (n > 0) LAUNCH(c, k_owned_mask, nblk(n), kBlock, n, S, c->grid, report_solids ? 1 : 0, c->mask);
     if (n > 0) LAUNCH(c, k_owned_mask, nblk(n), kBlock, n, S, c->grid, 2, c->mask2);
     int rc = MPHX_OK;
-    auto vec3 = [&](double *host, const double *a, const double *b, const double *cc, const double *sa, const double *sb_, const double *sc) -> int {
+    // owner_only: the solids' values live on the slab that evaluates them (Force in slab mode), not replicated
+    auto vec3 = [&](double *host, const double *a, const double *b, const double *cc, const double *sa, const double *sb_, const double *sc,
+                    bool owner_only = false) -> int {
         if (!host) return MPHX_OK;
+        owner_only = owner_only && c->slab;
         if (c->slab) CK(cudaMemsetAsync(d3, 0, sizeof(double) * 3 * N, c->stream));
         if (n > 0) LAUNCH(c, k_gather_vec3, nblk(n), kBlock, n, S.id, c->mask, a, b, cc, d3);
-        if (ns > 0 && sa && report_solids) LAUNCH(c, k_solid_vec3_to_orig, nblk(ns), kBlock, so, sa, sb_, sc, d3);
+        if (ns > 0 && sa && (report_solids || owner_only))
+            LAUNCH(c, k_solid_vec3_to_orig, nblk(ns), kBlock, so, sa, sb_, sc, d3, owner_only ? (const int *)S.type : (const int *)nullptr);
         CK(cudaMemcpyAsync(host, d3, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-        return MPHX_OK;
+        return MPHX_OK; // (no synchronisation per field: the staging buffer is reused in stream order)
     };
     auto scal = [&](double *host, const double *a) -> int {
         if (!host) return MPHX_OK;
         if (c->slab) CK(cudaMemsetAsync(d1, 0, sizeof(double) * N, c->stream));
         if (n > 0) LAUNCH(c, k_gather_scalar, nblk(n), kBlock, n, S.id, c->mask2, a, d1);
         CK(cudaMemcpyAsync(host, d1, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
     };
     auto ints = [&](int *host, const int *a, const int *msk) -> int {
@@ -1124,7 +1301,6 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         if (c->slab) CK(cudaMemsetAsync(di, 0, sizeof(int) * N, c->stream));
         if (n > 0) LAUNCH(c, k_gather_int, nblk(n), kBlock, n, S.id, msk, a, di);
         CK(cudaMemcpyAsync(host, di, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
     };
     auto tens = [&](double *host, const double *M) -> int {
@@ -1136,7 +1312,6 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         CK(cudaMemsetAsync(d9, 0, sizeof(double) * 9 * N, c->stream));
         if (ns > 0 && report_solids) LAUNCH(c, k_solid_tensor_to_orig, nblk(ns), kBlock, so, M, d9);
         CK(cudaMemcpyAsync(host, d9, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
     };
     auto solid_scal = [&](double *host, const double *a) -> int {
@@ -1144,7 +1319,6 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         CK(cudaMemsetAsync(d1, 0, sizeof(double) * N, c->stream));
         if (ns > 0 && report_solids) LAUNCH(c, k_solid_scalar_to_orig, nblk(ns), kBlock, so, a, d1);
         CK(cudaMemcpyAsync(host, d1, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
         return MPHX_OK;
     };
     do {
@@ -1154,7 +1328,7 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         }
         if ((rc = vec3(v->position, S.x, S.y, S.z, so.x, so.y, so.z))) break;
         if ((rc = vec3(v->velocity, S.vx, S.vy, S.vz, so.vx, so.vy, so.vz))) break;
-        if ((rc = vec3(v->force, c->fx, c->fy, c->fz, so.fx, so.fy, so.fz))) break;
+        if ((rc = vec3(v->force, c->fx, c->fy, c->fz, so.fx, so.fy, so.fz, true))) break;
         if ((rc = vec3(v->acceleration, c->ax, c->ay, c->az, nullptr, nullptr, nullptr))) break;
         if ((rc = scal(v->pressure_p, c->P))) break;
         if ((rc = scal(v->vol_strain_p, c->volStrain))) break;
@@ -1168,20 +1342,14 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         }
         if (v->neighbor_count) {
             if (!c->inited) { rc = MPHX_ERR_INVALID; break; }
-            if (!c->buckets_valid) {
-                if (c->slab) { rc = MPHX_ERR_INVALID; break; }
-                if ((rc = rebuild_buckets(c, false))) break;
-            }
             std::vector<long long> off;
-            long long total = 0;
-            if ((rc = exact_lists(c, false, false, 0, (int)N, off, nullptr, &total))) break;
+            if ((rc = exact_lists_current(c, off, nullptr))) break;
             for (size_t i = 0; i < N; ++i) v->neighbor_count[i] = (int)(off[i + 1] - off[i]);
         }
         if (v->initial_structure_neighbor_count) {
             CK(cudaMemsetAsync(di, 0, sizeof(int) * N, c->stream));
             if (ns > 0 && so.off && report_solids) LAUNCH(c, k_solid_rowlen_to_orig, nblk(ns), kBlock, so, di);
             CK(cudaMemcpyAsync(v->initial_structure_neighbor_count, di, sizeof(int) * N, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
         }
         if ((rc = tens(v->normalizer, so.Linv))) break;
         if ((rc = tens(v->deform_gradient, so.Fm))) break;
@@ -1190,6 +1358,7 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         if ((rc = solid_scal(v->lambda_lames, so.lam))) break;
         if ((rc = solid_scal(v->mu_lames, so.mu))) break;
     } while (0);
+    CK(cudaStreamSynchronize(c->stream)); // the one synchronisation of the call
     if (rc == MPHX_OK) { CK(cudaGetLastError()); }
     return rc;
 }
@@ -1222,12 +1391,13 @@ int mphx_download_owned(mphx_ctx *ctx, int capacity, int *ids, double *position,
     { int jrc = join_solids(c); if (jrc) return jrc; }
     int rc = owned_prepare(c);
     if (rc) return rc;
-    const int n = c->n;
+    int n = 0;
+    if ((rc = read_n(c, &n))) return rc;
     LAUNCH(c, k_owned_mask, nblk(n), kBlock, n, c->S, c->grid, 1, c->mask);
     const int nb = (int)(((long long)n + kScanChunk - 1) / kScanChunk);
-    LAUNCH(c, k_scan_reduce, nb, kScanThreads, c->mask, n, c->own_sums);
-    LAUNCH(c, k_scan_top, 1, kScanThreads, c->own_sums, nb);
-    LAUNCH(c, k_scan_apply, nb, kScanThreads, c->mask, n, c->own_sums, c->own_scan);
+    LAUNCH(c, k_scan_reduce, nb, kScanThreads, (const Ctl *)nullptr, c->mask, n, c->own_sums);
+    LAUNCH(c, k_scan_top, 1, kScanThreads, (const Ctl *)nullptr, c->own_sums, nb);
+    LAUNCH(c, k_scan_apply, nb, kScanThreads, (const Ctl *)nullptr, c->mask, n, c->own_sums, c->own_scan, 0);
     int total = 0;
     CK(cudaMemcpyAsync(&total, c->own_scan + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     LAUNCH(c, k_compact_owned, nblk(n), kBlock, n, c->S, c->sol, c->mask, c->own_scan, c->own_slot, c->own_ids, c->own_x, c->own_v);
@@ -1257,15 +1427,16 @@ int mphx_upload_owned(mphx_ctx *ctx, int count, const int *ids, const double *po
     CK(cudaMemcpyAsync(c->own_ids, ids, sizeof(int) * (size_t)count, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->own_x, position, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->own_v, velocity, sizeof(double) * 3 * (size_t)count, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
-    LAUNCH(c, k_scatter_owned, nblk(count), kBlock, count, c->S, c->sol, c->own_slot, c->own_ids, c->own_x, c->own_v, c->d_err);
+    int *d_err = c->own_scan; // (scratch: free between a download and the next one)
+    CK(cudaMemsetAsync(d_err, 0, sizeof(int), c->stream));
+    LAUNCH(c, k_scatter_owned, nblk(count), kBlock, count, c->S, c->sol, c->own_slot, c->own_ids, c->own_x, c->own_v, d_err);
     int err = 0;
-    CK(cudaMemcpyAsync(&err, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&err, d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (err) { set_last_error("mphx_upload_owned: ids do not match the rows of the last download"); return MPHX_ERR_INVALID; }
-    c->buckets_valid = false;
+    c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
     CK(cudaGetLastError());
-    return MPHX_OK;
+    return request_rebuild(c); // arbitrary new positions: the next step rebuilds buckets and list
 }
 
 int mphx_debug_neighbors(mphx_ctx *ctx, long long *offsets, int *ids, long long cap)
@@ -1274,16 +1445,13 @@ int mphx_debug_neighbors(mphx_ctx *ctx, long long *offsets, int *ids, long long 
     if (!c || !c->inited || !offsets) return MPHX_ERR_INVALID;
     CK(cudaSetDevice(c->device));
     std::vector<long long> off;
-    long long total = 0;
-    int *d_ids = nullptr;
-    if (!c->buckets_valid) return MPHX_ERR_INVALID;
-    int rc = exact_lists(c, false, false, 0, c->n_global, off, ids ? &d_ids : nullptr, &total);
+    std::vector<int> rows;
+    int rc = exact_lists_current(c, off, ids ? &rows : nullptr);
     if (rc) return rc;
     std::memcpy(offsets, off.data(), sizeof(long long) * ((size_t)c->n_global + 1));
     if (ids) {
-        if (cap < total) { cudaFree(d_ids); return MPHX_ERR_OVERFLOW; }
-        CK(cudaMemcpy(ids, d_ids, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost));
-        cudaFree(d_ids);
+        if (cap < (long long)rows.size()) return MPHX_ERR_OVERFLOW;
+        std::memcpy(ids, rows.data(), sizeof(int) * rows.size());
     }
     return MPHX_OK;
 }

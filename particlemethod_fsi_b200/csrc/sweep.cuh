@@ -285,13 +285,25 @@ struct PairList {
     int cap, L;
 };
 
+// slab mode: ghosts and parked solids are only ever neighbours; a (replicated) solid is evaluated by the slab
+// that owned its column when the list was built
+__device__ __forceinline__ bool particle_active(const GridDesc &g, int i, int n, int tflag, int key)
+{
+    bool active = i < n && key < g.ncells && !(tflag & kGhost);
+    if (g.slab && is_structure_type(tflag)) active = i < n && !(tflag & kGhost) && (tflag & kSolidOwned);
+    return active;
+}
+
 // K5a "filter": phase A alone, for every particle at once.  No fp64, no shared-memory queue, few
 // registers: the kernel runs at full occupancy, which hides the latency of the candidate loads.
 // Candidates are tested in pairs with the packed f32x2 instructions (see sweep()).
 template <int DIM>
 __global__ void __launch_bounds__(kSweepThreads, MPHX_FILTER_MINB)
-k_filter(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, float filt2, PairList pl)
+k_filter(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, GridDesc g, PairList pl)
 {
+    if (!ctl->rebuild) return; // the list of an earlier step is still a superset of every cut-off set
+    const int n = ctl->n;
+    const float filt2 = ctl->filt2;
     __shared__ int s_dlo[kMaxStencil], s_dhi[kMaxStencil], s_sdx[kMaxStencil], s_sdy[kMaxStencil], s_sh[kMaxStencil];
     for (int e = threadIdx.x; e < g.nsten; e += blockDim.x) {
         const int dx = g.sdx[e], dy = g.sdy[e], h = g.sh[e];
@@ -302,8 +314,7 @@ k_filter(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, floa
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int tflag = p.type[i], keyi = p.key[i];
-    bool active = keyi < g.ncells && !(tflag & kGhost);
-    if (g.slab && is_structure_type(tflag) && active) active = column_owned(g, key_column(g, keyi));
+    const bool active = particle_active(g, i, n, tflag, keyi);
     if (!active) { pl.count[i] = 0; return; }
     const PfPair *__restrict__ pf = p.pf;
     const float *fo = reinterpret_cast<const float *>(pf + (i >> 1)) + (i & 1);
@@ -420,8 +431,7 @@ pass1_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
     const bool solid_i = is_structure_type(ti);
     // slab mode: ghosts and parked solids are only ever neighbours; a solid is evaluated by the slab
     // that owns its current column
-    bool active = i0 < n && keyi < g.ncells && !(tflag & kGhost);
-    if (g.slab && solid_i && active) active = column_owned(g, key_column(g, keyi));
+    const bool active = particle_active(g, i0, n, tflag, keyi);
     const double rp2 = ph.rp2, irp = ph.irp, ra2 = ph.ra2, ira = ph.ira;
     double nP = 0.0, dv = 0.0, nA = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0; // nP, dv without their constant factors
     const Rec *__restrict__ RA = p.ra;
@@ -521,11 +531,16 @@ pass1_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
 // reads the step's overflow flag and otherwise loops over the virtual blocks.
 template <int DIM, bool ST, bool LIST>
 __global__ void __launch_bounds__(kSweepThreads, LIST ? (ST ? MPHX_P1ST_MINB : MPHX_P1_MINB) : 1)
-k_pass1_v3(int vblocks, int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
+k_pass1_v3(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, int batch,
            double *__restrict__ P, double *__restrict__ volStrain, double *__restrict__ divP, double *__restrict__ densA,
            double *__restrict__ gcx, double *__restrict__ gcy, double *__restrict__ gcz, double *__restrict__ PA, PairList pl)
 {
+    const int n = ctl->n;
+    if (n <= 0) return;
+    const float filt2 = ctl->filt2;
+    const int vblocks = (n + kSweepThreads - 1) / kSweepThreads;
     if constexpr (LIST) {
+        if ((int)blockIdx.x >= vblocks) return;
         pass1_block<DIM, ST, true>(blockIdx.x, n, p, cellStart, g, ph, filt2, batch, P, volStrain, divP, densA, gcx, gcy, gcz, PA, pl);
     } else {
         if (pl.count && *reinterpret_cast<volatile const int *>(pl.flags) == 0) return; // no list overflowed in this step
@@ -544,13 +559,12 @@ k_pass1_v3(int vblocks, int n, Particles p, const int *__restrict__ cellStart, G
 //                 (and the block exits at once if it has none), otherwise all particles.
 template <int DIM, bool ST, bool LIST>
 __device__ __forceinline__ void
-pass2_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, const GridDesc &g, const Phys &ph, float filt2, int batch,
+pass2_block(Ctl *ctl, int vblock, int n, Particles p, const int *__restrict__ cellStart, const GridDesc &g, const Phys &ph, float filt2, int batch,
            const double *__restrict__ P, const double *__restrict__ PA, const double *__restrict__ gcx,
            const double *__restrict__ gcy, const double *__restrict__ gcz, double *__restrict__ ox,
            double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ovx, double *__restrict__ ovy,
            double *__restrict__ ovz, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
-           double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az, Solid sol,
-           double *__restrict__ solbuf, PairList pl, Subset sub)
+           double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az, Solid sol, PairList pl, Subset sub)
 {
     __shared__ double s_visc[kTypeCount][kTypeCount];
     // pair viscosity table with the constant factors of the viscous term folded in:
@@ -572,8 +586,7 @@ pass2_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
     __syncthreads();
     const double xi = p.x[i], yi = p.y[i], zi = p.z[i];
     const double vxi = p.vx[i], vyi = p.vy[i], vzi = p.vz[i];
-    bool active = i0 < n && keyi < g.ncells && !(tflag & kGhost);
-    if (g.slab && solid_i && active) active = column_owned(g, key_column(g, keyi));
+    const bool active = particle_active(g, i0, n, tflag, keyi);
     const double Pi = P[i];
     const double rp2 = ph.rp2, irp = ph.irp, rv2 = ph.rv2, irv = ph.irv;
     const double rpv2 = rp2 > rv2 ? rp2 : rv2;
@@ -712,39 +725,41 @@ pass2_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
             a0 = __ddiv_rn(F0, m); a1 = __ddiv_rn(F1, m); a2 = __ddiv_rn(F2, m);
             nx = __dadd_rn(xi, __dmul_rn(nvx, ph.dt)); ny = __dadd_rn(yi, __dmul_rn(nvy, ph.dt)); nz = __dadd_rn(zi, __dmul_rn(nvz, ph.dt));
         } else {
+            // (slab mode: the owner's values; the velocity is published to every rank by k_solid_publish_V, the force
+            // stays with the owner, who reports it)
             const int s = p.id[i] - sol.sb;
-            if (solbuf) { // slab mode: published through an all-reduce (all other slabs add zeros)
-                const size_t ns = sol.ns;
-                solbuf[s] = nvx; solbuf[ns + s] = nvy; solbuf[2 * ns + s] = nvz;
-                solbuf[3 * ns + s] = F0; solbuf[4 * ns + s] = F1; solbuf[5 * ns + s] = F2;
-            } else {
-                sol.vx[s] = nvx; sol.vy[s] = nvy; sol.vz[s] = nvz;
-                sol.fx[s] = F0; sol.fy[s] = F1; sol.fz[s] = F2;
-            }
+            sol.vx[s] = nvx; sol.vy[s] = nvy; sol.vz[s] = nvz;
+            sol.fx[s] = F0; sol.fy[s] = F1; sol.fz[s] = F2;
         }
     }
+    if (!(nx - nx == 0.0) || !(ny - ny == 0.0) || !(nz - nz == 0.0)) atomicOr(&ctl->err, kErrNaN); // health flag: non-finite position
     ox[i] = nx; oy[i] = ny; oz[i] = nz; ovx[i] = nvx; ovy[i] = nvy; ovz[i] = nvz;
     fx[i] = F0; fy[i] = F1; fz[i] = F2; ax[i] = a0; ay[i] = a1; az[i] = a2;
 }
 
 template <int DIM, bool ST, bool LIST>
 __global__ void __launch_bounds__(kSweepThreads, LIST ? (ST ? MPHX_P2ST_MINB : MPHX_P2_MINB) : 1)
-k_pass2_v3(int vblocks, int n, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, float filt2, int batch,
+k_pass2_v3(Ctl *ctl, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, int batch,
            const double *__restrict__ P, const double *__restrict__ PA, const double *__restrict__ gcx,
            const double *__restrict__ gcy, const double *__restrict__ gcz, double *__restrict__ ox,
            double *__restrict__ oy, double *__restrict__ oz, double *__restrict__ ovx, double *__restrict__ ovy,
            double *__restrict__ ovz, double *__restrict__ fx, double *__restrict__ fy, double *__restrict__ fz,
            double *__restrict__ ax, double *__restrict__ ay, double *__restrict__ az, Solid sol,
-           double *__restrict__ solbuf, PairList pl, Subset sub)
+           PairList pl, Subset sub)
 {
+    const int n = ctl->n;
+    if (n <= 0) return;
+    const float filt2 = ctl->filt2;
+    const int vblocks = ((sub.slots ? sub.count : n) + kSweepThreads - 1) / kSweepThreads;
     if constexpr (LIST) {
-        pass2_block<DIM, ST, true>(blockIdx.x, n, p, cellStart, g, ph, filt2, batch, P, PA, gcx, gcy, gcz, ox, oy, oz, ovx, ovy, ovz, fx, fy,
-                                   fz, ax, ay, az, sol, solbuf, pl, sub);
+        if ((int)blockIdx.x >= vblocks) return;
+        pass2_block<DIM, ST, true>(ctl, blockIdx.x, n, p, cellStart, g, ph, filt2, batch, P, PA, gcx, gcy, gcz, ox, oy, oz, ovx, ovy, ovz, fx, fy,
+                                   fz, ax, ay, az, sol, pl, sub);
     } else {
         if (pl.count && *reinterpret_cast<volatile const int *>(pl.flags) == 0) return; // no list overflowed in this step
         for (int vb = blockIdx.x; vb < vblocks; vb += gridDim.x) {
-            pass2_block<DIM, ST, false>(vb, n, p, cellStart, g, ph, filt2, batch, P, PA, gcx, gcy, gcz, ox, oy, oz, ovx, ovy, ovz, fx, fy,
-                                        fz, ax, ay, az, sol, solbuf, pl, sub);
+            pass2_block<DIM, ST, false>(ctl, vb, n, p, cellStart, g, ph, filt2, batch, P, PA, gcx, gcy, gcz, ox, oy, oz, ovx, ovy, ovz, fx, fy,
+                                        fz, ax, ay, az, sol, pl, sub);
             __syncthreads();
         }
     }

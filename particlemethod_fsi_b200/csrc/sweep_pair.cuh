@@ -22,21 +22,15 @@ namespace mphx {
 #define MPHX_FILTER2_MINB 8
 #endif
 
-// slab mode: ghosts and parked solids are only ever neighbours; a solid is evaluated by the slab that
-// owns its current column
-__device__ __forceinline__ bool particle_active(const GridDesc &g, int i, int n, int tflag, int key)
-{
-    bool active = i < n && key < g.ncells && !(tflag & kGhost);
-    if (g.slab && is_structure_type(tflag) && active) active = column_owned(g, key_column(g, key));
-    return active;
-}
-
 // K5a, two particles per thread; same outputs as k_filter (one list per particle).
 // BIG: the list has 2^32 or more slots (e.g. 10^8 particles on one GPU): 64-bit offsets.
 template <int DIM, bool BIG>
 __global__ void __launch_bounds__(kSweepThreads, MPHX_FILTER2_MINB)
-k_filter2(int n, Particles p, const int *__restrict__ cellStart, GridDesc g, float filt2, PairList pl)
+k_filter2(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, GridDesc g, PairList pl)
 {
+    if (!ctl->rebuild) return; // the list of an earlier step is still a superset of every cut-off set
+    const int n = ctl->n;
+    const float filt2 = ctl->filt2;
     using off_t = typename std::conditional<BIG, unsigned long long, unsigned>::type;
     __shared__ int s_dlo[kMaxStencil], s_dhi[kMaxStencil], s_sdx[kMaxStencil], s_sdy[kMaxStencil], s_sh[kMaxStencil];
     for (int e = threadIdx.x; e < g.nsten; e += blockDim.x) {

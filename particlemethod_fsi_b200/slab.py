@@ -1,23 +1,23 @@
 """Multi-GPU host side: 1-D x-slab decomposition of the explicit step.
 
 The reference has no distributed path (no MPI/NCCL anywhere in src/main.cpp); what is decomposed
-here is its loop body (src/main.cpp:596-663).  One process drives one B200 and one slab context
-of libmphx.so; this module only moves the packed device buffers between ranks:
+here is its loop body (src/main.cpp:596-663).  The exchange itself -- migration, halo, PressureP of
+the halo copies, the replicated solids, the rebuild votes -- lives in libmphx.so and is device-side:
+every slab context owns a mailbox that its peers write into over NVLink, and `mphx_step` on a slab
+context is a fixed sequence of kernel launches without a host synchronisation (csrc/slab.inc).
+This module is only the plumbing around it:
 
-    phase A  mphx_slab_begin       pre-step + emigrants packed   -> ring exchange -> mphx_slab_append(ghost=0)
-    phase B  mphx_slab_pack_halo   halo layers packed            -> ring exchange -> mphx_slab_append(ghost=1)
-    phase C  mphx_slab_build_pass1 buckets + pass 1              -> ring exchange of PressureP, all-reduce(solP)
-    phase D  mphx_slab_pass2       pass 2 + integration          -> all-reduce(solbuf)
-    phase E  mphx_slab_finish      solid sub-steps (replicated), Time += Dt
+  * `plan()`        cuts the bucket columns on the particle histogram (mphx_partition_columns) and
+                    sizes the slots / messages -- the same rule as mphx_multi_upload;
+  * `DistSlab`      one process per GPU (torchrun): creates its slab context and carries the 64-byte
+                    CUDA IPC handles of the mailboxes between the ranks with ONE torch.distributed
+                    all_gather at start-up (NCCL on the GPU box, gloo in the CPU tests of this plumbing);
+                    afterwards a step is a single C call per rank;
+  * `MultiSolver`   one process, N contexts (mphx_multi_*: what csrc/main.cpp uses with MPHX_NGPU).  The
+                    contexts may share a device, which is how the slab kernels are parity-tested on a
+                    one-GPU box against the single-context result.
 
-The exchanges are torch.distributed point-to-point operations (NCCL over NVLink on the GPU box,
-gloo on CPU for the host-logic tests); every axis of the reference's domain is periodic
-(CellId wrap src/main.cpp:123-125), so the slabs form a ring.  All compute is in the CUDA library:
-there is no Python or CPU implementation of any phase here.
-
-`LocalRing` runs all slabs of a ring inside ONE process on ONE device (the exchange is a device
-copy): it is how the slab kernels are parity-tested on a single-GPU box against the single-context
-result.
+There is no Python or CPU implementation of any phase here.
 """
 from __future__ import annotations
 
@@ -30,10 +30,10 @@ import numpy as np
 
 from . import abi
 
-MSG_DOUBLES = 7  # kMsgDoubles in csrc/kernels.cuh: x y z vx vy vz (type<<32|id)
+IPC_HANDLE_BYTES = 64   # sizeof(cudaIpcMemHandle_t)
 
 
-# ---- host logic (no GPU needed; covered by the gloo tests) -----------------------------------------
+# ---- host logic (no GPU needed; covered by the CPU tests) -----------------------------------------
 def column_of(x, domain_min0: float, cell_width: float, ncols: int):
     """global bucket column of an x coordinate -- the reference's key expression (src/main.cpp:1671)"""
     c = np.floor((np.asarray(x, dtype=np.float64) - domain_min0) / cell_width).astype(np.int64) % ncols
@@ -42,365 +42,272 @@ def column_of(x, domain_min0: float, cell_width: float, ncols: int):
 
 def partition_columns(hist: np.ndarray, nranks: int, halo: int):
     """Cut the bucket columns [0, ncols) into `nranks` contiguous slabs of roughly equal particle
-    count.  Every slab is at least `halo` columns wide (a particle's stencil must not reach past the
-    neighbouring slab) and the whole ring must be wider than one slab plus its two halos.
-    Returns [(lo, hi)] * nranks."""
-    hist = np.asarray(hist, dtype=np.int64)
-    ncols = int(hist.shape[0])
+    count (mphx_partition_columns: the rule lives in the library so that the C++ driver, this module
+    and the tests agree).  Returns [(lo, hi)] * nranks; raises ValueError when the halo-width
+    constraints cannot be met."""
+    from .solver import lib
+    hist = np.ascontiguousarray(hist, dtype=np.int64)
     if nranks < 1:
         raise ValueError("nranks must be positive")
-    if nranks == 1:
-        return [(0, ncols)]
-    # every slab at most ncols - 2*halo wide <=> the other slabs together span >= 2*halo columns
-    minw = halo if nranks >= 3 else 2 * halo
-    if ncols < nranks * minw:
-        raise ValueError(f"{ncols} bucket columns cannot hold {nranks} slabs of >= {minw} columns")
-    if int(hist.sum()) == 0:
-        hist = np.ones(ncols, dtype=np.int64)        # nothing to balance (e.g. a solid-only case): equal widths
-    cum = np.concatenate([[0], np.cumsum(hist)])
-    total = int(cum[-1])
-    cuts = [0]
-    for r in range(1, nranks):
-        target = total * r / nranks
-        c = int(np.searchsorted(cum, target, side="left"))
-        lo = cuts[-1] + minw                         # previous slab wide enough
-        hi = ncols - (nranks - r) * minw             # room for the remaining slabs
-        cuts.append(min(max(c, lo), hi))
-    cuts.append(ncols)
-    out = [(cuts[r], cuts[r + 1]) for r in range(nranks)]
-    for lo, hi in out:
-        if hi - lo < halo or ncols < (hi - lo) + 2 * halo:
-            raise ValueError("slab partition violates the halo-width constraint")
-    return out
+    cuts = (C.c_int * (nranks + 1))()
+    rc = lib.mphx_partition_columns(hist.ctypes.data, int(hist.shape[0]), nranks, halo, C.cast(cuts, C.c_void_p))
+    if rc != abi.MPHX_OK:
+        raise ValueError(f"{int(hist.shape[0])} bucket columns cannot hold {nranks} slabs: {lib.mphx_last_error().decode()}")
+    return [(cuts[r], cuts[r + 1]) for r in range(nranks)]
 
 
 def ring_neighbours(rank: int, nranks: int):
     return (rank - 1) % nranks, (rank + 1) % nranks
 
 
-# ---- transports ----------------------------------------------------------------------------------
-class DistTransport:
-    """torch.distributed ring (one slab per process).  Works on CUDA tensors with the nccl backend and
-    on CPU tensors with gloo (used by the CPU tests of this plumbing)."""
-
-    def __init__(self, group=None):
-        import torch.distributed as dist
-        self.dist = dist
-        self.group = group
-        self.rank = dist.get_rank(group)
-        self.world = dist.get_world_size(group)
-        self.left, self.right = ring_neighbours(self.rank, self.world)
-
-    def local_ranks(self):
-        return [self.rank]
-
-    def _p2p(self, ops):
-        for w in self.dist.batch_isend_irecv(ops):
-            w.wait()
-
-    def exchange_counts(self, counts_list):
-        """counts_list[0]: int tensor [>=2] = (to_left, to_right) -> [(from_left, from_right)]"""
-        import torch
-        dist = self.dist
-        c = counts_list[0]
-        recv = torch.zeros(2, dtype=c.dtype, device=c.device)
-        sl, sr = c[0:1].clone(), c[1:2].clone()
-        # order matters when left == right (2 ranks): a message sent "to the left" arrives at its
-        # receiver "from the right", so receives are posted right-first
-        ops = [dist.P2POp(dist.isend, sl, self.left, self.group), dist.P2POp(dist.isend, sr, self.right, self.group),
-               dist.P2POp(dist.irecv, recv[1:2], self.right, self.group), dist.P2POp(dist.irecv, recv[0:1], self.left, self.group)]
-        self._p2p(ops)
-        return [recv]
-
-    def exchange(self, items):
-        """items[0] = (send_left, n_left, send_right, n_right, recv_left, m_left, recv_right, m_right, width):
-        send the first n*width elements of each send buffer, receive m*width into the recv buffers"""
-        dist = self.dist
-        sl, nl, sr, nr, rl, ml, rr, mr, w = items[0]
-        ops = []
-        if nl > 0:
-            ops.append(dist.P2POp(dist.isend, sl[: nl * w], self.left, self.group))
-        if nr > 0:
-            ops.append(dist.P2POp(dist.isend, sr[: nr * w], self.right, self.group))
-        if mr > 0:
-            ops.append(dist.P2POp(dist.irecv, rr[: mr * w], self.right, self.group))
-        if ml > 0:
-            ops.append(dist.P2POp(dist.irecv, rl[: ml * w], self.left, self.group))
-        if ops:
-            self._p2p(ops)
-
-    def allreduce_sum(self, tensors):
-        self.dist.all_reduce(tensors[0], op=self.dist.ReduceOp.SUM, group=self.group)
-
-    def allreduce_max_float(self, v: float, device) -> float:
-        import torch
-        t = torch.tensor([v], dtype=torch.float64, device=device)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
-        return float(t.item())
-
-    def barrier(self):
-        self.dist.barrier(group=self.group)
+def plan(case, world: int, constants=None):
+    """column cuts, message capacity (the same on every rank) and slot capacity per rank -- mirrors
+    mphx_multi_upload (csrc/slab.inc)"""
+    from . import solver
+    k = constants or solver.compute_constants(case.params)
+    R, ncols = k.stencil_range, k.cell_count[0]
+    t = case.property
+    solid = (t >= 2) & (t < 4)
+    ns = int(solid.sum())
+    col = column_of(case.position[~solid, 0], case.params.domain_min[0], k.cell_width, ncols)
+    hist = np.bincount(col, minlength=ncols).astype(np.int64)
+    parts = partition_columns(hist, world, R)
+    # a halo is R columns; allow twice the densest R-column window seen initially (+ slack)
+    ring = np.concatenate([hist, hist[:R]])
+    win = int(np.convolve(ring, np.ones(R, dtype=np.int64), mode="valid").max())
+    msg_cap = int(min(case.n, max(2 * win + 1024, 4096)))
+    caps = []
+    for lo, hi in parts:
+        owned = int(hist[lo:hi].sum())
+        caps.append(int(min(case.n + 2 * msg_cap, int(1.5 * owned) + 4 * msg_cap + ns + 4096)))
+    return dict(partition=parts, msg_capacity=msg_cap, capacity=caps, ns=ns, hist=hist)
 
 
-class LocalRing:
-    """all `world` slabs in this process on one device: the exchange is a device-to-device copy"""
+def gather_handles(mine: bytes, dist=None, group=None, device=None):
+    """all ranks' mailbox handles, in rank order (one all_gather of 64 bytes per rank)"""
+    import torch
+    import torch.distributed as tdist
+    dist = dist or tdist
+    world = dist.get_world_size(group)
+    assert len(mine) == IPC_HANDLE_BYTES
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).clone()
+    if device is not None:
+        t = t.to(device)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)
+    return [bytes(o.cpu().numpy().tobytes()) for o in out]
 
-    def __init__(self, world: int):
-        self.world = world
 
-    def local_ranks(self):
-        return list(range(self.world))
+def _views_for(n, names):
+    out, hv = {}, abi.HostViews()
+    for nm in names:
+        shape, is_int = abi.VIEW_FIELDS[nm]
+        a = np.zeros((n,) + shape, dtype=np.int32 if is_int else np.float64)
+        setattr(hv, nm, a.ctypes.data_as(C.POINTER(C.c_int if is_int else C.c_double)))
+        out[nm] = a
+    return hv, out
 
-    def exchange_counts(self, counts_list):
-        import torch
-        out = []
-        for r in range(self.world):
-            l, rt = ring_neighbours(r, self.world)
-            # from_left = what the left neighbour sent to ITS right; from_right = what the right sent to its left
-            out.append(torch.stack([counts_list[l][1], counts_list[rt][0]]))
+
+# ---- one process, N contexts ------------------------------------------------------------------------
+class MultiSolver:
+    """mphx_multi_*: the explicit step on `world` x-slabs driven by ONE process.  devices=None puts slab r
+    on CUDA device r; a list may repeat a device (parity tests on a one-GPU box)."""
+
+    def __init__(self, case, world: int, devices=None, list_reuse: bool | None = None):
+        from . import solver
+        self.lib, self._ck = solver.lib, solver._ck
+        self.case, self.n, self.world = case, case.n, world
+        self._m = C.c_void_p()
+        dev = None
+        if devices is not None:
+            assert len(devices) == world
+            dev = (C.c_int * world)(*devices)
+        self._ck("mphx_multi_create", self.lib.mphx_multi_create(C.byref(self._m), C.byref(case.params), world,
+                                                                  C.cast(dev, C.c_void_p) if dev is not None else None))
+        if list_reuse is not None:
+            for r in range(world):
+                self._ck("mphx_set_list_reuse", self.lib.mphx_set_list_reuse(self.context(r), 1 if list_reuse else 0, 0.0))
+        t = np.ascontiguousarray(case.property, dtype=np.int32)
+        x, x0, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (case.position, case.initial_position, case.velocity))
+        self._ck("mphx_multi_upload", self.lib.mphx_multi_upload(self._m, case.n, t.ctypes.data, x.ctypes.data, x0.ctypes.data, v.ctypes.data))
+        self._ck("mphx_multi_init", self.lib.mphx_multi_init(self._m))
+
+    def context(self, r: int):
+        return C.c_void_p(self.lib.mphx_multi_context(self._m, r))
+
+    def close(self):
+        if self._m:
+            self.lib.mphx_multi_destroy(self._m)
+            self._m = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, nsteps: int = 1):
+        self._ck("mphx_multi_step", self.lib.mphx_multi_step(self._m, nsteps))
+
+    def sync(self):
+        self._ck("mphx_multi_sync", self.lib.mphx_multi_sync(self._m))
+
+    def timed_steps(self, nsteps: int) -> float:
+        ms = C.c_double()
+        self._ck("mphx_multi_timed_steps", self.lib.mphx_multi_timed_steps(self._m, nsteps, C.byref(ms)))
+        return ms.value
+
+    @property
+    def time(self) -> float:
+        return self.lib.mphx_multi_time(self._m)
+
+    def download(self, *names):
+        hv, out = _views_for(self.n, names)
+        self._ck("mphx_multi_download", self.lib.mphx_multi_download(self._m, C.byref(hv)))
         return out
 
-    def exchange(self, items):
+    def info(self):
+        res = []
         for r in range(self.world):
-            l, rt = ring_neighbours(r, self.world)
-            _sl, _nl, _sr, _nr, rl, ml, rr, mr, w = items[r]
-            if ml > 0:
-                rl[: ml * w].copy_(items[l][2][: ml * w])    # left neighbour's send_right
-            if mr > 0:
-                rr[: mr * w].copy_(items[rt][0][: mr * w])   # right neighbour's send_left
+            a, st = (C.c_int * 4)(), (C.c_int * 8)()
+            self._ck("mphx_slab_info", self.lib.mphx_slab_info(self.context(r), C.byref(a)))
+            self._ck("mphx_get_status", self.lib.mphx_get_status(self.context(r), C.byref(st)))
+            res.append(dict(rank=r, held=a[0], capacity=a[1], ghosts=a[2], msg_capacity=a[3], err=st[0], builds=st[2], reuses=st[3]))
+        return res
 
-    def allreduce_sum(self, tensors):
+    def download_owned(self, r: int):
+        """(ids, position, velocity) rows of slab r (its owned fluid/wall particles + all replicated solids)"""
+        cap = self.info()[r]["capacity"]
+        ids = np.empty(cap, dtype=np.int32)
+        x, v = np.empty((cap, 3)), np.empty((cap, 3))
+        n = C.c_int()
+        self._ck("mphx_download_owned", self.lib.mphx_download_owned(self.context(r), cap, ids.ctypes.data, x.ctypes.data, v.ctypes.data, C.byref(n)))
+        return n.value, ids, x, v
+
+    def upload_owned(self, r: int, count, ids, x, v):
+        return self.lib.mphx_upload_owned(self.context(r), count, ids.ctypes.data, x.ctypes.data, v.ctypes.data)
+
+
+# ---- one process per GPU (torchrun) -------------------------------------------------------------------
+class DistSlab:
+    """This rank's slab of the ring.  torch.distributed is used once, to all_gather the mailbox handles
+    (and in download() to sum the per-rank reports); stepping is `mphx_step` on the slab context."""
+
+    def __init__(self, case, device_index: int = 0, group=None, list_reuse: bool | None = None):
         import torch
-        tot = torch.stack(list(tensors)).sum(dim=0)
-        for t in tensors:
-            t.copy_(tot)
-
-    def allreduce_max_float(self, v: float, device) -> float:
-        return v
-
-    def barrier(self):
-        pass
-
-
-# ---- one slab context --------------------------------------------------------------------------------
-class _Slab:
-    def __init__(self, lib, case_params, rank, world, cols, capacity, msg_cap, ns, device, torch):
-        self.lib, self.rank, self.world = lib, rank, world
+        import torch.distributed as dist
+        from . import solver
+        self.lib, self._ck = solver.lib, solver._ck
+        self.dist, self.group, self.torch = dist, group, torch
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.case, self.n = case, case.n
+        self.device = torch.device("cuda", device_index)
+        self.plan = plan(case, self.world)
+        self.partition = self.plan["partition"]
+        lo, hi = self.partition[self.rank]
         self.ctx = C.c_void_p()
-        from .solver import _ck
-        self._ck = _ck
-        _ck("mphx_create", lib.mphx_create(C.byref(self.ctx), C.byref(case_params), device.index or 0))
-        stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0  # (cpu: protocol tests)
-        _ck("mphx_set_stream", lib.mphx_set_stream(self.ctx, C.c_void_p(stream)))
-        _ck("mphx_slab_configure", lib.mphx_slab_configure(self.ctx, rank, world, cols[0], cols[1], capacity, msg_cap))
-        f64 = dict(dtype=torch.float64, device=device)
-        self.send = [torch.zeros(MSG_DOUBLES * msg_cap, **f64) for _ in range(2)]
-        self.recv = [torch.zeros(MSG_DOUBLES * msg_cap, **f64) for _ in range(2)]
-        self.psend = [torch.zeros(msg_cap, **f64) for _ in range(2)]
-        self.precv = [torch.zeros(msg_cap, **f64) for _ in range(2)]
-        self.counts = torch.zeros(4, dtype=torch.int32, device=device)
-        self.solP = torch.zeros(max(ns, 1), **f64)
-        self.solbuf = torch.zeros(6 * max(ns, 1), **f64)
-        self.halo_sent = (0, 0)
-        self.halo_recv = (0, 0)
+        self._ck("mphx_create", self.lib.mphx_create(C.byref(self.ctx), C.byref(case.params), device_index))
+        if list_reuse is not None:
+            self._ck("mphx_set_list_reuse", self.lib.mphx_set_list_reuse(self.ctx, 1 if list_reuse else 0, 0.0))
+        self._ck("mphx_slab_configure", self.lib.mphx_slab_configure(self.ctx, self.rank, self.world, lo, hi, self.plan["capacity"][self.rank],
+                                                                     self.plan["msg_capacity"]))
+        t = np.ascontiguousarray(case.property, dtype=np.int32)
+        x, x0, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (case.position, case.initial_position, case.velocity))
+        self._ck("mphx_upload", self.lib.mphx_upload(self.ctx, case.n, t.ctypes.data, x.ctypes.data, x0.ctypes.data, v.ctypes.data))
+        h = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        self._ck("mphx_slab_mailbox", self.lib.mphx_slab_mailbox(self.ctx, C.cast(h, C.c_void_p), None, None))
+        handles = gather_handles(bytes(h), dist, group, self.device)      # (also: every rank has zeroed its mailbox by now)
+        blob = (C.c_ubyte * (IPC_HANDLE_BYTES * self.world)).from_buffer_copy(b"".join(handles))
+        # the ranks' GPUs as this process sees them: torchrun leaves every device visible, rank r uses LOCAL_RANK = r
+        devs = self._gather_ints(device_index)
+        darr = (C.c_int * self.world)(*devs)
+        self._ck("mphx_slab_connect", self.lib.mphx_slab_connect(self.ctx, C.cast(blob, C.c_void_p), None, C.cast(darr, C.c_void_p)))
+        dist.barrier(group)
+        self._ck("mphx_init", self.lib.mphx_init(self.ctx))               # (collective: the halos are exchanged)
+        dist.barrier(group)
+
+    def _gather_ints(self, v: int):
+        t = self.torch.tensor([v], dtype=self.torch.int32, device=self.device)
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t, group=self.group)
+        return [int(o.item()) for o in out]
 
     def close(self):
         if self.ctx:
             self.lib.mphx_destroy(self.ctx)
             self.ctx = C.c_void_p()
 
-
-class SlabSolver:
-    """The explicit step on `world` x-slabs.  With a DistTransport every process holds one slab
-    (rank = torch.distributed rank); with a LocalRing this object holds them all."""
-
-    def __init__(self, case, transport, device=None, capacity: int | None = None, msg_capacity: int | None = None, lib=None):
-        import torch
-        from . import solver
-        self.torch = torch
-        self.lib = lib if lib is not None else solver.lib   # (lib: a stand-in with the mphx_slab_* contract, for the
-        #                                                      CPU tests of this orchestration; never a compute path)
-        self.tr = transport
-        self.case = case
-        self.n = case.n
-        world = transport.world
-        if device is None:
-            device = torch.device("cuda", torch.cuda.current_device())
-        self.device = device
-        k = solver.compute_constants(case.params)
-        self.constants = k
-        R = k.stencil_range
-        ncols = k.cell_count[0]
-        t = case.property
-        solid = (t >= 2) & (t < 4)
-        self.ns = int(solid.sum())
-        col = column_of(case.position[~solid, 0], case.params.domain_min[0], k.cell_width, ncols)
-        hist = np.bincount(col, minlength=ncols)
-        self.partition = partition_columns(hist, world, R)
-        per_col = k.cell_count[1] * k.cell_count[2]
-        if msg_capacity is None:
-            # a halo is R columns; allow twice the densest R-column window seen initially (+ slack)
-            win = np.convolve(hist, np.ones(R, dtype=np.int64), mode="full").max()
-            msg_capacity = int(min(self.n, max(2 * win + 1024, 4096)))
-        self.slabs = []
-        for r in transport.local_ranks():
-            lo, hi = self.partition[r]
-            owned = int(hist[lo:hi].sum())
-            cap = capacity
-            if cap is None:
-                cap = int(min(self.n + 2 * msg_capacity, 1.5 * owned + 4 * msg_capacity + self.ns + 4096))
-            s = _Slab(self.lib, case.params, r, world, (lo, hi), cap, msg_capacity, self.ns, device, torch)
-            solver._ck("mphx_upload", self.lib.mphx_upload(
-                s.ctx, case.n, np.ascontiguousarray(case.property, dtype=np.int32).ctypes.data,
-                np.ascontiguousarray(case.position).ctypes.data, np.ascontiguousarray(case.initial_position).ctypes.data,
-                np.ascontiguousarray(case.velocity).ctypes.data))
-            solver._ck("mphx_init", self.lib.mphx_init(s.ctx))
-            self.slabs.append(s)
-        self._per_col = per_col
-        # host mirror of the wall centres (src/main.cpp:3066-3070: advanced every step), carried across rebalance()
-        self._wall_center = [[case.params.wall_center[t][d] for d in range(3)] for t in range(abi.TYPE_COUNT)]
-        self._msg_capacity_arg, self._capacity_arg = None, capacity
-
-    def close(self):
-        for s in self.slabs:
-            s.close()
-        self.slabs = []
-
-    # -- one step --------------------------------------------------------------------------------------
-    def _ptr(self, t):
-        return C.c_void_p(t.data_ptr())
-
-    def _counts(self, what):
-        """Own (to_left, to_right) and received (from_left, from_right) counts of every local slab with ONE
-        device->host read per slab: the neighbours' counts are exchanged device-side first."""
-        recv = self.tr.exchange_counts([s.counts for s in self.slabs])
-        sent, got = [], []
-        for s, r in zip(self.slabs, recv):
-            c = self.torch.cat([s.counts[:3], r.to(s.counts.dtype)]).cpu().numpy()
-            if c[2]:
-                raise RuntimeError(f"slab {s.rank}: {what}: exchange error flags {int(c[2])} "
-                                   "(1: a particle crossed more than one halo width in a step, 2: message buffer too small)")
-            sent.append((int(c[0]), int(c[1])))
-            got.append((int(c[3]), int(c[4])))
-        return sent, got
-
     def step(self, nsteps: int = 1):
-        lib, tr, ck = self.lib, self.tr, self.slabs[0]._ck
-        for _ in range(nsteps):
-            # A: pre-step + migration
-            for s in self.slabs:
-                ck("mphx_slab_begin", lib.mphx_slab_begin(s.ctx, self._ptr(s.send[0]), self._ptr(s.send[1]), self._ptr(s.counts)))
-            sent, got = self._counts("migration")
-            tr.exchange([(s.send[0], sent[i][0], s.send[1], sent[i][1], s.recv[0], got[i][0], s.recv[1], got[i][1], MSG_DOUBLES)
-                         for i, s in enumerate(self.slabs)])
-            for i, s in enumerate(self.slabs):
-                ck("mphx_slab_append", lib.mphx_slab_append(s.ctx, self._ptr(s.recv[0]), got[i][0], self._ptr(s.recv[1]), got[i][1], 0))
-            # B: halo
-            for s in self.slabs:
-                ck("mphx_slab_pack_halo", lib.mphx_slab_pack_halo(s.ctx, self._ptr(s.send[0]), self._ptr(s.send[1]), self._ptr(s.counts)))
-            sent, got = self._counts("halo")
-            tr.exchange([(s.send[0], sent[i][0], s.send[1], sent[i][1], s.recv[0], got[i][0], s.recv[1], got[i][1], MSG_DOUBLES)
-                         for i, s in enumerate(self.slabs)])
-            for i, s in enumerate(self.slabs):
-                s.halo_sent, s.halo_recv = sent[i], got[i]
-                ck("mphx_slab_append", lib.mphx_slab_append(s.ctx, self._ptr(s.recv[0]), got[i][0], self._ptr(s.recv[1]), got[i][1], 1))
-            # C: buckets + pass 1, PressureP of the halo copies and of the replicated solids
-            for s in self.slabs:
-                ck("mphx_slab_build_pass1", lib.mphx_slab_build_pass1(s.ctx, s.halo_sent[0], s.halo_sent[1], self._ptr(s.psend[0]),
-                                                                      self._ptr(s.psend[1]), self._ptr(s.solP)))
-            tr.exchange([(s.psend[0], s.halo_sent[0], s.psend[1], s.halo_sent[1], s.precv[0], s.halo_recv[0], s.precv[1],
-                          s.halo_recv[1], 1) for s in self.slabs])
-            if self.ns > 0:
-                tr.allreduce_sum([s.solP for s in self.slabs])
-            # D: pass 2 + integration
-            for s in self.slabs:
-                ck("mphx_slab_pass2", lib.mphx_slab_pass2(s.ctx, self._ptr(s.precv[0]), self._ptr(s.precv[1]), self._ptr(s.solP),
-                                                          self._ptr(s.solbuf)))
-            if self.ns > 0:
-                tr.allreduce_sum([s.solbuf for s in self.slabs])
-            # E: solid sub-steps
-            for s in self.slabs:
-                ck("mphx_slab_finish", lib.mphx_slab_finish(s.ctx, self._ptr(s.solbuf)))
-            p = self.case.params
-            for t in range(4, abi.TYPE_COUNT):
-                for d in range(3):
-                    self._wall_center[t][d] += p.wall_velocity[t][d] * p.dt
-
-    def imbalance(self) -> float:
-        """largest / mean number of particle slots held by a slab (1.0 = perfectly balanced)"""
-        held = [i["held"] for i in self.info()]
-        if isinstance(self.tr, DistTransport) and self.tr.world > 1:
-            t = self.torch.tensor([float(held[0])], dtype=self.torch.float64, device=self.device)
-            mx = self.tr.allreduce_max_float(float(held[0]), self.device)
-            self.tr.allreduce_sum([t])
-            return mx / (t.item() / self.tr.world)
-        return max(held) / (sum(held) / len(held))
-
-    def rebalance(self):
-        """Re-cut the slabs on the CURRENT particle distribution (a dam break empties some
-        slabs and fills others).  The state is gathered through the hosts and the slab contexts are rebuilt
-        from it: a coarse operation meant for every few hundred steps.  The continuation is bit-identical
-        (same in-bucket order, same sums); Time and the wall centres carry over."""
-        from . import cases
-        full = self.download("position", "velocity")
-        case = self.case
-        p = case.params.copy()
-        p.time0 = self.time
-        for t in range(abi.TYPE_COUNT):
-            for d in range(3):
-                p.wall_center[t][d] = self._wall_center[t][d]
-        new_case = cases.Case(case.name, p, case.rc, case.property, full["position"], case.initial_position, full["velocity"],
-                              getattr(case, "cuboids", []))
-        tr, device, cap, lib = self.tr, self.device, self._capacity_arg, self.lib
-        old = self.partition
-        self.close()
-        self.__init__(new_case, tr, device=device, capacity=cap, lib=lib)
-        return old, self.partition
-
-    def join(self):
-        """the contexts' streams wait (device-side) for the sub-steps still running on the internal streams"""
-        for s in self.slabs:
-            s._ck("mphx_join", self.lib.mphx_join(s.ctx))
+        self._ck("mphx_step", self.lib.mphx_step(self.ctx, nsteps))
 
     def sync(self):
-        if self.device.type == "cuda":
-            self.torch.cuda.synchronize(self.device)
+        self._ck("mphx_sync", self.lib.mphx_sync(self.ctx))
 
-    def info(self):
-        out = []
-        for s in self.slabs:
-            a = (C.c_int * 4)()
-            self.lib.mphx_slab_info(s.ctx, C.byref(a))
-            out.append(dict(rank=s.rank, held=a[0], capacity=a[1], ghosts=a[2], msg_capacity=a[3], columns=self.partition[s.rank]))
-        return out
-
-    @property
-    def launch_count(self) -> int:
-        return sum(self.lib.mphx_launch_count(s.ctx) for s in self.slabs)
+    def timed_steps(self, nsteps: int) -> float:
+        """device milliseconds of `nsteps` steps on this rank (CUDA events on the context's stream)"""
+        ms = C.c_double()
+        self._ck("mphx_timed_steps", self.lib.mphx_timed_steps(self.ctx, nsteps, C.byref(ms)))
+        return ms.value
 
     @property
     def time(self) -> float:
-        return self.lib.mphx_time(self.slabs[0].ctx)
+        return self.lib.mphx_time(self.ctx)
 
-    # -- download: every slab reports the particles it owns (zeros elsewhere); the sum is the case -----
+    @property
+    def launch_count(self) -> int:
+        return self.lib.mphx_launch_count(self.ctx)
+
+    def status(self):
+        st, a = (C.c_int * 8)(), (C.c_int * 4)()
+        self._ck("mphx_get_status", self.lib.mphx_get_status(self.ctx, C.byref(st)))
+        self._ck("mphx_slab_info", self.lib.mphx_slab_info(self.ctx, C.byref(a)))
+        return dict(err=st[0], held=st[1], builds=st[2], reuses=st[3], ghosts=st[7], capacity=a[1], msg_capacity=a[3])
+
     def download(self, *names):
-        torch = self.torch
-        out = {}
+        """every rank reports the particles it owns (zeros elsewhere); the all-reduced sum is the case"""
+        hv, out = _views_for(self.n, names)
+        self._ck("mphx_download", self.lib.mphx_download(self.ctx, C.byref(hv)))
         for nm in names:
-            shape, is_int = abi.VIEW_FIELDS[nm]
-            tot = None
-            for s in self.slabs:
-                a = np.zeros((self.n,) + shape, dtype=np.int32 if is_int else np.float64)
-                hv = abi.HostViews()
-                setattr(hv, nm, a.ctypes.data_as(C.POINTER(C.c_int if is_int else C.c_double)))
-                s._ck("mphx_download", self.lib.mphx_download(s.ctx, C.byref(hv)))
-                tot = a if tot is None else tot + a
-            if isinstance(self.tr, DistTransport) and self.tr.world > 1:
-                t = torch.from_numpy(tot).to(self.device)
-                self.tr.allreduce_sum([t])
-                tot = t.cpu().numpy()
-            out[nm] = tot
+            t = self.torch.from_numpy(out[nm]).to(self.device)
+            self.dist.all_reduce(t, group=self.group)
+            out[nm] = t.cpu().numpy()
         return out
+
+
+def verify_ring(device_index: int, particles: float = 2.0e5, steps: int = 12, list_reuse: bool | None = None):
+    """Correctness of the data plane that is being timed: the NVLink ring of slabs against ONE context on rank 0, on a
+    down-scaled replica of the same case, same steps.  Returns (on rank 0) per-field bit-equality and the largest
+    difference; every rank must call it."""
+    import torch.distributed as dist
+    from . import cases
+    from .solver import Solver
+    case = cases.fsi3d_for_count(particles)
+    ring = DistSlab(case, device_index, list_reuse=list_reuse)
+    ring.step(steps)
+    ring.sync()
+    fields = ("position", "velocity", "pressure_p", "cell_index")
+    got = ring.download(*fields)
+    st = ring.status()
+    ring.close()
+    res = None
+    if dist.get_rank() == 0:
+        ref = Solver.from_case(case, device=device_index, list_reuse=list_reuse)
+        ref.step(steps, sync=True)
+        want = ref.download(*fields)
+        ref.close()
+        res = {"particles": case.n, "steps": steps, "world": dist.get_world_size(), "fields": {}}
+        ok = True
+        for f in fields:
+            a, b = want[f].astype(np.float64), got[f].astype(np.float64)
+            d = float(np.abs(a - b).max())
+            s = float(np.abs(a).max())
+            eq = bool(np.array_equal(want[f], got[f]))
+            res["fields"][f] = {"bit_equal": eq, "max_abs_diff": d, "max_norm_rel": d / s if s > 0 else d}
+            ok = ok and (eq or d <= 1e-12 * max(s, 1e-300))
+        res["ok"] = ok
+        res["rank0_status"] = st
+    dist.barrier()
+    return res
 
 
 # ---- bench.py, N > 1 (launched by torchrun: one rank per GPU) -------------------------------------------
@@ -415,71 +322,88 @@ def bench_main(args, METRIC, UNIT, WORKLOAD, peaks, ClockSampler, cpu_reference_
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=device)
-    tr = DistTransport()
+
+    def allmax(v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v: float) -> float:
+        t = torch.tensor([v], dtype=torch.float64, device=device)
+        dist.all_reduce(t)
+        return float(t.item())
+
+    # correctness of the exchange that is about to be timed (ring of slabs == one context, on a replica)
+    verify = None if args.no_verify else verify_ring(local, particles=args.verify_particles)
+
     case = cases.fsi3d_for_count(args.particles)
     n = case.n
     nf, ns, nw = case.counts()
-    s = SlabSolver(case, tr, device=device)
+    s = DistSlab(case, local)
     K, W = args.steps, args.warmup
     s.step(W)
     s.sync()
     l0 = s.launch_count
     sampler = ClockSampler(local)
-    tr.barrier()
+    dist.barrier()
     torch.cuda.synchronize()
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    s.step(K)
-    s.join()   # the last step's solid sub-steps run on the library's second stream: the timed region ends after them
-    e1.record()
+    ms_local = s.timed_steps(K)          # CUDA events on the context's stream; ends after the last step's sub-steps
     torch.cuda.synchronize()
-    ms_local = e0.elapsed_time(e1)
-    tr.barrier()
+    dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
-    ms = tr.allreduce_max_float(ms_local, device)
-    launches = s.launch_count - l0
-    lt = torch.tensor([float(launches)], dtype=torch.float64, device=device)
-    dist.all_reduce(lt)
-    info = s.info()[0]
-    held = torch.tensor([float(info["held"])], dtype=torch.float64, device=device)
-    dist.all_reduce(held, op=dist.ReduceOp.MAX)
+    ms = allmax(ms_local)
+    launches = allsum(float(s.launch_count - l0))
+    st = s.status()
+    held = allmax(float(st["held"]))
+    errs = allmax(float(st["err"]))
+    builds, reuses = st["builds"], st["reuses"]
+
+    # what was timed is a valid trajectory: every particle is still owned by exactly one rank, and the state is finite
+    rows_cap = st["capacity"]
+    hid = torch.empty(rows_cap, dtype=torch.int32).pin_memory()
+    hx = torch.empty((rows_cap, 3), dtype=torch.float64).pin_memory()
+    hv = torch.empty((rows_cap, 3), dtype=torch.float64).pin_memory()
+    nrow = C.c_int()
+
+    def fetch():
+        s._ck("mphx_download_owned", s.lib.mphx_download_owned(
+            s.ctx, rows_cap, C.c_void_p(hid.data_ptr()), C.c_void_p(hx.data_ptr()), C.c_void_p(hv.data_ptr()), C.byref(nrow)))
+
+    fetch()
+    m = nrow.value
+    ids = hid[:m].numpy()
+    fluidwall = ~((case.property[ids] >= 2) & (case.property[ids] < 4))
+    owned_total = allsum(float(fluidwall.sum()))
+    finite = allsum(float(not (bool(torch.isfinite(hx[:m]).all()) and bool(torch.isfinite(hv[:m]).all()))))
+    chk_x = allsum(float(hx[:m][torch.from_numpy(fluidwall)].sum()))
+    chk_v = allsum(float(hv[:m][torch.from_numpy(fluidwall)].abs().sum()))
+    state_check = {"owned_fluid_wall_particles": int(owned_total), "expected": nf + nw, "all_finite": finite == 0.0,
+                   "error_flags": int(errs), "sum_position": chk_x, "sum_abs_velocity": chk_v,
+                   "ok": int(owned_total) == nf + nw and finite == 0.0 and int(errs) & ~32 == 0}
 
     # end to end through the C-ABI with HOST buffers, every step: mphx_upload_owned (ids, Position, Velocity
     # of the particles this rank owns + the replicated solids, from page-locked memory), one slab step,
     # mphx_download_owned back into page-locked memory.  Copies are inside the timed region; every rank
     # moves its own share over its own PCIe link.
-    ctx0 = s.slabs[0].ctx
-    rows_cap = s.info()[0]["capacity"]
-    hid = torch.empty(rows_cap, dtype=torch.int32).pin_memory()
-    hx = torch.empty((rows_cap, 3), dtype=torch.float64).pin_memory()
-    hv = torch.empty((rows_cap, 3), dtype=torch.float64).pin_memory()
     ke = max(1, min(K, args.e2e_steps))
-    nrow = C.c_int()
-
-    def fetch():
-        s.slabs[0]._ck("mphx_download_owned", s.lib.mphx_download_owned(
-            ctx0, rows_cap, C.c_void_p(hid.data_ptr()), C.c_void_p(hx.data_ptr()), C.c_void_p(hv.data_ptr()), C.byref(nrow)))
 
     def e2e_step():
-        s.slabs[0]._ck("mphx_upload_owned", s.lib.mphx_upload_owned(
-            ctx0, nrow.value, C.c_void_p(hid.data_ptr()), C.c_void_p(hx.data_ptr()), C.c_void_p(hv.data_ptr())))
+        s._ck("mphx_upload_owned", s.lib.mphx_upload_owned(
+            s.ctx, nrow.value, C.c_void_p(hid.data_ptr()), C.c_void_p(hx.data_ptr()), C.c_void_p(hv.data_ptr())))
         s.step(1)
         fetch()
 
-    fetch()
     e2e_step()
-    tr.barrier()
+    dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(ke):
         e2e_step()
     torch.cuda.synchronize()
-    te = tr.allreduce_max_float(time.perf_counter() - t0, device)
-    rt = torch.tensor([float(nrow.value)], dtype=torch.float64, device=device)
-    dist.all_reduce(rt)
-    rows_total = rt.item()
+    te = allmax(time.perf_counter() - t0)
+    rows_total = allsum(float(nrow.value))
     s.close()
     if rank == 0:
         pk, pk_kind = peaks()
@@ -491,18 +415,23 @@ def bench_main(args, METRIC, UNIT, WORKLOAD, peaks, ClockSampler, cpu_reference_
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "particles": n, "fluid": nf, "solid": ns, "wall": nw, "dim": 3,
                            "particle_spacing": case.params.particle_spacing, "dt": case.params.dt, "solid_substeps": nsub,
-                           "cache": "inputs larger than L2", "parallelism": f"{world} x-slabs (ring), halo + migration over NCCL",
-                           "partition_columns": s.partition, "max_slots_held": int(held.item())},
+                           "cache": "inputs larger than L2",
+                           "parallelism": f"{world} x-slabs (ring); migration, halo, PressureP and solid exchange are device-side stores "
+                                          "into peer mailboxes over NVLink (CUDA IPC), no host synchronisation per step; NCCL carries "
+                                          "only the start-up handles and the timing/verification reductions",
+                           "partition_columns": s.partition, "max_slots_held": int(held),
+                           "list_builds": builds, "list_reuses": reuses},
                 "clocks": clocks,
                 "e2e": {"value": n * ke / te, "unit": UNIT, "h2d_bytes_per_step": int(rows_total) * 52,
                         "d2h_bytes_per_step": int(rows_total) * 52, "steps": ke, "ms_per_step": 1e3 * te / ke,
                         "path": "per rank: mphx_upload_owned + slab step + mphx_download_owned (ids+Position+Velocity of the owned "
                                 "particles and the replicated solids, pinned host buffers); bytes summed over ranks"},
-                "gpu_launches": int(lt.item()),
+                "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "kernel": "whole step (all ranks)", "achieved": agg, "peak": pk["hbm_gbs"] * world,
                              "unit": "GB/s", "frac": agg / (pk["hbm_gbs"] * world), "traffic": None,
                              "peak_source": pk_kind + " (MEASURED_PEAKS.json hbm_gbs x n_gpus)",
                              "algorithmic_bytes_per_step": step_bytes},
+                "verify": {"ring_vs_single_context": verify, "timed_state": state_check},
                 "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()

@@ -77,15 +77,28 @@ def _load():
     L.mphx_launch_count.restype = C.c_longlong
     L.mphx_algorithmic_bytes_per_step.argtypes = [vp]
     L.mphx_algorithmic_bytes_per_step.restype = C.c_double
+    L.mphx_set_list_reuse.argtypes = [vp, C.c_int, C.c_double]
+    L.mphx_get_status.argtypes = [vp, C.POINTER(C.c_int * 8)]
     L.mphx_set_stream.argtypes = [vp, vp]
+    L.mphx_partition_columns.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp]
     L.mphx_slab_configure.argtypes = [vp] + [C.c_int] * 6
-    L.mphx_slab_begin.argtypes = [vp, vp, vp, vp]
-    L.mphx_slab_append.argtypes = [vp, vp, C.c_int, vp, C.c_int, C.c_int]
-    L.mphx_slab_pack_halo.argtypes = [vp, vp, vp, vp]
-    L.mphx_slab_build_pass1.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp]
-    L.mphx_slab_pass2.argtypes = [vp, vp, vp, vp, vp]
-    L.mphx_slab_finish.argtypes = [vp, vp]
+    L.mphx_slab_mailbox.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_longlong)]
+    L.mphx_slab_connect.argtypes = [vp, vp, vp, vp]
     L.mphx_slab_info.argtypes = [vp, C.POINTER(C.c_int * 4)]
+    L.mphx_multi_create.argtypes = [C.POINTER(vp), C.POINTER(abi.Params), C.c_int, vp]
+    L.mphx_multi_destroy.argtypes = [vp]
+    L.mphx_multi_destroy.restype = None
+    L.mphx_multi_count.argtypes = [vp]
+    L.mphx_multi_context.argtypes = [vp, C.c_int]
+    L.mphx_multi_context.restype = vp
+    L.mphx_multi_upload.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.mphx_multi_init.argtypes = [vp]
+    L.mphx_multi_step.argtypes = [vp, C.c_int]
+    L.mphx_multi_sync.argtypes = [vp]
+    L.mphx_multi_time.argtypes = [vp]
+    L.mphx_multi_time.restype = C.c_double
+    L.mphx_multi_download.argtypes = [vp, C.POINTER(abi.HostViews)]
+    L.mphx_multi_timed_steps.argtypes = [vp, C.c_int, C.POINTER(C.c_double)]
     return L
 
 
@@ -206,8 +219,10 @@ class Solver:
         self.n = 0
 
     @classmethod
-    def from_case(cls, case, device: int = 0, init: bool = True):
+    def from_case(cls, case, device: int = 0, init: bool = True, list_reuse: bool | None = None, skin: float = 0.0):
         s = cls(case.params, device)
+        if list_reuse is not None or skin > 0.0:
+            s.set_list_reuse(True if list_reuse is None else list_reuse, skin)
         s.upload(case.property, case.position, case.initial_position, case.velocity)
         if init:
             s.init()
@@ -262,6 +277,15 @@ class Solver:
 
     def init(self):
         _ck("mphx_init", lib.mphx_init(self._ctx))
+
+    def set_list_reuse(self, on: bool, skin: float = 0.0):
+        """candidate-list reuse (internal Verlet skin); skin in particle spacings, only before upload"""
+        _ck("mphx_set_list_reuse", lib.mphx_set_list_reuse(self._ctx, 1 if on else 0, float(skin)))
+
+    def status(self) -> dict:
+        a = (C.c_int * 8)()
+        _ck("mphx_get_status", lib.mphx_get_status(self._ctx, C.byref(a)))
+        return dict(err=a[0], slots=a[1], builds=a[2], reuses=a[3], age=a[4], skin_on=a[5], solid_multi_occupancy=a[6], ghosts=a[7])
 
     def constants(self) -> abi.Constants:
         k = abi.Constants()

@@ -5,6 +5,10 @@ import sys
 import numpy as np
 import pytest
 
+# several slab contexts share one device in the slab parity tests and wait for each other's flags inside
+# kernels: every context's streams need their own hardware queue (set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

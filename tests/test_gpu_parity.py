@@ -281,6 +281,54 @@ def test_determinism_and_reupload():
         assert np.array_equal(outs[0][f], outs[1][f]), f   # atomics only order arrival, never sums
 
 
+@pytest.mark.parametrize("name", ["fsi3d_mini", "dam2d"])
+def test_candidate_list_reuse_equals_rebuilding_every_step(name):
+    """SURVEY 8(f) N3 / VERDICT r1 item 4: the candidate list carries a skin and is reused until a particle has
+    moved skin/2 (decided on the device).  The list is only a superset -- every pair is still tested in fp64 -- so
+    the trajectory equals the every-step-rebuild trajectory up to the order of the sums (the reused list keeps the
+    particle order of its build step)."""
+    case = getattr(cases, name)()
+    a = Solver.from_case(case, list_reuse=False)
+    b = Solver.from_case(case, list_reuse=True)
+    a.step(60, sync=True)
+    b.step(60, sync=True)
+    sa, sb = a.status(), b.status()
+    assert sa["reuses"] == 0 and sa["builds"] == 61          # (+1: the list of mphx_init)
+    assert sb["reuses"] > 30 and sb["builds"] + sb["reuses"] == 61, sb
+    assert sa["err"] == 0 and sb["err"] == 0
+    fa = a.download("position", "velocity", "pressure_p", "force", "cell_index")
+    fb = b.download("position", "velocity", "pressure_p", "force", "cell_index")
+    assert np.array_equal(fa["cell_index"], fb["cell_index"])
+    fp = pressure_floor(case, a.constants())
+    for f, floor in (("position", 0.0), ("velocity", 0.0), ("pressure_p", fp), ("force", None)):
+        err, scale = record(("reuse_vs_rebuild", name), f, fb[f], fa[f], floor or 0.0)
+        if floor is not None:
+            assert err <= RTOL * scale + floor, (f, err, scale)
+    # bit-exact neighbour sets are served from the positions of the last pass 1, whatever the list's age
+    offa, idsa = a.neighbors()
+    offb, idsb = b.neighbors()
+    assert np.array_equal(offa, offb) and np.array_equal(idsa, idsb)
+    a.close()
+    b.close()
+
+
+def test_list_reuse_with_fast_flow_matches_oracle():
+    """a dam break whose water moves 0.15 l0 per step: lists expire every step or two, the skin switches itself
+    off and is probed again (k_decide); 100 steps against the oracle at 1e-10"""
+    case = cases.dam2d()
+    case.velocity[case.property < 2, 0] = 1.5
+    o = Oracle.from_case(case)
+    o.init()
+    s = Solver.from_case(case, list_reuse=True)
+    s.step(100, sync=True)
+    o.step(100)
+    check_fields(case, s, o.get, "dam2d_fast_reuse")
+    st = s.status()
+    assert st["builds"] > 40 and st["err"] == 0, st
+    s.close()
+    o.close()
+
+
 def test_scale_properties_3d_300k():
     """size-independent properties at a size the oracle cannot do in seconds"""
     case = cases.fsi3d_for_count(3.0e5)

@@ -1,9 +1,11 @@
 """Slab decomposition parity (-m gpu): the ring of x-slabs must reproduce the single-context step.
 
-All slabs of the ring run in ONE process on ONE device (slab.LocalRing: the exchange is a device
-copy), so this exercises every slab kernel -- migration, halo pack/unpack, PressureP exchange,
-replicated solids -- on the single-GPU box.  The in-bucket order (by original id) and the stencil
-order are the same in a slab and in the whole domain, so the sums are the same bits.
+All slabs of the ring run in ONE process on ONE device (slab.MultiSolver with a repeated device: the
+mailboxes are ordinary device memory then), so this exercises every slab kernel -- votes, migration, halo
+pack / push / unpack, halo refresh on list-reuse steps, PressureP exchange, replicated solids -- and the
+device-side flag protocol on the single-GPU box.  The in-bucket order (by original id) and the stencil
+order are the same in a slab and in the whole domain, and the rebuild / reuse decision is the OR of the
+slabs' votes (= the single context's decision), so the sums are the same bits.
 """
 import numpy as np
 import pytest
@@ -15,9 +17,9 @@ pytestmark = pytest.mark.gpu
 FIELDS = ("position", "velocity", "pressure_p", "force", "cell_index", "stress", "property")
 
 
-def _compare(case, world, steps, exact=True, fields=FIELDS, atol=None):
-    ref = Solver.from_case(case)
-    ring = slab.SlabSolver(case, slab.LocalRing(world))
+def _compare(case, world, steps, exact=True, fields=FIELDS, atol=None, list_reuse=None):
+    ref = Solver.from_case(case, list_reuse=list_reuse)
+    ring = slab.MultiSolver(case, world, devices=[0] * world, list_reuse=list_reuse)
     done = 0
     for target in steps:
         ref.step(target - done, sync=True)
@@ -34,6 +36,10 @@ def _compare(case, world, steps, exact=True, fields=FIELDS, atol=None):
                 assert float(np.abs(a[f] - b[f]).max()) <= 1e-12 * scale + (atol or {}).get(f, 0.0), (case.name, world, target, f)
         assert ring.time == ref.time
     info = ring.info()
+    st = ref.status()
+    assert all(i["err"] == 0 for i in info), info
+    # every slab took the same rebuild / reuse decisions as the single context
+    assert all((i["builds"], i["reuses"]) == (st["builds"], st["reuses"]) for i in info), (info, st)
     ref.close()
     ring.close()
     return info
@@ -41,12 +47,18 @@ def _compare(case, world, steps, exact=True, fields=FIELDS, atol=None):
 
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_fsi3d_ring_equals_single_context(world):
-    _compare(cases.fsi3d_mini(), world, [1, 5, 40])
+    info = _compare(cases.fsi3d_mini(), world, [1, 5, 40])
+    assert info[0]["reuses"] > 0   # (the candidate lists really were reused: the halo-refresh path ran)
 
 
 @pytest.mark.parametrize("name,world", [("dam2d", 2), ("dam2d", 4), ("fsi2d", 3), ("bar2d", 2)])
 def test_2d_ring_equals_single_context(name, world):
     _compare(getattr(cases, name)(), world, [1, 10, 60])
+
+
+def test_ring_without_list_reuse_equals_single_context():
+    """every step rebuilds (the reference's own schedule): migration + fresh halos every step"""
+    _compare(cases.fsi3d_mini(), 3, [1, 12], list_reuse=False)
 
 
 def test_particles_migrate_between_slabs():
@@ -56,6 +68,7 @@ def test_particles_migrate_between_slabs():
     case.velocity[fl, 0] = 1.5   # 1.5 m/s * 1e-4 s = 0.15 l0 per step
     info = _compare(case, 4, [1, 20, 120])
     assert sum(i["held"] for i in info) >= case.n
+    assert info[0]["builds"] > 10
 
 
 def test_flow_through_the_periodic_seam():
@@ -98,39 +111,39 @@ def test_solid_next_to_the_periodic_seam():
 def test_compact_owned_io_round_trip():
     """mphx_download_owned / mphx_upload_owned: rows of every slab together are the whole case (+ the
     replicated solids once per slab); taking them back unchanged and stepping equals plain stepping."""
-    import ctypes as C
     case = cases.fsi3d_mini()
     ref = Solver.from_case(case)
-    ring = slab.SlabSolver(case, slab.LocalRing(3))
+    ring = slab.MultiSolver(case, 3, devices=[0, 0, 0])
     ref.step(3, sync=True)
     ring.step(3)
+    ring.sync()
     ns = case.counts()[1]
     seen = np.zeros(case.n, dtype=np.int64)
     want = ref.download("position", "velocity")
     bufs = []
-    for s in ring.slabs:
-        cap = ring.info()[s.rank]["capacity"]
-        ids = np.empty(cap, dtype=np.int32)
-        x = np.empty((cap, 3))
-        v = np.empty((cap, 3))
-        n = C.c_int()
-        s._ck("mphx_download_owned", ring.lib.mphx_download_owned(s.ctx, cap, ids.ctypes.data, x.ctypes.data, v.ctypes.data, C.byref(n)))
-        m = n.value
+    for r in range(3):
+        m, ids, x, v = ring.download_owned(r)
         np.add.at(seen, ids[:m], 1)
         assert np.array_equal(x[:m], want["position"][ids[:m]])
         assert np.array_equal(v[:m], want["velocity"][ids[:m]])
-        bufs.append((s, m, ids, x, v))
+        bufs.append((r, m, ids, x, v))
     solid = (case.property >= 2) & (case.property < 4)
     assert np.all(seen[~solid] == 1) and np.all(seen[solid] == 3) and int(solid.sum()) == ns
-    for s, m, ids, x, v in bufs:
-        s._ck("mphx_upload_owned", ring.lib.mphx_upload_owned(s.ctx, m, ids.ctypes.data, x.ctypes.data, v.ctypes.data))
+    for r, m, ids, x, v in bufs:
+        assert ring.upload_owned(r, m, ids, x, v) == 0
+    # (an upload replaces the state: both sides rebuild their lists at the next step, so the sums stay the same bits)
+    ids0 = np.empty(case.n, dtype=np.int32)
+    x0, v0 = np.empty((case.n, 3)), np.empty((case.n, 3))
+    m0 = ref.download_owned(ids0, x0, v0)
+    ref.upload_owned(m0, ids0, x0, v0)
     ref.step(4, sync=True)
     ring.step(4)
+    ring.sync()
     a, b = ref.download("position", "velocity"), ring.download("position", "velocity")
     assert np.array_equal(a["position"], b["position"]) and np.array_equal(a["velocity"], b["velocity"])
     # a stale upload (a step happened since the download) is refused
-    s, m, ids, x, v = bufs[0]
-    assert ring.lib.mphx_upload_owned(s.ctx, m, ids.ctypes.data, x.ctypes.data, v.ctypes.data) != 0
+    r, m, ids, x, v = bufs[0]
+    assert ring.upload_owned(r, m, ids, x, v) != 0
     # single context: owned = everything; modified rows are taken over
     ids = np.empty(case.n, dtype=np.int32)
     x = np.empty((case.n, 3))
@@ -141,31 +154,5 @@ def test_compact_owned_io_round_trip():
     ref.upload_owned(m, ids, x, v)
     got = ref.download("velocity")["velocity"]
     assert np.array_equal(got[ids], v)
-    ref.close()
-    ring.close()
-
-
-def test_rebalance_recuts_the_slabs_and_continues_bit_identically():
-    """the fluid drifts in +x, so the balanced cuts move; after rebalance() the ring still reproduces the
-    single-context run bit for bit (Time carries over)"""
-    case = cases.dam2d()
-    fl = case.property < 2
-    case.velocity[fl, 0] = 2.5
-    ref = Solver.from_case(case)
-    ring = slab.SlabSolver(case, slab.LocalRing(3))
-    ref.step(60, sync=True)
-    ring.step(60)
-    before = ring.imbalance()
-    old, new = ring.rebalance()
-    assert old != new, (old, new)
-    assert ring.time == ref.time
-    assert ring.imbalance() <= before + 1e-12
-    ref.step(40, sync=True)
-    ring.step(40)
-    ring.sync()
-    a, b = ref.download(*FIELDS), ring.download(*FIELDS)
-    for f in FIELDS:
-        assert np.array_equal(a[f], b[f]), (f, float(np.abs(a[f] - b[f]).max()))
-    assert ring.time == ref.time
     ref.close()
     ring.close()
