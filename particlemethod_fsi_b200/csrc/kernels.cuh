@@ -54,7 +54,8 @@ struct GridDesc {
 enum { kErrLost = 1,      // a particle crossed more than one halo width in a step
        kErrMsgFull = 2,   // exchange message buffer too small
        kErrArrival = 4,   // a received particle does not belong where it was sent
-       kErrTimeout = 8,   // a peer's flag did not arrive (exchange wait timed out)
+       kErrTimeout = 8,   // a peer's flag did not arrive (exchange wait timed out); bits 8.. say which: 256 votes, 512 migrants,
+                          // 1024 halo, 2048 PressureP, 4096 solids' PressureP, 8192 solids' velocity
        kErrCapacity = 16, // particle slots exhausted
        kErrNaN = 32 };    // a non-finite position came out of the integration
 
@@ -238,8 +239,9 @@ constexpr unsigned long long kWaitTimeoutNs = 4000000000ull; // a missing peer b
 // OR of the votes goes to ctl->need)
 // (the epoch is a kernel argument, not device state: the waits of the solid sub-steps run on a second stream
 // while the context's stream may already be enqueuing the next step)
+enum { kWaitVote = 0, kWaitMig, kWaitHalo, kWaitP, kWaitSolP, kWaitSolV };
 template <int SHIFT>
-__global__ void k_wait(Ctl *ctl, unsigned long long epoch, const unsigned long long *flags, int nflags)
+__global__ void k_wait(Ctl *ctl, unsigned long long epoch, const unsigned long long *flags, int nflags, int tag)
 {
     const int lane = threadIdx.x;
     const unsigned long long want = epoch;
@@ -249,7 +251,7 @@ __global__ void k_wait(Ctl *ctl, unsigned long long epoch, const unsigned long l
         for (;;) {
             v = ld_flag(flags + lane);
             if ((v >> SHIFT) >= want) break;
-            if (global_ns() - t0 > kWaitTimeoutNs) { atomicOr(&ctl->err, kErrTimeout); break; }
+            if (global_ns() - t0 > kWaitTimeoutNs) { atomicOr(&ctl->err, kErrTimeout | (256 << tag)); break; }
             __nanosleep(64);
         }
     }

@@ -356,6 +356,32 @@ static DecideArgs decide_args(const Ctx *c)
 
 static void timer_mark(Ctx *c);
 
+// CUDA loads kernels lazily, at their first launch, and that load may wait for every kernel running on the device.
+// A slab step parks one-warp kernels that spin on a peer's flag; a first-time load issued behind such a kernel would
+// stall until the wait times out.  So every kernel of the stepping path is loaded when a context is created.
+template <class K> static void preload(K kernel)
+{
+    cudaFuncAttributes a;
+    cudaFuncGetAttributes(&a, kernel);
+}
+static void preload_kernels(int dim)
+{
+    preload(k_prestep); preload(k_need); preload(k_decide); preload(k_vote); preload(k_wait<0>); preload(k_wait<1>);
+    preload(k_count); preload(k_clamp_counts); preload(k_push); preload(k_push_scalar); preload(k_unpack_particles);
+    preload(k_advance_n); preload(k_halo_pack); preload(k_halo_repack); preload(k_unpack_refresh); preload(k_slab_slots);
+    preload(k_unpack_scalar); preload(k_solid_owned_list); preload(k_solid_publish_P); preload(k_solid_spread_P);
+    preload(k_solid_publish_V); preload(k_solid_apply_update); preload(k_scan_reduce); preload(k_scan_top); preload(k_scan_apply);
+    preload(k_scatter_index); preload(k_permute); preload(k_set_n);
+#define PRELOAD_DIM(D)                                                                                                   \
+    preload(k_filter<D>); preload(k_filter2<D, false>); preload(k_filter2<D, true>);                                     \
+    preload(k_pass1_v3<D, false, false>); preload(k_pass1_v3<D, false, true>); preload(k_pass1_v3<D, true, false>);      \
+    preload(k_pass1_v3<D, true, true>); preload(k_pass2_v3<D, false, false>); preload(k_pass2_v3<D, false, true>);       \
+    preload(k_pass2_v3<D, true, false>); preload(k_pass2_v3<D, true, true>); preload(k_solid_pass1<D>); preload(k_solid_pass2<D>)
+    if (dim == 3) { PRELOAD_DIM(3); } else { PRELOAD_DIM(2); }
+#undef PRELOAD_DIM
+    cudaGetLastError();
+}
+
 // ---- exchange between slabs: all device-side (see kernels.cuh "Exchange between slabs") --------------------
 constexpr int kPushBlocks = 64, kPushThreads = 256;
 enum { kPushMigL = 0, kPushMigR, kPushHaloL, kPushHaloR, kPushPL, kPushPR, kPushSolP, kPushSolV };
@@ -372,7 +398,7 @@ static int exchange_particles(Ctx *c, bool halo)
            (halo ? L.cnt_halo : L.cnt_mig) + 1, (halo ? L.fhalo : L.fmig) + 1);
     LAUNCH(c, k_push, kPushBlocks, kPushThreads, ctl, c->epoch, w0 + 1, stage[1], cnt + 1, kMsgDoubles, halo ? R.halo[0] : R.mig[0],
            (halo ? R.cnt_halo : R.cnt_mig) + 0, (halo ? R.fhalo : R.fmig) + 0);
-    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, halo ? c->mine.fhalo : c->mine.fmig, 2);
+    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, halo ? c->mine.fhalo : c->mine.fmig, 2, halo ? kWaitHalo : kWaitMig);
     CK(cudaGetLastError());
     return MPHX_OK;
 }
@@ -413,7 +439,7 @@ static int stage_build(Ctx *c, bool motion)
     LAUNCH(c, k_need, 1, 1, ctl, da, (const int *)c->pl.flags);
     if (c->slab) {
         LAUNCH(c, k_vote, 1, 32, ctl, c->epoch, c->peers);
-        LAUNCH(c, k_wait<1>, 1, 32, ctl, c->epoch, c->mine.vote, c->nranks);
+        LAUNCH(c, k_wait<1>, 1, 32, ctl, c->epoch, c->mine.vote, c->nranks, kWaitVote);
     }
     LAUNCH(c, k_decide, 1, 1, ctl, da, c->pl.flags);
     SlabSend snd{};
@@ -510,11 +536,11 @@ static int exchange_pressure(Ctx *c)
     LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPL, 0, c->haloSlot[0], c->P, L.p[1], L.fp + 1);
     LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPR, 1, c->haloSlot[1], c->P, R.p[0], R.fp + 0);
     if (c->ns > 0) LAUNCH(c, k_solid_publish_P, kPushBlocks, kPushThreads, ctl, c->epoch, kPushSolP, c->S, c->sol, c->own_sol, c->P, c->peers);
-    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fp, 2);
+    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fp, 2, kWaitP);
     const int mb = nblk(c->msg_cap);
     for (int side = 0; side < 2; ++side) LAUNCH(c, k_unpack_scalar, mb, kBlock, ctl, side, c->ghostSlot[side], c->mine.p[side], c->P, c->S.rb);
     if (c->ns > 0) {
-        LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fsolP, c->nranks);
+        LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fsolP, c->nranks, kWaitSolP);
         LAUNCH(c, k_solid_spread_P, nblk(c->nmax), kBlock, ctl, c->S, c->grid, c->sol, c->mine.solP, c->P);
     }
     CK(cudaGetLastError());
@@ -575,7 +601,7 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
     const int ns = c->ns;
     const int dbl = (c->p.ref_compat & MPHX_COMPAT_DOUBLE_UPDATE) ? 1 : 0;
     if (c->slab) { // every rank takes the owners' coupled velocities, then runs the identical sub-steps
-        LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, c->epoch, c->mine.fsolV, c->nranks);
+        LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, c->epoch, c->mine.fsolV, c->nranks, kWaitSolV);
         LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV);
     }
     for (int s = 0; s < substeps; ++s) {
@@ -957,6 +983,7 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
         delete c;
         return MPHX_ERR_CUDA;
     }
+    preload_kernels(p->dim);
     {
         Ctl init{};
         init.force = 1;

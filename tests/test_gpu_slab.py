@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 FIELDS = ("position", "velocity", "pressure_p", "force", "cell_index", "stress", "property")
 
 
-def _compare(case, world, steps, exact=True, fields=FIELDS, atol=None, list_reuse=None):
+def _compare(case, world, steps, exact=True, fields=FIELDS, atol=None, list_reuse=None, rtol=1e-12):
     ref = Solver.from_case(case, list_reuse=list_reuse)
     ring = slab.MultiSolver(case, world, devices=[0] * world, list_reuse=list_reuse)
     done = 0
@@ -33,7 +33,7 @@ def _compare(case, world, steps, exact=True, fields=FIELDS, atol=None, list_reus
                 assert np.array_equal(a[f], b[f]), (case.name, world, target, f, float(np.abs(a[f] - b[f]).max()))
             else:
                 scale = max(float(np.abs(a[f]).max()), 1e-300)
-                assert float(np.abs(a[f] - b[f]).max()) <= 1e-12 * scale + (atol or {}).get(f, 0.0), (case.name, world, target, f)
+                assert float(np.abs(a[f] - b[f]).max()) <= rtol * scale + (atol or {}).get(f, 0.0), (case.name, world, target, f)
         assert ring.time == ref.time
     info = ring.info()
     st = ref.status()
@@ -103,9 +103,11 @@ def test_solid_next_to_the_periodic_seam():
     case = cases._assemble("seam_solid", p, rc, l0, (0.0, -7 * l0, 0.0), (0.08, 0.06, l0), cubs)
     assert case.counts()[1] > 0
     fields = ("position", "velocity", "pressure_p", "force", "cell_index", "property")
-    # (PressureP of water at rest is rounding noise around zero, ~1e-11 for kappa = 1e4: absolute floors)
+    # (PressureP of water at rest is rounding noise around zero, ~1e-11 for kappa = 1e4: absolute floors; the one-ulp
+    # differences of the shifted separations feed kappa (sum w - N0p) and grow to ~1e-10 of the velocity in 60 steps)
     for world in (2, 3):
-        _compare(case, world, [1, 10, 60], exact=False, fields=fields, atol=dict(pressure_p=1e-9, force=1e-12))
+        _compare(case, world, [1, 10], exact=False, fields=fields, atol=dict(pressure_p=1e-9, force=1e-12))
+        _compare(case, world, [60], exact=False, fields=fields, atol=dict(pressure_p=1e-9, force=1e-12), rtol=1e-9)
 
 
 def test_compact_owned_io_round_trip():
