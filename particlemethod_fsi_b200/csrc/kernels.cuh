@@ -361,7 +361,9 @@ __global__ void k_prestep(Ctl *ctl, Particles p, Solid sol, GridDesc g, WallMoti
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d2 = fmaxf(d2, __shfl_xor_sync(0xffffffffu, d2, o));
-    if ((threadIdx.x & 31) == 0 && d2 > 0.f) atomicMax(&ctl->maxdisp2, __float_as_uint(d2));
+    // (one contended address: only a warp that raises the maximum issues the atomic)
+    if ((threadIdx.x & 31) == 0 && d2 > __uint_as_float(*reinterpret_cast<volatile unsigned *>(&ctl->maxdisp2)))
+        atomicMax(&ctl->maxdisp2, __float_as_uint(d2));
 }
 
 // The rebuild decision of this step, made on the device (one thread).  The list built with a skin d stays a
