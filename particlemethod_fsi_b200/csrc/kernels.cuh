@@ -123,7 +123,8 @@ struct Particles {
 struct Solid {
     int ns, sb;
     double *x, *y, *z, *vx, *vy, *vz, *x0, *y0, *z0, *fx, *fy, *fz;
-    double *Linv, *Fm, *E, *S, *Pk; // 9 planes of ns doubles each: M[k*ns+s], k = 3*row+col
+    double *Linv, *Fm, *E, *S; // 9 planes of ns doubles each: M[k*ns+s], k = 3*row+col
+    double *PkA;               // first Piola-Kirchhoff stress, 9 doubles per solid (AoS: a neighbour's thread gathers all nine)
     double *lam, *mu;
     int *type;
     int *off, *nbr;   // InitialStructureNeighbor as CSR (solid-local ids, rows in the reference's list order)
@@ -136,7 +137,13 @@ struct Solid {
     int *enbr, *ernbr;               // ELL neighbour ids (own rows / transposed rows)
     double *d0x, *d0y, *d0z, *w;     // own rows
     double *rd0x, *rd0y, *rd0z, *rw; // transposed: x0_js as row j computes it
-    double *ux, *uy, *uz;            // displacement u = minimg(x - x0) of the current positions
+    Rec *u;                          // displacement u = minimg(x - x0) of the current positions (x, y, z, -: one 256-bit gather)
+    // Static pair data as a DICTIONARY: a lattice solid has a few thousand distinct (x0_ij, w) tuples among its
+    // ~80 pairs per particle, so each pair stores a 16-bit index into `ttab` instead of four doubles (the sub-steps
+    // are bound by streaming this data: 36 -> 6 bytes per pair).  packed = 0 (more than 65535 tuples): the raw arrays.
+    int packed;
+    unsigned short *tix, *rtix;      // ELL, own rows / transposed rows
+    Rec *ttab;                       // (x0_ij.x, .y, .z, weight(x0_ij))
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -348,9 +355,10 @@ __global__ void k_prestep(Ctl *ctl, Particles p, Solid sol, GridDesc g, WallMoti
             p.x[i] = x; p.y[i] = y; p.z[i] = z;
             if (s >= 0) {
                 sol.x[s] = x; sol.y[s] = y; sol.z[s] = z;
-                sol.ux[s] = minimg_exact(x, sol.x0[s], g.W[0]); // :2712, from the (wrapped) position the sub-steps start from
-                sol.uy[s] = minimg_exact(y, sol.y0[s], g.W[1]);
-                sol.uz[s] = minimg_exact(z, sol.z0[s], g.W[2]);
+                Rec u; // :2712, from the (wrapped) position the sub-steps start from
+                u.a = minimg_exact(x, sol.x0[s], g.W[0]); u.b = minimg_exact(y, sol.y0[s], g.W[1]); u.c = minimg_exact(z, sol.z0[s], g.W[2]);
+                u.d = 0.0;
+                sol.u[s] = u;
             }
             p.key[i] = cell_key(g, x, y, z);
             // (a particle that wrapped through the box shows up a box width away: conservative, it forces a rebuild)
@@ -996,14 +1004,22 @@ __global__ void k_solid_normalizer(Solid so, double W0, double W1, double W2, do
 
 // K7 "solid pass 1": deformation gradient (:2701-2752), Green-Lagrange strain and 2nd PK stress
 // (:2768-2808), and P = F S L^-1 (:2837-2852), all in registers.
-template <int DIMS>
+// PACKED: the static pair data comes from the tuple dictionary (see Solid).
+__device__ __forceinline__ Rec ld_rec_ro(const Rec *p)
+{
+    Rec r;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+    return r;
+}
+template <int DIMS, bool PACKED>
 __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double radius, double cw)
 {
     using namespace ex;
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= so.ns) return;
     const int ns = so.ns;
-    const double ui[3] = {so.ux[s], so.uy[s], DIMS == 3 ? so.uz[s] : 0.0};
+    const Rec uo = so.u[s];
+    const double ui[3] = {uo.a, uo.b, DIMS == 3 ? uo.c : 0.0};
     double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     const int len = so.len[s];
     // (unrolled so that the loads of four list entries are in flight together; the sum order is unchanged)
@@ -1011,11 +1027,18 @@ __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double 
     for (int kk = 0; kk < len; ++kk) {
         const size_t k = (size_t)kk * ns + s;
         const int j = __ldg(&so.enbr[k]);
-        const double d0[3] = {__ldg(&so.d0x[k]), __ldg(&so.d0y[k]), DIMS == 3 ? __ldg(&so.d0z[k]) : 0.0};
-        const double uj[3] = {so.ux[j], so.uy[j], DIMS == 3 ? so.uz[j] : 0.0};
+        double d0[3], w;
+        if (PACKED) {
+            const Rec t = ld_rec_ro(so.ttab + __ldg(&so.tix[k]));
+            d0[0] = t.a; d0[1] = t.b; d0[2] = DIMS == 3 ? t.c : 0.0; w = t.d;
+        } else {
+            d0[0] = __ldg(&so.d0x[k]); d0[1] = __ldg(&so.d0y[k]); d0[2] = DIMS == 3 ? __ldg(&so.d0z[k]) : 0.0;
+            w = __ldg(&so.w[k]);
+        }
+        const Rec un = ld_rec_ro(so.u + j); // (written by the previous kernel: read-only here)
+        const double uj[3] = {un.a, un.b, DIMS == 3 ? un.c : 0.0};
         double d[3];
         for (int a = 0; a < DIMS; ++a) d[a] = add(d0[a], sub(uj[a], ui[a])); // :2716
-        const double w = __ldg(&so.w[k]);
         for (int a = 0; a < DIMS; ++a)
             for (int b = 0; b < DIMS; ++b) G[a][b] = add(G[a][b], mul(mul(w, d[a]), d0[b])); // :2726
     }
@@ -1042,12 +1065,14 @@ __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double 
             S[a][b] = mul(mul(2.0, mu), E[a][b]); // :2804
             if (a == b) S[a][b] = add(S[a][b], mul(lam, tr));
         }
-    for (int a = 0; a < DIMS; ++a)
-        for (int b = 0; b < DIMS; ++b) {
+    double *Pk = so.PkA + 9 * (size_t)s;
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            if (a >= DIMS || b >= DIMS) { Pk[3 * a + b] = 0.0; continue; }
             double sum = 0.0;
             for (int k = 0; k < DIMS; ++k)
                 for (int l = 0; l < DIMS; ++l) sum = add(sum, mul(mul(F[a][k], S[k][l]), L[l][b])); // :2847
-            MPHX_T(so.Pk, a, b, s, ns) = sum;
+            Pk[3 * a + b] = sum;
             MPHX_T(so.Fm, a, b, s, ns) = F[a][b];
             MPHX_T(so.E, a, b, s, ns) = E[a][b];
             MPHX_T(so.S, a, b, s, ns) = S[a][b];
@@ -1059,7 +1084,7 @@ __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double 
 // order, the terms of rows j<s that list s, then its own row, then rows j>s (transposed list), so
 // the result is deterministic, atomic-free and equal to the reference's CPU bits.
 // Then updateElasticPosition (:1916-2081) incl. the clamp modules and quirk Q1.
-template <int DIMS>
+template <int DIMS, bool PACKED>
 __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double radius, double cw, double edt,
                               int module, int double_update, const double *__restrict__ inv_density)
 {
@@ -1072,11 +1097,18 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
     double v[3] = {so.vx[s], so.vy[s], so.vz[s]};
     auto scattered_from = [&](int kk, int j) { // row j lists s:  v_s -= invRho_s * (w P_j x0_js) * dt
         const size_t k = (size_t)kk * ns + s;
-        const double d0[3] = {__ldg(&so.rd0x[k]), __ldg(&so.rd0y[k]), DIMS == 3 ? __ldg(&so.rd0z[k]) : 0.0};
-        const double w = __ldg(&so.rw[k]);
+        double d0[3], w;
+        if (PACKED) {
+            const Rec t = ld_rec_ro(so.ttab + __ldg(&so.rtix[k]));
+            d0[0] = t.a; d0[1] = t.b; d0[2] = DIMS == 3 ? t.c : 0.0; w = t.d;
+        } else {
+            d0[0] = __ldg(&so.rd0x[k]); d0[1] = __ldg(&so.rd0y[k]); d0[2] = DIMS == 3 ? __ldg(&so.rd0z[k]) : 0.0;
+            w = __ldg(&so.rw[k]);
+        }
+        const double *Pj = so.PkA + 9 * (size_t)j;
         for (int a = 0; a < DIMS; ++a) {
             double f = 0.0;
-            for (int b = 0; b < DIMS; ++b) f = add(f, mul(MPHX_T(so.Pk, a, b, j, ns), d0[b]));
+            for (int b = 0; b < DIMS; ++b) f = add(f, mul(Pj[3 * a + b], d0[b]));
             f = mul(f, w);
             v[a] = sub(v[a], mul(mul(ir, f), edt)); // :2885
         }
@@ -1086,14 +1118,21 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
     for (int kr = 0; kr < rsplit; ++kr) scattered_from(kr, __ldg(&so.ernbr[(size_t)kr * ns + s]));
     {
         double Pi[3][3];
+        const double *Ps = so.PkA + 9 * (size_t)s;
         for (int a = 0; a < 3; ++a)
-            for (int b = 0; b < 3; ++b) Pi[a][b] = (a < DIMS && b < DIMS) ? MPHX_T(so.Pk, a, b, s, ns) : 0.0;
+            for (int b = 0; b < 3; ++b) Pi[a][b] = (a < DIMS && b < DIMS) ? Ps[3 * a + b] : 0.0;
         const int len = so.len[s];
 #pragma unroll 4
         for (int kk = 0; kk < len; ++kk) { // own row: v_s += invRho_s * (w P_s x0_sj) * dt
             const size_t q = (size_t)kk * ns + s;
-            const double d0[3] = {__ldg(&so.d0x[q]), __ldg(&so.d0y[q]), DIMS == 3 ? __ldg(&so.d0z[q]) : 0.0};
-            const double w = __ldg(&so.w[q]);
+            double d0[3], w;
+            if (PACKED) {
+                const Rec t = ld_rec_ro(so.ttab + __ldg(&so.tix[q]));
+                d0[0] = t.a; d0[1] = t.b; d0[2] = DIMS == 3 ? t.c : 0.0; w = t.d;
+            } else {
+                d0[0] = __ldg(&so.d0x[q]); d0[1] = __ldg(&so.d0y[q]); d0[2] = DIMS == 3 ? __ldg(&so.d0z[q]) : 0.0;
+                w = __ldg(&so.w[q]);
+            }
             for (int a = 0; a < DIMS; ++a) {
                 double f = 0.0;
                 for (int b = 0; b < DIMS; ++b) f = add(f, mul(Pi[a][b], d0[b]));
@@ -1122,7 +1161,9 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
     }
     so.x[s] = x[0]; so.y[s] = x[1]; so.z[s] = x[2];
     so.vx[s] = v[0]; so.vy[s] = v[1]; so.vz[s] = v[2];
-    so.ux[s] = minimg_exact(x[0], xi0, W0); so.uy[s] = minimg_exact(x[1], yi0, W1); so.uz[s] = minimg_exact(x[2], zi0, W2);
+    Rec u;
+    u.a = minimg_exact(x[0], xi0, W0); u.b = minimg_exact(x[1], yi0, W1); u.c = minimg_exact(x[2], zi0, W2); u.d = 0.0;
+    so.u[s] = u;
 }
 
 // static pair data of the reference configuration (once, after the lists are known)

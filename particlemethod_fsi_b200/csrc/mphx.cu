@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -67,6 +68,7 @@ struct Ctx {
     int *where = nullptr;
     bool external_stream = false;
     bool uploaded = false, inited = false, surface_tension = false;
+    int solid_tuples = 0; // entries of the solids' pair-data dictionary (0: raw arrays in use)
     bool solid_multi_occupancy = false; // several solids share a bucket of the reference configuration (see init_solid)
     unsigned long long epoch = 0; // exchange epoch: one per bucket stage, identical on every rank (flags carry it)
     double time = 0.0;
@@ -376,7 +378,8 @@ static void preload_kernels(int dim)
     preload(k_filter<D>); preload(k_filter2<D, false>); preload(k_filter2<D, true>);                                     \
     preload(k_pass1_v3<D, false, false>); preload(k_pass1_v3<D, false, true>); preload(k_pass1_v3<D, true, false>);      \
     preload(k_pass1_v3<D, true, true>); preload(k_pass2_v3<D, false, false>); preload(k_pass2_v3<D, false, true>);       \
-    preload(k_pass2_v3<D, true, false>); preload(k_pass2_v3<D, true, true>); preload(k_solid_pass1<D>); preload(k_solid_pass2<D>)
+    preload(k_pass2_v3<D, true, false>); preload(k_pass2_v3<D, true, true>); preload(k_solid_pass1<D, false>);           \
+    preload(k_solid_pass2<D, false>); preload(k_solid_pass1<D, true>); preload(k_solid_pass2<D, true>)
     if (dim == 3) { PRELOAD_DIM(3); } else { PRELOAD_DIM(2); }
 #undef PRELOAD_DIM
     cudaGetLastError();
@@ -604,17 +607,17 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
         LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, c->epoch, c->mine.fsolV, c->nranks, kWaitSolV);
         LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV);
     }
+#define SOLID_STEP(D, PK)                                                                                                                 \
+    do {                                                                                                                                    \
+        LAUNCH_ON(c, strm, (k_solid_pass1<D, PK>), nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw); \
+        LAUNCH_ON(c, strm, (k_solid_pass2<D, PK>), nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw, \
+                  c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);                                                               \
+    } while (0)
     for (int s = 0; s < substeps; ++s) {
-        if (c->p.dim == 3) {
-            LAUNCH_ON(c, strm, k_solid_pass1<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw);
-            LAUNCH_ON(c, strm, k_solid_pass2<3>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw,
-                   c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);
-        } else {
-            LAUNCH_ON(c, strm, k_solid_pass1<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw);
-            LAUNCH_ON(c, strm, k_solid_pass2<2>, nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw,
-                   c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);
-        }
+        if (c->p.dim == 3) { if (c->sol.packed) SOLID_STEP(3, true); else SOLID_STEP(3, false); }
+        else               { if (c->sol.packed) SOLID_STEP(2, true); else SOLID_STEP(2, false); }
     }
+#undef SOLID_STEP
     CK(cudaGetLastError());
     return MPHX_OK;
 }
@@ -886,6 +889,60 @@ static int init_solid(Ctx *c)
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaGetLastError());
+    // The static pair data as a dictionary (see Solid): the sub-steps stream 6 instead of 36 bytes per pair.
+    c->sol.packed = 0;
+    if (!std::getenv("MPHX_SOLID_RAW") && total > 0) {
+        std::vector<int> len(ns), rlen(ns);
+        CK(cudaMemcpy(len.data(), c->sol.len, sizeof(int) * ns, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rlen.data(), c->sol.rlen, sizeof(int) * ns, cudaMemcpyDeviceToHost));
+        int maxlen = 0, rmaxlen = 0;
+        for (int s = 0; s < ns; ++s) { maxlen = std::max(maxlen, len[s]); rmaxlen = std::max(rmaxlen, rlen[s]); }
+        struct Tuple { unsigned long long v[4]; bool operator==(const Tuple &o) const { return !std::memcmp(v, o.v, sizeof(v)); } };
+        struct Hash { size_t operator()(const Tuple &t) const { unsigned long long h = 1469598103934665603ull; for (auto x : t.v) { h ^= x; h *= 1099511628211ull; h ^= h >> 29; } return (size_t)h; } };
+        std::unordered_map<Tuple, int, Hash> dict;
+        std::vector<Rec> table;
+        bool ok = true;
+        auto pack = [&](const double *dx, const double *dy, const double *dz, const double *dw, const std::vector<int> &ln, int ml,
+                        std::vector<unsigned short> &out) {
+            const size_t cnt = (size_t)ml * ns;
+            std::vector<double> hx(cnt), hy(cnt), hz(cnt), hw(cnt);
+            if (cudaMemcpy(hx.data(), dx, sizeof(double) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(hy.data(), dy, sizeof(double) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(hz.data(), dz, sizeof(double) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                cudaMemcpy(hw.data(), dw, sizeof(double) * cnt, cudaMemcpyDeviceToHost) != cudaSuccess) { ok = false; return; }
+            out.assign(cnt, 0);
+            for (int s = 0; s < ns && ok; ++s)
+                for (int kk = 0; kk < ln[s]; ++kk) {
+                    const size_t q = (size_t)kk * ns + s;
+                    Tuple t;
+                    std::memcpy(&t.v[0], &hx[q], 8); std::memcpy(&t.v[1], &hy[q], 8); std::memcpy(&t.v[2], &hz[q], 8); std::memcpy(&t.v[3], &hw[q], 8);
+                    auto it = dict.find(t);
+                    int idx;
+                    if (it == dict.end()) {
+                        idx = (int)table.size();
+                        if (idx > 65535) { ok = false; break; }
+                        dict.emplace(t, idx);
+                        Rec r; r.a = hx[q]; r.b = hy[q]; r.c = hz[q]; r.d = hw[q];
+                        table.push_back(r);
+                    } else idx = it->second;
+                    out[q] = (unsigned short)idx;
+                }
+        };
+        std::vector<unsigned short> tix, rtix;
+        pack(c->sol.d0x, c->sol.d0y, c->sol.d0z, c->sol.w, len, maxlen, tix);
+        if (ok) pack(c->sol.rd0x, c->sol.rd0y, c->sol.rd0z, c->sol.rw, rlen, rmaxlen, rtix);
+        cudaGetLastError();
+        if (ok) {
+            int e2 = 0;
+            e2 |= c->alloc(&c->sol.tix, tix.size()); e2 |= c->alloc(&c->sol.rtix, rtix.size()); e2 |= c->alloc(&c->sol.ttab, table.size());
+            if (e2) return MPHX_ERR_NOMEM;
+            CK(cudaMemcpy(c->sol.tix, tix.data(), sizeof(unsigned short) * tix.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(c->sol.rtix, rtix.data(), sizeof(unsigned short) * rtix.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(c->sol.ttab, table.data(), sizeof(Rec) * table.size(), cudaMemcpyHostToDevice));
+            c->sol.packed = 1;
+            c->solid_tuples = (int)table.size();
+        }
+    }
     return MPHX_OK;
 }
 
@@ -1110,10 +1167,10 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         Solid &so = c->sol;
         so.ns = c->ns; so.sb = c->ns > 0 ? r[2] : 0;
         const size_t ns = (size_t)c->ns;
-        double **sv[] = {&so.x, &so.y, &so.z, &so.vx, &so.vy, &so.vz, &so.x0, &so.y0, &so.z0, &so.fx, &so.fy, &so.fz, &so.lam, &so.mu,
-                         &so.ux, &so.uy, &so.uz};
+        double **sv[] = {&so.x, &so.y, &so.z, &so.vx, &so.vy, &so.vz, &so.x0, &so.y0, &so.z0, &so.fx, &so.fy, &so.fz, &so.lam, &so.mu};
         for (double **q : sv) e |= c->alloc(q, ns);
-        double **st[] = {&so.Linv, &so.Fm, &so.E, &so.S, &so.Pk};
+        e |= c->alloc(&so.u, ns);
+        double **st[] = {&so.Linv, &so.Fm, &so.E, &so.S, &so.PkA};
         for (double **q : st) e |= c->alloc(q, 9 * ns);
         e |= c->alloc(&so.type, ns); e |= c->alloc(&so.slot, ns);
         if (e) return MPHX_ERR_NOMEM;

@@ -354,6 +354,17 @@ def bench_main(args, METRIC, UNIT, WORKLOAD, peaks, ClockSampler, cpu_reference_
     dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
     ms = allmax(ms_local)
+    # where a step's time goes on each rank (a few more steps with the phase events on; not part of the timed region)
+    s._ck("mphx_set_timing", s.lib.mphx_set_timing(s.ctx, 1))
+    s.step(min(K, 10))
+    s.sync()
+    kms = (C.c_double * 5)()
+    s._ck("mphx_get_kernel_timers", s.lib.mphx_get_kernel_timers(s.ctx, C.byref(kms)))
+    s._ck("mphx_set_timing", s.lib.mphx_set_timing(s.ctx, 0))
+    pt = torch.tensor([v / min(K, 10) for v in kms], dtype=torch.float64, device=device)
+    allp = [torch.empty_like(pt) for _ in range(world)]
+    dist.all_gather(allp, pt)
+    phases = [[round(float(v), 4) for v in t.cpu()] for t in allp]
     launches = allsum(float(s.launch_count - l0))
     st = s.status()
     held = allmax(float(st["held"]))
@@ -420,6 +431,8 @@ def bench_main(args, METRIC, UNIT, WORKLOAD, peaks, ClockSampler, cpu_reference_
                                           "into peer mailboxes over NVLink (CUDA IPC), no host synchronisation per step; NCCL carries "
                                           "only the start-up handles and the timing/verification reductions",
                            "partition_columns": s.partition, "max_slots_held": int(held),
+                           "phase_ms_per_step_by_rank": {"columns": ["buckets+exchange", "filter", "pass1+P exchange", "pass2", "solid sub-steps (2nd stream)"],
+                                                         "rows": phases},
                            "list_builds": builds, "list_reuses": reuses},
                 "clocks": clocks,
                 "e2e": {"value": n * ke / te, "unit": UNIT, "h2d_bytes_per_step": int(rows_total) * 52,
