@@ -1011,120 +1011,71 @@ __device__ __forceinline__ Rec ld_rec_ro(const Rec *p)
     asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
     return r;
 }
-// The sub-step kernels are latency bound (~10^5 solids, two dependent loads per pair: list entry -> gather), so
-//   * FOUR lanes work on one solid, one per Cartesian component (row a of the deformation-gradient sum in pass 1,
-//     velocity component a in pass 2; the fourth lane idles): three times the threads in flight, a third of the
-//     arithmetic per thread, and the lanes of a group read the same addresses (one transaction);
-//   * the list entries of the NEXT batch of kSolidBatch pairs are fetched while the current batch is processed,
-//     and the gathers of kSolidGather pairs are issued together.
-// Every accumulation chain is still the reference's: same operands, same serial order, explicitly rounded.
-#ifndef MPHX_SOLID_BATCH
-#define MPHX_SOLID_BATCH 8
-#endif
-#ifndef MPHX_SOLID_GATHER
-#define MPHX_SOLID_GATHER 4
-#endif
-constexpr int kSolidBatch = MPHX_SOLID_BATCH, kSolidGather = MPHX_SOLID_GATHER;
-constexpr int kSolidThreads = 128; // 32 solids per block
-__device__ __forceinline__ double pick3(int a, double x, double y, double z) { return a == 0 ? x : (a == 1 ? y : z); }
-
 template <int DIMS, bool PACKED>
-__global__ void __launch_bounds__(kSolidThreads) k_solid_pass1(Solid so, double W0, double W1, double W2, double radius, double cw)
+__global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double radius, double cw)
 {
     using namespace ex;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int a = gid & 3;
-    const bool valid = (gid >> 2) < so.ns;
-    const int s = valid ? (gid >> 2) : so.ns - 1;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= so.ns) return;
     const int ns = so.ns;
-    const bool work = valid && a < DIMS;
     const Rec uo = so.u[s];
-    const double uia = pick3(a, uo.a, uo.b, uo.c);
-    double Gr[3] = {0.0, 0.0, 0.0}; // row a of sum_j w d (x) d0
+    const double ui[3] = {uo.a, uo.b, DIMS == 3 ? uo.c : 0.0};
+    double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     const int len = so.len[s];
-    int jn[kSolidBatch];
-    unsigned tn[kSolidBatch];
-    auto fetch = [&](int kk0) {
-#pragma unroll
-        for (int u = 0; u < kSolidBatch; ++u) {
-            const int kk = kk0 + u < len ? kk0 + u : (len > 0 ? len - 1 : 0);
-            const size_t k = (size_t)kk * ns + s;
-            jn[u] = len > 0 ? __ldg(&so.enbr[k]) : s;
-            tn[u] = (PACKED && len > 0) ? (unsigned)__ldg(&so.tix[k]) : 0u;
+    // (unrolled so that the loads of four list entries are in flight together; the sum order is unchanged)
+#pragma unroll 4
+    for (int kk = 0; kk < len; ++kk) {
+        const size_t k = (size_t)kk * ns + s;
+        const int j = __ldg(&so.enbr[k]);
+        double d0[3], w;
+        if (PACKED) {
+            const Rec t = ld_rec_ro(so.ttab + __ldg(&so.tix[k]));
+            d0[0] = t.a; d0[1] = t.b; d0[2] = DIMS == 3 ? t.c : 0.0; w = t.d;
+        } else {
+            d0[0] = __ldg(&so.d0x[k]); d0[1] = __ldg(&so.d0y[k]); d0[2] = DIMS == 3 ? __ldg(&so.d0z[k]) : 0.0;
+            w = __ldg(&so.w[k]);
         }
-    };
-    fetch(0);
-    for (int kk0 = 0; kk0 < len; kk0 += kSolidBatch) {
-        int jc[kSolidBatch];
-        unsigned tc[kSolidBatch];
-#pragma unroll
-        for (int u = 0; u < kSolidBatch; ++u) { jc[u] = jn[u]; tc[u] = tn[u]; }
-        if (kk0 + kSolidBatch < len) fetch(kk0 + kSolidBatch);
-#pragma unroll
-        for (int h = 0; h < kSolidBatch; h += kSolidGather) {
-            Rec tt[kSolidGather], un[kSolidGather];
-#pragma unroll
-            for (int u = 0; u < kSolidGather; ++u) {
-                const size_t k = (size_t)(kk0 + h + u < len ? kk0 + h + u : 0) * ns + s;
-                if (PACKED) tt[u] = ld_rec_ro(so.ttab + tc[h + u]);
-                else {
-                    tt[u].a = __ldg(&so.d0x[k]); tt[u].b = __ldg(&so.d0y[k]); tt[u].c = DIMS == 3 ? __ldg(&so.d0z[k]) : 0.0;
-                    tt[u].d = __ldg(&so.w[k]);
-                }
-                un[u] = ld_rec_ro(so.u + jc[h + u]); // (written by the previous kernel: read-only here)
-            }
-#pragma unroll
-            for (int u = 0; u < kSolidGather; ++u) {
-                if (kk0 + h + u >= len || !work) break;
-                const double d0[3] = {tt[u].a, tt[u].b, DIMS == 3 ? tt[u].c : 0.0};
-                const double da = add(pick3(a, d0[0], d0[1], d0[2]), sub(pick3(a, un[u].a, un[u].b, un[u].c), uia)); // :2716
-                const double wd = mul(tt[u].d, da);
-                for (int b = 0; b < DIMS; ++b) Gr[b] = add(Gr[b], mul(wd, d0[b])); // :2726
-            }
-        }
+        const Rec un = ld_rec_ro(so.u + j); // (written by the previous kernel: read-only here)
+        const double uj[3] = {un.a, un.b, DIMS == 3 ? un.c : 0.0};
+        double d[3];
+        for (int a = 0; a < DIMS; ++a) d[a] = add(d0[a], sub(uj[a], ui[a])); // :2716
+        for (int a = 0; a < DIMS; ++a)
+            for (int b = 0; b < DIMS; ++b) G[a][b] = add(G[a][b], mul(mul(w, d[a]), d0[b])); // :2726
     }
-    // the group's first lane collects the three rows and finishes the particle
-    double G[3][3];
-    const int base = threadIdx.x & 28;
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int b = 0; b < 3; ++b) G[r][b] = __shfl_sync(0xffffffffu, Gr[b], base + r);
-    if (a != 0 || !valid) return;
     double L[3][3], F[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int r = 0; r < 3; ++r)
-        for (int b = 0; b < 3; ++b) L[r][b] = MPHX_T(so.Linv, r, b, s, ns);
-    for (int r = 0; r < DIMS; ++r)
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) L[a][b] = MPHX_T(so.Linv, a, b, s, ns);
+    for (int a = 0; a < DIMS; ++a)
         for (int b = 0; b < DIMS; ++b) {
             double sum = 0.0;
-            for (int k = 0; k < DIMS; ++k) sum = add(sum, mul(G[r][k], L[k][b])); // :2743
-            F[r][b] = sum;
+            for (int k = 0; k < DIMS; ++k) sum = add(sum, mul(G[a][k], L[k][b])); // :2743
+            F[a][b] = sum;
         }
     double E[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, S[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, tr = 0.0;
-    for (int r = 0; r < DIMS; ++r)
+    for (int a = 0; a < DIMS; ++a)
         for (int b = 0; b < DIMS; ++b) {
             double sum = 0.0;
-            for (int k = 0; k < DIMS; ++k) sum = add(sum, mul(F[k][r], F[k][b])); // :2780
-            E[r][b] = mul(0.5, sub(sum, (r == b ? 1.0 : 0.0)));
-            if (r == b) tr = add(tr, E[r][b]);
+            for (int k = 0; k < DIMS; ++k) sum = add(sum, mul(F[k][a], F[k][b])); // :2780
+            E[a][b] = mul(0.5, sub(sum, (a == b ? 1.0 : 0.0)));
+            if (a == b) tr = add(tr, E[a][b]);
         }
     const double mu = so.mu[s], lam = so.lam[s];
-    for (int r = 0; r < DIMS; ++r)
+    for (int a = 0; a < DIMS; ++a)
         for (int b = 0; b < DIMS; ++b) {
-            S[r][b] = mul(mul(2.0, mu), E[r][b]); // :2804
-            if (r == b) S[r][b] = add(S[r][b], mul(lam, tr));
+            S[a][b] = mul(mul(2.0, mu), E[a][b]); // :2804
+            if (a == b) S[a][b] = add(S[a][b], mul(lam, tr));
         }
     double *Pk = so.PkA + 9 * (size_t)s;
-    for (int r = 0; r < 3; ++r)
+    for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b) {
-            if (r >= DIMS || b >= DIMS) { Pk[3 * r + b] = 0.0; continue; }
+            if (a >= DIMS || b >= DIMS) { Pk[3 * a + b] = 0.0; continue; }
             double sum = 0.0;
             for (int k = 0; k < DIMS; ++k)
-                for (int l = 0; l < DIMS; ++l) sum = add(sum, mul(mul(F[r][k], S[k][l]), L[l][b])); // :2847
-            Pk[3 * r + b] = sum;
-            MPHX_T(so.Fm, r, b, s, ns) = F[r][b];
-            MPHX_T(so.E, r, b, s, ns) = E[r][b];
-            MPHX_T(so.S, r, b, s, ns) = S[r][b];
+                for (int l = 0; l < DIMS; ++l) sum = add(sum, mul(mul(F[a][k], S[k][l]), L[l][b])); // :2847
+            Pk[3 * a + b] = sum;
+            MPHX_T(so.Fm, a, b, s, ns) = F[a][b];
+            MPHX_T(so.E, a, b, s, ns) = E[a][b];
+            MPHX_T(so.S, a, b, s, ns) = S[a][b];
         }
 }
 
@@ -1132,103 +1083,87 @@ __global__ void __launch_bounds__(kSolidThreads) k_solid_pass1(Solid so, double 
 // serially / with atomics (:2855-2887); here every particle GATHERS, in the reference's serial
 // order, the terms of rows j<s that list s, then its own row, then rows j>s (transposed list), so
 // the result is deterministic, atomic-free and equal to the reference's CPU bits.
-// Then updateElasticPosition (:1916-2081) incl. the clamp modules and quirk Q1.  Lane a of a group owns component a.
+// Then updateElasticPosition (:1916-2081) incl. the clamp modules and quirk Q1.
 template <int DIMS, bool PACKED>
-__global__ void __launch_bounds__(kSolidThreads) k_solid_pass2(Solid so, double W0, double W1, double W2, double radius, double cw, double edt,
-                                                               int module, int double_update, const double *__restrict__ inv_density)
+__global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double radius, double cw, double edt,
+                              int module, int double_update, const double *__restrict__ inv_density)
 {
     using namespace ex;
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    const int a = gid & 3;
-    const int s = gid >> 2;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= so.ns) return;
     const int ns = so.ns;
-    const bool work = a < DIMS;
+    const double xi0 = so.x0[s], yi0 = so.y0[s], zi0 = so.z0[s];
     const double ir = inv_density[so.type[s]];
-    double *const va_p = a == 0 ? so.vx : (a == 1 ? so.vy : so.vz);
-    double va = a < 3 ? va_p[s] : 0.0;
-    // one row (own: sign +, P of s itself; transposed: sign -, P of the listing row j)
-    auto row = [&](const int *__restrict__ nbr, const unsigned short *__restrict__ tix, const double *__restrict__ ax, const double *__restrict__ ay,
-                   const double *__restrict__ az, const double *__restrict__ aw, int kb, int ke, bool own, const double (&Pia)[3]) {
-        if (ke - kb <= 0) return;
-        int jn[kSolidBatch];
-        unsigned tn[kSolidBatch];
-        auto fetch = [&](int kk0) {
-#pragma unroll
-            for (int u = 0; u < kSolidBatch; ++u) {
-                const int kk = kk0 + u < ke ? kk0 + u : ke - 1;
-                const size_t k = (size_t)kk * ns + s;
-                jn[u] = own ? s : __ldg(&nbr[k]);
-                tn[u] = PACKED ? (unsigned)__ldg(&tix[k]) : 0u;
-            }
-        };
-        fetch(kb);
-        for (int kk0 = kb; kk0 < ke; kk0 += kSolidBatch) {
-            int jc[kSolidBatch];
-            unsigned tc[kSolidBatch];
-#pragma unroll
-            for (int u = 0; u < kSolidBatch; ++u) { jc[u] = jn[u]; tc[u] = tn[u]; }
-            if (kk0 + kSolidBatch < ke) fetch(kk0 + kSolidBatch);
-#pragma unroll
-            for (int h = 0; h < kSolidBatch; h += kSolidGather) {
-                Rec tt[kSolidGather];
-                double Pj[kSolidGather][3];
-#pragma unroll
-                for (int u = 0; u < kSolidGather; ++u) {
-                    const size_t k = (size_t)(kk0 + h + u < ke ? kk0 + h + u : kb) * ns + s;
-                    if (PACKED) tt[u] = ld_rec_ro(so.ttab + tc[h + u]);
-                    else {
-                        tt[u].a = __ldg(&ax[k]); tt[u].b = __ldg(&ay[k]); tt[u].c = DIMS == 3 ? __ldg(&az[k]) : 0.0;
-                        tt[u].d = __ldg(&aw[k]);
-                    }
-                    if (!own && work) { // row a of the listing particle's stress
-                        const double *pp = so.PkA + 9 * (size_t)jc[h + u] + 3 * a;
-#pragma unroll
-                        for (int e = 0; e < 3; ++e) Pj[u][e] = e < DIMS ? __ldg(pp + e) : 0.0;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < kSolidGather; ++u) {
-                    if (kk0 + h + u >= ke || !work) break;
-                    const double d0[3] = {tt[u].a, tt[u].b, DIMS == 3 ? tt[u].c : 0.0};
-                    double f = 0.0;
-                    for (int b = 0; b < DIMS; ++b) f = add(f, mul(own ? Pia[b] : Pj[u][b], d0[b]));
-                    f = mul(f, tt[u].d);
-                    if (own) va = add(va, mul(mul(ir, f), edt)); // :2883  v_s += invRho_s * (w P_s x0_sj) * dt
-                    else va = sub(va, mul(mul(ir, f), edt));     // :2885  row j lists s: v_s -= invRho_s * (w P_j x0_js) * dt
-                }
-            }
+    double v[3] = {so.vx[s], so.vy[s], so.vz[s]};
+    auto scattered_from = [&](int kk, int j) { // row j lists s:  v_s -= invRho_s * (w P_j x0_js) * dt
+        const size_t k = (size_t)kk * ns + s;
+        double d0[3], w;
+        if (PACKED) {
+            const Rec t = ld_rec_ro(so.ttab + __ldg(&so.rtix[k]));
+            d0[0] = t.a; d0[1] = t.b; d0[2] = DIMS == 3 ? t.c : 0.0; w = t.d;
+        } else {
+            d0[0] = __ldg(&so.rd0x[k]); d0[1] = __ldg(&so.rd0y[k]); d0[2] = DIMS == 3 ? __ldg(&so.rd0z[k]) : 0.0;
+            w = __ldg(&so.rw[k]);
+        }
+        const double *Pj = so.PkA + 9 * (size_t)j;
+        for (int a = 0; a < DIMS; ++a) {
+            double f = 0.0;
+            for (int b = 0; b < DIMS; ++b) f = add(f, mul(Pj[3 * a + b], d0[b]));
+            f = mul(f, w);
+            v[a] = sub(v[a], mul(mul(ir, f), edt)); // :2885
         }
     };
     const int rlen = so.rlen[s], rsplit = so.rsplit[s]; // transposed entries [0, rsplit) are rows j < s
-    double Pia[3] = {0.0, 0.0, 0.0};
-    if (work) {
-        const double *Ps = so.PkA + 9 * (size_t)s + 3 * a;
-        for (int b = 0; b < DIMS; ++b) Pia[b] = Ps[b];
+#pragma unroll 4
+    for (int kr = 0; kr < rsplit; ++kr) scattered_from(kr, __ldg(&so.ernbr[(size_t)kr * ns + s]));
+    {
+        double Pi[3][3];
+        const double *Ps = so.PkA + 9 * (size_t)s;
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) Pi[a][b] = (a < DIMS && b < DIMS) ? Ps[3 * a + b] : 0.0;
+        const int len = so.len[s];
+#pragma unroll 4
+        for (int kk = 0; kk < len; ++kk) { // own row: v_s += invRho_s * (w P_s x0_sj) * dt
+            const size_t q = (size_t)kk * ns + s;
+            double d0[3], w;
+            if (PACKED) {
+                const Rec t = ld_rec_ro(so.ttab + __ldg(&so.tix[q]));
+                d0[0] = t.a; d0[1] = t.b; d0[2] = DIMS == 3 ? t.c : 0.0; w = t.d;
+            } else {
+                d0[0] = __ldg(&so.d0x[q]); d0[1] = __ldg(&so.d0y[q]); d0[2] = DIMS == 3 ? __ldg(&so.d0z[q]) : 0.0;
+                w = __ldg(&so.w[q]);
+            }
+            for (int a = 0; a < DIMS; ++a) {
+                double f = 0.0;
+                for (int b = 0; b < DIMS; ++b) f = add(f, mul(Pi[a][b], d0[b]));
+                f = mul(f, w);
+                v[a] = add(v[a], mul(mul(ir, f), edt)); // :2883
+            }
+        }
     }
-    row(so.ernbr, so.rtix, so.rd0x, so.rd0y, so.rd0z, so.rw, 0, rsplit, false, Pia);
-    row(so.enbr, so.tix, so.d0x, so.d0y, so.d0z, so.w, 0, so.len[s], true, Pia);
-    row(so.ernbr, so.rtix, so.rd0x, so.rd0y, so.rd0z, so.rw, rsplit, rlen, false, Pia);
-    if (a == 3) { reinterpret_cast<double *>(so.u + s)[3] = 0.0; return; }
-    const double xi0 = so.x0[s], yi0 = so.y0[s];
-    double *const xa_p = a == 0 ? so.x : (a == 1 ? so.y : so.z);
-    double *const fa_p = a == 0 ? so.fx : (a == 1 ? so.fy : so.fz);
-    const double x0a = (a == 0 ? so.x0 : (a == 1 ? so.y0 : so.z0))[s];
-    const double Wa = a == 0 ? W0 : (a == 1 ? W1 : W2);
-    double xa = xa_p[s];
+#pragma unroll 4
+    for (int kr = rsplit; kr < rlen; ++kr) scattered_from(kr, __ldg(&so.ernbr[(size_t)kr * ns + s]));
+    double x[3] = {so.x[s], so.y[s], so.z[s]};
     // Acceleration of solids is 0 (:2892): v += 0*dt leaves v unchanged
     if (module != 0) {
         const bool clamped = (module == 1) ? (xi0 < 0.001) : (yi0 < 0.002); // :1919 / :1968
         if (clamped) {
-            xa = x0a;
-            va = 0.0;
-            fa_p[s] = 0.0;
-        } else xa = add(xa, mul(va, edt));
-        if (double_update) xa = add(xa, mul(va, edt)); // Q1 (:2070-2079)
-    } else xa = add(xa, mul(va, edt));
-    xa_p[s] = xa;
-    va_p[s] = va;
-    reinterpret_cast<double *>(so.u + s)[a] = minimg_exact(xa, x0a, Wa);
+            x[0] = xi0; x[1] = yi0; x[2] = zi0;
+            v[0] = v[1] = v[2] = 0.0;
+            so.fx[s] = 0.0; so.fy[s] = 0.0; so.fz[s] = 0.0;
+        } else {
+            for (int a = 0; a < 3; ++a) x[a] = add(x[a], mul(v[a], edt));
+        }
+        if (double_update) // Q1 (:2070-2079)
+            for (int a = 0; a < 3; ++a) x[a] = add(x[a], mul(v[a], edt));
+    } else {
+        for (int a = 0; a < 3; ++a) x[a] = add(x[a], mul(v[a], edt));
+    }
+    so.x[s] = x[0]; so.y[s] = x[1]; so.z[s] = x[2];
+    so.vx[s] = v[0]; so.vy[s] = v[1]; so.vz[s] = v[2];
+    Rec u;
+    u.a = minimg_exact(x[0], xi0, W0); u.b = minimg_exact(x[1], yi0, W1); u.c = minimg_exact(x[2], zi0, W2); u.d = 0.0;
+    so.u[s] = u;
 }
 
 // static pair data of the reference configuration (once, after the lists are known)

@@ -608,11 +608,10 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
         LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV);
     }
 #define SOLID_STEP(D, PK)                                                                                                                 \
-    do { /* four lanes per solid */                                                                                                         \
-        LAUNCH_ON(c, strm, (k_solid_pass1<D, PK>), nblk(4LL * ns, kSolidThreads), kSolidThreads, c->sol, k.domain_width[0], k.domain_width[1], \
-                  k.domain_width[2], k.radius_p, cw);                                                                                       \
-        LAUNCH_ON(c, strm, (k_solid_pass2<D, PK>), nblk(4LL * ns, kSolidThreads), kSolidThreads, c->sol, k.domain_width[0], k.domain_width[1], \
-                  k.domain_width[2], k.radius_p, cw, c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);                            \
+    do {                                                                                                                                    \
+        LAUNCH_ON(c, strm, (k_solid_pass1<D, PK>), nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw); \
+        LAUNCH_ON(c, strm, (k_solid_pass2<D, PK>), nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw, \
+                  c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);                                                               \
     } while (0)
     for (int s = 0; s < substeps; ++s) {
         if (c->p.dim == 3) { if (c->sol.packed) SOLID_STEP(3, true); else SOLID_STEP(3, false); }
