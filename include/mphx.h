@@ -227,6 +227,8 @@ int mphx_get_timers(mphx_ctx *ctx, double ms[4]);
 /* the same split by kernel group: [0] bucket rebuild, [1] candidate filter (k_filter), [2] pass 1 over the
  * candidate list, [3] pass 2 over the candidate list (+ integration), [4] solid sub-steps */
 int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5]);
+/* accumulated device milliseconds of calculateVirialStressAtParticle (the reference's "virial calculation" timer, :674) */
+double mphx_get_virial_ms(const mphx_ctx *ctx);
 /* the solid sub-steps normally run on a second stream, overlapping pass 2 and the start of the next step;
  * on = 0 serialises them on the context's stream (isolated per-kernel timings), on = 1 restores the default */
 int mphx_set_overlap(mphx_ctx *ctx, int on);

@@ -312,6 +312,21 @@ extern "C" int mphx_write_vtk_file(const char *filename, int n, const double *in
     o.puts("SCALARS neighbor float 1\n");
     o.puts("LOOKUP_TABLE default\n");
     for (int i = 0; i < n; ++i) o.used += std::snprintf(o.reserve(32), 32, "%d\n", f->neighbor_count[i]);
+    // the virial sections the reference keeps commented out (:1128-1143), written when the caller asks for them
+    if (f->virial_pressure) {
+        o.puts("SCALARS VirialPressureAtParticle float 1\n");
+        o.puts("LOOKUP_TABLE default\n");
+        for (int i = 0; i < n; ++i) o.used += std::snprintf(o.reserve(32), 32, "%e\n", (float)f->virial_pressure[i]);
+        o.puts("\n");
+    }
+    if (f->virial_stress)
+        for (int a = 0; a < 2; ++a)      // (iD, jD < DIM-1 with DIM = 3: the four in-plane components, :1134-1135)
+            for (int c = 0; c < 2; ++c) {
+                o.used += std::snprintf(o.reserve(64), 64, "SCALARS VirialStressAtParticle[%d][%d] float 1\n", a, c);
+                o.puts("LOOKUP_TABLE default\n");
+                for (int i = 0; i < n; ++i) o.used += std::snprintf(o.reserve(32), 32, "%e\n", (float)f->virial_stress[9 * (size_t)i + 3 * a + c]);
+                o.puts("\n");
+            }
     o.puts("VECTORS velocity float\n"); // Q8: the section appears twice (:1062 and :1169)
     for (int i = 0; i < n; ++i) vec3f(f->velocity + 3 * (size_t)i);
     o.puts("\n");

@@ -101,7 +101,7 @@ class Writer {
 // a snapshot of everything one output file needs (the writer thread owns it)
 struct Snapshot {
     std::vector<int> property, nbc, inbc;
-    std::vector<double> position, velocity, force, accel, stress, strain;
+    std::vector<double> position, velocity, force, accel, stress, strain, virial, virialp;
 };
 
 static int parse_module(const char *s)
@@ -196,6 +196,9 @@ int main(int argc, char *argv[])
             if (e2) die("writeProfFile", e2);
         });
     };
+    // the reference computes the virial stress on VTK steps but keeps its VTK sections commented out; MPHX_VTK_VIRIAL=1
+    // evaluates it (single GPU) and writes those sections
+    const bool vtk_virial = getenv("MPHX_VTK_VIRIAL") && atoi(getenv("MPHX_VTK_VIRIAL")) != 0 && !multi;
     auto write_vtk = [&](const std::string &fn) {
         auto snap = std::make_shared<Snapshot>();
         snap->property.resize(N); snap->nbc.resize(N); snap->inbc.resize(N);
@@ -206,6 +209,10 @@ int main(int argc, char *argv[])
         v.property = snap->property.data(); v.position = snap->position.data(); v.velocity = snap->velocity.data();
         v.force = snap->force.data(); v.acceleration = snap->accel.data(); v.stress = snap->stress.data(); v.strain = snap->strain.data();
         v.neighbor_count = snap->nbc.data(); v.initial_structure_neighbor_count = snap->inbc.data();
+        if (vtk_virial) { // calculateVirialStressAtParticle on output steps (:671-673) and its VTK sections (:1128-1143)
+            snap->virial.resize(9 * N); snap->virialp.resize(N);
+            v.virial_stress = snap->virial.data(); v.virial_pressure = snap->virialp.data();
+        }
         int e = do_download(&v);
         if (e) die("mphx_download", e);
         writer.submit([=]() {
@@ -262,7 +269,7 @@ int main(int argc, char *argv[])
         const double neigh = ms[0] * 1e-3, expl = (ms[0] > 0 ? (ms[1] + ms[2] + ms[3]) * 1e-3 : sStep);
         log_printf("neighbor search:         %lf [CPU sec]\n", neigh);
         log_printf("explicit calculation:    %lf [CPU sec]\n", expl);
-        log_printf("virial calculation:      %lf [CPU sec]\n", 0.0);
+        log_printf("virial calculation:      %lf [CPU sec]\n", mphx_get_virial_ms(ctx) * 1e-3);
         log_printf("other calculation:       %lf [CPU sec]\n", sOther);
         log_printf("total:                   %lf [CPU sec]\n", neigh + expl + sOther);
         log_printf("total (check):           %lf [CPU sec]\n", now() - tStart);

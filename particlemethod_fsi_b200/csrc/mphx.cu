@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "sweep.cuh"
 #include "sweep_pair.cuh"
+#include "virial.cuh"
 #include "mphx.h"
 #include "mphx_internal.h"
 
@@ -121,6 +122,7 @@ struct Ctx {
     cudaEvent_t side_ev[2] = {nullptr, nullptr}; // sub-steps on the side stream (timing)
     std::vector<cudaEvent_t> side_marks;
     double side_ms = 0.0;
+    double virial_ms = 0.0; // device time spent in calculateVirialStressAtParticle (the reference's "virial calculation" timer)
 
     template <class Tp> int alloc(Tp **ptr, size_t count)
     {
@@ -754,6 +756,49 @@ static int exact_lists_current(Ctx *c, std::vector<long long> &offsets, std::vec
     if ((rc = join_solids(c))) return rc;
     if ((rc = read_n(c, &n))) return rc;
     return exact_lists(c, n, c->bx, c->by, c->bz, c->S.type, c->S.id, c->grid, false, false, 0, c->n_global, offsets, ids_out);
+}
+
+// calculateVirialStressAtParticle (:3077-3318) on the state after the last step, over the reference's lists of that
+// step (pre-step positions c->bx, bit-exact predicate); results in ORIGINAL particle order on the device
+static int compute_virial(Ctx *c, double *d_out9, double *d_outp)
+{
+    if (c->slab) { set_last_error("the virial stress diagnostic needs the post-step state of the halo: single context only"); return MPHX_ERR_UNSUPPORTED; }
+    int n = 0, rc;
+    if ((rc = join_solids(c))) return rc;
+    if ((rc = read_n(c, &n))) return rc;
+    Scratch tmp;
+    double *sx, *sy, *sz, *cur[6];
+    int *stype, *sslot, *skey, *key, *slot, *iota, *cellCount, *cellStart, *blockSums;
+    const GridDesc &grid = c->grid;
+    const size_t nn = (size_t)std::max(n, 1), nc = (size_t)grid.ncells + 2;
+    const int sb_blocks = (int)((nc + kScanChunk - 1) / kScanChunk);
+    int e = 0;
+    e |= tmp.get(&sx, nn); e |= tmp.get(&sy, nn); e |= tmp.get(&sz, nn);
+    for (double *&q : cur) e |= tmp.get(&q, nn);
+    e |= tmp.get(&stype, nn); e |= tmp.get(&sslot, nn); e |= tmp.get(&skey, nn); e |= tmp.get(&key, nn); e |= tmp.get(&slot, nn); e |= tmp.get(&iota, nn);
+    e |= tmp.get(&cellCount, nc); e |= tmp.get(&cellStart, nc + 1); e |= tmp.get(&blockSums, (size_t)sb_blocks + 1);
+    if (e) return MPHX_ERR_NOMEM;
+    CK(cudaMemsetAsync(cellCount, 0, sizeof(int) * nc, c->stream));
+    CK(cudaMemsetAsync(d_out9, 0, sizeof(double) * 9 * (size_t)c->n_global, c->stream));
+    CK(cudaMemsetAsync(d_outp, 0, sizeof(double) * (size_t)c->n_global, c->stream));
+    LAUNCH(c, k_iota, nblk(n), kBlock, n, iota);
+    LAUNCH(c, k_dbg_keycount, nblk(n), kBlock, n, c->bx, c->by, c->bz, grid, key, cellCount, slot);
+    LAUNCH(c, k_scan_reduce, sb_blocks, kScanThreads, (const Ctl *)nullptr, cellCount, (int)nc, blockSums);
+    LAUNCH(c, k_scan_top, 1, kScanThreads, (const Ctl *)nullptr, blockSums, sb_blocks);
+    LAUNCH(c, k_scan_apply, sb_blocks, kScanThreads, (const Ctl *)nullptr, cellCount, (int)nc, blockSums, cellStart, 0);
+    LAUNCH(c, k_dbg_gather, nblk(n), kBlock, n, c->bx, c->by, c->bz, c->S.type, iota, key, slot, cellStart, sx, sy, sz, stype, sslot, skey);
+    LAUNCH(c, k_current_state, nblk(n), kBlock, n, c->S, c->sol, cur[0], cur[1], cur[2], cur[3], cur[4], cur[5]);
+    VirialIn in{};
+    in.sx = sx; in.sy = sy; in.sz = sz; in.sslot = sslot; in.skey = skey; in.cellStart = cellStart;
+    in.cx = cur[0]; in.cy = cur[1]; in.cz = cur[2]; in.cvx = cur[3]; in.cvy = cur[4]; in.cvz = cur[5];
+    in.type = c->S.type; in.id = c->S.id; in.P = c->P; in.PA = c->PA; in.gcx = c->gcx; in.gcy = c->gcy; in.gcz = c->gcz;
+    in.out9 = d_out9; in.outp = d_outp;
+    const double cut = c->c.max_radius + 0.1 * c->p.particle_spacing;
+    if (grid.dim == 3) LAUNCH(c, k_virial<3>, nblk(n), kBlock, n, in, grid, c->phys, cut * cut, c->surface_tension ? 1 : 0);
+    else               LAUNCH(c, k_virial<2>, nblk(n), kBlock, n, in, grid, c->phys, cut * cut, c->surface_tension ? 1 : 0);
+    CK(cudaStreamSynchronize(c->stream)); // (the scratch buffers are released on return)
+    CK(cudaGetLastError());
+    return MPHX_OK;
 }
 
 // ---- initial structure lists (calculateInitialNeighbor :1497-1644) + Lame + Normalizer ----------
@@ -1441,6 +1486,24 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
         if ((rc = tens(v->stress, so.S))) break;
         if ((rc = solid_scal(v->lambda_lames, so.lam))) break;
         if ((rc = solid_scal(v->mu_lames, so.mu))) break;
+        if (v->virial_stress || v->virial_pressure) { // calculateVirialStressAtParticle :3077-3318 (N2)
+            if (!c->inited) { rc = MPHX_ERR_INVALID; break; }
+            if (!d9) {
+                if (c->alloc(&c->stage9, 9 * N)) return MPHX_ERR_NOMEM;
+                d9 = c->stage9;
+            }
+            cudaEvent_t t0 = timer_event(c), t1 = timer_event(c);
+            cudaEventRecord(t0, c->stream);
+            if ((rc = compute_virial(c, d9, d1))) break;
+            cudaEventRecord(t1, c->stream);
+            cudaEventSynchronize(t1);
+            float vms = 0.f;
+            cudaEventElapsedTime(&vms, t0, t1);
+            c->virial_ms += vms;
+            c->ev_pool.push_back(t0); c->ev_pool.push_back(t1);
+            if (v->virial_stress) CK(cudaMemcpyAsync(v->virial_stress, d9, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, c->stream));
+            if (v->virial_pressure) CK(cudaMemcpyAsync(v->virial_pressure, d1, sizeof(double) * N, cudaMemcpyDeviceToHost, c->stream));
+        }
     } while (0);
     CK(cudaStreamSynchronize(c->stream)); // the one synchronisation of the call
     if (rc == MPHX_OK) { CK(cudaGetLastError()); }
@@ -1583,6 +1646,9 @@ int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5])
     for (int i = 0; i < 5; ++i) ms[i] = c->ms[i];
     return MPHX_OK;
 }
+
+/* accumulated device milliseconds of the virial stress diagnostic (the reference's "virial calculation" timer, :674) */
+double mphx_get_virial_ms(const mphx_ctx *ctx) { return ctx ? reinterpret_cast<const Ctx *>(ctx)->virial_ms : 0.0; }
 
 int mphx_set_overlap(mphx_ctx *ctx, int on)
 {

@@ -71,6 +71,8 @@ def _load():
     L.mphx_set_timing.argtypes = [vp, C.c_int]
     L.mphx_get_timers.argtypes = [vp, C.POINTER(C.c_double * 4)]
     L.mphx_get_kernel_timers.argtypes = [vp, C.POINTER(C.c_double * 5)]
+    L.mphx_get_virial_ms.argtypes = [vp]
+    L.mphx_get_virial_ms.restype = C.c_double
     L.mphx_set_overlap.argtypes = [vp, C.c_int]
     L.mphx_join.argtypes = [vp]
     L.mphx_launch_count.argtypes = [vp]

@@ -233,6 +233,34 @@ def test_surface_tension_path_matches_oracle(name, amp):
     o.close()
 
 
+@pytest.mark.parametrize("name,st", [("tiny2d", False), ("tiny2d", True), ("fsi3d_mini", False), ("tiny3d", True)])
+def test_virial_stress_matches_oracle(name, st):
+    """calculateVirialStressAtParticle (src/main.cpp:3077-3318) on the state after a step, over the
+    step's neighbour lists.  The oracle's restatement is pinned bit for bit on the live reference
+    (tests/test_oracle.py); the CUDA kernel sums in bucket order: 1e-10 (+ the floor PressureP's own noise implies)."""
+    case = getattr(cases, name)()
+    if st:
+        case.params.surface_tension[0] = case.params.surface_tension[1] = 0.072
+        case.params.interaction_ratio[1][4] = 0.6
+    o = Oracle.from_case(case)
+    o.init()
+    s = Solver.from_case(case)
+    for steps in (1, 9):
+        s.step(steps, sync=True)
+        o.step(steps)
+        o.call("calculateVirialStressAtParticle")
+        got = s.download("virial_stress", "virial_pressure")
+        k = s.constants()
+        # |dS| <= dP * sum_j |grad w| |x_ij| <= dP * n * |w'|max * r_max (per unit volume the particle volume cancels)
+        floor = pressure_floor(case, k) * k.n0p_count * abs(2.0 / k.radius_p / k.swp / (k.radius_p ** case.params.dim)) * k.radius_p
+        for f, r in (("virial_stress", "VirialStressAtParticle"), ("virial_pressure", "VirialPressureAtParticle")):
+            ref = o.get(r)
+            err, scale = record(("virial", name, st, steps), f, got[f], ref, floor)
+            assert scale > 0 and err <= RTOL * scale + floor, (name, st, steps, f, err, scale)
+    s.close()
+    o.close()
+
+
 def test_moving_wall_and_periodic_wrap_are_bit_exact():
     """calculateWall (:3036-3060) and calculatePeriodicBoundary (:3330) use explicitly rounded ops"""
     case = cases.tiny2d()
