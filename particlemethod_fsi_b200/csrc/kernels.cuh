@@ -214,7 +214,7 @@ struct Mailbox {               // pointers into ONE context's mailbox (the layou
     unsigned long long *fsolP, *fsolV;     // [nranks]
     int *cnt_mig, *cnt_halo;   // [2] each
     double *mig[2], *halo[2];  // [7 * msg_cap]
-    double *p[2];              // [msg_cap]  PressureP of the halo copies
+    double *p[2];              // [5][msg_cap]  PressureP (+ PressureA, GravityCenter) of the halo copies
     double *solP, *solV;       // [ns], [3 * ns]  replicated solids: PressureP and the coupled velocity
 };
 struct Peers {                 // the mailboxes a context writes into
@@ -552,21 +552,28 @@ __global__ void k_slab_slots(Ctl *ctl, const int *__restrict__ where, const int 
     if (q < ctl->ghost_cnt[0]) ghostSlot0[q] = where[ctl->ghost_base[0] + q];
     if (q < ctl->ghost_cnt[1]) ghostSlot1[q] = where[ctl->ghost_base[1] + q];
 }
-// second exchange: PressureP of the halo particles, in the order they were packed, straight into the neighbour's mailbox
-__global__ void k_push_scalar(Ctl *ctl, unsigned long long epoch, int which, int dir, const int *__restrict__ haloSlot, const double *__restrict__ a, double *dst,
-                              unsigned long long *dst_flag)
+// second exchange: what pass 1 computed for the halo particles, in the order they were packed, straight into the
+// neighbour's mailbox: PressureP (plane 0) and, with surface tension, PressureA and GravityCenter (planes 1..4);
+// plane p of halo particle q at dst[p * msg_cap + q]
+struct PassOneFields { const double *a[5]; int count; };
+struct PassOneTargets { double *a[5]; int count; };
+__global__ void k_push_scalar(Ctl *ctl, unsigned long long epoch, int which, int dir, const int *__restrict__ haloSlot, PassOneFields f, int msg_cap,
+                              double *dst, unsigned long long *dst_flag)
 {
     const int cnt = ctl->halo_cnt[dir];
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) dst[q] = a[haloSlot[q]];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+        const int i = haloSlot[q];
+        for (int p = 0; p < f.count; ++p) dst[(size_t)p * msg_cap + q] = f.a[p][i];
+    }
     push_complete(ctl, epoch, which, nullptr, 0, dst_flag);
 }
-__global__ void k_unpack_scalar(Ctl *ctl, int side, const int *__restrict__ ghostSlot, const double *__restrict__ buf, double *__restrict__ a,
+__global__ void k_unpack_scalar(Ctl *ctl, int side, const int *__restrict__ ghostSlot, const double *__restrict__ buf, int msg_cap, PassOneTargets f,
                                 Rec *__restrict__ rb)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= ctl->ghost_cnt[side]) return;
     const int w = ghostSlot[q];
-    a[w] = buf[q];
+    for (int p = 0; p < f.count; ++p) f.a[p][w] = buf[(size_t)p * msg_cap + q];
     rb[w].c = buf[q]; // PressureP slot of the gather record
 }
 // replicated solids: the slab that owns a solid particle (kSolidOwned: by its column when the list was built)
@@ -598,7 +605,10 @@ __global__ void k_solid_publish_P(Ctl *ctl, unsigned long long epoch, int which,
         }
     }
 }
-__global__ void k_solid_spread_P(Ctl *ctl, Particles p, GridDesc g, Solid sol, const double *__restrict__ solP, double *__restrict__ P)
+// (with surface tension -- PA != nullptr -- the replicated solids also get what calculateDensityA / GravityCenter /
+// PressureA give a structure particle: DensityA = 0, GravityCenter = 0 (:2149, :2183: i not structure), PressureA from nA = 0)
+__global__ void k_solid_spread_P(Ctl *ctl, Particles p, GridDesc g, Solid sol, const double *__restrict__ solP, double *__restrict__ P,
+                                 double *__restrict__ PA, double *__restrict__ gcx, double *__restrict__ gcy, double *__restrict__ gcz, Phys ph)
 {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= ctl->n) return;
@@ -606,6 +616,11 @@ __global__ void k_solid_spread_P(Ctl *ctl, Particles p, GridDesc g, Solid sol, c
     const double v = solP[p.id[q] - sol.sb];
     P[q] = v;
     p.rb[q].c = v;
+    if (PA) {
+        double pa = ph.cofa[real_type(p.type[q])] * (0.0 - ph.n0a) / ph.l0; // :2219
+        if (ph.n0a <= 0.0) pa = 0.0;
+        PA[q] = pa; gcx[q] = 0.0; gcy[q] = 0.0; gcz[q] = 0.0;
+    }
 }
 // the owner's coupled velocities (pass 2 wrote them into its solid arrays) -> every rank's mailbox
 __global__ void k_solid_publish_V(Ctl *ctl, unsigned long long epoch, int which, Particles p, Solid sol, const int *__restrict__ own_sol, Peers peers)

@@ -538,15 +538,24 @@ static int exchange_pressure(Ctx *c)
 {
     Ctl *ctl = c->ctl;
     Mailbox &L = c->peers.left, &R = c->peers.right;
-    LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPL, 0, c->haloSlot[0], c->P, L.p[1], L.fp + 1);
-    LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPR, 1, c->haloSlot[1], c->P, R.p[0], R.fp + 0);
+    PassOneFields pf{};
+    PassOneTargets pt{};
+    pf.a[0] = c->P; pt.a[0] = c->P; pf.count = pt.count = 1;
+    if (c->surface_tension) { // PressureA and GravityCenter of the halo copies feed pass 2's surface-tension terms
+        double *st[4] = {c->PA, c->gcx, c->gcy, c->gcz};
+        for (int p = 0; p < 4; ++p) { pf.a[1 + p] = st[p]; pt.a[1 + p] = st[p]; }
+        pf.count = pt.count = 5;
+    }
+    LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPL, 0, c->haloSlot[0], pf, c->msg_cap, L.p[1], L.fp + 1);
+    LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPR, 1, c->haloSlot[1], pf, c->msg_cap, R.p[0], R.fp + 0);
     if (c->ns > 0) LAUNCH(c, k_solid_publish_P, kPushBlocks, kPushThreads, ctl, c->epoch, kPushSolP, c->S, c->sol, c->own_sol, c->P, c->peers);
     LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fp, 2, kWaitP);
     const int mb = nblk(c->msg_cap);
-    for (int side = 0; side < 2; ++side) LAUNCH(c, k_unpack_scalar, mb, kBlock, ctl, side, c->ghostSlot[side], c->mine.p[side], c->P, c->S.rb);
+    for (int side = 0; side < 2; ++side) LAUNCH(c, k_unpack_scalar, mb, kBlock, ctl, side, c->ghostSlot[side], c->mine.p[side], c->msg_cap, pt, c->S.rb);
     if (c->ns > 0) {
         LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fsolP, c->nranks, kWaitSolP);
-        LAUNCH(c, k_solid_spread_P, nblk(c->nmax), kBlock, ctl, c->S, c->grid, c->sol, c->mine.solP, c->P);
+        LAUNCH(c, k_solid_spread_P, nblk(c->nmax), kBlock, ctl, c->S, c->grid, c->sol, c->mine.solP, c->P, c->surface_tension ? c->PA : (double *)nullptr,
+               c->gcx, c->gcy, c->gcz, c->phys);
     }
     CK(cudaGetLastError());
     return MPHX_OK;

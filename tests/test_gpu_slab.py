@@ -61,6 +61,15 @@ def test_ring_without_list_reuse_equals_single_context():
     _compare(cases.fsi3d_mini(), 3, [1, 12], list_reuse=False)
 
 
+@pytest.mark.parametrize("name,world", [("tiny2d", 2), ("tiny3d", 3)])
+def test_surface_tension_ring_equals_single_context(name, world):
+    """a16/a17 on slabs: the second exchange also carries PressureA and GravityCenter of the halo copies"""
+    case = getattr(cases, name)()
+    case.params.surface_tension[0] = case.params.surface_tension[1] = 0.072
+    case.params.interaction_ratio[1][4] = 0.6
+    _compare(case, world, [1, 10, 40], fields=FIELDS + ("pressure_a", "gravity_center", "density_a"))
+
+
 def test_particles_migrate_between_slabs():
     """give the fluid a uniform x velocity so that particles cross slab faces every few steps"""
     case = cases.dam2d()
