@@ -227,6 +227,11 @@ int mphx_get_timers(mphx_ctx *ctx, double ms[4]);
 /* the same split by kernel group: [0] bucket rebuild, [1] candidate filter (k_filter), [2] pass 1 over the
  * candidate list, [3] pass 2 over the candidate list (+ integration), [4] solid sub-steps */
 int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5]);
+/* roofline helpers (measurement only): dense FP64 FMA throughput of a device in TFLOP/s (CUDA events around a pure DFMA
+ * kernel), and the candidates / in-radius pairs of the current lists (out[0], out[1]) -- a sweep's algorithmic FP64 work
+ * is ~15 flop per candidate examined + ~45 per in-radius pair */
+int mphx_measure_fp64_peak(int device, double *tflops);
+int mphx_count_pairs(mphx_ctx *ctx, unsigned long long out[2]);
 /* accumulated device milliseconds of calculateVirialStressAtParticle (the reference's "virial calculation" timer, :674) */
 double mphx_get_virial_ms(const mphx_ctx *ctx);
 /* the solid sub-steps normally run on a second stream, overlapping pass 2 and the start of the next step;

@@ -1656,6 +1656,56 @@ int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5])
     return MPHX_OK;
 }
 
+/* dense FP64 FMA throughput of `device` in TFLOP/s, measured with CUDA events (best of 5 launches of a pure DFMA kernel) */
+int mphx_measure_fp64_peak(int device, double *tflops)
+{
+    if (!tflops) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(device));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    double *d = nullptr;
+    CK(cudaMalloc(&d, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int iters = 1 << 15, blocks = sms * 8, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CK(cudaEventRecord(e0, 0));
+        k_fp64_peak<<<blocks, threads>>>(d, iters);
+        CK(cudaEventRecord(e1, 0));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0) best = std::max(best, tf);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    CK(cudaGetLastError());
+    *tflops = best;
+    return MPHX_OK;
+}
+
+/* candidates held by the current lists and pairs within the largest kernel radius, summed over the particles of this
+ * context (out[0], out[1]); synchronises.  The algorithmic FP64 work of one sweep is ~15 flop per candidate + ~45 per
+ * in-radius pair. */
+int mphx_count_pairs(mphx_ctx *ctx, unsigned long long out[2])
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !c->inited || !out || !c->pl.nbr) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
+    Scratch tmp;
+    unsigned long long *d;
+    if (tmp.get(&d, 2)) return MPHX_ERR_NOMEM;
+    CK(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), c->stream));
+    const double r = sweep_radius(c);
+    LAUNCH(c, k_count_pairs, nblk(c->nmax), kBlock, c->ctl, c->S, c->grid, c->pl, r * r, d);
+    CK(cudaMemcpyAsync(out, d, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    return MPHX_OK;
+}
+
 /* accumulated device milliseconds of the virial stress diagnostic (the reference's "virial calculation" timer, :674) */
 double mphx_get_virial_ms(const mphx_ctx *ctx) { return ctx ? reinterpret_cast<const Ctx *>(ctx)->virial_ms : 0.0; }
 

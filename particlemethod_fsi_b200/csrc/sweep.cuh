@@ -557,6 +557,43 @@ k_pass1_v3(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, GridD
 //   LIST = true : neighbours come from pass 1's list; particles whose list overflowed are skipped.
 //   LIST = false: stencil sweep; with pl.count set only the overflowed particles are processed
 //                 (and the block exits at once if it has none), otherwise all particles.
+// measurement helpers (not part of the step) ------------------------------------------------------------------
+// dense FP64 FMA throughput of the device: 8 independent chains per thread (the roofline's second denominator)
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0, a7 = a0 + 7.0;
+    const double m = 1.0 + 1e-12, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 1.2345e300) out[0] = r; // (never true: keeps the chains alive)
+}
+// candidates in the current lists and pairs within the largest kernel radius (the algorithmic FP64 work of a sweep:
+// SURVEY 8(d) counts ~15 flop per candidate examined and ~45 per in-radius pair)
+__global__ void k_count_pairs(const Ctl *ctl, Particles p, GridDesc g, PairList pl, double r2max, unsigned long long *out /* [2] */)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long cand = 0, in = 0;
+    if (i < ctl->n && pl.count[i] <= pl.L) {
+        const int cnt = pl.count[i];
+        const Rec a = p.ra[i];
+        const MinImage mi(g);
+        for (int k = 0; k < cnt; ++k) {
+            const int j = pl.nbr[(size_t)k * pl.cap + i];
+            const Rec b = p.ra[j];
+            double dx = b.a - a.a, dy = b.b - a.b, dz = b.c - a.c;
+            mi.apply(dx, dy, dz);
+            if (j != i && dx * dx + dy * dy + dz * dz <= r2max) ++in;
+        }
+        cand = (unsigned long long)cnt;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cand += __shfl_xor_sync(0xffffffffu, cand, o); in += __shfl_xor_sync(0xffffffffu, in, o); }
+    if ((threadIdx.x & 31) == 0 && cand) { atomicAdd(&out[0], cand); atomicAdd(&out[1], in); }
+}
+
 template <int DIM, bool ST, bool LIST>
 __device__ __forceinline__ void
 pass2_block(Ctl *ctl, int vblock, int n, Particles p, const int *__restrict__ cellStart, const GridDesc &g, const Phys &ph, float filt2, int batch,

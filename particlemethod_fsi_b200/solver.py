@@ -71,6 +71,8 @@ def _load():
     L.mphx_set_timing.argtypes = [vp, C.c_int]
     L.mphx_get_timers.argtypes = [vp, C.POINTER(C.c_double * 4)]
     L.mphx_get_kernel_timers.argtypes = [vp, C.POINTER(C.c_double * 5)]
+    L.mphx_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.mphx_count_pairs.argtypes = [vp, C.POINTER(C.c_ulonglong * 2)]
     L.mphx_get_virial_ms.argtypes = [vp]
     L.mphx_get_virial_ms.restype = C.c_double
     L.mphx_set_overlap.argtypes = [vp, C.c_int]
@@ -199,6 +201,13 @@ def device_count() -> int:
     return lib.mphx_device_count()
 
 
+def measure_fp64_peak(device: int = 0) -> float:
+    """dense FP64 FMA throughput of the device in TFLOP/s (measured, CUDA events)"""
+    t = C.c_double()
+    _ck("mphx_measure_fp64_peak", lib.mphx_measure_fp64_peak(device, C.byref(t)))
+    return t.value
+
+
 def _addr(a):
     """host address of a numpy array or a torch (pinned) tensor"""
     return C.c_void_p(a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data)
@@ -279,6 +288,12 @@ class Solver:
 
     def init(self):
         _ck("mphx_init", lib.mphx_init(self._ctx))
+
+    def count_pairs(self):
+        """(candidates in the current lists, pairs within the largest kernel radius)"""
+        out = (C.c_ulonglong * 2)()
+        _ck("mphx_count_pairs", lib.mphx_count_pairs(self._ctx, C.byref(out)))
+        return int(out[0]), int(out[1])
 
     def set_list_reuse(self, on: bool, skin: float = 0.0):
         """candidate-list reuse (internal Verlet skin); skin in particle spacings, only before upload"""

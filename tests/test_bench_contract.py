@@ -38,3 +38,13 @@ def test_product_arm_fails_loudly_without_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--particles", "2e4"],
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """the reference arm must run the reference's CPU build only -- importing what it imports (bench,
+    cases, the reference harness) must not load libmphx.so (the package binds it lazily, at the first call)"""
+    code = ("import sys; sys.path.insert(0, %r); import bench; from particlemethod_fsi_b200 import cases; "
+            "from oracle import refharness; c = cases.tiny2d(); print('libmphx' in open('/proc/self/maps').read())" % ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip().splitlines()[-1] == "False"
