@@ -37,10 +37,20 @@ enum {
 };
 
 /* ---- parameters ----------------------------------------------------------------------------- */
-/* clamp module: the reference selects it with a compile-time #define (src/main.cpp:54-59);
- * here it is a run-time field.  Only the modules of the BASELINE configs are supported. */
-enum { MPHX_MODULE_NONE = 0, MPHX_MODULE_BAR = 1 /* :54, clamp x0[0]<0.001 :1919 */,
-       MPHX_MODULE_DAM = 2 /* :55, clamp x0[1]<0.002 :1968 */ };
+/* clamp module: the reference selects it with a compile-time #define (src/main.cpp:54-59); here it is a
+ * run-time field.  All six clamp variants of updateElasticPosition (:1910-2082) are covered. */
+enum { MPHX_MODULE_NONE = 0,
+       MPHX_MODULE_BAR = 1          /* :54  Bar_Module:   clamp x0[0] < 0.001                 :1919 */,
+       MPHX_MODULE_DAM = 2          /* :55  DAM_Module:   clamp x0[1] < 0.002                 :1968 */,
+       MPHX_MODULE_TUREK_HRON = 3   /* :56  Turek_Hron:   clamp x0[0] < 0.205, Force kept     :1944 */,
+       MPHX_MODULE_ROLLING1 = 4     /* :57  Rolling1:     clamp x0[1] < 0.003                 :1992 */,
+       MPHX_MODULE_HYDROELASTIC = 5 /* :59  Hydroelastic: clamp x0[0] < 0.01 or > 1.99        :2016 */,
+       MPHX_MODULE_ROLLING2 = 6     /*      Rolling2:     clamp x0[1] > 0.3420, and the only variant WITHOUT the
+                                            second position update of quirk Q1 (:2040-2069)         */ };
+/* wall kinematics (mphx_params.wall_module): 0 = translate / rotate with the .data file's Wall6 / Wall7 rows while
+ * Time < 0.2 (:3033-3070); 1 = the reference's `#define Rolling` (:2958-3031): the walls roll about z through their
+ * centres, theta(t) = 2 deg * sin(2 pi t / 1.646 s), at every step */
+enum { MPHX_WALL_DEFAULT = 0, MPHX_WALL_ROLLING = 1 };
 
 /* ref_compat bits: reproduce reference quirks (SURVEY.md Q-list).  Default: all on. */
 enum { MPHX_COMPAT_DOUBLE_UPDATE = 1 /* Q1: updateElasticPosition advances twice, :2070-2079 */ };
@@ -49,7 +59,7 @@ typedef struct mphx_params {
     int dim;            /* 2 or 3: `#define TWO_DIMENSIONAL` src/main.cpp:50                   */
     int clamp_module;   /* MPHX_MODULE_*                                                       */
     int ref_compat;     /* MPHX_COMPAT_* bits                                                  */
-    int reserved0;
+    int wall_module;    /* MPHX_WALL_*                                                         */
     double time0;             /* Time from line 1 of the grid file          :797               */
     double dt;                /* Dt                                          :743              */
     double elastic_dt;        /* ElasticDt                                   :744              */
@@ -157,6 +167,14 @@ int mphx_write_prof_file(const char *filename, double time, const mphx_params *p
 /* src/main.cpp:984-1189 (byte-identical text incl. the duplicated `velocity` section) */
 int mphx_write_vtk_file(const char *filename, int n, const double *initial_position,
                         const mphx_host_views *fields);
+/* lossless binary checkpoint: every double bit for bit plus the wall centres, which the 7-digit
+ * .prof text (:973-978) cannot carry.  mphx_write_checkpoint takes host arrays (p->wall_center = the CURRENT centres,
+ * see mphx_get_wall_centers); mphx_read_checkpoint allocates the four arrays with malloc (free with mphx_free_host) and
+ * fills time0, dim, particle_spacing, domain_*, wall_center of *p, so that create/upload/init continue the run. */
+int mphx_write_checkpoint(const char *filename, double time, const mphx_params *p, int n, const int *property,
+                          const double *position, const double *initial_position, const double *velocity);
+int mphx_read_checkpoint(const char *filename, mphx_params *p, int *n_out, int **property, double **position,
+                         double **initial_position, double **velocity);
 /* first..last index of each particle class, src/main.cpp:909-929; ranges[6] =
  * {FluidBegin,FluidEnd,StructureBegin,StructureEnd,WallBegin,WallEnd} (-1 when absent) */
 void mphx_class_ranges(int n, const int *property, int ranges[6]);
@@ -173,6 +191,18 @@ void mphx_destroy(mphx_ctx *ctx);
 /* replaces `acc update device` (src/main.cpp:549-560, 946-950).  The caller keeps its arrays. */
 int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *position,
                 const double *initial_position, const double *velocity);
+/* Device-side generator: the lattice fill of the reference's pre-processor
+ * (generator/generator.cpp:654-680: per Cuboid, start at lower + spacing/2, accumulate while p < upper - 0.49 spacing,
+ * x outer / y / z inner) written straight into device memory -- the particle set equals what the solver would read from
+ * the generator's .grid text (`%e`, 7 digits), without the text and without host arrays (a 10^8-particle .grid is 12 GB).
+ * Cuboids in file order; each particle class must be contiguous.  Replaces mphx_upload on a single context. */
+typedef struct mphx_cuboid {
+    int type;
+    int reserved;
+    double lower[3], upper[3], spacing, velocity[3];
+} mphx_cuboid;
+long long mphx_generate_count(const mphx_cuboid *cuboids, int ncuboids); /* particles the cuboids hold (-1: invalid) */
+int mphx_upload_generated(mphx_ctx *ctx, const mphx_cuboid *cuboids, int ncuboids);
 /* per-step variant of the above for a caller that keeps the state on the host: replaces Position
  * and Velocity only (original order, [N][3]); asynchronous on the context's stream, so pass
  * page-locked buffers and keep them alive until the next mphx_sync/mphx_download */
@@ -181,6 +211,8 @@ int mphx_upload_state(mphx_ctx *ctx, const double *position, const double *veloc
  * calculateNeighbor/DensityA/GravityCenter/DensityP, calculateLamesconstant, calculateNormalizer) */
 int mphx_init(mphx_ctx *ctx);
 int mphx_get_constants(const mphx_ctx *ctx, mphx_constants *c);
+/* the wall centres as advanced so far (src/main.cpp:3066-3070: WallCenter += WallVelocity * Dt every step) */
+int mphx_get_wall_centers(const mphx_ctx *ctx, double centers[MPHX_TYPE_COUNT][3]);
 
 /* ---- the hot path ------------------------------------------------------------------------------ */
 /* `nsteps` iterations of the loop body src/main.cpp:596-663 followed by Time += Dt (:685).

@@ -8,7 +8,8 @@
 # streaming the file through `sed` straight into the compiler's stdin -- no copy of any reference
 # source is ever written into this repository.
 #
-# Products, per variant V in {2d_bar, 2d_dam, 3d_dam, 3d_bar} (+ _nb128 big-N flavours):
+# Products, per variant V in {2d_bar, 2d_dam, 3d_dam, 3d_bar, 2d_turek, 2d_rolling1, 2d_hydro, 2d_rolling2, 2d_rollwall}
+# (+ _nb128 big-N flavours):
 #   oracle/_ref/Mph_Elastic_Explicit_V      the reference executable (CLI of src/main.cpp:501-508)
 #   oracle/_ref/libref_V.so                 same TU + oracle/ref_harness_tail.cpp (stage-level API)
 #   oracle/_ref/GeneratorForMph             the reference pre-processor (generator/generator.cpp)
@@ -29,11 +30,17 @@ CXXFLAGS="-O3 -fopenmp -ffp-contract=off -Wno-write-strings -Wno-unused-result -
 
 variant_sed() {  # $1 = variant name -> sed program on stdout
     local v="$1" prog=""
+    local nobar='s|^#define Bar_Module|//#define Bar_Module|'
     case "$v" in
         2d_bar*) prog="" ;;
-        2d_dam*) prog='s|^#define Bar_Module|//#define Bar_Module|;s|^//#define DAM_Module|#define DAM_Module|' ;;
-        3d_dam*) prog='s|^#define TWO_DIMENSIONAL|//#define TWO_DIMENSIONAL|;s|^#define Bar_Module|//#define Bar_Module|;s|^//#define DAM_Module|#define DAM_Module|' ;;
+        2d_dam*) prog="$nobar"';s|^//#define DAM_Module|#define DAM_Module|' ;;
+        3d_dam*) prog='s|^#define TWO_DIMENSIONAL|//#define TWO_DIMENSIONAL|;'"$nobar"';s|^//#define DAM_Module|#define DAM_Module|' ;;
         3d_bar*) prog='s|^#define TWO_DIMENSIONAL|//#define TWO_DIMENSIONAL|' ;;
+        2d_turek*) prog="$nobar"';s|^//#define Turek_Hron|#define Turek_Hron|' ;;
+        2d_rolling1*) prog="$nobar"';s|^//#define Rolling1|#define Rolling1|' ;;
+        2d_hydro*) prog="$nobar"';s|^// #define Hydroelastic|#define Hydroelastic|' ;;
+        2d_rolling2*) prog="$nobar"';s|^#define DIM 3|#define Rolling2\n#define DIM 3|' ;;   # (no switch line exists for Rolling2)
+        2d_rollwall*) prog='s|^#define DIM 3|#define Rolling\n#define DIM 3|' ;;             # Bar_Module + the rolling wall
         *) echo "unknown variant $v" >&2; exit 1 ;;
     esac
     case "$v" in
@@ -59,7 +66,7 @@ build_variant() {
     fi
 }
 
-VARIANTS=${VARIANTS:-"2d_bar 2d_dam 3d_dam 3d_dam_nb128"}
+VARIANTS=${VARIANTS:-"2d_bar 2d_dam 3d_dam 3d_dam_nb128 2d_turek 2d_rolling1 2d_hydro 2d_rolling2 2d_rollwall"}
 for v in $VARIANTS; do build_variant "$v"; done
 
 # the reference pre-processor (generator/makefile builds the same three files)

@@ -18,7 +18,8 @@ MPHX_ERR_NOMEM = -5
 MPHX_ERR_UNSUPPORTED = -6
 MPHX_ERR_OVERFLOW = -7
 
-MODULE_NONE, MODULE_BAR, MODULE_DAM = 0, 1, 2
+MODULE_NONE, MODULE_BAR, MODULE_DAM, MODULE_TUREK_HRON, MODULE_ROLLING1, MODULE_HYDROELASTIC, MODULE_ROLLING2 = 0, 1, 2, 3, 4, 5, 6
+WALL_DEFAULT, WALL_ROLLING = 0, 1
 COMPAT_DOUBLE_UPDATE = 1
 
 _d = C.c_double
@@ -28,7 +29,7 @@ _V3 = _d * 3
 
 class Params(C.Structure):
     _fields_ = [
-        ("dim", C.c_int), ("clamp_module", C.c_int), ("ref_compat", C.c_int), ("reserved0", C.c_int),
+        ("dim", C.c_int), ("clamp_module", C.c_int), ("ref_compat", C.c_int), ("wall_module", C.c_int),
         ("time0", _d), ("dt", _d), ("elastic_dt", _d), ("particle_spacing", _d),
         ("domain_min", _V3), ("domain_max", _V3),
         ("radius_ratio_a", _d), ("radius_ratio_p", _d), ("radius_ratio_v", _d),
@@ -70,6 +71,10 @@ _pi = C.POINTER(C.c_int)
 _pd = C.POINTER(C.c_double)
 
 
+class CuboidC(C.Structure):
+    _fields_ = [("type", C.c_int), ("reserved", C.c_int), ("lower", _V3), ("upper", _V3), ("spacing", _d), ("velocity", _V3)]
+
+
 class HostViews(C.Structure):
     _fields_ = [
         ("property", _pi), ("position", _pd), ("velocity", _pd), ("force", _pd), ("acceleration", _pd),
@@ -98,9 +103,9 @@ VIEW_FIELDS = {
 EXPORTS = [
     "mphx_version", "mphx_strerror", "mphx_last_error", "mphx_device_count", "mphx_abi_sizeof",
     "mphx_params_default", "mphx_read_data_file", "mphx_read_grid_file", "mphx_free_host",
-    "mphx_write_prof_file", "mphx_write_vtk_file", "mphx_class_ranges",
+    "mphx_write_prof_file", "mphx_write_vtk_file", "mphx_write_checkpoint", "mphx_read_checkpoint", "mphx_class_ranges",
     "mphx_compute_constants",
-    "mphx_create", "mphx_destroy", "mphx_upload", "mphx_upload_state", "mphx_init", "mphx_get_constants",
+    "mphx_create", "mphx_destroy", "mphx_upload", "mphx_generate_count", "mphx_upload_generated", "mphx_upload_state", "mphx_init", "mphx_get_constants", "mphx_get_wall_centers",
     "mphx_step", "mphx_step_fluid_only", "mphx_sync", "mphx_time", "mphx_set_time", "mphx_download",
     "mphx_download_owned", "mphx_upload_owned",
     "mphx_debug_neighbors", "mphx_debug_initial_structure_neighbors",

@@ -234,6 +234,28 @@ def tiny3d() -> Case:
     return c
 
 
+def module_case(module: str) -> Case:
+    """small 2D FSI case for one of the reference's other compile-time variants (src/main.cpp:56-59): a water block next
+    to a plate standing on a floor, placed so that the variant's clamp condition (updateElasticPosition :1910-2082) holds
+    for part of the plate.  module: turek | rolling1 | hydro | rolling2 | rollwall (Bar_Module + `#define Rolling`)."""
+    l0 = 2.0e-3
+    mod = dict(turek=abi.MODULE_TUREK_HRON, rolling1=abi.MODULE_ROLLING1, hydro=abi.MODULE_HYDROELASTIC,
+               rolling2=abi.MODULE_ROLLING2, rollwall=abi.MODULE_BAR)[module]
+    px, py = dict(turek=(0.201, 0.0), rolling1=(0.05, 0.0), hydro=(0.005, 0.0), rolling2=(0.05, 0.33), rollwall=(0.05, 0.0))[module]
+    p, rc = default_params(2, mod)
+    p.elastic_dt = 2.0e-5
+    w = 3 * l0
+    cubs = [Cuboid(1, (px - 0.022, py, 0.0), (px - l0, py + 0.012, l0), l0),
+            Cuboid(2, (px, py, 0.0), (px + w, py + 0.02, l0), l0),
+            Cuboid(4, (px - 0.03, py - w, 0.0), (px + 0.03, py, l0), l0)]
+    if module == "rollwall":
+        p.wall_module = abi.WALL_ROLLING
+        p.wall_center[4][0], p.wall_center[4][1] = px, py
+    m = 7 * l0
+    c = _assemble("module_" + module, p, rc, l0, (px - 0.03 - m, py - w - m, 0.0), (px + 0.03 + m, py + 0.04, l0), cubs)
+    return c
+
+
 def fsi3d_for_count(n_target: float, **kw) -> Case:
     """scale l0 so that the default 3D geometry has about n_target particles (walls scale with the
     surface, so the spacing is found by a few fixed-point iterations on coarse counts)"""

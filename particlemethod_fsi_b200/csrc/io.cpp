@@ -338,3 +338,62 @@ extern "C" int mphx_write_vtk_file(const char *filename, int n, const double *in
     std::fclose(fp);
     return MPHX_OK;
 }
+
+// ---- lossless binary checkpoint ------------------------------------------------------------
+// The reference restarts from its .prof files, which carry 7 significant digits (`%e`, :973-978): a restarted run is a
+// different trajectory.  This format keeps every double bit for bit, plus what the text file does not carry at all: the
+// wall centres (advanced every step, :3066-3070).  Little-endian, fixed layout:
+//   "MPHXCKP1" | int32 n | int32 dim | f64 time | f64 spacing | f64 domain_min[3] | f64 domain_max[3] |
+//   f64 wall_center[6][3] | int32 property[n] | f64 position[n][3] | f64 initial_position[n][3] | f64 velocity[n][3]
+static const char kCkpMagic[8] = {'M', 'P', 'H', 'X', 'C', 'K', 'P', '1'};
+
+extern "C" int mphx_write_checkpoint(const char *filename, double time, const mphx_params *p, int n, const int *property,
+                                     const double *position, const double *initial_position, const double *velocity)
+{
+    if (!filename || !p || n <= 0 || !property || !position || !initial_position || !velocity) return MPHX_ERR_INVALID;
+    FILE *fp = std::fopen(filename, "wb");
+    if (!fp) { mphx::set_last_error(std::string("error in open ") + filename); return MPHX_ERR_IO; }
+    bool ok = std::fwrite(kCkpMagic, 1, 8, fp) == 8;
+    const int hdr[2] = {n, p->dim};
+    ok = ok && std::fwrite(hdr, sizeof(int), 2, fp) == 2;
+    ok = ok && std::fwrite(&time, sizeof(double), 1, fp) == 1;
+    ok = ok && std::fwrite(&p->particle_spacing, sizeof(double), 1, fp) == 1;
+    ok = ok && std::fwrite(p->domain_min, sizeof(double), 3, fp) == 3 && std::fwrite(p->domain_max, sizeof(double), 3, fp) == 3;
+    ok = ok && std::fwrite(p->wall_center, sizeof(double), 3 * MPHX_TYPE_COUNT, fp) == 3 * MPHX_TYPE_COUNT;
+    const size_t N = (size_t)n;
+    ok = ok && std::fwrite(property, sizeof(int), N, fp) == N && std::fwrite(position, sizeof(double), 3 * N, fp) == 3 * N &&
+         std::fwrite(initial_position, sizeof(double), 3 * N, fp) == 3 * N && std::fwrite(velocity, sizeof(double), 3 * N, fp) == 3 * N;
+    ok = (std::fclose(fp) == 0) && ok;
+    if (!ok) { mphx::set_last_error(std::string("error writing ") + filename); return MPHX_ERR_IO; }
+    return MPHX_OK;
+}
+
+extern "C" int mphx_read_checkpoint(const char *filename, mphx_params *p, int *n_out, int **property, double **position,
+                                    double **initial_position, double **velocity)
+{
+    if (!filename || !p || !n_out || !property || !position || !initial_position || !velocity) return MPHX_ERR_INVALID;
+    *property = nullptr; *position = *initial_position = *velocity = nullptr;
+    FILE *fp = std::fopen(filename, "rb");
+    if (!fp) { mphx::set_last_error(std::string("error in open ") + filename); return MPHX_ERR_IO; }
+    char magic[8];
+    int hdr[2] = {0, 0};
+    double time = 0.0;
+    bool ok = std::fread(magic, 1, 8, fp) == 8 && !std::memcmp(magic, kCkpMagic, 8) && std::fread(hdr, sizeof(int), 2, fp) == 2 && hdr[0] > 0 &&
+              std::fread(&time, sizeof(double), 1, fp) == 1 && std::fread(&p->particle_spacing, sizeof(double), 1, fp) == 1 &&
+              std::fread(p->domain_min, sizeof(double), 3, fp) == 3 && std::fread(p->domain_max, sizeof(double), 3, fp) == 3 &&
+              std::fread(p->wall_center, sizeof(double), 3 * MPHX_TYPE_COUNT, fp) == 3 * MPHX_TYPE_COUNT;
+    if (!ok) { std::fclose(fp); mphx::set_last_error(std::string(filename) + " is not an mphx checkpoint"); return MPHX_ERR_IO; }
+    const size_t N = (size_t)hdr[0];
+    int *t = (int *)std::malloc(sizeof(int) * N);
+    double *x = (double *)std::malloc(sizeof(double) * 3 * N), *x0 = (double *)std::malloc(sizeof(double) * 3 * N),
+           *v = (double *)std::malloc(sizeof(double) * 3 * N);
+    if (!t || !x || !x0 || !v) { std::free(t); std::free(x); std::free(x0); std::free(v); std::fclose(fp); return MPHX_ERR_NOMEM; }
+    ok = std::fread(t, sizeof(int), N, fp) == N && std::fread(x, sizeof(double), 3 * N, fp) == 3 * N &&
+         std::fread(x0, sizeof(double), 3 * N, fp) == 3 * N && std::fread(v, sizeof(double), 3 * N, fp) == 3 * N;
+    std::fclose(fp);
+    if (!ok) { std::free(t); std::free(x); std::free(x0); std::free(v); mphx::set_last_error(std::string(filename) + " is truncated"); return MPHX_ERR_IO; }
+    p->time0 = time;
+    p->dim = hdr[1];
+    *n_out = hdr[0]; *property = t; *position = x; *initial_position = x0; *velocity = v;
+    return MPHX_OK;
+}

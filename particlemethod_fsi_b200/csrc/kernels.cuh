@@ -1094,6 +1094,21 @@ __global__ void k_solid_pass1(Solid so, double W0, double W1, double W2, double 
         }
 }
 
+// the clamp variants of updateElasticPosition (MPHX_MODULE_*: Bar :1919, DAM :1968, Turek_Hron :1944, Rolling1 :1992,
+// Hydroelastic :2016, Rolling2 :2040)
+__host__ __device__ inline bool solid_clamped(int module, double x0, double y0)
+{
+    switch (module) {
+    case 1: return x0 < 0.001;
+    case 2: return y0 < 0.002;
+    case 3: return x0 < 0.205;
+    case 4: return y0 < 0.003;
+    case 5: return x0 < 0.01 || x0 > 1.99;
+    case 6: return y0 > 0.3420;
+    default: return false;
+    }
+}
+
 // K8 "solid pass 2": the reference scatters  v_i += w P_i x0_ij /rho_i dt,  v_j -= (same)/rho_j dt
 // serially / with atomics (:2855-2887); here every particle GATHERS, in the reference's serial
 // order, the terms of rows j<s that list s, then its own row, then rows j>s (transposed list), so
@@ -1161,11 +1176,10 @@ __global__ void k_solid_pass2(Solid so, double W0, double W1, double W2, double 
     double x[3] = {so.x[s], so.y[s], so.z[s]};
     // Acceleration of solids is 0 (:2892): v += 0*dt leaves v unchanged
     if (module != 0) {
-        const bool clamped = (module == 1) ? (xi0 < 0.001) : (yi0 < 0.002); // :1919 / :1968
-        if (clamped) {
+        if (solid_clamped(module, xi0, yi0)) {
             x[0] = xi0; x[1] = yi0; x[2] = zi0;
             v[0] = v[1] = v[2] = 0.0;
-            so.fx[s] = 0.0; so.fy[s] = 0.0; so.fz[s] = 0.0;
+            if (module != 3) { so.fx[s] = 0.0; so.fy[s] = 0.0; so.fz[s] = 0.0; } // (Turek_Hron leaves Force alone, :1944-1953)
         } else {
             for (int a = 0; a < 3; ++a) x[a] = add(x[a], mul(v[a], edt));
         }
@@ -1231,6 +1245,36 @@ __global__ void k_upload_split(int n, const int *__restrict__ ids, const int *__
     p.type[i] = type[id]; p.id[i] = id; p.key[i] = 0;
     if (solid_slot && is_structure_type(type[id])) solid_slot[id - solid_base] = i;
 }
+// device-side generator: the lattice fill of generator/generator.cpp:654-680.  The host computes the
+// three axis tables of every cuboid exactly as the generator + its `%e` text do (a few hundred doubles); the particles --
+// x outer, y, z inner, cuboid after cuboid -- are written straight into device memory.
+struct GenCuboid {
+    long long first;  // index of the cuboid's first particle
+    int nx, ny, nz;   // lattice points per axis
+    int ax, ay, az;   // offsets of its axis tables in `axes`
+    int type;
+    double v[3];
+};
+constexpr int kMaxCuboids = 64;
+struct GenPlan { int count; GenCuboid c[kMaxCuboids]; };
+__global__ void k_generate(long long n, GenPlan plan, const double *__restrict__ axes, int *__restrict__ type, double *__restrict__ x3,
+                           double *__restrict__ x03, double *__restrict__ v3)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int q = 0;
+    while (q + 1 < plan.count && plan.c[q + 1].first <= i) ++q;
+    const GenCuboid &g = plan.c[q];
+    const long long r = i - g.first;
+    const int iz = (int)(r % g.nz), iy = (int)((r / g.nz) % g.ny), ix = (int)(r / ((long long)g.nz * g.ny));
+    const double x = axes[g.ax + ix], y = axes[g.ay + iy], z = axes[g.az + iz];
+    const size_t o = 3 * (size_t)i;
+    type[i] = g.type;
+    x3[o] = x; x3[o + 1] = y; x3[o + 2] = z;
+    x03[o] = x; x03[o + 1] = y; x03[o + 2] = z;
+    v3[o] = g.v[0]; v3[o + 1] = g.v[1]; v3[o + 2] = g.v[2];
+}
+
 // the solids in their reference configuration as a particle set (for the initial-list build)
 __global__ void k_solid_reference_particles(Solid so, Particles p)
 {

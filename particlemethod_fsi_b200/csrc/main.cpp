@@ -109,8 +109,12 @@ static int parse_module(const char *s)
     if (!s) return MPHX_MODULE_BAR;
     if (!strcmp(s, "bar") || !strcmp(s, "Bar_Module") || !strcmp(s, "1")) return MPHX_MODULE_BAR;
     if (!strcmp(s, "dam") || !strcmp(s, "DAM_Module") || !strcmp(s, "2")) return MPHX_MODULE_DAM;
+    if (!strcmp(s, "turek") || !strcmp(s, "Turek_Hron") || !strcmp(s, "3")) return MPHX_MODULE_TUREK_HRON;
+    if (!strcmp(s, "rolling1") || !strcmp(s, "Rolling1") || !strcmp(s, "4")) return MPHX_MODULE_ROLLING1;
+    if (!strcmp(s, "hydroelastic") || !strcmp(s, "Hydroelastic") || !strcmp(s, "5")) return MPHX_MODULE_HYDROELASTIC;
+    if (!strcmp(s, "rolling2") || !strcmp(s, "Rolling2") || !strcmp(s, "6")) return MPHX_MODULE_ROLLING2;
     if (!strcmp(s, "none") || !strcmp(s, "0")) return MPHX_MODULE_NONE;
-    fprintf(stderr, "unknown module '%s' (bar|dam|none)\n", s);
+    fprintf(stderr, "unknown module '%s' (bar|dam|turek|rolling1|hydroelastic|rolling2|none)\n", s);
     exit(1);
 }
 
@@ -137,11 +141,15 @@ int main(int argc, char *argv[])
     mphx_params_default(&p, &rc_);
     if (dim_s) p.dim = atoi(dim_s);
     p.clamp_module = parse_module(mod_s);
+    if (getenv("MPHX_WALL") && !strcmp(getenv("MPHX_WALL"), "rolling")) p.wall_module = MPHX_WALL_ROLLING; // `#define Rolling`
     int rc = mphx_read_data_file(datafilename.c_str(), &p, &rc_, invalid_line, nullptr);
     if (rc) die("readDataFile", rc);
     int n = 0, *property = nullptr;
     double *position = nullptr, *initial_position = nullptr, *velocity = nullptr;
-    rc = mphx_read_grid_file(gridfilename.c_str(), &p, &n, &property, &position, &initial_position, &velocity);
+    // a grid argument ending in .ckp is a lossless checkpoint of this driver (MPHX_CHECKPOINT), not the reference's text
+    const bool restart = gridfilename.size() > 4 && gridfilename.compare(gridfilename.size() - 4, 4, ".ckp") == 0;
+    rc = restart ? mphx_read_checkpoint(gridfilename.c_str(), &p, &n, &property, &position, &initial_position, &velocity)
+                 : mphx_read_grid_file(gridfilename.c_str(), &p, &n, &property, &position, &initial_position, &velocity);
     if (rc) die("readGridFile", rc);
     {
         int r[6];
@@ -182,6 +190,7 @@ int main(int argc, char *argv[])
 
     const size_t N = (size_t)n;
     Writer writer(!(getenv("MPHX_SYNC_IO") && atoi(getenv("MPHX_SYNC_IO")) != 0));
+    int iStepNow = 0;
     auto write_prof = [&](const std::string &fn, double time) { // state BEFORE the step (Q8)
         auto snap = std::make_shared<Snapshot>();
         snap->position.resize(3 * N); snap->velocity.resize(3 * N);
@@ -191,9 +200,17 @@ int main(int argc, char *argv[])
         v.velocity = snap->velocity.data();
         int e = do_download(&v);
         if (e) die("mphx_download", e);
+        mphx_params pc = p; // (with the wall centres as advanced so far: the checkpoint carries them)
+        mphx_get_wall_centers(ctx, pc.wall_center);
+        const char *ckp = getenv("MPHX_CHECKPOINT"); // e.g. run%03d.ckp: a lossless restart file next to every .prof
+        const std::string ckpfn = ckp ? [&] { char b[2048]; snprintf(b, sizeof(b), ckp, iStepNow); return std::string(b); }() : std::string();
         writer.submit([=, &p]() {
             int e2 = mphx_write_prof_file(fn.c_str(), time, &p, n, property, snap->position.data(), initial_position, snap->velocity.data());
             if (e2) die("writeProfFile", e2);
+            if (!ckpfn.empty()) {
+                e2 = mphx_write_checkpoint(ckpfn.c_str(), time, &pc, n, property, snap->position.data(), initial_position, snap->velocity.data());
+                if (e2) die("writeCheckpoint", e2);
+            }
         });
     };
     // the reference computes the virial stress on VTK steps but keeps its VTK sections commented out; MPHX_VTK_VIRIAL=1
@@ -238,6 +255,7 @@ int main(int argc, char *argv[])
         if (Time + 1.0e-5 * Dt >= OutputNext) { // :583-589
             char filename[2048];
             snprintf(filename, sizeof(filename), proffilename.c_str(), iStep);
+            iStepNow = iStep;
             write_prof(filename, Time);
             log_printf("@ Prof Output Time : %e\n", Time);
             OutputNext += rc_.output_interval;

@@ -338,6 +338,7 @@ static float filter_radius2(const Ctx *c, double rmax)
 
 static bool walls_move(const Ctx *c)
 {
+    if (c->nw > 0 && c->p.wall_module == MPHX_WALL_ROLLING) return true;
     if (c->nw <= 0 || !(c->time < 0.2)) return false; // Q7 (:3037)
     for (int t = 4; t < kTypeCount; ++t)
         for (int d = 0; d < 3; ++d)
@@ -418,8 +419,27 @@ static int stage_build(Ctx *c, bool motion)
     WallMotion wm;
     std::memset(&wm, 0, sizeof(wm));
     wm.dt = c->p.dt;
-    wm.active = (motion && c->time < 0.2 && c->nw > 0) ? 1 : 0; // Q7 (:3037)
-    if (wm.active)
+    const bool rolling = c->p.wall_module == MPHX_WALL_ROLLING;
+    wm.active = (motion && c->nw > 0 && (rolling || c->time < 0.2)) ? 1 : 0; // Q7 (:3037); the Rolling variant has no time gate
+    if (wm.active && rolling) {
+        // `#define Rolling` (:2958-3031): the walls turn about z by theta(t) - theta(t - Dt), theta = 2 deg sin(2 pi t / 1.646 s);
+        // v = (0, 0, dtheta/dt) x r_rot, x = r_rot + centre (no translation term) -- the generic wall formula of k_prestep
+        // with R = Rz(delta theta), omega = (0, 0, dtheta/dt), V = 0 gives the same bits (the extra terms are exact zeros)
+        const double max_angle = 2.0 * M_PI / 180.0, period = 1.646;
+        const double omega_t = 2.0 * M_PI / period;
+        const double theta = max_angle * std::sin(omega_t * c->time);
+        const double dtheta_dt = max_angle * omega_t * std::cos(omega_t * c->time);
+        const double theta_prev = max_angle * std::sin(omega_t * (c->time - c->p.dt));
+        const double delta_theta = theta - theta_prev;
+        const double cosD = std::cos(delta_theta), sinD = std::sin(delta_theta);
+        for (int t = 0; t < kTypeCount; ++t) {
+            for (int d = 0; d < 3; ++d) { wm.center[t][d] = c->wall_center[t][d]; wm.vel[t][d] = 0.0; wm.omega[t][d] = 0.0; }
+            wm.omega[t][2] = dtheta_dt;
+            const double Rz[3][3] = {{cosD, -sinD, 0.0}, {sinD, cosD, 0.0}, {0.0, 0.0, 1.0}};
+            for (int d = 0; d < 3; ++d)
+                for (int e = 0; e < 3; ++e) wm.R[t][d][e] = Rz[d][e];
+        }
+    } else if (wm.active)
         for (int t = 0; t < kTypeCount; ++t)
             for (int d = 0; d < 3; ++d) {
                 wm.center[t][d] = c->wall_center[t][d];
@@ -613,7 +633,8 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
     const mphx_constants &k = c->c;
     const double cw = c->cw_tl;
     const int ns = c->ns;
-    const int dbl = (c->p.ref_compat & MPHX_COMPAT_DOUBLE_UPDATE) ? 1 : 0;
+    // Q1: the second position update is the `#else` tail of the Rolling2 block (:2070-2079): every variant but Rolling2
+    const int dbl = ((c->p.ref_compat & MPHX_COMPAT_DOUBLE_UPDATE) && c->p.clamp_module != MPHX_MODULE_ROLLING2) ? 1 : 0;
     if (c->slab) { // every rank takes the owners' coupled velocities, then runs the identical sub-steps
         LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, c->epoch, c->mine.fsolV, c->nranks, kWaitSolV);
         LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV);
@@ -1065,7 +1086,8 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
     if (!out || !p) return MPHX_ERR_INVALID;
     *out = nullptr;
     if (p->dim != 2 && p->dim != 3) return MPHX_ERR_INVALID;
-    if (p->clamp_module < 0 || p->clamp_module > 2) return MPHX_ERR_UNSUPPORTED;
+    if (p->clamp_module < 0 || p->clamp_module > MPHX_MODULE_ROLLING2) return MPHX_ERR_UNSUPPORTED;
+    if (p->wall_module != MPHX_WALL_DEFAULT && p->wall_module != MPHX_WALL_ROLLING) return MPHX_ERR_UNSUPPORTED;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
         cudaGetLastError();
@@ -1142,44 +1164,9 @@ void mphx_destroy(mphx_ctx *ctx)
     delete c;
 }
 
-int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *position,
-                const double *initial_position, const double *velocity)
+// device allocations of the first upload (slots, lists, buckets, solid arrays) for `nloc` local particles of `n`
+static int upload_allocate(Ctx *c, int n, int nloc, const int r[6])
 {
-    Ctx *c = reinterpret_cast<Ctx *>(ctx);
-    if (!c || n <= 0 || !property || !position || !initial_position || !velocity) return MPHX_ERR_INVALID;
-    if (c->uploaded && n != c->n_global) return MPHX_ERR_INVALID; // re-upload must keep the particle count
-    if (c->uploaded && c->slab) { set_last_error("re-upload is not supported on a slab context"); return MPHX_ERR_UNSUPPORTED; }
-    CK(cudaSetDevice(c->device));
-    { int jrc = join_solids(c); if (jrc) return jrc; }
-    for (int i = 0; i < n; ++i)
-        if (property[i] < 0 || property[i] >= kTypeCount) { set_last_error("particle type outside 0..5"); return MPHX_ERR_INVALID; }
-    int r[6];
-    mphx_class_ranges(n, property, r);
-    // each class must be one contiguous block of the file order, as the reference's range loops
-    // (src/main.cpp:909-929, e.g. :2922, :2442) assume
-    for (int cls = 0; cls < 3; ++cls)
-        for (int i = std::max(r[2 * cls], 0); i < r[2 * cls + 1]; ++i) {
-            const int t = property[i];
-            const int k = t < 2 ? 0 : t < 4 ? 1 : 2;
-            if (k != cls) { set_last_error("particle classes are not contiguous in file order"); return MPHX_ERR_UNSUPPORTED; }
-        }
-    // slab mode: this context keeps the fluid/wall particles of its own columns and ALL solids
-    std::vector<int> ids;
-    if (c->slab) {
-        const GridDesc &g = c->grid;
-        for (int i = 0; i < n; ++i) {
-            bool keep = property[i] >= 2 && property[i] < 4;
-            if (!keep) {
-                int cx = ((int)std::floor((position[3 * (size_t)i] - g.mn0g) / g.cellw)) % g.nxg; // :1671
-                cx = (cx % g.nxg + g.nxg) % g.nxg;
-                cx -= g.xoff;
-                if (cx < 0) cx += g.nxg; else if (cx >= g.nxg) cx -= g.nxg;
-                keep = cx >= g.range && cx < g.nx - g.range;
-            }
-            if (keep) ids.push_back(i);
-        }
-    }
-    const int nloc = c->slab ? (int)ids.size() : n;
     const bool first = !c->uploaded;
     if (first) {
         c->n_global = n;
@@ -1187,7 +1174,7 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         c->nmax = c->cap;
         if (nloc > c->cap) { set_last_error("slab capacity too small for the initial particle set"); return MPHX_ERR_NOMEM; }
         const size_t cap = (size_t)c->cap;
-        std::memcpy(c->ranges, r, sizeof(r));
+        std::memcpy(c->ranges, r, sizeof(int) * 6);
         c->nf = r[0] >= 0 ? r[1] - r[0] : 0;
         c->ns = r[2] >= 0 ? r[3] - r[2] : 0;
         c->nw = r[4] >= 0 ? r[5] - r[4] : 0;
@@ -1237,6 +1224,63 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         if (ns > 0)
             for (double **q : st) CK(cudaMemsetAsync(*q, 0, sizeof(double) * 9 * ns, c->stream));
     }
+    return MPHX_OK;
+}
+
+// device staging arrays (original order, AoS) -> the context's slots and solid arrays; frees nothing
+static int upload_finish(Ctx *c, int nloc, const int *d_ids, const int *d_t, const double *d_x, const double *d_x0, const double *d_v)
+{
+    if (nloc > 0) LAUNCH(c, k_upload_split, nblk(nloc), kBlock, nloc, d_ids, d_t, d_x, d_v, c->S, c->sol.slot, c->sol.sb);
+    if (c->ns > 0) LAUNCH(c, k_solid_upload, nblk(c->ns), kBlock, c->sol, d_t, d_x, d_x0, d_v);
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    CK(cudaMemcpy(&c->ctl->n, &nloc, sizeof(int), cudaMemcpyHostToDevice));
+    c->uploaded = true;
+    c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
+    { int rrc = request_rebuild(c); if (rrc) return rrc; } // (state replaced: the next step rebuilds buckets and list)
+    CK(cudaStreamSynchronize(c->stream));
+    return MPHX_OK;
+}
+
+int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *position,
+                const double *initial_position, const double *velocity)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || n <= 0 || !property || !position || !initial_position || !velocity) return MPHX_ERR_INVALID;
+    if (c->uploaded && n != c->n_global) return MPHX_ERR_INVALID; // re-upload must keep the particle count
+    if (c->uploaded && c->slab) { set_last_error("re-upload is not supported on a slab context"); return MPHX_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
+    for (int i = 0; i < n; ++i)
+        if (property[i] < 0 || property[i] >= kTypeCount) { set_last_error("particle type outside 0..5"); return MPHX_ERR_INVALID; }
+    int r[6];
+    mphx_class_ranges(n, property, r);
+    // each class must be one contiguous block of the file order, as the reference's range loops
+    // (src/main.cpp:909-929, e.g. :2922, :2442) assume
+    for (int cls = 0; cls < 3; ++cls)
+        for (int i = std::max(r[2 * cls], 0); i < r[2 * cls + 1]; ++i) {
+            const int t = property[i];
+            const int k = t < 2 ? 0 : t < 4 ? 1 : 2;
+            if (k != cls) { set_last_error("particle classes are not contiguous in file order"); return MPHX_ERR_UNSUPPORTED; }
+        }
+    // slab mode: this context keeps the fluid/wall particles of its own columns and ALL solids
+    std::vector<int> ids;
+    if (c->slab) {
+        const GridDesc &g = c->grid;
+        for (int i = 0; i < n; ++i) {
+            bool keep = property[i] >= 2 && property[i] < 4;
+            if (!keep) {
+                int cx = ((int)std::floor((position[3 * (size_t)i] - g.mn0g) / g.cellw)) % g.nxg; // :1671
+                cx = (cx % g.nxg + g.nxg) % g.nxg;
+                cx -= g.xoff;
+                if (cx < 0) cx += g.nxg; else if (cx >= g.nxg) cx -= g.nxg;
+                keep = cx >= g.range && cx < g.nx - g.range;
+            }
+            if (keep) ids.push_back(i);
+        }
+    }
+    const int nloc = c->slab ? (int)ids.size() : n;
+    { int arc = upload_allocate(c, n, nloc, r); if (arc) return arc; }
     // stage the host arrays (global, original order), split to SoA on the device
     int *d_t = nullptr, *d_ids = nullptr;
     double *d_x = nullptr, *d_v = nullptr, *d_x0 = nullptr;
@@ -1252,18 +1296,97 @@ int mphx_upload(mphx_ctx *ctx, int n, const int *property, const double *positio
         CK(cudaMalloc(&d_ids, sizeof(int) * (size_t)std::max(nloc, 1)));
         CK(cudaMemcpyAsync(d_ids, ids.data(), sizeof(int) * (size_t)nloc, cudaMemcpyHostToDevice, c->stream));
     }
-    if (nloc > 0) LAUNCH(c, k_upload_split, nblk(nloc), kBlock, nloc, d_ids, d_t, d_x, d_v, c->S, c->sol.slot, c->sol.sb);
-    if (c->ns > 0) LAUNCH(c, k_solid_upload, nblk(c->ns), kBlock, c->sol, d_t, d_x, d_x0, d_v);
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaGetLastError());
+    const int frc = upload_finish(c, nloc, d_ids, d_t, d_x, d_x0, d_v);
     cudaFree(d_t); cudaFree(d_x); cudaFree(d_v); cudaFree(d_x0);
     if (d_ids) cudaFree(d_ids);
-    CK(cudaMemcpy(&c->ctl->n, &nloc, sizeof(int), cudaMemcpyHostToDevice));
-    c->uploaded = true;
-    c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
-    { int rrc = request_rebuild(c); if (rrc) return rrc; } // (state replaced: the next step rebuilds buckets and list)
-    CK(cudaStreamSynchronize(c->stream));
+    return frc;
+}
+
+// ---- device-side generator --------------------------------------------------------------
+// value after a printf("%e") / strtod round trip: what the solver reads from the generator's .grid text
+static double through_e(double v)
+{
+    char b[64];
+    std::snprintf(b, sizeof(b), "%e", v);
+    return std::strtod(b, nullptr);
+}
+// one axis of generator/generator.cpp:654-680: start at lower + spacing/2, accumulate `p += spacing` while p < upper - 0.49 spacing
+static void generator_axis(double lo, double hi, double space, std::vector<double> &out)
+{
+    const double width = hi - lo;
+    const int count = (int)std::round(width / space);
+    const double spacing = width / count;
+    for (double p = lo + 0.5 * spacing; p < hi - 0.49 * spacing; p += spacing) out.push_back(through_e(p));
+}
+static int generator_plan(const mphx_cuboid *cubs, int ncub, GenPlan &plan, std::vector<double> &axes, long long &total, int r[6])
+{
+    if (!cubs || ncub < 1 || ncub > kMaxCuboids) return MPHX_ERR_INVALID;
+    plan.count = ncub;
+    total = 0;
+    for (int k = 0; k < 6; ++k) r[k] = -1;
+    int last_cls = -1;
+    bool seen[3] = {false, false, false};
+    for (int q = 0; q < ncub; ++q) {
+        const mphx_cuboid &cb = cubs[q];
+        if (cb.type < 0 || cb.type >= kTypeCount || !(cb.spacing > 0.0)) return MPHX_ERR_INVALID;
+        GenCuboid &g = plan.c[q];
+        g.first = total; g.type = cb.type;
+        int cnt[3];
+        for (int d = 0; d < 3; ++d) {
+            const size_t before = axes.size();
+            generator_axis(cb.lower[d], cb.upper[d], cb.spacing, axes);
+            cnt[d] = (int)(axes.size() - before);
+            (d == 0 ? g.ax : d == 1 ? g.ay : g.az) = (int)before;
+            g.v[d] = through_e(cb.velocity[d]);
+        }
+        g.nx = cnt[0]; g.ny = cnt[1]; g.nz = cnt[2];
+        const long long np = (long long)cnt[0] * cnt[1] * cnt[2];
+        if (np <= 0) continue;
+        const int cls = cb.type < 2 ? 0 : cb.type < 4 ? 1 : 2;
+        // each class must be one contiguous block of the file order (src/main.cpp:909-929)
+        if (cls != last_cls && seen[cls]) { set_last_error("particle classes are not contiguous in cuboid order"); return MPHX_ERR_UNSUPPORTED; }
+        seen[cls] = true; last_cls = cls;
+        if (r[2 * cls] < 0) r[2 * cls] = (int)total;
+        total += np;
+        r[2 * cls + 1] = (int)total;
+    }
+    if (total <= 0 || total > 0x7fffffffLL) return MPHX_ERR_INVALID;
     return MPHX_OK;
+}
+
+long long mphx_generate_count(const mphx_cuboid *cuboids, int ncuboids)
+{
+    GenPlan plan;
+    std::vector<double> axes;
+    long long total = 0;
+    int r[6];
+    return generator_plan(cuboids, ncuboids, plan, axes, total, r) == MPHX_OK ? total : -1;
+}
+
+int mphx_upload_generated(mphx_ctx *ctx, const mphx_cuboid *cuboids, int ncuboids)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || c->uploaded) return MPHX_ERR_INVALID;
+    if (c->slab) { set_last_error("mphx_upload_generated: single context only (slabs take host arrays)"); return MPHX_ERR_UNSUPPORTED; }
+    CK(cudaSetDevice(c->device));
+    GenPlan plan;
+    std::vector<double> axes;
+    long long total = 0;
+    int r[6];
+    int rc = generator_plan(cuboids, ncuboids, plan, axes, total, r);
+    if (rc) return rc;
+    const int n = (int)total;
+    if ((rc = upload_allocate(c, n, n, r))) return rc;
+    Scratch tmp;
+    int *d_t;
+    double *d_x, *d_x0, *d_v, *d_axes;
+    if (tmp.get(&d_t, (size_t)n) || tmp.get(&d_x, 3 * (size_t)n) || tmp.get(&d_x0, 3 * (size_t)n) || tmp.get(&d_v, 3 * (size_t)n) ||
+        tmp.get(&d_axes, axes.size()))
+        return MPHX_ERR_NOMEM;
+    CK(cudaMemcpyAsync(d_axes, axes.data(), sizeof(double) * axes.size(), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_generate, nblk(n), kBlock, (long long)n, plan, d_axes, d_t, d_x, d_x0, d_v);
+    CK(cudaGetLastError());
+    return upload_finish(c, n, nullptr, d_t, d_x, d_x0, d_v);
 }
 
 // replace Position and Velocity of every particle (original order) on an initialised context:
@@ -1309,6 +1432,14 @@ int mphx_get_constants(const mphx_ctx *ctx, mphx_constants *k)
     const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
     if (!c || !k) return MPHX_ERR_INVALID;
     *k = c->c;
+    return MPHX_OK;
+}
+
+int mphx_get_wall_centers(const mphx_ctx *ctx, double centers[MPHX_TYPE_COUNT][3])
+{
+    const Ctx *c = reinterpret_cast<const Ctx *>(ctx);
+    if (!c || !centers) return MPHX_ERR_INVALID;
+    std::memcpy(centers, c->wall_center, sizeof(double) * 3 * MPHX_TYPE_COUNT);
     return MPHX_OK;
 }
 

@@ -46,6 +46,9 @@ def _load():
     L.mphx_free_host.restype = None
     L.mphx_write_prof_file.argtypes = [C.c_char_p, C.c_double, C.POINTER(abi.Params), C.c_int, vp, vp, vp, vp]
     L.mphx_write_vtk_file.argtypes = [C.c_char_p, C.c_int, vp, C.POINTER(abi.HostViews)]
+    L.mphx_write_checkpoint.argtypes = [C.c_char_p, C.c_double, C.POINTER(abi.Params), C.c_int, vp, vp, vp, vp]
+    L.mphx_read_checkpoint.argtypes = [C.c_char_p, C.POINTER(abi.Params), ip, C.POINTER(ip), C.POINTER(dp), C.POINTER(dp), C.POINTER(dp)]
+    L.mphx_get_wall_centers.argtypes = [vp, vp]
     L.mphx_class_ranges.argtypes = [C.c_int, vp, C.POINTER(C.c_int * 6)]
     L.mphx_class_ranges.restype = None
     L.mphx_compute_constants.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Constants)]
@@ -53,6 +56,9 @@ def _load():
     L.mphx_destroy.argtypes = [vp]
     L.mphx_destroy.restype = None
     L.mphx_upload.argtypes = [vp, C.c_int, vp, vp, vp, vp]
+    L.mphx_generate_count.argtypes = [vp, C.c_int]
+    L.mphx_generate_count.restype = C.c_longlong
+    L.mphx_upload_generated.argtypes = [vp, vp, C.c_int]
     L.mphx_upload_state.argtypes = [vp, vp, vp]
     L.mphx_init.argtypes = [vp]
     L.mphx_get_constants.argtypes = [vp, C.POINTER(abi.Constants)]
@@ -166,6 +172,30 @@ def write_prof_file(fn: str, time: float, p: abi.Params, property, position, ini
                                                          x.ctypes.data, x0.ctypes.data, v.ctypes.data))
 
 
+def write_checkpoint(fn: str, time: float, p: abi.Params, property, position, initial_position, velocity):
+    """lossless binary checkpoint (mphx_write_checkpoint)"""
+    t = np.ascontiguousarray(property, dtype=np.int32)
+    x, x0, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (position, initial_position, velocity))
+    _ck("mphx_write_checkpoint", lib.mphx_write_checkpoint(fn.encode(), time, C.byref(p), t.shape[0], t.ctypes.data, x.ctypes.data,
+                                                           x0.ctypes.data, v.ctypes.data))
+
+
+def read_checkpoint(fn: str, p: abi.Params):
+    """fills time0 / dim / spacing / domain / wall_center of p; returns (type, x, x0, v)"""
+    n = C.c_int()
+    t = C.POINTER(C.c_int)()
+    x, x0, v = (C.POINTER(C.c_double)() for _ in range(3))
+    _ck("mphx_read_checkpoint", lib.mphx_read_checkpoint(fn.encode(), C.byref(p), C.byref(n), C.byref(t), C.byref(x), C.byref(x0), C.byref(v)))
+    N = n.value
+    try:
+        T = np.ctypeslib.as_array(t, shape=(N,)).copy()
+        X, X0, V = (np.ctypeslib.as_array(q, shape=(N, 3)).copy() for q in (x, x0, v))
+    finally:
+        for q in (t, x, x0, v):
+            lib.mphx_free_host(C.cast(q, C.c_void_p))
+    return T, X, X0, V
+
+
 def _views(n: int, fields: dict):
     hv = abi.HostViews()
     keep = {}
@@ -195,6 +225,20 @@ def class_ranges(property) -> list:
     r = (C.c_int * 6)()
     lib.mphx_class_ranges(t.shape[0], t.ctypes.data, C.byref(r))
     return list(r)
+
+
+def _cuboid_array(cuboids):
+    arr = (abi.CuboidC * len(cuboids))()
+    for q, cb in enumerate(cuboids):
+        arr[q].type, arr[q].spacing = int(cb.type), float(cb.spacing)
+        for d in range(3):
+            arr[q].lower[d], arr[q].upper[d], arr[q].velocity[d] = float(cb.lower[d]), float(cb.upper[d]), float(cb.velocity[d])
+    return arr
+
+
+def generate_count(cuboids) -> int:
+    """particles a list of cases.Cuboid holds under the generator's lattice rule (host only)"""
+    return int(lib.mphx_generate_count(C.cast(_cuboid_array(cuboids), C.c_void_p), len(cuboids)))
 
 
 def device_count() -> int:
@@ -258,6 +302,12 @@ class Solver:
                                            v.ctypes.data))
         self.n = t.shape[0]
 
+    def upload_generated(self, cuboids):
+        """device-side generator: cuboids = cases.Cuboid list in file order (mphx_upload_generated)"""
+        arr = _cuboid_array(cuboids)
+        _ck("mphx_upload_generated", lib.mphx_upload_generated(self._ctx, C.cast(arr, C.c_void_p), len(cuboids)))
+        self.n = int(lib.mphx_generate_count(C.cast(arr, C.c_void_p), len(cuboids)))
+
     def upload_state(self, position, velocity):
         """per-step H2D of Position/Velocity (original order); arrays must stay alive until sync"""
         assert position.dtype == np.float64 and velocity.dtype == np.float64
@@ -303,6 +353,21 @@ class Solver:
         a = (C.c_int * 8)()
         _ck("mphx_get_status", lib.mphx_get_status(self._ctx, C.byref(a)))
         return dict(err=a[0], slots=a[1], builds=a[2], reuses=a[3], age=a[4], skin_on=a[5], solid_multi_occupancy=a[6], ghosts=a[7])
+
+    def wall_centers(self):
+        a = ((C.c_double * 3) * abi.TYPE_COUNT)()
+        _ck("mphx_get_wall_centers", lib.mphx_get_wall_centers(self._ctx, C.cast(a, C.c_void_p)))
+        return np.array([[a[t][d] for d in range(3)] for t in range(abi.TYPE_COUNT)])
+
+    def checkpoint(self, fn: str, property, initial_position):
+        """write the state of this context (Position, Velocity, Time, wall centres) to a lossless checkpoint"""
+        g = self.download("position", "velocity")
+        p = self.params.copy()
+        wc = self.wall_centers()
+        for t in range(abi.TYPE_COUNT):
+            for d in range(3):
+                p.wall_center[t][d] = wc[t][d]
+        write_checkpoint(fn, self.time, p, property, g["position"], initial_position, g["velocity"])
 
     def constants(self) -> abi.Constants:
         k = abi.Constants()

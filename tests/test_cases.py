@@ -66,3 +66,11 @@ def test_lattice_rule_matches_reference_generator(tmp_path):
     mine = tmp_path / "mine.grid"
     cases.write_grid_file(str(mine), c)
     assert open(mine, "rb").read() == open(tmp_path / "t.grid", "rb").read()
+
+
+def test_generator_count_matches_the_lattice_rule():
+    """mphx_generate_count (host part of the device-side generator) counts what cases.py builds"""
+    from particlemethod_fsi_b200 import solver
+    for c in (cases.dam2d(), cases.fsi3d_mini(), cases.tiny2d(), cases.bar2d()):
+        assert solver.generate_count(c.cuboids) == c.n, c.name
+    assert solver.generate_count([cases.Cuboid(9, (0, 0, 0), (1, 1, 1), 0.1)]) == -1     # invalid type

@@ -261,6 +261,27 @@ def test_virial_stress_matches_oracle(name, st):
     o.close()
 
 
+@pytest.mark.parametrize("module", ["turek", "rolling1", "hydro", "rolling2", "rollwall"])
+def test_other_reference_variants_match_oracle(module):
+    """Turek_Hron / Rolling1 / Hydroelastic / Rolling2 clamps and the rolling wall (`#define Rolling`) as
+    run-time modules.  The solid path and the wall kinematics are bit-exact, the fluid 1e-10."""
+    case = cases.module_case(module)
+    o = Oracle.from_case(case)
+    o.init()
+    s = Solver.from_case(case)
+    s.step(20, sync=True)
+    o.step(20)
+    got = check_fields(case, s, o.get, ("module", module))
+    assert np.array_equal(got["cell_index"], o.cell_of_particle())
+    if module == "rollwall":
+        w = case.property >= 4
+        g2 = s.download("position", "velocity")
+        assert np.array_equal(g2["position"][w], o.get("Position")[w]) and np.array_equal(g2["velocity"][w], o.get("Velocity")[w])
+        assert np.abs(g2["position"][w] - case.position[w]).max() > 0
+    s.close()
+    o.close()
+
+
 def test_moving_wall_and_periodic_wrap_are_bit_exact():
     """calculateWall (:3036-3060) and calculatePeriodicBoundary (:3330) use explicitly rounded ops"""
     case = cases.tiny2d()
@@ -355,6 +376,71 @@ def test_list_reuse_with_fast_flow_matches_oracle():
     assert st["builds"] > 40 and st["err"] == 0, st
     s.close()
     o.close()
+
+
+def test_restart_from_checkpoint_is_bit_identical(tmp_path):
+    """12 steps, lossless checkpoint, a new context from the file, 8 more steps == 20 steps in one go,
+    bit for bit (walls moving, so the wall centres must travel too).  Lists are rebuilt every step on both sides: a reused
+    list keeps the particle order of its build step, which a restart cannot know (then the difference is 1e-13)."""
+    case = cases.tiny2d()
+    case.params.wall_velocity[4][0] = 0.3
+    case.params.wall_center[4][0] = 0.05
+    a = Solver.from_case(case, list_reuse=False)
+    a.step(12, sync=True)
+    fn = str(tmp_path / "restart.ckp")
+    a.checkpoint(fn, case.property, case.initial_position)
+    a.step(8, sync=True)
+    want = a.download("position", "velocity", "pressure_p", "stress")
+    p = case.params.copy()
+    t, x, x0, v = solver.read_checkpoint(fn, p)
+    assert abs(p.time0 - 12 * case.params.dt) < 1e-15 and p.wall_center[4][0] != case.params.wall_center[4][0]
+    b = Solver(p)
+    b.set_list_reuse(False)
+    b.upload(t, x, x0, v)
+    b.init()
+    b.step(8, sync=True)
+    got = b.download("position", "velocity", "pressure_p", "stress")
+    for f in want:
+        assert np.array_equal(want[f], got[f]), (f, float(np.abs(want[f] - got[f]).max()))
+    assert b.time == a.time
+    # with list reuse on (the default) the restarted run differs only by the order of the sums
+    c = Solver.from_case(case)
+    c.step(12, sync=True)
+    c.checkpoint(fn, case.property, case.initial_position)
+    c.step(8, sync=True)
+    p2 = case.params.copy()
+    t, x, x0, v = solver.read_checkpoint(fn, p2)
+    d = Solver(p2)
+    d.upload(t, x, x0, v)
+    d.init()
+    d.step(8, sync=True)
+    wc, wd = c.download("position", "velocity"), d.download("position", "velocity")
+    for f in wc:
+        assert rel_err(wd[f], wc[f]) <= 1e-12, f
+    for s_ in (a, b, c, d):
+        s_.close()
+
+
+@pytest.mark.parametrize("name", ["dam2d", "fsi3d_mini"])
+def test_device_side_generator_equals_the_generated_grid(name):
+    """mphx_upload_generated fills the generator's lattice (generator/generator.cpp:654-680, through the
+    `%e` text) on the device; the particle set -- and therefore the run -- equals uploading the .grid arrays, bit for bit"""
+    case = getattr(cases, name)()
+    a = Solver.from_case(case)
+    b = Solver(case.params)
+    b.upload_generated(case.cuboids)
+    assert b.n == case.n
+    b.init()
+    g0 = b.download("property", "position", "velocity")
+    assert np.array_equal(g0["property"], case.property)
+    assert np.array_equal(g0["position"], case.position) and np.array_equal(g0["velocity"], case.velocity)
+    a.step(10, sync=True)
+    b.step(10, sync=True)
+    fa, fb = a.download("position", "velocity", "pressure_p", "stress"), b.download("position", "velocity", "pressure_p", "stress")
+    for f in fa:
+        assert np.array_equal(fa[f], fb[f]), f
+    a.close()
+    b.close()
 
 
 def test_scale_properties_3d_300k():

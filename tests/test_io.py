@@ -4,6 +4,7 @@ import gzip
 import os
 
 import numpy as np
+import pytest
 
 from conftest import GOLDEN
 from particlemethod_fsi_b200 import abi, cases, solver
@@ -91,3 +92,30 @@ def test_vtk_writer_is_byte_identical_to_reference_text(tmp_path):
         o.step(3)   # t003.vtk after the 4th step
         assert emit(str(tmp_path / "b.vtk")) == _gold(f"{name}_t003.vtk")
         o.close()
+
+
+def test_checkpoint_round_trip_is_lossless(tmp_path):
+    """the binary checkpoint keeps every bit (the .prof text keeps 7 digits) and the wall centres"""
+    from particlemethod_fsi_b200 import abi, cases, solver
+    c = cases.tiny3d()
+    rng = np.random.default_rng(12345)
+    x = c.position + rng.uniform(-1e-4, 1e-4, c.position.shape) * np.pi      # not representable in 7 digits
+    v = rng.standard_normal(c.velocity.shape)
+    p = c.params.copy()
+    p.wall_center[4][0], p.wall_center[5][2] = 0.123456789012345, -7.0 / 3.0
+    fn = str(tmp_path / "s.ckp")
+    solver.write_checkpoint(fn, 0.0123456789, p, c.property, x, c.initial_position, v)
+    q = abi.Params()
+    t, x2, x02, v2 = solver.read_checkpoint(fn, q)
+    assert np.array_equal(t, c.property) and np.array_equal(x2, x) and np.array_equal(x02, c.initial_position) and np.array_equal(v2, v)
+    assert q.time0 == 0.0123456789 and q.dim == 3 and q.particle_spacing == p.particle_spacing
+    assert list(q.domain_min) == list(p.domain_min) and list(q.domain_max) == list(p.domain_max)
+    assert q.wall_center[4][0] == 0.123456789012345 and q.wall_center[5][2] == -7.0 / 3.0
+    # the text format of the reference loses the state (this is why the checkpoint exists)
+    solver.write_prof_file(str(tmp_path / "s.prof"), 0.0, p, c.property, x, c.initial_position, v)
+    _time, _hdr, _t, xp, _x0, _v = cases.read_grid_file(str(tmp_path / "s.prof"))
+    assert not np.array_equal(xp, x)
+    with open(str(tmp_path / "bad.ckp"), "wb") as f:
+        f.write(b"not a checkpoint")
+    with pytest.raises(solver.MphxError):
+        solver.read_checkpoint(str(tmp_path / "bad.ckp"), q)

@@ -93,6 +93,39 @@ def test_oracle_stage_by_stage_vs_live_reference(name, variant, steps, tmp_path)
     o.close()
 
 
+@pytest.mark.skipif(not REF_PRESENT, reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("module", ["turek", "rolling1", "hydro", "rolling2", "rollwall"])
+def test_oracle_other_modules_vs_live_reference(module, tmp_path):
+    """the reference's other compile-time variants (Turek_Hron, Rolling1, Hydroelastic, Rolling2 clamps of
+    updateElasticPosition :1910-2082; the rolling wall of `#define Rolling` :2958-3031), each compiled from the untouched
+    source by oracle/build_ref.sh, against the oracle's restatement: bit for bit over 5 steps."""
+    from oracle.refharness import RefHarness
+    c = cases.module_case(module)
+    cases.write_grid_file(str(tmp_path / "c.grid"), c)
+    cases.write_data_file(str(tmp_path / "c.data"), c.params, c.rc)
+    h = RefHarness("2d_" + module, str(tmp_path / "c.data"), str(tmp_path / "c.grid"), nthreads=2)
+    h.init()
+    o = Oracle.from_case(c)
+    o.init()
+    x0 = c.initial_position
+    solid = (c.property >= 2) & (c.property < 4)
+    if module != "rollwall":      # the clamp really splits the plate
+        from particlemethod_fsi_b200 import abi
+        cl = {abi.MODULE_TUREK_HRON: x0[:, 0] < 0.205, abi.MODULE_ROLLING1: x0[:, 1] < 0.003,
+              abi.MODULE_HYDROELASTIC: (x0[:, 0] < 0.01) | (x0[:, 0] > 1.99), abi.MODULE_ROLLING2: x0[:, 1] > 0.3420}[c.params.clamp_module]
+        assert 0 < int((cl & solid).sum()) < int(solid.sum())
+    for _ in range(5):
+        h.step(1)
+        o.step(1)
+        for f in ["Position", "Velocity", "Force", "PressureP", "Stress", "NeighborCount"]:
+            assert np.array_equal(h.get(f), o.get(f)), (module, f)
+    if module == "rollwall":
+        w = c.property >= 4
+        assert np.abs(o.get("Position")[w] - c.position[w]).max() > 0   # the walls did move
+    h.close()
+    o.close()
+
+
 def test_oracle_surface_tension_path_runs_and_is_symmetric_free():
     """surface tension on: PressureA / diffuse-interface forces are exercised (all shipped data has 0)"""
     c = cases.tiny2d()
