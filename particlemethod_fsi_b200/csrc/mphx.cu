@@ -22,6 +22,7 @@
 #include "sweep.cuh"
 #include "sweep_pair.cuh"
 #include "virial.cuh"
+#include "brick.cuh"
 #include "mphx.h"
 #include "mphx_internal.h"
 
@@ -102,6 +103,11 @@ struct Ctx {
     PairList pl{};         // candidate list (nbr == nullptr: disabled, both passes walk the buckets)
     int list_cap = -1;     // list slots per particle (-1: default by dimension, 0: no list)
     bool filter2 = true;   // build the lists two particles per thread (k_filter2, sweep_pair.cuh)
+    // pass 1 with the neighbourhood staged in shared memory, one block per brick of buckets (brick.cuh; MPHX_BRICK=1)
+    bool brick = false;
+    int *lnbr = nullptr;                 // the candidate list re-indexed to brick-local positions
+    unsigned char *brick_ok = nullptr, *in_brick = nullptr;
+    int nbricks = 0;
     // candidate-list reuse (internal Verlet skin): the list is built with radius + skin and serves until a
     // particle has moved skin/2 from its build position (decided on the device, k_decide)
     bool list_reuse = true;
@@ -376,7 +382,7 @@ static void preload_kernels(int dim)
     preload(k_advance_n); preload(k_halo_pack); preload(k_halo_repack); preload(k_unpack_refresh); preload(k_slab_slots);
     preload(k_unpack_scalar); preload(k_solid_owned_list); preload(k_solid_publish_P); preload(k_solid_spread_P);
     preload(k_solid_publish_V); preload(k_solid_apply_update); preload(k_scan_reduce); preload(k_scan_top); preload(k_scan_apply);
-    preload(k_scatter_index); preload(k_permute); preload(k_set_n);
+    preload(k_scatter_index); preload(k_permute); preload(k_set_n); preload(k_brick_localize); preload(k_brick_pass1<3>);
 #define PRELOAD_DIM(D)                                                                                                   \
     preload(k_filter<D>); preload(k_filter2<D, false>); preload(k_filter2<D, true>);                                     \
     preload(k_pass1_v3<D, false, false>); preload(k_pass1_v3<D, false, true>); preload(k_pass1_v3<D, true, false>);      \
@@ -536,12 +542,22 @@ static int run_pass1(Ctx *c, bool timed = false)
             else               LAUNCH(c, k_filter<2>, nblk(nmax, kSweepThreads), kSweepThreads, ctl, c->S, c->cellStart, c->grid, c->pl);
         }
     }
+    PairList pl1 = c->pl; // (pass 1's view of the list: with the staged path on, its particles are masked out of the list kernel)
+    if (c->brick && c->lnbr) {
+        LAUNCH(c, k_brick_localize, c->nbricks, 256, ctl, c->S, c->cellStart, c->grid, c->pl, c->lnbr, c->brick_ok, c->in_brick);
+        pl1.skip = c->in_brick;
+    }
     if (timed) timer_mark(c);
+    if (c->brick && c->lnbr) {
+        k_brick_pass1<3><<<c->nbricks, kBrickThreads, kBrickCap * (sizeof(Rec) + sizeof(double2)), c->stream>>>(
+            ctl, c->S, c->cellStart, c->grid, c->phys, c->pl, c->lnbr, c->brick_ok, c->P, c->volStrain, c->divP);
+        ++c->launches;
+    }
     // fused-sweep fall-backs: a small persistent grid when they only have to look at the overflow flag
     const int vblocks = nblk(nmax, kSweepThreads);
 #define SWEEP_GRID(LIST) ((LIST) || !c->pl.nbr ? vblocks : std::min(vblocks, 4 * 148))
 #define P1(D, ST, LIST) LAUNCH(c, (k_pass1_v3<D, ST, LIST>), SWEEP_GRID(LIST), kSweepThreads, ctl, c->S, c->cellStart, c->grid, c->phys, \
-                         batch, c->P, c->volStrain, c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA, c->pl)
+                         batch, c->P, c->volStrain, c->divP, c->densA, c->gcx, c->gcy, c->gcz, c->PA, pl1)
 #define P1D(ST, LIST) do { if (c->p.dim == 3) P1(3, ST, LIST); else P1(2, ST, LIST); } while (0)
     if (c->pl.nbr) { // list traversal, then the fused sweep for particles whose list overflowed (normally none)
         if (c->surface_tension) P1D(true, true); else P1D(false, true);
@@ -1129,6 +1145,8 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
     if (const char *e = std::getenv("MPHX_SWEEP_BATCH")) c->sweep_batch = std::max(1, std::atoi(e));
     if (const char *e = std::getenv("MPHX_LIST_CAP")) c->list_cap = std::max(0, std::atoi(e)); // 0: no list, fused sweeps
     if (const char *e = std::getenv("MPHX_FILTER2")) c->filter2 = std::atoi(e) != 0;           // 0: one particle per thread
+    if (const char *e = std::getenv("MPHX_BRICK")) c->brick = std::atoi(e) != 0;               // 1: pass 1 staged in shared memory (3D)
+    cudaFuncSetAttribute(k_brick_pass1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBrickCap * (sizeof(Rec) + sizeof(double2))));
     for (int k = 0; k < 2; ++k) cudaEventCreate(&c->tev[k]);
     if (const char *e = std::getenv("MPHX_OVERLAP_SOLID")) c->overlap_solid = std::atoi(e) != 0;
     {   // highest priority: the few blocks of a sub-step kernel must get SM slots as pass-2 blocks retire,
@@ -1192,6 +1210,12 @@ static int upload_allocate(Ctx *c, int n, int nloc, const int r[6])
                 e |= c->alloc(&c->pl.flags, 4);
                 c->pl.cap = (int)cap; c->pl.L = L;
             }
+        }
+        if (c->brick && c->pl.nbr && c->p.dim == 3 && !c->surface_tension && c->grid.range <= kBrickMaxRange) {
+            c->nbricks = brick_grid(c->grid).nbricks;
+            e |= c->alloc(&c->lnbr, ((size_t)c->pl.L + 1) * cap);
+            e |= c->alloc(&c->brick_ok, (size_t)c->nbricks); e |= c->alloc(&c->in_brick, cap);
+            if (!e) { cudaMemset(c->brick_ok, 0, (size_t)c->nbricks); cudaMemset(c->in_brick, 0, cap); }
         }
         e |= c->alloc(&c->cellCount, (size_t)c->grid.ncells + 2);
         e |= c->alloc(&c->cellStart, (size_t)c->grid.ncells + 3);

@@ -283,6 +283,7 @@ struct PairList {
     int *count;  // [cap] entries of particle i; L + 1 = overflowed (that particle is swept instead)
     int *flags;  // [0] != 0: some list overflowed in this step
     int cap, L;
+    const unsigned char *skip; // pass 1 only: skip[i] != 0 = particle i is handled by the staged kernel (brick.cuh)
 };
 
 // slab mode: ghosts and parked solids are only ever neighbours; a (replicated) solid is evaluated by the slab
@@ -423,6 +424,7 @@ pass1_block(int vblock, int n, Particles p, const int *__restrict__ cellStart, c
     if (pl.count) {
         mycount = pl.count[i];
         mine = mine && (LIST ? mycount <= pl.L : mycount > pl.L);
+        if (LIST && pl.skip && pl.skip[i]) mine = false; // done from shared memory by k_brick_pass1
         if (!LIST && !__syncthreads_or(mine ? 1 : 0)) return; // no overflowed particle in this block
     }
     const double xi = p.x[i], yi = p.y[i], zi = p.z[i];

@@ -443,6 +443,34 @@ def test_device_side_generator_equals_the_generated_grid(name):
     b.close()
 
 
+def test_staged_pass1_matches_list_kernel_and_oracle(monkeypatch):
+    """MPHX_BRICK=1: pass 1 of the interior bricks runs from shared memory (brick.cuh: halo staged by bulk async copies,
+    candidate list re-indexed to staged positions).  Same pairs, same order as the global-gather list kernel: identical
+    up to FMA contraction (1e-13), and 1e-10 against the oracle; jittered positions give ragged runs and 0..3 particles
+    per bucket; list reuse keeps the staged lists for several steps."""
+    case = _jittered(cases.fsi3d_for_count(1.0e5), 0.3)
+    ref = Solver.from_case(case)
+    ref.step(8, sync=True)
+    a = ref.download("position", "velocity", "pressure_p", "vol_strain_p", "divergence_p")
+    ref.close()
+    monkeypatch.setenv("MPHX_BRICK", "1")
+    s = Solver.from_case(case)
+    o = Oracle.from_case(case, max_neighbor_count=128)
+    o.init()
+    s.step(8, sync=True)
+    o.step(8)
+    b = s.download("position", "velocity", "pressure_p", "vol_strain_p", "divergence_p")
+    fp = pressure_floor(case, s.constants())
+    for f in a:
+        err, scale = record("staged_vs_list", f, b[f], a[f], fp if f == "pressure_p" else 0.0, 1e-13)
+        assert err <= 1e-13 * scale + (fp if f == "pressure_p" else 0.0), (f, err, scale)
+    check_fields(case, s, o.get, "staged_pass1_vs_oracle")
+    st = s.status()
+    assert st["err"] == 0 and st["reuses"] > 0, st
+    s.close()
+    o.close()
+
+
 def test_scale_properties_3d_300k():
     """size-independent properties at a size the oracle cannot do in seconds"""
     case = cases.fsi3d_for_count(3.0e5)
