@@ -54,27 +54,32 @@ __device__ __forceinline__ void brick_runs(BrickRuns &br, const GridDesc &g, con
     __syncthreads();
     if (br.edge) return;
     const int nry = br.nry, nruns = br.nruns;
-    for (int r = threadIdx.x; r < nruns; r += blockDim.x) {
+    // run lengths and their exclusive scans (block-wide shuffles scans: blockDim >= 256 covers the 196 runs in one go)
+    int len = 0, olen = 0;
+    const int r = threadIdx.x;
+    if (r < nruns) {
         const int cx = br.bx0 - R + r / nry, cy = br.by0 - R + r % nry;
         const int k0 = (cx * g.ny + cy) * g.nz + (br.bz0 - R);
-        const int s0 = cellStart[k0], s1 = cellStart[k0 + kBrick + 2 * R];
+        const int s0 = cellStart[k0];
         br.start[r] = s0;
-        br.off[r + 1] = s1 - s0; // (lengths; scanned below)
+        len = cellStart[k0 + kBrick + 2 * R] - s0;
     }
-    for (int o = threadIdx.x; o < kBrickOwnRuns; o += blockDim.x) {
-        const int cx = br.bx0 + o / kBrick, cy = br.by0 + o % kBrick;
+    if (r < kBrickOwnRuns) {
+        const int cx = br.bx0 + r / kBrick, cy = br.by0 + r % kBrick;
         const int k0 = (cx * g.ny + cy) * g.nz + br.bz0;
-        const int s0 = cellStart[k0], s1 = cellStart[k0 + kBrick];
-        br.own_beg[o] = s0;
-        br.own_off[o + 1] = s1 - s0;
+        const int s0 = cellStart[k0];
+        br.own_beg[r] = s0;
+        olen = cellStart[k0 + kBrick] - s0;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) { // (two short serial scans: 196 + 64 entries)
-        br.off[0] = 0;
-        for (int r = 0; r < nruns; ++r) br.off[r + 1] += br.off[r];
-        br.own_off[0] = 0;
-        for (int o = 0; o < kBrickOwnRuns; ++o) br.own_off[o + 1] += br.own_off[o];
-        if (br.off[nruns] > kBrickCap) br.edge = 1; // too many particles to stage
+    __shared__ int tot, otot;
+    const int ex = block_exclusive_scan(len, &tot);
+    const int oex = block_exclusive_scan(olen, &otot);
+    if (r < nruns) br.off[r] = ex;
+    if (r < kBrickOwnRuns) br.own_off[r] = oex;
+    if (r == 0) {
+        br.off[nruns] = tot;
+        br.own_off[kBrickOwnRuns] = otot;
+        if (tot > kBrickCap) br.edge = 1; // too many particles to stage
     }
     __syncthreads();
 }
@@ -91,11 +96,31 @@ __device__ __forceinline__ void brick_owned(const BrickRuns &br, int range, int 
     local = br.off[r] + (slot - br.start[r]);
 }
 
+// Rebuild steps: owned particles per brick (its exclusive scan, brick_base, is where the brick's rows of the staged
+// list start: the list is stored in BRICK order so that the threads of a brick read consecutive entries)
+__global__ void k_brick_count(const Ctl *ctl, const int *__restrict__ cellStart, GridDesc g, int nbricks, int *__restrict__ nown)
+{
+    if (!ctl->rebuild) return;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbricks) return;
+    const BrickGrid bg = brick_grid(g);
+    const int bz0 = (b % bg.nbz) * kBrick, t = b / bg.nbz, by0 = (t % bg.nby) * kBrick, bx0 = (t / bg.nby) * kBrick;
+    const int z1 = min(bz0 + kBrick, g.nz);
+    int cnt = 0;
+    for (int cx = bx0; cx < min(bx0 + kBrick, g.nx); ++cx)
+        for (int cy = by0; cy < min(by0 + kBrick, g.ny); ++cy) {
+            const int k0 = (cx * g.ny + cy) * g.nz;
+            cnt += cellStart[k0 + z1] - cellStart[k0 + bz0];
+        }
+    nown[b] = cnt;
+}
+
 // Rebuild steps: decide which bricks take the staged path (flag 1) and re-index their particles' candidate lists to
-// staged positions.  in_brick[i] = 1: particle i is handled by k_brick_pass1 (the list kernel skips it).
+// staged positions (16 bit), stored at the particle's rank in brick order.  in_brick[i] = 1: particle i is handled by
+// k_brick_pass1 (the list kernel skips it).
 __global__ void __launch_bounds__(256)
-k_brick_localize(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, GridDesc g, PairList pl, int *__restrict__ lnbr,
-                 unsigned char *__restrict__ brick_ok, unsigned char *__restrict__ in_brick)
+k_brick_localize(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, GridDesc g, PairList pl, unsigned short *__restrict__ lnbr,
+                 const int *__restrict__ brick_base, unsigned char *__restrict__ brick_ok, unsigned char *__restrict__ in_brick)
 {
     if (!ctl->rebuild) return;
     __shared__ BrickRuns br;
@@ -117,6 +142,7 @@ k_brick_localize(const Ctl *ctl, Particles p, const int *__restrict__ cellStart,
     nown = br.own_off[kBrickOwnRuns];
     if (threadIdx.x == 0) brick_ok[b] = nown > 0 ? 1 : 0; // (an empty brick launches a block that returns at once)
     const int per = g.ny * g.nz;
+    const size_t base = (size_t)brick_base[b];
     for (int t = threadIdx.x; t < nown; t += blockDim.x) {
         int i, li;
         brick_owned(br, R, t, i, li);
@@ -125,12 +151,11 @@ k_brick_localize(const Ctl *ctl, Particles p, const int *__restrict__ cellStart,
         in_brick[i] = listed ? 1 : 0;
         if (!listed) continue;
         for (int k = 0; k < cnt; ++k) {
-            const size_t e = (size_t)k * pl.cap + i;
-            const int j = pl.nbr[e];
+            const int j = pl.nbr[(size_t)k * pl.cap + i];
             const int kj = p.key[j];
             const int cx = kj / per, cy = (kj / g.nz) % g.ny;
             const int r = (cx - (br.bx0 - R)) * br.nry + (cy - (br.by0 - R));
-            lnbr[e] = br.off[r] + (j - br.start[r]);
+            lnbr[(size_t)k * pl.cap + base + t] = (unsigned short)(br.off[r] + (j - br.start[r]));
         }
     }
 }
@@ -140,8 +165,9 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 // K5 "pass 1", staged: VolStrainP, DivergenceP -> PressureP for the owned particles of one interior brick.
 template <int DIM>
 __global__ void __launch_bounds__(kBrickThreads, 1)
-k_brick_pass1(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, PairList pl, const int *__restrict__ lnbr,
-              const unsigned char *__restrict__ brick_ok, double *__restrict__ P, double *__restrict__ volStrain, double *__restrict__ divP)
+k_brick_pass1(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, GridDesc g, Phys ph, PairList pl, const unsigned short *__restrict__ lnbr,
+              const int *__restrict__ brick_base, const unsigned char *__restrict__ brick_ok, double *__restrict__ P, double *__restrict__ volStrain,
+              double *__restrict__ divP)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Rec *sra = reinterpret_cast<Rec *>(smem_raw);                                   // [kBrickCap] x y z vx
@@ -199,7 +225,7 @@ k_brick_pass1(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, Gr
         const double2 ownv = svb[li];
         const double xi = own.a, yi = own.b, zi = own.c, vxi = own.d, vyi = ownv.x, vzi = ownv.y;
         double nP = 0.0, dv = 0.0;
-        const int *lp = lnbr + i;
+        const unsigned short *lp = lnbr + (size_t)brick_base[b] + t; // (brick order: the threads of a warp read consecutive entries)
         const size_t ls = (size_t)pl.cap;
         auto pair = [&](int lj) { // same straight-line form as k_pass1_v3 (a masked pair contributes exact zeros)
             const Rec a = sra[lj];
@@ -214,18 +240,20 @@ k_brick_pass1(const Ctl *ctl, Particles p, const int *__restrict__ cellStart, Gr
             const double ux = a.d - vxi, uy = bv.x - vyi, uz = bv.y - vzi;
             dv -= (ux * dx + uy * dy + uz * dz) * rinv * q;
         };
-        int k = 0;
-        int j0 = 0, j1 = 0;
-        if (cnt > 0) j0 = __ldcs(lp);
-        if (cnt > 1) j1 = __ldcs(lp + ls);
-        for (; k + 1 < cnt; k += 2) { // two pairs per trip; the next two list entries are fetched first
-            const int a_j = j0, b_j = j1;
-            if (k + 2 < cnt) j0 = __ldcs(lp + (size_t)(k + 2) * ls);
-            if (k + 3 < cnt) j1 = __ldcs(lp + (size_t)(k + 3) * ls);
-            pair(a_j);
-            pair(b_j);
+        // the list entries of the NEXT four pairs are in flight while four pairs are evaluated (the list streams from HBM;
+        // the neighbours themselves come from shared memory)
+        int jn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) jn[u] = u < cnt ? (int)__ldcs(lp + (size_t)u * ls) : li;
+        for (int k = 0; k < cnt; k += 4) {
+            int jc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) jc[u] = jn[u];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) jn[u] = k + 4 + u < cnt ? (int)__ldcs(lp + (size_t)(k + 4 + u) * ls) : li;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) pair(jc[u]); // (a padding entry is the particle itself: masked, exact zeros)
         }
-        if (k < cnt) pair(j0);
         nP *= ph.cwp;
         dv *= ph.cdp;
         const double vs = nP - ph.n0p;                        // :2339

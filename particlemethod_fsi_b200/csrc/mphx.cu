@@ -105,7 +105,9 @@ struct Ctx {
     bool filter2 = true;   // build the lists two particles per thread (k_filter2, sweep_pair.cuh)
     // pass 1 with the neighbourhood staged in shared memory, one block per brick of buckets (brick.cuh; MPHX_BRICK=1)
     bool brick = false;
-    int *lnbr = nullptr;                 // the candidate list re-indexed to brick-local positions
+    unsigned short *lnbr = nullptr;      // the candidate list re-indexed to brick-local positions, in brick order
+    int *brick_nown = nullptr, *brick_base = nullptr, *brick_sums = nullptr;
+    int brick_scan_blocks = 0;
     unsigned char *brick_ok = nullptr, *in_brick = nullptr;
     int nbricks = 0;
     // candidate-list reuse (internal Verlet skin): the list is built with radius + skin and serves until a
@@ -382,7 +384,7 @@ static void preload_kernels(int dim)
     preload(k_advance_n); preload(k_halo_pack); preload(k_halo_repack); preload(k_unpack_refresh); preload(k_slab_slots);
     preload(k_unpack_scalar); preload(k_solid_owned_list); preload(k_solid_publish_P); preload(k_solid_spread_P);
     preload(k_solid_publish_V); preload(k_solid_apply_update); preload(k_scan_reduce); preload(k_scan_top); preload(k_scan_apply);
-    preload(k_scatter_index); preload(k_permute); preload(k_set_n); preload(k_brick_localize); preload(k_brick_pass1<3>);
+    preload(k_scatter_index); preload(k_permute); preload(k_set_n); preload(k_brick_localize); preload(k_brick_count); preload(k_brick_pass1<3>);
 #define PRELOAD_DIM(D)                                                                                                   \
     preload(k_filter<D>); preload(k_filter2<D, false>); preload(k_filter2<D, true>);                                     \
     preload(k_pass1_v3<D, false, false>); preload(k_pass1_v3<D, false, true>); preload(k_pass1_v3<D, true, false>);      \
@@ -544,13 +546,17 @@ static int run_pass1(Ctx *c, bool timed = false)
     }
     PairList pl1 = c->pl; // (pass 1's view of the list: with the staged path on, its particles are masked out of the list kernel)
     if (c->brick && c->lnbr) {
-        LAUNCH(c, k_brick_localize, c->nbricks, 256, ctl, c->S, c->cellStart, c->grid, c->pl, c->lnbr, c->brick_ok, c->in_brick);
+        LAUNCH(c, k_brick_count, nblk(c->nbricks), kBlock, ctl, c->cellStart, c->grid, c->nbricks, c->brick_nown);
+        LAUNCH(c, k_scan_reduce, c->brick_scan_blocks, kScanThreads, ctl, c->brick_nown, c->nbricks, c->brick_sums);
+        LAUNCH(c, k_scan_top, 1, kScanThreads, ctl, c->brick_sums, c->brick_scan_blocks);
+        LAUNCH(c, k_scan_apply, c->brick_scan_blocks, kScanThreads, ctl, c->brick_nown, c->nbricks, c->brick_sums, c->brick_base, 0);
+        LAUNCH(c, k_brick_localize, c->nbricks, 256, ctl, c->S, c->cellStart, c->grid, c->pl, c->lnbr, c->brick_base, c->brick_ok, c->in_brick);
         pl1.skip = c->in_brick;
     }
     if (timed) timer_mark(c);
     if (c->brick && c->lnbr) {
         k_brick_pass1<3><<<c->nbricks, kBrickThreads, kBrickCap * (sizeof(Rec) + sizeof(double2)), c->stream>>>(
-            ctl, c->S, c->cellStart, c->grid, c->phys, c->pl, c->lnbr, c->brick_ok, c->P, c->volStrain, c->divP);
+            ctl, c->S, c->cellStart, c->grid, c->phys, c->pl, c->lnbr, c->brick_base, c->brick_ok, c->P, c->volStrain, c->divP);
         ++c->launches;
     }
     // fused-sweep fall-backs: a small persistent grid when they only have to look at the overflow flag
@@ -1215,6 +1221,9 @@ static int upload_allocate(Ctx *c, int n, int nloc, const int r[6])
             c->nbricks = brick_grid(c->grid).nbricks;
             e |= c->alloc(&c->lnbr, ((size_t)c->pl.L + 1) * cap);
             e |= c->alloc(&c->brick_ok, (size_t)c->nbricks); e |= c->alloc(&c->in_brick, cap);
+            c->brick_scan_blocks = (c->nbricks + kScanChunk - 1) / kScanChunk;
+            e |= c->alloc(&c->brick_nown, (size_t)c->nbricks); e |= c->alloc(&c->brick_base, (size_t)c->nbricks + 1);
+            e |= c->alloc(&c->brick_sums, (size_t)c->brick_scan_blocks + 1);
             if (!e) { cudaMemset(c->brick_ok, 0, (size_t)c->nbricks); cudaMemset(c->in_brick, 0, cap); }
         }
         e |= c->alloc(&c->cellCount, (size_t)c->grid.ncells + 2);
