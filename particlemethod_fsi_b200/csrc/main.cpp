@@ -166,7 +166,12 @@ int main(int argc, char *argv[])
     mphx_ctx *ctx = nullptr;    // single context, or slab 0 of the multi-GPU run (constants, timers)
     mphx_multi *multi = nullptr;
     if (ngpu > 1) {
-        if ((rc = mphx_multi_create(&multi, &p, ngpu, nullptr))) die("mphx_multi_create", rc);
+        // MPHX_DEVICES=0,1,2,... picks the devices (default 0..N-1; a device may repeat: slabs sharing one GPU)
+        std::vector<int> devs;
+        if (const char *ds = getenv("MPHX_DEVICES"))
+            for (const char *q = ds; *q;) { devs.push_back(atoi(q)); q = strchr(q, ','); if (!q) break; ++q; }
+        if (!devs.empty() && (int)devs.size() != ngpu) { log_printf("MPHX_DEVICES must list MPHX_NGPU devices\n"); exit(1); }
+        if ((rc = mphx_multi_create(&multi, &p, ngpu, devs.empty() ? nullptr : devs.data()))) die("mphx_multi_create", rc);
         ctx = mphx_multi_context(multi, 0);
     } else {
         rc = mphx_create(&ctx, &p, getenv("MPHX_DEVICE") ? atoi(getenv("MPHX_DEVICE")) : 0);

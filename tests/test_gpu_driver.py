@@ -66,3 +66,42 @@ def test_driver_outputs_match_reference_cli(name, dim, module, sync_io, tmp_path
     for key in ("neighbor search:", "explicit calculation:", "virial calculation:", "other calculation:", "total:",
                 "total (check):", "N0p ="):
         assert key in log
+
+
+def test_driver_on_several_slabs_writes_the_same_files(tmp_path):
+    """MPHX_NGPU: the same C++ main drives N slab contexts through mphx_multi_* (here two slabs sharing the one GPU of
+    the test box); the ring reproduces the single context bit for bit, so every output file is byte-identical.
+    Also: the virial sections behind MPHX_VTK_VIRIAL and the lossless checkpoint next to every .prof (MPHX_CHECKPOINT)."""
+    c = cases.tiny3d()
+    c.rc.end_time = 3.5 * c.params.dt
+    c.rc.output_interval = 2.0 * c.params.dt
+    c.rc.vtk_output_interval = 3.0 * c.params.dt
+    outs = {}
+    for tag, env in (("one", {}), ("two", dict(MPHX_NGPU="2", MPHX_DEVICES="0,0", CUDA_DEVICE_MAX_CONNECTIONS="32"))):
+        d = tmp_path / tag
+        d.mkdir()
+        cases.write_grid_file(str(d / "c.grid"), c)
+        cases.write_data_file(str(d / "t.data"), c.params, c.rc)
+        r = subprocess.run([EXE, "t.data", "c.grid", "t%03d.prof", "t%03d.vtk", "t.log", "4", "3", "dam"], cwd=d, capture_output=True,
+                           text=True, env=dict(os.environ, **env), timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = {f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.endswith((".prof", ".vtk"))}
+    assert list(outs["one"]) == list(outs["two"]) and len(outs["one"]) == 5
+    for f in outs["one"]:
+        assert outs["one"][f] == outs["two"][f], f
+    d = tmp_path / "virial"
+    d.mkdir()
+    cases.write_grid_file(str(d / "c.grid"), c)
+    cases.write_data_file(str(d / "t.data"), c.params, c.rc)
+    r = subprocess.run([EXE, "t.data", "c.grid", "t%03d.prof", "t%03d.vtk", "t.log", "4", "3", "dam"], cwd=d, capture_output=True, text=True,
+                       env=dict(os.environ, MPHX_VTK_VIRIAL="1", MPHX_CHECKPOINT="t%03d.ckp"), timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    vtk = (d / "t003.vtk").read_text()
+    assert "SCALARS VirialPressureAtParticle float 1" in vtk and "SCALARS VirialStressAtParticle[1][0] float 1" in vtk
+    assert vtk.replace("\r", "").count("\n") > outs["one"]["t003.vtk"].count(b"\n")
+    assert sorted(f for f in os.listdir(d) if f.endswith(".ckp")) == ["t000.ckp", "t002.ckp"]
+    # restart from the checkpoint of step 2: the run continues (Time and step index come from the file)
+    r = subprocess.run([EXE, "t.data", "t002.ckp", "r%03d.prof", "r%03d.vtk", "r.log", "4", "3", "dam"], cwd=d, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert (d / "r003.vtk").exists()
