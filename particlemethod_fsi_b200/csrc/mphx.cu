@@ -63,6 +63,10 @@ struct Ctx {
     size_t mailbox_bytes = 0;
     Mailbox mine{};
     Peers peers{};
+    // split solid sub-steps: this rank advances the solids [s_lo, s_hi) and stores P / u / the final state into the peers' arrays
+    bool split_substeps = true;
+    int s_lo = 0, s_hi = 0;
+    SolidRing ring{};
     void *peer_base[kMaxRanks] = {};
     bool peer_ipc[kMaxRanks] = {};
     double *stage_mig[2] = {nullptr, nullptr}, *stage_halo[2] = {nullptr, nullptr};
@@ -389,8 +393,10 @@ static void preload_kernels(int dim)
     preload(k_filter<D>); preload(k_filter2<D, false>); preload(k_filter2<D, true>);                                     \
     preload(k_pass1_v3<D, false, false>); preload(k_pass1_v3<D, false, true>); preload(k_pass1_v3<D, true, false>);      \
     preload(k_pass1_v3<D, true, true>); preload(k_pass2_v3<D, false, false>); preload(k_pass2_v3<D, false, true>);       \
-    preload(k_pass2_v3<D, true, false>); preload(k_pass2_v3<D, true, true>); preload(k_solid_pass1<D, false>);           \
-    preload(k_solid_pass2<D, false>); preload(k_solid_pass1<D, true>); preload(k_solid_pass2<D, true>)
+    preload(k_pass2_v3<D, true, false>); preload(k_pass2_v3<D, true, true>);                                             \
+    preload(k_solid_pass1<D, false, false>); preload(k_solid_pass2<D, false, false>); preload(k_solid_pass1<D, true, false>); \
+    preload(k_solid_pass2<D, true, false>); preload(k_solid_pass1<D, false, true>); preload(k_solid_pass2<D, false, true>); \
+    preload(k_solid_pass1<D, true, true>); preload(k_solid_pass2<D, true, true>)
     if (dim == 3) { PRELOAD_DIM(3); } else { PRELOAD_DIM(2); }
 #undef PRELOAD_DIM
     cudaGetLastError();
@@ -653,24 +659,41 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
     if (c->ns <= 0) return MPHX_OK;
     const int substeps = (int)(c->p.dt / c->p.elastic_dt + 0.5); // :653
     const mphx_constants &k = c->c;
-    const double cw = c->cw_tl;
     const int ns = c->ns;
     // Q1: the second position update is the `#else` tail of the Rolling2 block (:2070-2079): every variant but Rolling2
     const int dbl = ((c->p.ref_compat & MPHX_COMPAT_DOUBLE_UPDATE) && c->p.clamp_module != MPHX_MODULE_ROLLING2) ? 1 : 0;
-    if (c->slab) { // every rank takes the owners' coupled velocities, then runs the identical sub-steps
+    // slab mode: the owners' coupled velocities arrive, then either every rank runs identical sub-steps of all solids, or
+    // (split sub-steps, the default) every rank advances its share [s_lo, s_hi) and the ranks trade P and u after every
+    // pass: 2 * substeps phases, counted by epoch * kSubPhases + phase in every rank's fsub flags
+    const bool ring = c->slab && c->split_substeps;
+    SolidRing rg = c->ring;
+    if (!ring) rg.nranks = 0;
+    if (ring && 2 * substeps + 1 >= kSubPhases) { set_last_error("too many solid sub-steps per step for the split exchange"); return MPHX_ERR_UNSUPPORTED; }
+    const unsigned long long seq0 = c->epoch * (unsigned long long)kSubPhases;
+    if (c->slab) {
         LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, c->epoch, c->mine.fsolV, c->nranks, kWaitSolV);
-        LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV);
+        LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV, c->s_lo, c->s_hi, c->p.clamp_module);
     }
-#define SOLID_STEP(D, PK)                                                                                                                 \
-    do {                                                                                                                                    \
-        LAUNCH_ON(c, strm, (k_solid_pass1<D, PK>), nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw); \
-        LAUNCH_ON(c, strm, (k_solid_pass2<D, PK>), nblk(ns), kBlock, c->sol, k.domain_width[0], k.domain_width[1], k.domain_width[2], k.radius_p, cw, \
-                  c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density);                                                               \
+    const int cnt = c->s_hi - c->s_lo;
+    const int grid = ring ? std::max(nblk(cnt), 1) : nblk(cnt); // (an empty share still posts its phase counters)
+#define SOLID_STEP(D, PK, RG)                                                                                                          \
+    do {                                                                                                                                 \
+        LAUNCH_ON(c, strm, (k_solid_pass1<D, PK, RG>), grid, kBlock, c->ctl, c->sol, c->s_lo, c->s_hi, rg);                               \
+        if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
+        ++rg.seq;                                                                                                                        \
+        LAUNCH_ON(c, strm, (k_solid_pass2<D, PK, RG>), grid, kBlock, c->ctl, c->sol, c->s_lo, c->s_hi, k.domain_width[0],                 \
+                  k.domain_width[1], k.domain_width[2], c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density, rg);                  \
+        if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
+        ++rg.seq;                                                                                                                        \
     } while (0)
+#define SOLID_STEP_D(D) do { if (c->sol.packed) { if (ring) SOLID_STEP(D, true, true); else SOLID_STEP(D, true, false); } \
+                             else { if (ring) SOLID_STEP(D, false, true); else SOLID_STEP(D, false, false); } } while (0)
+    rg.seq = seq0 + 1;
     for (int s = 0; s < substeps; ++s) {
-        if (c->p.dim == 3) { if (c->sol.packed) SOLID_STEP(3, true); else SOLID_STEP(3, false); }
-        else               { if (c->sol.packed) SOLID_STEP(2, true); else SOLID_STEP(2, false); }
+        rg.last = s == substeps - 1 ? 1 : 0;
+        if (c->p.dim == 3) SOLID_STEP_D(3); else SOLID_STEP_D(2);
     }
+#undef SOLID_STEP_D
 #undef SOLID_STEP
     CK(cudaGetLastError());
     return MPHX_OK;
@@ -940,6 +963,27 @@ static int init_solid(Ctx *c)
         for (int s = 0; s < ns; ++s)
             for (int k = off32[s]; k < off32[s + 1]; ++k) rnbr[fill[ids[k]]++] = s;
     }
+    // split sub-steps (slab mode): which ranks' rows read solid j -- rank(i) for every i whose own row lists j (pass 1
+    // gathers u_j) or whose transposed row lists j (pass 2 gathers P_j); the rank advancing j itself needs no copy
+    if (c->slab && c->split_substeps) {
+        auto rank_of = [&](int s) { // inverse of s_lo = ns * r / nranks
+            int r = (int)(((long long)s * c->nranks + c->nranks - 1) / ns);
+            r = std::min(std::max(r, 0), c->nranks - 1);
+            while (r > 0 && s < (int)((long long)ns * r / c->nranks)) --r;
+            while (r < c->nranks - 1 && s >= (int)((long long)ns * (r + 1) / c->nranks)) ++r;
+            return r;
+        };
+        std::vector<int> rk((size_t)ns);
+        for (int s = 0; s < ns; ++s) rk[s] = rank_of(s);
+        std::vector<unsigned short> pm((size_t)ns, 0);
+        for (int i = 0; i < ns; ++i) {
+            for (int q = off32[i]; q < off32[i + 1]; ++q) pm[ids[q]] |= (unsigned short)(1u << rk[i]);
+            for (int q = roff[i]; q < roff[i + 1]; ++q) pm[rnbr[q]] |= (unsigned short)(1u << rk[i]);
+        }
+        for (int s = 0; s < ns; ++s) pm[s] &= (unsigned short)~(1u << rk[s]);
+        if (c->alloc(&c->sol.pmask, (size_t)ns)) return MPHX_ERR_NOMEM;
+        CK(cudaMemcpy(c->sol.pmask, pm.data(), sizeof(unsigned short) * (size_t)ns, cudaMemcpyHostToDevice));
+    }
     int e = 0;
     e |= c->alloc(&c->sol.off, (size_t)ns + 1); e |= c->alloc(&c->sol.nbr, (size_t)total);
     e |= c->alloc(&c->sol.roff, (size_t)ns + 1); e |= c->alloc(&c->sol.rnbr, (size_t)total);
@@ -1155,6 +1199,7 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
     cudaFuncSetAttribute(k_brick_pass1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBrickCap * (sizeof(Rec) + sizeof(double2))));
     for (int k = 0; k < 2; ++k) cudaEventCreate(&c->tev[k]);
     if (const char *e = std::getenv("MPHX_OVERLAP_SOLID")) c->overlap_solid = std::atoi(e) != 0;
+    if (const char *e = std::getenv("MPHX_SPLIT_SUBSTEPS")) c->split_substeps = std::atoi(e) != 0; // 0: every slab runs all solids' sub-steps
     {   // highest priority: the few blocks of a sub-step kernel must get SM slots as pass-2 blocks retire,
         // not after the whole pass-2 grid has been issued
         int lo = 0, hi = 0;
@@ -1241,21 +1286,38 @@ static int upload_allocate(Ctx *c, int n, int nloc, const int r[6])
         Solid &so = c->sol;
         so.ns = c->ns; so.sb = c->ns > 0 ? r[2] : 0;
         const size_t ns = (size_t)c->ns;
-        double **sv[] = {&so.x, &so.y, &so.z, &so.vx, &so.vy, &so.vz, &so.x0, &so.y0, &so.z0, &so.fx, &so.fy, &so.fz, &so.lam, &so.mu};
+        c->s_lo = 0; c->s_hi = c->ns;
+        if (c->slab) { // the mailbox first: the solid arrays other ranks store into (x, v, u, P) live inside it
+            int src = slab_allocate(c);
+            if (src) return src;
+            so.x = c->mine.sxv[0]; so.y = c->mine.sxv[1]; so.z = c->mine.sxv[2];
+            so.vx = c->mine.sxv[3]; so.vy = c->mine.sxv[4]; so.vz = c->mine.sxv[5];
+            so.u = c->mine.su; so.PkA = c->mine.sPk;
+            if (c->split_substeps) { // equal shares of the static solid order
+                c->s_lo = (int)((long long)c->ns * c->rank / c->nranks);
+                c->s_hi = (int)((long long)c->ns * (c->rank + 1) / c->nranks);
+            }
+        } else {
+            double **sx[] = {&so.x, &so.y, &so.z, &so.vx, &so.vy, &so.vz};
+            for (double **q : sx) e |= c->alloc(q, ns);
+            e |= c->alloc(&so.u, ns);
+            e |= c->alloc(&so.PkA, 9 * ns);
+        }
+        double **sv[] = {&so.x0, &so.y0, &so.z0, &so.fx, &so.fy, &so.fz, &so.lam, &so.mu};
         for (double **q : sv) e |= c->alloc(q, ns);
-        e |= c->alloc(&so.u, ns);
-        double **st[] = {&so.Linv, &so.Fm, &so.E, &so.S, &so.PkA};
+        double **st[] = {&so.Linv, &so.Fm, &so.E, &so.S};
         for (double **q : st) e |= c->alloc(q, 9 * ns);
         e |= c->alloc(&so.type, ns); e |= c->alloc(&so.slot, ns);
         if (e) return MPHX_ERR_NOMEM;
         CK(cudaMemcpy(c->d_inv_density, c->phys.inv_density, sizeof(double) * kTypeCount, cudaMemcpyHostToDevice));
         CK(cudaMemsetAsync(c->cellCount, 0, sizeof(int) * ((size_t)c->grid.ncells + 2), c->stream)); // (all-zero outside a rebuild)
-        if (c->slab) { int src = slab_allocate(c); if (src) return src; }
         double *zs[] = {c->P, c->volStrain, c->divP, c->fx, c->fy, c->fz, c->ax, c->ay, c->az, c->densA, c->gcx, c->gcy, c->gcz, c->PA,
                         c->ancx, c->ancy, c->ancz};
         for (double *q : zs) CK(cudaMemsetAsync(q, 0, sizeof(double) * cap, c->stream));
-        if (ns > 0)
+        if (ns > 0) {
             for (double **q : st) CK(cudaMemsetAsync(*q, 0, sizeof(double) * 9 * ns, c->stream));
+            CK(cudaMemsetAsync(so.PkA, 0, sizeof(double) * 9 * ns, c->stream));
+        }
     }
     return MPHX_OK;
 }
@@ -1612,7 +1674,10 @@ int mphx_download(mphx_ctx *ctx, const mphx_host_views *v)
             d9 = c->stage9;
         }
         CK(cudaMemsetAsync(d9, 0, sizeof(double) * 9 * N, c->stream));
-        if (ns > 0 && report_solids) LAUNCH(c, k_solid_tensor_to_orig, nblk(ns), kBlock, so, M, d9);
+        // split sub-steps: F, E, S of a solid live on the rank that advances it (the sum over the slabs is the case)
+        const bool ranged = c->slab && c->split_substeps;
+        const int lo = ranged ? c->s_lo : 0, hi = ranged ? c->s_hi : ns;
+        if (ns > 0 && (report_solids || ranged)) LAUNCH(c, k_solid_tensor_to_orig, nblk(hi - lo), kBlock, so, M, d9, lo, hi);
         CK(cudaMemcpyAsync(host, d9, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, c->stream));
         return MPHX_OK;
     };
