@@ -364,6 +364,7 @@ def main():
                     help="lattice: the headline only; both: also the developed-state companion number (config.developed_state)")
     ap.add_argument("--no-verify", action="store_true", help="N > 1: skip the ring-vs-single-context check of the exchange")
     ap.add_argument("--verify-particles", type=float, default=2.0e5)
+    ap.add_argument("--trace", default="", help="N > 1: after the timed region, write a device-side timeline of 3 steps per rank to <prefix>_rank<r>.json")
     ap.add_argument("--list-reuse", type=int, default=-1, help="1/0: candidate-list reuse on/off (default: the library's default, on)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "mphx" else args.warmup

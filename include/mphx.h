@@ -259,6 +259,11 @@ int mphx_get_timers(mphx_ctx *ctx, double ms[4]);
 /* the same split by kernel group: [0] bucket rebuild, [1] candidate filter (k_filter), [2] pass 1 over the
  * candidate list, [3] pass 2 over the candidate list (+ integration), [4] solid sub-steps */
 int mphx_get_kernel_timers(mphx_ctx *ctx, double ms[5]);
+/* Device-side timeline (no reference counterpart; the reference has wall-clock phase timers only, src/main.cpp:695-700):
+   capacity > 0 switches on (code, %globaltimer ns) marks written by the wait / push / marker kernels of the following
+   steps, 0 switches them off; mphx_trace_read returns the marks recorded so far (out[2i] = code, out[2i+1] = ns). */
+int mphx_trace_enable(mphx_ctx *ctx, int capacity);
+int mphx_trace_read(mphx_ctx *ctx, unsigned long long *out, int max_marks, int *count);
 /* roofline helpers (measurement only): dense FP64 FMA throughput of a device in TFLOP/s (CUDA events around a pure DFMA
  * kernel), and the candidates / in-radius pairs of the current lists (out[0], out[1]) -- a sweep's algorithmic FP64 work
  * is ~15 flop per candidate examined + ~45 per in-radius pair */

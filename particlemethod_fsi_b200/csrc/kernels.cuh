@@ -81,6 +81,9 @@ struct Ctl {
     int ghost_base[2], ghost_cnt[2]; // pre-permute slots of the ghosts received from left / right (current list)
     unsigned push_done[8]; // block counters of the push kernels
     unsigned sub_done[2];  // block counters of the split solid sub-steps (pass 1 / pass 2)
+    // device-side timeline (mphx_trace_*): (code, %globaltimer) pairs appended by the wait / push / marker kernels
+    unsigned long long *trace;
+    int trace_cap, trace_n;
 };
 
 struct Phys {
@@ -144,6 +147,7 @@ struct Solid {
     // are bound by streaming this data: 36 -> 6 bytes per pair).  packed = 0 (more than 65535 tuples): the raw arrays.
     int packed;
     unsigned short *tix, *rtix;      // ELL, own rows / transposed rows
+    unsigned short *ctix, *crtix;    // the same indices in CSR order (off / roff): what the team kernels read
     Rec *ttab;                       // (x0_ij.x, .y, .z, weight(x0_ij))
     unsigned short *pmask;           // slab mode, split sub-steps: bit r = rank r's rows reference this solid (r != the rank advancing it)
 };
@@ -256,6 +260,16 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 constexpr unsigned long long kWaitTimeoutNs = 4000000000ull; // a missing peer becomes an error flag, never a hang
+// timeline marks (off unless mphx_trace_enable gave the context a buffer): 1..99 step phases (k_mark), 100 + tag / 200 + tag
+// a wait begins / ends, 300 + which the last block of a solid sub-step kernel posts its phase, 400 + which a push completes
+__device__ __forceinline__ void trace_mark(Ctl *ctl, int code)
+{
+    if (ctl->trace_cap > 0) {
+        const int i = atomicAdd(&ctl->trace_n, 1);
+        if (i < ctl->trace_cap) { ctl->trace[2 * i] = (unsigned long long)code; ctl->trace[2 * i + 1] = global_ns(); }
+    }
+}
+__global__ void k_mark(Ctl *ctl, int code) { trace_mark(ctl, code); }
 
 // wait until flags[0..nflags) carry this step's epoch (SHIFT = 1: the flag also carries a vote bit, the
 // OR of the votes goes to ctl->need)
@@ -263,16 +277,28 @@ constexpr unsigned long long kWaitTimeoutNs = 4000000000ull; // a missing peer b
 // while the context's stream may already be enqueuing the next step)
 enum { kWaitVote = 0, kWaitMig, kWaitHalo, kWaitP, kWaitSolP, kWaitSolV, kWaitSub };
 constexpr int kSubPhases = 4096; // phase counters of the split solid sub-steps: epoch * kSubPhases + phase
+struct DecideArgs {
+    int reuse_enabled; // host switch (MPHX_LIST_REUSE, moving walls, slab support)
+    float half_skin2;  // (skin / 2)^2 in metres^2
+    float filt2_plain, filt2_skin;
+};
+__device__ __forceinline__ void decide_body(Ctl *ctl, const DecideArgs &a, int *__restrict__ list_flags);
+// (flags2 / nflags2: a second set of flags waited for by the following lanes, e.g. the halo's PressureP and the replicated
+//  solids' PressureP together; only_rebuild: the message only exists on steps that rebuild the buckets)
 template <int SHIFT>
-__global__ void k_wait(Ctl *ctl, unsigned long long epoch, const unsigned long long *flags, int nflags, int tag)
+__global__ void k_wait(Ctl *ctl, unsigned long long epoch, const unsigned long long *flags, int nflags, int tag, int only_rebuild = 0,
+                       const unsigned long long *flags2 = nullptr, int nflags2 = 0)
 {
+    if (only_rebuild && !ctl->rebuild) return;
     const int lane = threadIdx.x;
     const unsigned long long want = epoch;
     unsigned long long v = want << SHIFT;
-    if (lane < nflags) {
+    if (lane == 0) trace_mark(ctl, 100 + tag);
+    if (lane < nflags + nflags2) {
+        const unsigned long long *f = lane < nflags ? flags + lane : flags2 + (lane - nflags);
         const unsigned long long t0 = global_ns();
         for (;;) {
-            v = ld_flag(flags + lane);
+            v = ld_flag(f);
             if ((v >> SHIFT) >= want) break;
             if (global_ns() - t0 > kWaitTimeoutNs) { atomicOr(&ctl->err, kErrTimeout | (256 << tag)); break; }
             __nanosleep(64);
@@ -283,12 +309,44 @@ __global__ void k_wait(Ctl *ctl, unsigned long long epoch, const unsigned long l
         const unsigned any = __ballot_sync(0xffffffffu, lane < nflags && (v & 1ull));
         if (lane == 0 && any) ctl->need = 1;
     }
+    __syncwarp();
+    if (lane == 0) trace_mark(ctl, 200 + tag);
 }
-// post this rank's rebuild vote into every rank's mailbox
-__global__ void k_vote(Ctl *ctl, unsigned long long epoch, Peers peers)
+// this rank's rebuild vote (k_need's rule) into every rank's mailbox
+__device__ __forceinline__ int local_need(const Ctl *ctl, const DecideArgs &a, const int *__restrict__ list_flags)
+{
+    const bool overflowed = list_flags && list_flags[0] != 0;
+    return (ctl->force || !a.reuse_enabled || !ctl->skin_on || overflowed || __uint_as_float(ctl->maxdisp2) > a.half_skin2) ? 1 : 0;
+}
+__global__ void k_vote(Ctl *ctl, unsigned long long epoch, Peers peers, DecideArgs a, const int *__restrict__ list_flags)
 {
     const int r = threadIdx.x;
-    if (r < peers.nranks) st_flag(peers.vote[r] + peers.rank, (epoch << 1) | (unsigned long long)(ctl->need != 0));
+    const int need = local_need(ctl, a, list_flags);
+    if (r == 0) ctl->need = need;
+    if (r < peers.nranks) st_flag(peers.vote[r] + peers.rank, (epoch << 1) | (unsigned long long)need);
+}
+// wait for every rank's vote, OR them, decide (k_decide's rule): one launch
+__global__ void k_wait_decide(Ctl *ctl, unsigned long long epoch, const unsigned long long *flags, int nflags, DecideArgs a, int *__restrict__ list_flags)
+{
+    const int lane = threadIdx.x;
+    unsigned long long v = epoch << 1;
+    if (lane == 0) trace_mark(ctl, 100 + kWaitVote);
+    if (lane < nflags) {
+        const unsigned long long t0 = global_ns();
+        for (;;) {
+            v = ld_flag(flags + lane);
+            if ((v >> 1) >= epoch) break;
+            if (global_ns() - t0 > kWaitTimeoutNs) { atomicOr(&ctl->err, kErrTimeout | (256 << kWaitVote)); break; }
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+    const unsigned any = __ballot_sync(0xffffffffu, lane < nflags && (v & 1ull));
+    if (lane == 0) {
+        if (any) ctl->need = 1;
+        decide_body(ctl, a, list_flags);
+        trace_mark(ctl, 200 + kWaitVote);
+    }
 }
 // the last block of a pushing kernel publishes the message: count (optional), then the flag
 __device__ __forceinline__ void push_complete(Ctl *ctl, unsigned long long epoch, int which, int *dst_cnt, int cnt, unsigned long long *dst_flag)
@@ -303,17 +361,43 @@ __device__ __forceinline__ void push_complete(Ctl *ctl, unsigned long long epoch
             if (dst_cnt) *dst_cnt = cnt;
             __threadfence_system();
             st_flag(dst_flag, epoch);
+            trace_mark(ctl, 400 + which);
         }
     }
 }
-// copy cnt * width doubles of a packed message into the neighbour's mailbox (coalesced stores over NVLink)
-__global__ void k_push(Ctl *ctl, unsigned long long epoch, int which, const double *__restrict__ src, const int *cnt_p, int width, double *dst, int *dst_cnt,
-                       unsigned long long *dst_flag)
+// copy cnt * width doubles of a packed message into the neighbour's mailbox (coalesced stores over NVLink); both
+// directions in one launch: blockIdx.y = 0 to the left neighbour, 1 to the right.  The count is clamped to the message
+// capacity where it is published (cnt_p is written back).  only_rebuild: the message only exists on rebuild steps.
+struct PushPair {
+    const double *src[2];
+    int *cnt[2];               // this context's counts (ctl->mig_cnt / ctl->halo_cnt)
+    double *dst[2];            // the neighbours' mailbox buffers
+    int *dst_cnt[2];
+    unsigned long long *dst_flag[2];
+};
+__global__ void k_push(Ctl *ctl, unsigned long long epoch, int which0, PushPair pp, int width, int cap, int only_rebuild)
 {
-    const int cnt = *cnt_p;
+    if (only_rebuild && !ctl->rebuild) return;
+    const int dir = blockIdx.y;
+    const int cnt = min(*pp.cnt[dir], cap);
     const long long total = (long long)cnt * width;
+    const double *__restrict__ src = pp.src[dir];
+    double *__restrict__ dst = pp.dst[dir];
     for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) dst[k] = src[k];
-    push_complete(ctl, epoch, which, dst_cnt, cnt, dst_flag);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        const unsigned done = atomicAdd(&ctl->push_done[which0 + dir], 1u);
+        if (done == gridDim.x - 1) {
+            ctl->push_done[which0 + dir] = 0;
+            *pp.cnt[dir] = cnt;
+            *pp.dst_cnt[dir] = cnt;
+            __threadfence_system();
+            st_flag(pp.dst_flag[dir], epoch);
+            trace_mark(ctl, 400 + which0 + dir);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -398,18 +482,9 @@ __global__ void k_prestep(Ctl *ctl, Particles p, Solid sol, GridDesc g, WallMoti
 //   * the skin costs candidates (all the physics kernels traverse the longer lists), so it is only kept
 //     while it pays: a list that served fewer than 2 steps switches the skin off for the following builds,
 //     every 16th build tries it again.
-struct DecideArgs {
-    int reuse_enabled; // host switch (MPHX_LIST_REUSE, moving walls, slab support)
-    float half_skin2;  // (skin / 2)^2 in metres^2
-    float filt2_plain, filt2_skin;
-};
 // local vote (before the exchange of votes in slab mode)
-__global__ void k_need(Ctl *ctl, DecideArgs a, const int *__restrict__ list_flags)
-{
-    const bool overflowed = list_flags && list_flags[0] != 0;
-    ctl->need = (ctl->force || !a.reuse_enabled || !ctl->skin_on || overflowed || __uint_as_float(ctl->maxdisp2) > a.half_skin2) ? 1 : 0;
-}
-__global__ void k_decide(Ctl *ctl, DecideArgs a, int *__restrict__ list_flags)
+__global__ void k_need(Ctl *ctl, DecideArgs a, const int *__restrict__ list_flags) { ctl->need = local_need(ctl, a, list_flags); }
+__device__ __forceinline__ void decide_body(Ctl *ctl, const DecideArgs &a, int *__restrict__ list_flags)
 {
     const int rebuild = ctl->need ? 1 : 0;
     ctl->rebuild = rebuild;
@@ -435,6 +510,7 @@ __global__ void k_decide(Ctl *ctl, DecideArgs a, int *__restrict__ list_flags)
         ++ctl->reuses;
     }
 }
+__global__ void k_decide(Ctl *ctl, DecideArgs a, int *__restrict__ list_flags) { decide_body(ctl, a, list_flags); }
 
 // K1 (rebuild steps): per-bucket count + arrival slot.  Slab mode: ghosts of the previous list die; fluid/wall
 // particles whose column left the owned range are packed for the neighbouring slab (migration) and die here.
@@ -445,66 +521,62 @@ struct SlabSend {
 __global__ void k_count(Ctl *ctl, Particles p, GridDesc g, int *__restrict__ cellCount, int *__restrict__ slot, SlabSend snd)
 {
     if (!ctl->rebuild) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ctl->n) return;
-    const int t = p.type[i];
-    int k;
-    if (t & kGhost) k = g.ncells + 1; // last list's halo copy
-    else {
-        k = p.key[i];
-        if (g.slab && !is_structure_type(t)) {
-            if (k >= g.ncells) { atomicOr(&ctl->err, kErrLost); k = g.ncells + 1; } // moved further than one halo width: lost
-            else {
-                const int col = key_column(g, k);
-                if (!column_owned(g, col)) { // migrate: hand the particle to the neighbouring slab
-                    const int dir = (col < g.range) ? 0 : 1;
-                    const int q = atomicAdd(&ctl->mig_cnt[dir], 1);
-                    if (q < snd.capacity)
-                        pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], t, p.id[i]);
-                    else atomicOr(&ctl->err, kErrMsgFull);
-                    k = g.ncells + 1;
+    const int n = ctl->n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int t = p.type[i];
+        int k;
+        if (t & kGhost) k = g.ncells + 1; // last list's halo copy
+        else {
+            k = p.key[i];
+            if (g.slab && !is_structure_type(t)) {
+                if (k >= g.ncells) { atomicOr(&ctl->err, kErrLost); k = g.ncells + 1; } // moved further than one halo width: lost
+                else {
+                    const int col = key_column(g, k);
+                    if (!column_owned(g, col)) { // migrate: hand the particle to the neighbouring slab
+                        const int dir = (col < g.range) ? 0 : 1;
+                        const int q = atomicAdd(&ctl->mig_cnt[dir], 1);
+                        if (q < snd.capacity)
+                            pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], t, p.id[i]);
+                        else atomicOr(&ctl->err, kErrMsgFull);
+                        k = g.ncells + 1;
+                    }
                 }
             }
         }
-    }
-    p.key[i] = k;
-    slot[i] = atomicAdd(&cellCount[k], 1);
-}
-// the counts as they travel: never more than a message holds
-__global__ void k_clamp_counts(Ctl *ctl, int cap)
-{
-    if (threadIdx.x < 2) {
-        ctl->mig_cnt[threadIdx.x] = min(ctl->mig_cnt[threadIdx.x], cap);
-        ctl->halo_cnt[threadIdx.x] = min(ctl->halo_cnt[threadIdx.x], cap);
+        p.key[i] = k;
+        slot[i] = atomicAdd(&cellCount[k], 1);
     }
 }
-
 // slab mode, rebuild steps: append the particles received from a neighbour (migrants: ghost_flag 0; halo copies:
 // ghost_flag kGhost, x shifted by +-W across the periodic seam so separations need no wrap in x).
 // side 0 = from the left neighbour, 1 = from the right; cnt_in[2] are the received counts.
-__global__ void k_unpack_particles(Ctl *ctl, int side, const double *__restrict__ buf, const int *cnt_in, int msg_cap, int cap,
-                                   double xshift, int ghost_flag, Particles p, GridDesc g, int *__restrict__ cellCount,
-                                   int *__restrict__ slot, double *__restrict__ ancx, double *__restrict__ ancy, double *__restrict__ ancz)
+struct SidePair { const double *buf[2]; double xshift[2]; };
+__global__ void k_unpack_particles(Ctl *ctl, SidePair sp, const int *cnt_in, int msg_cap, int cap, int ghost_flag, Particles p, GridDesc g,
+                                   int *__restrict__ cellCount, int *__restrict__ slot, double *__restrict__ ancx, double *__restrict__ ancy,
+                                   double *__restrict__ ancz)
 {
     if (!ctl->rebuild) return;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int side = blockIdx.y;
     const int cl = min(max(cnt_in[0], 0), msg_cap), cr = min(max(cnt_in[1], 0), msg_cap);
-    if (q >= (side ? cr : cl)) return;
-    const int i = ctl->n + (side ? cl : 0) + q;
-    if (i >= cap) { atomicOr(&ctl->err, kErrCapacity); return; }
-    const double *m = buf + (size_t)kMsgDoubles * q;
-    const double x = m[0] + xshift, y = m[1], z = m[2];
-    const long long meta = __double_as_longlong(m[6]);
-    p.x[i] = x; p.y[i] = y; p.z[i] = z; p.vx[i] = m[3]; p.vy[i] = m[4]; p.vz[i] = m[5];
-    p.type[i] = (int)(meta >> 32) | ghost_flag;
-    p.id[i] = (int)(meta & 0xffffffffLL);
-    ancx[i] = x; ancy[i] = y; ancz[i] = z;
-    int col;
-    int k = cell_key(g, x, y, z, &col);
-    const bool owned = column_owned(g, col);
-    if (k >= g.ncells || (ghost_flag ? owned : !owned)) { atomicOr(&ctl->err, kErrArrival); k = g.ncells + 1; }
-    p.key[i] = k;
-    slot[i] = atomicAdd(&cellCount[k], 1);
+    const double *__restrict__ buf = sp.buf[side];
+    const double xshift = sp.xshift[side];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < (side ? cr : cl); q += gridDim.x * blockDim.x) {
+        const int i = ctl->n + (side ? cl : 0) + q;
+        if (i >= cap) { atomicOr(&ctl->err, kErrCapacity); return; }
+        const double *m = buf + (size_t)kMsgDoubles * q;
+        const double x = m[0] + xshift, y = m[1], z = m[2];
+        const long long meta = __double_as_longlong(m[6]);
+        p.x[i] = x; p.y[i] = y; p.z[i] = z; p.vx[i] = m[3]; p.vy[i] = m[4]; p.vz[i] = m[5];
+        p.type[i] = (int)(meta >> 32) | ghost_flag;
+        p.id[i] = (int)(meta & 0xffffffffLL);
+        ancx[i] = x; ancy[i] = y; ancz[i] = z;
+        int col;
+        int k = cell_key(g, x, y, z, &col);
+        const bool owned = column_owned(g, col);
+        if (k >= g.ncells || (ghost_flag ? owned : !owned)) { atomicOr(&ctl->err, kErrArrival); k = g.ncells + 1; }
+        p.key[i] = k;
+        slot[i] = atomicAdd(&cellCount[k], 1);
+    }
 }
 __global__ void k_advance_n(Ctl *ctl, const int *cnt_in, int msg_cap, int cap, int ghost)
 {
@@ -520,86 +592,118 @@ __global__ void k_advance_n(Ctl *ctl, const int *cnt_in, int msg_cap, int cap, i
 __global__ void k_halo_pack(Ctl *ctl, Particles p, GridDesc g, SlabSend snd, int *__restrict__ haloSrc0, int *__restrict__ haloSrc1)
 {
     if (!ctl->rebuild) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ctl->n) return;
-    const int k = p.key[i], t = p.type[i];
-    if (k >= g.ncells || (t & kGhost) || is_structure_type(t)) return;
-    const int col = key_column(g, k);
-    if (!column_owned(g, col)) return;
-    for (int dir = 0; dir < 2; ++dir) {
-        const bool in = dir == 0 ? (col < 2 * g.range) : (col >= g.nx - 2 * g.range);
-        if (!in) continue;
-        const int q = atomicAdd(&ctl->halo_cnt[dir], 1);
-        if (q < snd.capacity) {
-            pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], t, p.id[i]);
-            (dir == 0 ? haloSrc0 : haloSrc1)[q] = i;
-        } else atomicOr(&ctl->err, kErrMsgFull);
+    const int n = ctl->n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int k = p.key[i], t = p.type[i];
+        if (k >= g.ncells || (t & kGhost) || is_structure_type(t)) continue;
+        const int col = key_column(g, k);
+        if (!column_owned(g, col)) continue;
+        for (int dir = 0; dir < 2; ++dir) {
+            const bool in = dir == 0 ? (col < 2 * g.range) : (col >= g.nx - 2 * g.range);
+            if (!in) continue;
+            const int q = atomicAdd(&ctl->halo_cnt[dir], 1);
+            if (q < snd.capacity) {
+                pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], t, p.id[i]);
+                (dir == 0 ? haloSrc0 : haloSrc1)[q] = i;
+            } else atomicOr(&ctl->err, kErrMsgFull);
+        }
     }
 }
-// reuse steps: the SAME halo particles (sorted slots haloSlot, fixed when the list was built) with their current state
-__global__ void k_halo_repack(Ctl *ctl, Particles p, SlabSend snd, const int *__restrict__ haloSlot0, const int *__restrict__ haloSlot1)
+// reuse steps: the SAME halo particles (sorted slots haloSlot, fixed when the list was built) with their current state,
+// packed straight into the neighbours' mailboxes (blockIdx.y = direction) and completed by the flag: one launch
+__global__ void k_halo_resend(Ctl *ctl, unsigned long long epoch, int which0, Particles p, const int *__restrict__ haloSlot0,
+                              const int *__restrict__ haloSlot1, PushPair pp)
 {
     if (ctl->rebuild) return;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int dir = 0; dir < 2; ++dir) {
-        if (q >= ctl->halo_cnt[dir]) continue;
-        const int i = (dir == 0 ? haloSlot0 : haloSlot1)[q];
-        pack_particle(snd.buf[dir] + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], p.type[i], p.id[i]);
+    const int dir = blockIdx.y;
+    const int cnt = ctl->halo_cnt[dir];
+    const int *__restrict__ hs = dir == 0 ? haloSlot0 : haloSlot1;
+    double *__restrict__ dst = pp.dst[dir];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+        const int i = hs[q];
+        pack_particle(dst + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], p.type[i], p.id[i]);
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(&ctl->push_done[which0 + dir], 1u) == gridDim.x - 1) {
+            ctl->push_done[which0 + dir] = 0;
+            *pp.dst_cnt[dir] = cnt;
+            __threadfence_system();
+            st_flag(pp.dst_flag[dir], epoch);
+            trace_mark(ctl, 400 + which0 + dir);
+        }
     }
 }
-// reuse steps: refresh the ghost slots with the state their owners sent
-__global__ void k_unpack_refresh(Ctl *ctl, int side, const double *__restrict__ buf, double xshift, Particles p, const int *__restrict__ ghostSlot)
+// reuse steps: refresh the ghost slots with the state their owners sent (blockIdx.y = side)
+__global__ void k_unpack_refresh(Ctl *ctl, SidePair sp, Particles p, const int *__restrict__ ghostSlot0, const int *__restrict__ ghostSlot1)
 {
     if (ctl->rebuild) return;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= ctl->ghost_cnt[side]) return;
-    const double *m = buf + (size_t)kMsgDoubles * q;
-    const int i = ghostSlot[q];
-    p.x[i] = m[0] + xshift; p.y[i] = m[1]; p.z[i] = m[2]; p.vx[i] = m[3]; p.vy[i] = m[4]; p.vz[i] = m[5];
+    const int side = blockIdx.y;
+    const int cnt = ctl->ghost_cnt[side];
+    const double *__restrict__ buf = sp.buf[side];
+    const int *__restrict__ gs = side == 0 ? ghostSlot0 : ghostSlot1;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+        const double *m = buf + (size_t)kMsgDoubles * q;
+        const int i = gs[q];
+        p.x[i] = m[0] + sp.xshift[side]; p.y[i] = m[1]; p.z[i] = m[2]; p.vx[i] = m[3]; p.vy[i] = m[4]; p.vz[i] = m[5];
+    }
 }
 // after the permute of a rebuild step: the sorted slots of the halo particles sent / the ghosts received
 __global__ void k_slab_slots(Ctl *ctl, const int *__restrict__ where, const int *__restrict__ haloSrc0, const int *__restrict__ haloSrc1,
                              int *__restrict__ haloSlot0, int *__restrict__ haloSlot1, int *__restrict__ ghostSlot0, int *__restrict__ ghostSlot1)
 {
     if (!ctl->rebuild) return;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < ctl->halo_cnt[0]) haloSlot0[q] = where[haloSrc0[q]];
-    if (q < ctl->halo_cnt[1]) haloSlot1[q] = where[haloSrc1[q]];
-    if (q < ctl->ghost_cnt[0]) ghostSlot0[q] = where[ctl->ghost_base[0] + q];
-    if (q < ctl->ghost_cnt[1]) ghostSlot1[q] = where[ctl->ghost_base[1] + q];
+    const int m = max(max(ctl->halo_cnt[0], ctl->halo_cnt[1]), max(ctl->ghost_cnt[0], ctl->ghost_cnt[1]));
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < m; q += gridDim.x * blockDim.x) {
+        if (q < ctl->halo_cnt[0]) haloSlot0[q] = where[haloSrc0[q]];
+        if (q < ctl->halo_cnt[1]) haloSlot1[q] = where[haloSrc1[q]];
+        if (q < ctl->ghost_cnt[0]) ghostSlot0[q] = where[ctl->ghost_base[0] + q];
+        if (q < ctl->ghost_cnt[1]) ghostSlot1[q] = where[ctl->ghost_base[1] + q];
+    }
 }
 // second exchange: what pass 1 computed for the halo particles, in the order they were packed, straight into the
 // neighbour's mailbox: PressureP (plane 0) and, with surface tension, PressureA and GravityCenter (planes 1..4);
 // plane p of halo particle q at dst[p * msg_cap + q]
 struct PassOneFields { const double *a[5]; int count; };
 struct PassOneTargets { double *a[5]; int count; };
-__global__ void k_push_scalar(Ctl *ctl, unsigned long long epoch, int which, int dir, const int *__restrict__ haloSlot, PassOneFields f, int msg_cap,
-                              double *dst, unsigned long long *dst_flag)
+struct ScalarPush { double *dst[2]; unsigned long long *dst_flag[2]; };
+__global__ void k_push_scalar(Ctl *ctl, unsigned long long epoch, int which0, const int *__restrict__ haloSlot0, const int *__restrict__ haloSlot1,
+                              PassOneFields f, int msg_cap, ScalarPush sp)
 {
+    const int dir = blockIdx.y;
     const int cnt = ctl->halo_cnt[dir];
+    const int *__restrict__ hs = dir == 0 ? haloSlot0 : haloSlot1;
+    double *__restrict__ dst = sp.dst[dir];
     for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
-        const int i = haloSlot[q];
+        const int i = hs[q];
         for (int p = 0; p < f.count; ++p) dst[(size_t)p * msg_cap + q] = f.a[p][i];
     }
-    push_complete(ctl, epoch, which, nullptr, 0, dst_flag);
+    push_complete(ctl, epoch, which0 + dir, nullptr, 0, sp.dst_flag[dir]);
 }
-__global__ void k_unpack_scalar(Ctl *ctl, int side, const int *__restrict__ ghostSlot, const double *__restrict__ buf, int msg_cap, PassOneTargets f,
-                                Rec *__restrict__ rb)
+__global__ void k_unpack_scalar(Ctl *ctl, const int *__restrict__ ghostSlot0, const int *__restrict__ ghostSlot1, const double *__restrict__ buf0,
+                                const double *__restrict__ buf1, int msg_cap, PassOneTargets f, Rec *__restrict__ rb)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= ctl->ghost_cnt[side]) return;
-    const int w = ghostSlot[q];
-    for (int p = 0; p < f.count; ++p) f.a[p][w] = buf[(size_t)p * msg_cap + q];
-    rb[w].c = buf[q]; // PressureP slot of the gather record
+    const int side = blockIdx.y;
+    const int cnt = ctl->ghost_cnt[side];
+    const int *__restrict__ gs = side == 0 ? ghostSlot0 : ghostSlot1;
+    const double *__restrict__ buf = side == 0 ? buf0 : buf1;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+        const int w = gs[q];
+        for (int p = 0; p < f.count; ++p) f.a[p][w] = buf[(size_t)p * msg_cap + q];
+        rb[w].c = buf[q]; // PressureP slot of the gather record
+    }
 }
 // replicated solids: the slab that owns a solid particle (kSolidOwned: by its column when the list was built)
 // computes its PressureP / its fluid-coupled velocity update and stores them into EVERY rank's mailbox.
-__global__ void k_solid_owned_list(Ctl *ctl, Particles p, int *__restrict__ own_sol)
+__global__ void k_solid_owned_list(Ctl *ctl, Particles p, Solid sol, int *__restrict__ own_sol)
 {
     if (!ctl->rebuild) return;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= ctl->n) return;
-    if (p.type[q] & kSolidOwned) own_sol[atomicAdd(&ctl->n_own_sol, 1)] = q;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < sol.ns; s += gridDim.x * blockDim.x) {
+        const int q = sol.slot[s];
+        if (p.type[q] & kSolidOwned) own_sol[atomicAdd(&ctl->n_own_sol, 1)] = q;
+    }
 }
 __global__ void k_solid_publish_P(Ctl *ctl, unsigned long long epoch, int which, Particles p, Solid sol, const int *__restrict__ own_sol, const double *__restrict__ P, Peers peers)
 {
@@ -626,16 +730,17 @@ __global__ void k_solid_publish_P(Ctl *ctl, unsigned long long epoch, int which,
 __global__ void k_solid_spread_P(Ctl *ctl, Particles p, GridDesc g, Solid sol, const double *__restrict__ solP, double *__restrict__ P,
                                  double *__restrict__ PA, double *__restrict__ gcx, double *__restrict__ gcy, double *__restrict__ gcz, Phys ph)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= ctl->n) return;
-    if (p.key[q] >= g.ncells || !is_structure_type(p.type[q]) || (p.type[q] & kGhost)) return;
-    const double v = solP[p.id[q] - sol.sb];
-    P[q] = v;
-    p.rb[q].c = v;
-    if (PA) {
-        double pa = ph.cofa[real_type(p.type[q])] * (0.0 - ph.n0a) / ph.l0; // :2219
-        if (ph.n0a <= 0.0) pa = 0.0;
-        PA[q] = pa; gcx[q] = 0.0; gcy[q] = 0.0; gcz[q] = 0.0;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < sol.ns; s += gridDim.x * blockDim.x) {
+        const int q = sol.slot[s];
+        if (p.key[q] >= g.ncells || (p.type[q] & kGhost)) continue; // (parked outside this slab: never traversed)
+        const double v = solP[s];
+        P[q] = v;
+        p.rb[q].c = v;
+        if (PA) {
+            double pa = ph.cofa[real_type(p.type[q])] * (0.0 - ph.n0a) / ph.l0; // :2219
+            if (ph.n0a <= 0.0) pa = 0.0;
+            PA[q] = pa; gcx[q] = 0.0; gcy[q] = 0.0; gcz[q] = 0.0;
+        }
     }
 }
 // the owner's coupled velocities (pass 2 wrote them into its solid arrays) -> every rank's mailbox
@@ -768,9 +873,8 @@ __global__ void k_scatter_index(const Ctl *ctl, const int *__restrict__ key, con
                                 const int *__restrict__ cellStart, int *__restrict__ tmpIdx)
 {
     if (!ctl->rebuild) return;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ctl->n) return;
-    tmpIdx[cellStart[key[i]] + slot[i]] = i;
+    const int n = ctl->n;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) tmpIdx[cellStart[key[i]] + slot[i]] = i;
 }
 
 // K4: permute the SoA into bucket order and write the gather records.  Inside a bucket particles are ordered by
@@ -1081,9 +1185,12 @@ __device__ __forceinline__ void ring_complete(Ctl *ctl, int which, const SolidRi
             ctl->sub_done[which] = 0;
             __threadfence_system();
             for (int r = 0; r < ring.nranks; ++r) st_flag((unsigned long long *)(ring.base[r] + ring.off_flag) + ring.rank, ring.seq);
+            trace_mark(ctl, 300 + which);
         }
     }
 }
+template <int DIMS, bool RING>
+__device__ __forceinline__ void solid_pass1_finish(const Solid &so, const int s, const double (&G)[3][3], const SolidRing &ring);
 template <int DIMS, bool PACKED, bool RING>
 __device__ __forceinline__ void solid_pass1_row(const Solid &so, const int s, const SolidRing &ring)
 {
@@ -1137,6 +1244,14 @@ __device__ __forceinline__ void solid_pass1_row(const Solid &so, const int s, co
             }
         }
     }
+    solid_pass1_finish<DIMS, RING>(so, s, G, ring);
+}
+// F = G L^-1 (:2743), E (:2780), S (:2804), P = F S L^-1 (:2847) of solid s from its accumulated G
+template <int DIMS, bool RING>
+__device__ __forceinline__ void solid_pass1_finish(const Solid &so, const int s, const double (&G)[3][3], const SolidRing &ring)
+{
+    using namespace ex;
+    const int ns = so.ns;
     double L[3][3], F[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
     for (int a = 0; a < 3; ++a)
         for (int b = 0; b < 3; ++b) L[a][b] = MPHX_T(so.Linv, a, b, s, ns);
@@ -1183,9 +1298,13 @@ __device__ __forceinline__ void solid_pass1_row(const Solid &so, const int s, co
         }
     }
 }
-// (RING: a rank's share is ~ns/nranks solids -- fewer blocks than SMs -- so the pushing variants trade occupancy for registers)
+// (RING: a rank's share is ~ns/nranks solids, about one block per SM, and its kernels run beside the fluid's share of pass 2
+// on a high-priority stream: blocks of kRingBlock threads with <= 128 registers need no more of an SM than ONE retiring
+// pass-2 block frees (80 registers x 128 threads) -- a 218-register block of 128 threads waited for three to retire at once,
+// which the scheduler does not arrange: the sub-steps stretched over the whole of pass 2)
+constexpr int kRingBlock = 64;
 template <int DIMS, bool PACKED, bool RING>
-__global__ void __launch_bounds__(128, RING ? 2 : MPHX_S1_MINB)
+__global__ void __launch_bounds__(RING ? kRingBlock : 128, RING ? 8 : MPHX_S1_MINB)
 k_solid_pass1(Ctl *ctl, Solid so, int s_lo, int s_hi, SolidRing ring)
 {
     const int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
@@ -1213,6 +1332,9 @@ __host__ __device__ inline bool solid_clamped(int module, double x0, double y0)
 // order, the terms of rows j<s that list s, then its own row, then rows j>s (transposed list), so
 // the result is deterministic, atomic-free and equal to the reference's CPU bits.
 // Then updateElasticPosition (:1916-2081) incl. the clamp modules and quirk Q1.
+template <bool RING>
+__device__ __forceinline__ void solid_pass2_finish(const Solid &so, const int s, double (&v)[3], double W0, double W1, double W2, double edt,
+                                                   int module, int double_update, const SolidRing &ring);
 template <int DIMS, bool PACKED, bool RING>
 __device__ __forceinline__ void solid_pass2_row(const Solid &so, const int s, double W0, double W1, double W2, double edt, int module,
                                                 int double_update, const double *__restrict__ inv_density, const SolidRing &ring)
@@ -1288,6 +1410,15 @@ __device__ __forceinline__ void solid_pass2_row(const Solid &so, const int s, do
     row(so.ernbr, so.rtix, so.rd0x, so.rd0y, so.rd0z, so.rw, 0, rsplit, false, Pi);
     row(so.enbr, so.tix, so.d0x, so.d0y, so.d0z, so.w, 0, so.len[s], true, Pi);
     row(so.ernbr, so.rtix, so.rd0x, so.rd0y, so.rd0z, so.rw, rsplit, rlen, false, Pi);
+    solid_pass2_finish<RING>(so, s, v, W0, W1, W2, edt, module, double_update, ring);
+}
+// updateElasticPosition (:1916-2081) of solid s with its new velocity v, incl. the clamp modules and quirk Q1
+template <bool RING>
+__device__ __forceinline__ void solid_pass2_finish(const Solid &so, const int s, double (&v)[3], double W0, double W1, double W2, double edt,
+                                                   int module, int double_update, const SolidRing &ring)
+{
+    using namespace ex;
+    const double xi0 = so.x0[s], yi0 = so.y0[s], zi0 = so.z0[s];
     double x[3] = {so.x[s], so.y[s], so.z[s]};
     // Acceleration of solids is 0 (:2892): v += 0*dt leaves v unchanged
     if (module != 0) {
@@ -1321,12 +1452,168 @@ __device__ __forceinline__ void solid_pass2_row(const Solid &so, const int s, do
     }
 }
 template <int DIMS, bool PACKED, bool RING>
-__global__ void __launch_bounds__(128, RING ? 2 : MPHX_S2_MINB)
+__global__ void __launch_bounds__(RING ? kRingBlock : 128, RING ? 8 : MPHX_S2_MINB)
 k_solid_pass2(Ctl *ctl, Solid so, int s_lo, int s_hi, double W0, double W1, double W2, double edt, int module, int double_update,
               const double *__restrict__ inv_density, SolidRing ring)
 {
     const int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (s < s_hi) solid_pass2_row<DIMS, PACKED, RING>(so, s, W0, W1, W2, edt, module, double_update, inv_density, ring);
+    if (RING) ring_complete(ctl, 1, ring);
+}
+
+// ---- the sub-step kernels with a TEAM of lanes per solid (dictionary-packed solids) ------------------------------
+// One thread per solid walks ~80 (pass 1) / ~160 (pass 2) pairs with a dependent load per pair: ~60 us per launch whatever
+// the number of solids (measured: 113k solids on one GPU 58 us, a 28k share 72 us) -- a latency chain, 84 % long-scoreboard
+// stalls.  The pair TERMS are independent; only their SUM has the reference's serial order.  So a team of kTeam lanes
+// computes the terms of a solid in parallel (lane l takes pairs l, l + kTeam, ...: no loop-carried dependence, loads of
+// several pairs in flight per lane, kTeam times more lanes in flight) into shared memory, then one lane per tensor / vector
+// component adds them up in the serial order, and one thread per solid of the block does the small epilogue.  Same
+// operations on the same operands in the same order as the one-thread kernels: the same bits.
+// The lists are read in CSR order (Solid::off/nbr, roff/rnbr, ctix/crtix): a team's lanes read consecutive entries.
+constexpr int kTeam = 16;
+constexpr int kTeamBlock = 128; // 8 solids per block; a block needs no more registers than one retiring pass-2 block frees
+// A chunk = kTeam consecutive pairs of a row (one per lane).  The terms of a chunk go through a double-buffered
+// [kTeam][components] tile of shared memory; the gathers of the next chunk and the list entries of the one after are in
+// flight while the current chunk is computed and summed.
+template <int DIMS, bool RING>
+__global__ void __launch_bounds__(kTeamBlock, 6) k_solid_pass1_team(Ctl *ctl, Solid so, int s_lo, int s_hi, SolidRing ring)
+{
+    using namespace ex;
+    constexpr int NE = DIMS * DIMS, TEAMS = kTeamBlock / kTeam;
+    __shared__ double Ts[TEAMS][2][kTeam][NE];
+    __shared__ double Gs[TEAMS][NE];
+    const int team = threadIdx.x / kTeam, lane = threadIdx.x % kTeam;
+    const int s = s_lo + blockIdx.x * TEAMS + team;
+    if (s < s_hi) { // (a team is half a warp: both halves take the same number of trips only by chance, hence the masks)
+        const unsigned mask = 0xffffu << (16 * ((threadIdx.x / kTeam) & 1));
+        const int len = so.len[s], base = so.off[s];
+        const Rec uo = so.u[s];
+        const double ui[3] = {uo.a, uo.b, DIMS == 3 ? uo.c : 0.0};
+        double g = 0.0;
+        // pipeline: (j, ti) of chunk c + 2, (t, un) of chunk c + 1
+        int jn = 0; unsigned tin = 0;
+        Rec tn{}, un{};
+        if (lane < len) { jn = __ldg(&so.nbr[base + lane]); tin = __ldg(&so.ctix[base + lane]); }
+        if (lane < len) { tn = ld_rec_ro(so.ttab + tin); un = so.u[jn]; }
+        if (kTeam + lane < len) { jn = __ldg(&so.nbr[base + kTeam + lane]); tin = __ldg(&so.ctix[base + kTeam + lane]); }
+        int buf = 0;
+        for (int c0 = 0; c0 < len; c0 += kTeam, buf ^= 1) {
+            const Rec t = tn, uj = un;
+            if (c0 + kTeam + lane < len) { tn = ld_rec_ro(so.ttab + tin); un = so.u[jn]; }
+            if (c0 + 2 * kTeam + lane < len) { jn = __ldg(&so.nbr[base + c0 + 2 * kTeam + lane]); tin = __ldg(&so.ctix[base + c0 + 2 * kTeam + lane]); }
+            if (c0 + lane < len) {
+                const double d0[3] = {t.a, t.b, DIMS == 3 ? t.c : 0.0};
+                const double ujv[3] = {uj.a, uj.b, DIMS == 3 ? uj.c : 0.0};
+                double d[3];
+                for (int a = 0; a < DIMS; ++a) d[a] = add(d0[a], sub(ujv[a], ui[a])); // :2716
+                for (int a = 0; a < DIMS; ++a)
+                    for (int b2 = 0; b2 < DIMS; ++b2) Ts[team][buf][lane][a * DIMS + b2] = mul(mul(t.d, d[a]), d0[b2]); // the term of :2726
+            }
+            __syncwarp(mask);
+            if (lane < NE) { // :2726, serial order (all of the chunk's terms are read first, then the dependent adds)
+                const int m = len - c0;
+                double tv[kTeam];
+#pragma unroll
+                for (int p = 0; p < kTeam; ++p) tv[p] = Ts[team][buf][p][lane];
+#pragma unroll
+                for (int p = 0; p < kTeam; ++p) g = p < m ? add(g, tv[p]) : g;
+            }
+        }
+        if (lane < NE) Gs[team][lane] = g;
+    }
+    __syncthreads();
+    if (threadIdx.x < TEAMS) {
+        const int s2 = s_lo + blockIdx.x * TEAMS + threadIdx.x;
+        if (s2 < s_hi) {
+            double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            for (int a = 0; a < DIMS; ++a)
+                for (int b2 = 0; b2 < DIMS; ++b2) G[a][b2] = Gs[threadIdx.x][a * DIMS + b2];
+            solid_pass1_finish<DIMS, RING>(so, s2, G, ring);
+        }
+    }
+    if (RING) ring_complete(ctl, 0, ring);
+}
+template <int DIMS, bool RING>
+__global__ void __launch_bounds__(kTeamBlock, 6)
+k_solid_pass2_team(Ctl *ctl, Solid so, int s_lo, int s_hi, double W0, double W1, double W2, double edt, int module, int double_update,
+                   const double *__restrict__ inv_density, SolidRing ring)
+{
+    using namespace ex;
+    constexpr int TEAMS = kTeamBlock / kTeam;
+    __shared__ double Ts[TEAMS][2][kTeam][DIMS];
+    __shared__ double Vs[TEAMS][3];
+    const int team = threadIdx.x / kTeam, lane = threadIdx.x % kTeam;
+    const int s = s_lo + blockIdx.x * TEAMS + team;
+    if (s < s_hi) {
+        const unsigned mask = 0xffffu << (16 * ((threadIdx.x / kTeam) & 1));
+        // the reference's serial order (:2855-2887): rows j < s that list s, the own row, rows j > s
+        const int len = so.len[s], rlen = so.rlen[s], rsplit = so.rsplit[s];
+        const int base = so.off[s], rbase = so.roff[s];
+        const int total = len + rlen;
+        const double ir = inv_density[so.type[s]];
+        double v = lane == 0 ? so.vx[s] : lane == 1 ? so.vy[s] : lane == 2 ? so.vz[s] : 0.0;
+        // entry q of the serial order: (j, tuple index, own row?)
+        auto entry = [&](int q, int &j, unsigned &ti) {
+            const bool own = q >= rsplit && q < rsplit + len;
+            const int kr = q < rsplit ? q : q - len; // position in the transposed row
+            j = own ? s : __ldg(&so.rnbr[rbase + kr]);
+            ti = own ? __ldg(&so.ctix[base + q - rsplit]) : __ldg(&so.crtix[rbase + kr]);
+        };
+        int jn = s; unsigned tin = 0;
+        Rec tn{};
+        double Pn[DIMS * DIMS];
+        auto gather = [&]() {
+            tn = ld_rec_ro(so.ttab + tin);
+            const double *pp = so.PkA + 9 * (size_t)jn;
+#pragma unroll
+            for (int a = 0; a < DIMS; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < DIMS; ++b2) Pn[a * DIMS + b2] = pp[3 * a + b2];
+        };
+#pragma unroll
+        for (int e = 0; e < DIMS * DIMS; ++e) Pn[e] = 0.0;
+        if (lane < total) { entry(lane, jn, tin); gather(); }
+        if (kTeam + lane < total) entry(kTeam + lane, jn, tin);
+        int buf = 0;
+        for (int c0 = 0; c0 < total; c0 += kTeam, buf ^= 1) {
+            const Rec t = tn;
+            double P[DIMS * DIMS];
+#pragma unroll
+            for (int e = 0; e < DIMS * DIMS; ++e) P[e] = Pn[e];
+            if (c0 + kTeam + lane < total) gather();
+            if (c0 + 2 * kTeam + lane < total) entry(c0 + 2 * kTeam + lane, jn, tin);
+            const int q = c0 + lane;
+            if (q < total) {
+                const bool own = q >= rsplit && q < rsplit + len;
+                const double d0[3] = {t.a, t.b, DIMS == 3 ? t.c : 0.0};
+                for (int a = 0; a < DIMS; ++a) {
+                    double f = 0.0;
+                    for (int b2 = 0; b2 < DIMS; ++b2) f = add(f, mul(P[a * DIMS + b2], d0[b2]));
+                    f = mul(f, t.d);
+                    const double term = mul(mul(ir, f), edt);
+                    Ts[team][buf][lane][a] = own ? term : -term; // :2883 v_s += ..., :2885 v_s -= ... (a - b == a + (-b) exactly)
+                }
+            }
+            __syncwarp(mask);
+            if (lane < DIMS) {
+                const int m = total - c0;
+                double tv[kTeam];
+#pragma unroll
+                for (int p = 0; p < kTeam; ++p) tv[p] = Ts[team][buf][p][lane];
+#pragma unroll
+                for (int p = 0; p < kTeam; ++p) v = p < m ? add(v, tv[p]) : v;
+            }
+        }
+        if (lane < 3) Vs[team][lane] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < TEAMS) {
+        const int s2 = s_lo + blockIdx.x * TEAMS + threadIdx.x;
+        if (s2 < s_hi) {
+            double v[3] = {Vs[threadIdx.x][0], Vs[threadIdx.x][1], Vs[threadIdx.x][2]};
+            solid_pass2_finish<RING>(so, s2, v, W0, W1, W2, edt, module, double_update, ring);
+        }
+    }
     if (RING) ring_complete(ctl, 1, ring);
 }
 

@@ -64,6 +64,9 @@ struct Ctx {
     Mailbox mine{};
     Peers peers{};
     // split solid sub-steps: this rank advances the solids [s_lo, s_hi) and stores P / u / the final state into the peers' arrays
+    // sub-step kernels with a team of lanes per solid (kernels.cuh); 0: one thread per solid
+    bool solid_team = true, team_ok = false, solid_team_always = false;
+    int sol_maxlen = 0, sol_rmaxlen = 0;
     bool split_substeps = true;
     int s_lo = 0, s_hi = 0;
     SolidRing ring{};
@@ -126,6 +129,7 @@ struct Ctx {
     bool solids_pending = false;  // sub-steps enqueued on `side`, not yet joined by the main stream
     std::vector<void *> allocs;
 
+    bool tracing = false; // device-side timeline (mphx_trace_enable)
     // phase timers (src/main.cpp:695-700 split)
     bool timing = false;
     std::vector<cudaEvent_t> ev, ev_pool;
@@ -383,9 +387,9 @@ template <class K> static void preload(K kernel)
 }
 static void preload_kernels(int dim)
 {
-    preload(k_prestep); preload(k_need); preload(k_decide); preload(k_vote); preload(k_wait<0>); preload(k_wait<1>);
-    preload(k_count); preload(k_clamp_counts); preload(k_push); preload(k_push_scalar); preload(k_unpack_particles);
-    preload(k_advance_n); preload(k_halo_pack); preload(k_halo_repack); preload(k_unpack_refresh); preload(k_slab_slots);
+    preload(k_mark); preload(k_prestep); preload(k_need); preload(k_decide); preload(k_vote); preload(k_wait<0>); preload(k_wait<1>);
+    preload(k_count); preload(k_wait_decide); preload(k_halo_resend); preload(k_push); preload(k_push_scalar); preload(k_unpack_particles);
+    preload(k_advance_n); preload(k_halo_pack); preload(k_unpack_refresh); preload(k_slab_slots);
     preload(k_unpack_scalar); preload(k_solid_owned_list); preload(k_solid_publish_P); preload(k_solid_spread_P);
     preload(k_solid_publish_V); preload(k_solid_apply_update); preload(k_scan_reduce); preload(k_scan_top); preload(k_scan_apply);
     preload(k_scatter_index); preload(k_permute); preload(k_set_n); preload(k_brick_localize); preload(k_brick_count); preload(k_brick_pass1<3>);
@@ -396,7 +400,9 @@ static void preload_kernels(int dim)
     preload(k_pass2_v3<D, true, false>); preload(k_pass2_v3<D, true, true>);                                             \
     preload(k_solid_pass1<D, false, false>); preload(k_solid_pass2<D, false, false>); preload(k_solid_pass1<D, true, false>); \
     preload(k_solid_pass2<D, true, false>); preload(k_solid_pass1<D, false, true>); preload(k_solid_pass2<D, false, true>); \
-    preload(k_solid_pass1<D, true, true>); preload(k_solid_pass2<D, true, true>)
+    preload(k_solid_pass1<D, true, true>); preload(k_solid_pass2<D, true, true>);                                        \
+    preload(k_solid_pass1_team<D, false>); preload(k_solid_pass1_team<D, true>); preload(k_solid_pass2_team<D, false>);  \
+    preload(k_solid_pass2_team<D, true>)
     if (dim == 3) { PRELOAD_DIM(3); } else { PRELOAD_DIM(2); }
 #undef PRELOAD_DIM
     cudaGetLastError();
@@ -406,19 +412,40 @@ static void preload_kernels(int dim)
 constexpr int kPushBlocks = 64, kPushThreads = 256;
 enum { kPushMigL = 0, kPushMigR, kPushHaloL, kPushHaloR, kPushPL, kPushPR, kPushSolP, kPushSolV };
 
-static int exchange_particles(Ctx *c, bool halo)
+// grids of the kernels that only work on rebuild steps (or on a message): grid-stride, so that a step that reuses its
+// list does not pay for tens of thousands of blocks that return at once
+static int small_grid(long long n, int threads = kBlock) { return (int)std::max<long long>(1, std::min<long long>((n + threads - 1) / threads, 148 * 16)); }
+
+static PushPair push_pair(Ctx *c, bool halo)
 {
     // what I send "to the left" arrives in the left neighbour's mailbox as "from the right" (side 1), and vice versa
     Ctl *ctl = c->ctl;
-    double **stage = halo ? c->stage_halo : c->stage_mig;
-    const int *cnt = halo ? ctl->halo_cnt : ctl->mig_cnt;
-    const int w0 = halo ? kPushHaloL : kPushMigL;
     Mailbox &L = c->peers.left, &R = c->peers.right;
-    LAUNCH(c, k_push, kPushBlocks, kPushThreads, ctl, c->epoch, w0, stage[0], cnt + 0, kMsgDoubles, halo ? L.halo[1] : L.mig[1],
-           (halo ? L.cnt_halo : L.cnt_mig) + 1, (halo ? L.fhalo : L.fmig) + 1);
-    LAUNCH(c, k_push, kPushBlocks, kPushThreads, ctl, c->epoch, w0 + 1, stage[1], cnt + 1, kMsgDoubles, halo ? R.halo[0] : R.mig[0],
-           (halo ? R.cnt_halo : R.cnt_mig) + 0, (halo ? R.fhalo : R.fmig) + 0);
-    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, halo ? c->mine.fhalo : c->mine.fmig, 2, halo ? kWaitHalo : kWaitMig);
+    PushPair pp{};
+    double **stage = halo ? c->stage_halo : c->stage_mig;
+    int *cnt = halo ? ctl->halo_cnt : ctl->mig_cnt;
+    pp.src[0] = stage[0]; pp.src[1] = stage[1];
+    pp.cnt[0] = cnt + 0; pp.cnt[1] = cnt + 1;
+    pp.dst[0] = halo ? L.halo[1] : L.mig[1]; pp.dst[1] = halo ? R.halo[0] : R.mig[0];
+    pp.dst_cnt[0] = (halo ? L.cnt_halo : L.cnt_mig) + 1; pp.dst_cnt[1] = (halo ? R.cnt_halo : R.cnt_mig) + 0;
+    pp.dst_flag[0] = (halo ? L.fhalo : L.fmig) + 1; pp.dst_flag[1] = (halo ? R.fhalo : R.fmig) + 0;
+    return pp;
+}
+// migration: rebuild steps only (nothing is sent, nothing is waited for on a step that reuses its list);
+// halo: rebuild steps push the freshly packed staging buffers, reuse steps pack the same particles straight into the
+// neighbours' mailboxes (k_halo_resend); one wait for both neighbours
+static int exchange_particles(Ctx *c, bool halo)
+{
+    Ctl *ctl = c->ctl;
+    const PushPair pp = push_pair(c, halo);
+    const dim3 grid(kPushBlocks, 2);
+    k_push<<<grid, kPushThreads, 0, c->stream>>>(ctl, c->epoch, halo ? kPushHaloL : kPushMigL, pp, kMsgDoubles, c->msg_cap, 1);
+    ++c->launches;
+    if (halo) {
+        k_halo_resend<<<grid, kPushThreads, 0, c->stream>>>(ctl, c->epoch, kPushHaloL, c->S, c->haloSlot[0], c->haloSlot[1], pp);
+        ++c->launches;
+    }
+    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, halo ? c->mine.fhalo : c->mine.fmig, 2, halo ? kWaitHalo : kWaitMig, halo ? 0 : 1);
     CK(cudaGetLastError());
     return MPHX_OK;
 }
@@ -474,58 +501,61 @@ static int stage_build(Ctx *c, bool motion)
     if (motion) // :3066-3070 (host mirror of the wall centres)
         for (int t = 4; t < kTypeCount; ++t)
             for (int d = 0; d < 3; ++d) c->wall_center[t][d] += c->p.wall_velocity[t][d] * c->p.dt;
+    if (c->tracing) LAUNCH(c, k_mark, 1, 1, ctl, 9); // (pre-step done, incl. the wait for the previous step's sub-steps)
     // rebuild or reuse: every rank votes, the OR decides (one context: its own vote)
-    LAUNCH(c, k_need, 1, 1, ctl, da, (const int *)c->pl.flags);
     if (c->slab) {
-        LAUNCH(c, k_vote, 1, 32, ctl, c->epoch, c->peers);
-        LAUNCH(c, k_wait<1>, 1, 32, ctl, c->epoch, c->mine.vote, c->nranks, kWaitVote);
+        LAUNCH(c, k_vote, 1, 32, ctl, c->epoch, c->peers, da, (const int *)c->pl.flags);
+        LAUNCH(c, k_wait_decide, 1, 32, ctl, c->epoch, c->mine.vote, c->nranks, da, c->pl.flags);
+    } else {
+        LAUNCH(c, k_need, 1, 1, ctl, da, (const int *)c->pl.flags);
+        LAUNCH(c, k_decide, 1, 1, ctl, da, c->pl.flags);
     }
-    LAUNCH(c, k_decide, 1, 1, ctl, da, c->pl.flags);
     SlabSend snd{};
     snd.buf[0] = c->stage_mig[0]; snd.buf[1] = c->stage_mig[1]; snd.capacity = c->msg_cap;
-    LAUNCH(c, k_count, nb, kBlock, ctl, c->S, c->grid, c->cellCount, c->slot, snd);
+    LAUNCH(c, k_count, small_grid(c->nmax), kBlock, ctl, c->S, c->grid, c->cellCount, c->slot, snd);
     if (c->slab) {
         int rc;
-        const int mb = nblk(c->msg_cap);
+        const dim3 mb2(small_grid(c->msg_cap), 2);
         const double W0 = c->grid.W[0];
-        // (1) migration (rebuild steps; a reuse step sends empty messages)
-        LAUNCH(c, k_clamp_counts, 1, 32, ctl, c->msg_cap);
+        // (1) migration (rebuild steps only)
         if ((rc = exchange_particles(c, false))) return rc;
-        for (int side = 0; side < 2; ++side)
-            LAUNCH(c, k_unpack_particles, mb, kBlock, ctl, side, c->mine.mig[side], c->mine.cnt_mig, c->msg_cap, c->cap, 0.0, 0, c->S, c->grid,
-                   c->cellCount, c->slot, c->ancx, c->ancy, c->ancz);
+        SidePair mg{};
+        mg.buf[0] = c->mine.mig[0]; mg.buf[1] = c->mine.mig[1];
+        k_unpack_particles<<<mb2, kBlock, 0, c->stream>>>(ctl, mg, c->mine.cnt_mig, c->msg_cap, c->cap, 0, c->S, c->grid, c->cellCount, c->slot,
+                                                          c->ancx, c->ancy, c->ancz);
+        ++c->launches;
         LAUNCH(c, k_advance_n, 1, 1, ctl, c->mine.cnt_mig, c->msg_cap, c->cap, 0);
         // (2) halo: rebuild steps pack the particles within one halo width of the faces, reuse steps re-send the same ones
         SlabSend hs{};
         hs.buf[0] = c->stage_halo[0]; hs.buf[1] = c->stage_halo[1]; hs.capacity = c->msg_cap;
-        LAUNCH(c, k_halo_pack, nb, kBlock, ctl, c->S, c->grid, hs, c->haloSrc[0], c->haloSrc[1]);
-        LAUNCH(c, k_clamp_counts, 1, 32, ctl, c->msg_cap);
-        LAUNCH(c, k_halo_repack, mb, kBlock, ctl, c->S, hs, c->haloSlot[0], c->haloSlot[1]);
+        LAUNCH(c, k_halo_pack, small_grid(c->nmax), kBlock, ctl, c->S, c->grid, hs, c->haloSrc[0], c->haloSrc[1]);
         if ((rc = exchange_particles(c, true))) return rc;
         // halo copies that crossed the periodic seam are shifted by the box width so that separations in
         // x need no wrap inside a slab; migrants were already wrapped into the box by the sender
-        const double sh[2] = {c->rank == 0 ? -W0 : 0.0, c->rank == c->nranks - 1 ? W0 : 0.0};
-        for (int side = 0; side < 2; ++side) {
-            LAUNCH(c, k_unpack_particles, mb, kBlock, ctl, side, c->mine.halo[side], c->mine.cnt_halo, c->msg_cap, c->cap, sh[side], kGhost, c->S,
-                   c->grid, c->cellCount, c->slot, c->ancx, c->ancy, c->ancz);
-            LAUNCH(c, k_unpack_refresh, mb, kBlock, ctl, side, c->mine.halo[side], sh[side], c->S, c->ghostSlot[side]);
-        }
+        SidePair hl{};
+        hl.buf[0] = c->mine.halo[0]; hl.buf[1] = c->mine.halo[1];
+        hl.xshift[0] = c->rank == 0 ? -W0 : 0.0; hl.xshift[1] = c->rank == c->nranks - 1 ? W0 : 0.0;
+        k_unpack_particles<<<mb2, kBlock, 0, c->stream>>>(ctl, hl, c->mine.cnt_halo, c->msg_cap, c->cap, kGhost, c->S, c->grid, c->cellCount, c->slot,
+                                                          c->ancx, c->ancy, c->ancz);
+        k_unpack_refresh<<<mb2, kBlock, 0, c->stream>>>(ctl, hl, c->S, c->ghostSlot[0], c->ghostSlot[1]);
+        c->launches += 2;
         LAUNCH(c, k_advance_n, 1, 1, ctl, c->mine.cnt_halo, c->msg_cap, c->cap, 1);
     }
+    if (c->tracing) LAUNCH(c, k_mark, 1, 1, ctl, 10); // (migration + halo exchanged)
     const int nc = c->grid.ncells + 2; // + parked + dead buckets
     LAUNCH(c, k_scan_reduce, c->scan_blocks, kScanThreads, ctl, c->cellCount, nc, c->blockSums);
     LAUNCH(c, k_scan_top, 1, kScanThreads, ctl, c->blockSums, c->scan_blocks);
     LAUNCH(c, k_scan_apply, c->scan_blocks, kScanThreads, ctl, c->cellCount, nc, c->blockSums, c->cellStart, 1);
-    LAUNCH(c, k_scatter_index, nb, kBlock, ctl, c->S.key, c->slot, c->cellStart, c->tmpIdx);
+    LAUNCH(c, k_scatter_index, small_grid(c->nmax), kBlock, ctl, c->S.key, c->slot, c->cellStart, c->tmpIdx);
     LAUNCH(c, k_permute, nb, kBlock, ctl, c->S, c->T, c->cellStart, c->tmpIdx, c->grid, c->where, c->sol.slot, c->sol.sb, c->ancx, c->ancy,
            c->ancz);
     LAUNCH(c, k_set_n, 1, 1, ctl, c->cellStart, c->grid.ncells);
     std::swap(c->S, c->T);
     c->bx = c->S.x; c->by = c->S.y; c->bz = c->S.z;
     if (c->slab) {
-        LAUNCH(c, k_slab_slots, nblk(c->msg_cap), kBlock, ctl, c->where, c->haloSrc[0], c->haloSrc[1], c->haloSlot[0], c->haloSlot[1],
+        LAUNCH(c, k_slab_slots, small_grid(c->msg_cap), kBlock, ctl, c->where, c->haloSrc[0], c->haloSrc[1], c->haloSlot[0], c->haloSlot[1],
                c->ghostSlot[0], c->ghostSlot[1]);
-        if (c->ns > 0) LAUNCH(c, k_solid_owned_list, nb, kBlock, ctl, c->S, c->own_sol);
+        if (c->ns > 0) LAUNCH(c, k_solid_owned_list, small_grid(c->ns), kBlock, ctl, c->S, c->sol, c->own_sol);
     }
     CK(cudaGetLastError());
     return MPHX_OK;
@@ -594,17 +624,20 @@ static int exchange_pressure(Ctx *c)
         for (int p = 0; p < 4; ++p) { pf.a[1 + p] = st[p]; pt.a[1 + p] = st[p]; }
         pf.count = pt.count = 5;
     }
-    LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPL, 0, c->haloSlot[0], pf, c->msg_cap, L.p[1], L.fp + 1);
-    LAUNCH(c, k_push_scalar, kPushBlocks, kPushThreads, ctl, c->epoch, kPushPR, 1, c->haloSlot[1], pf, c->msg_cap, R.p[0], R.fp + 0);
+    ScalarPush sp{};
+    sp.dst[0] = L.p[1]; sp.dst[1] = R.p[0]; sp.dst_flag[0] = L.fp + 1; sp.dst_flag[1] = R.fp + 0;
+    k_push_scalar<<<dim3(kPushBlocks, 2), kPushThreads, 0, c->stream>>>(ctl, c->epoch, kPushPL, c->haloSlot[0], c->haloSlot[1], pf, c->msg_cap, sp);
+    ++c->launches;
     if (c->ns > 0) LAUNCH(c, k_solid_publish_P, kPushBlocks, kPushThreads, ctl, c->epoch, kPushSolP, c->S, c->sol, c->own_sol, c->P, c->peers);
-    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fp, 2, kWaitP);
-    const int mb = nblk(c->msg_cap);
-    for (int side = 0; side < 2; ++side) LAUNCH(c, k_unpack_scalar, mb, kBlock, ctl, side, c->ghostSlot[side], c->mine.p[side], c->msg_cap, pt, c->S.rb);
-    if (c->ns > 0) {
-        LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fsolP, c->nranks, kWaitSolP);
-        LAUNCH(c, k_solid_spread_P, nblk(c->nmax), kBlock, ctl, c->S, c->grid, c->sol, c->mine.solP, c->P, c->surface_tension ? c->PA : (double *)nullptr,
-               c->gcx, c->gcy, c->gcz, c->phys);
-    }
+    // one wait for the neighbours' PressureP and every rank's share of the replicated solids' PressureP
+    LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, c->mine.fp, 2, kWaitP, 0, c->ns > 0 ? c->mine.fsolP : (const unsigned long long *)nullptr,
+           c->ns > 0 ? c->nranks : 0);
+    k_unpack_scalar<<<dim3(small_grid(c->msg_cap), 2), kBlock, 0, c->stream>>>(ctl, c->ghostSlot[0], c->ghostSlot[1], c->mine.p[0], c->mine.p[1],
+                                                                             c->msg_cap, pt, c->S.rb);
+    ++c->launches;
+    if (c->ns > 0)
+        LAUNCH(c, k_solid_spread_P, small_grid(c->ns), kBlock, ctl, c->S, c->grid, c->sol, c->mine.solP, c->P,
+               c->surface_tension ? c->PA : (double *)nullptr, c->gcx, c->gcy, c->gcz, c->phys);
     CK(cudaGetLastError());
     return MPHX_OK;
 }
@@ -635,6 +668,7 @@ static int run_pass2(Ctx *c)
         // slab mode: the owners' coupled velocities go to every rank's mailbox
         if (c->slab) LAUNCH(c, k_solid_publish_V, kPushBlocks, kPushThreads, ctl, c->epoch, kPushSolV, c->S, c->sol, c->own_sol, c->peers);
         if (split) CK(cudaEventRecord(c->ev_solid_ready, c->stream));
+        if (c->tracing) LAUNCH(c, k_mark, 1, 1, ctl, 5);
         const Subset rest{nullptr, 0, 1};
         P2ALL(vblocks, rest);
     } else {
@@ -675,18 +709,37 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
         LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV, c->s_lo, c->s_hi, c->p.clamp_module);
     }
     const int cnt = c->s_hi - c->s_lo;
-    const int grid = ring ? std::max(nblk(cnt), 1) : nblk(cnt); // (an empty share still posts its phase counters)
+    const int threads = ring ? kRingBlock : kBlock;
+    const int grid = ring ? std::max(nblk(cnt, threads), 1) : nblk(cnt); // (an empty share still posts its phase counters)
 #define SOLID_STEP(D, PK, RG)                                                                                                          \
     do {                                                                                                                                 \
-        LAUNCH_ON(c, strm, (k_solid_pass1<D, PK, RG>), grid, kBlock, c->ctl, c->sol, c->s_lo, c->s_hi, rg);                               \
+        LAUNCH_ON(c, strm, (k_solid_pass1<D, PK, RG>), grid, threads, c->ctl, c->sol, c->s_lo, c->s_hi, rg);                               \
         if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
         ++rg.seq;                                                                                                                        \
-        LAUNCH_ON(c, strm, (k_solid_pass2<D, PK, RG>), grid, kBlock, c->ctl, c->sol, c->s_lo, c->s_hi, k.domain_width[0],                 \
+        LAUNCH_ON(c, strm, (k_solid_pass2<D, PK, RG>), grid, threads, c->ctl, c->sol, c->s_lo, c->s_hi, k.domain_width[0],                 \
                   k.domain_width[1], k.domain_width[2], c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density, rg);                  \
         if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
         ++rg.seq;                                                                                                                        \
     } while (0)
-#define SOLID_STEP_D(D) do { if (c->sol.packed) { if (ring) SOLID_STEP(D, true, true); else SOLID_STEP(D, true, false); } \
+#define TEAM_STEP(D, RG)                                                                                                               \
+    do {                                                                                                                                 \
+        k_solid_pass1_team<D, RG><<<tgrid, kTeamBlock, 0, strm>>>(c->ctl, c->sol, c->s_lo, c->s_hi, rg);                                  \
+        ++c->launches;                                                                                                                   \
+        if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
+        ++rg.seq;                                                                                                                        \
+        k_solid_pass2_team<D, RG><<<tgrid, kTeamBlock, 0, strm>>>(c->ctl, c->sol, c->s_lo, c->s_hi, k.domain_width[0],                    \
+            k.domain_width[1], k.domain_width[2], c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density, rg);                        \
+        ++c->launches;                                                                                                                   \
+        if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
+        ++rg.seq;                                                                                                                        \
+    } while (0)
+    // the team kernels need ~5x the instructions and L1 wavefronts (a team's gathers do not coalesce across lanes): on a full
+    // set of solids they lose to one thread per solid (113k solids: 116 + 211 us against 58 + 95 us per sub-step), on a
+    // rank's share -- about one warp per SM, a pure latency chain -- they win (28k solids: 72 + 52 us one thread per solid)
+    const bool team = c->team_ok && c->sol.packed && (c->solid_team_always || (ring && cnt * 2 <= ns));
+    const int tgrid = std::max(nblk(cnt, kTeamBlock / kTeam), 1);
+#define SOLID_STEP_D(D) do { if (team) { if (ring) TEAM_STEP(D, true); else TEAM_STEP(D, false); }                         \
+                             else if (c->sol.packed) { if (ring) SOLID_STEP(D, true, true); else SOLID_STEP(D, true, false); } \
                              else { if (ring) SOLID_STEP(D, false, true); else SOLID_STEP(D, false, false); } } while (0)
     rg.seq = seq0 + 1;
     for (int s = 0; s < substeps; ++s) {
@@ -694,6 +747,7 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
         if (c->p.dim == 3) SOLID_STEP_D(3); else SOLID_STEP_D(2);
     }
 #undef SOLID_STEP_D
+#undef TEAM_STEP
 #undef SOLID_STEP
     CK(cudaGetLastError());
     return MPHX_OK;
@@ -739,23 +793,31 @@ static void timer_resolve(Ctx *c)
     c->side_marks.clear();
 }
 
+#define TRACE_ON(strm, code) do { if (c->tracing) LAUNCH_ON(c, strm, k_mark, 1, 1, c->ctl, code); } while (0)
 static int one_step(Ctx *c, bool fluid_only)
 {
     int rc;
     if (c->slab && !c->connected) { set_last_error("slab context is not connected to its peers (mphx_slab_connect)"); return MPHX_ERR_INVALID; }
     timer_mark(c);
+    TRACE_ON(c->stream, 1);
     if ((rc = stage_build(c, true))) return rc;     // calculateWall, PeriodicBoundary, resets, calculateNeighbor
     timer_mark(c);
+    TRACE_ON(c->stream, 2);
     if ((rc = run_pass1(c, true))) return rc;       // filter; DensityA..DivergenceP, coefficients, PressureP/A
+    TRACE_ON(c->stream, 3);
     if (c->slab && (rc = exchange_pressure(c))) return rc;
     timer_mark(c);
+    TRACE_ON(c->stream, 4);
     if ((rc = run_pass2(c))) return rc;             // force sums, gravity, interface, acceleration, convection
     timer_mark(c);
+    TRACE_ON(c->stream, 6);
     if (!fluid_only) {
         if (solid_split(c)) { // sub-steps on the second stream: joined by the next pre-step (or by any reader)
             CK(cudaStreamWaitEvent(c->side, c->ev_solid_ready, 0));
+            TRACE_ON(c->side, 7);
             if (c->timing) { cudaEvent_t e = timer_event(c); cudaEventRecord(e, c->side); c->side_marks.push_back(e); }
             if ((rc = run_solid_substeps(c, c->side))) return rc;
+            TRACE_ON(c->side, 8);
             if (c->timing) { cudaEvent_t e = timer_event(c); cudaEventRecord(e, c->side); c->side_marks.push_back(e); }
             CK(cudaEventRecord(c->ev_solid_done, c->side));
             c->solids_pending = true;
@@ -1082,6 +1144,19 @@ static int init_solid(Ctx *c)
             CK(cudaMemcpy(c->sol.ttab, table.data(), sizeof(Rec) * table.size(), cudaMemcpyHostToDevice));
             c->sol.packed = 1;
             c->solid_tuples = (int)table.size();
+            // the same indices in CSR order for the team kernels (a team's lanes read consecutive entries of a row)
+            std::vector<unsigned short> ctix((size_t)std::max<long long>(total, 1)), crtix((size_t)std::max<long long>(total, 1));
+            for (int s = 0; s < ns; ++s) {
+                for (int kk = 0; kk < len[s]; ++kk) ctix[(size_t)off32[s] + kk] = tix[(size_t)kk * ns + s];
+                for (int kk = 0; kk < rlen[s]; ++kk) crtix[(size_t)roff[s] + kk] = rtix[(size_t)kk * ns + s];
+            }
+            if (c->alloc(&c->sol.ctix, ctix.size()) || c->alloc(&c->sol.crtix, crtix.size())) return MPHX_ERR_NOMEM;
+            CK(cudaMemcpy(c->sol.ctix, ctix.data(), sizeof(unsigned short) * ctix.size(), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(c->sol.crtix, crtix.data(), sizeof(unsigned short) * crtix.size(), cudaMemcpyHostToDevice));
+            c->sol_maxlen = maxlen; c->sol_rmaxlen = rmaxlen;
+            if (c->solid_team) {
+                c->team_ok = true;
+            }
         }
     }
     return MPHX_OK;
@@ -1199,6 +1274,10 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
     cudaFuncSetAttribute(k_brick_pass1<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kBrickCap * (sizeof(Rec) + sizeof(double2))));
     for (int k = 0; k < 2; ++k) cudaEventCreate(&c->tev[k]);
     if (const char *e = std::getenv("MPHX_OVERLAP_SOLID")) c->overlap_solid = std::atoi(e) != 0;
+    if (const char *e = std::getenv("MPHX_SOLID_TEAM")) { // 0: one thread per solid in the sub-steps, 2: a team per solid even on a full set
+        c->solid_team = std::atoi(e) != 0;
+        c->solid_team_always = std::atoi(e) == 2;
+    }
     if (const char *e = std::getenv("MPHX_SPLIT_SUBSTEPS")) c->split_substeps = std::atoi(e) != 0; // 0: every slab runs all solids' sub-steps
     {   // highest priority: the few blocks of a sub-step kernel must get SM slots as pass-2 blocks retire,
         // not after the whole pass-2 grid has been issued
@@ -1872,6 +1951,40 @@ int mphx_get_timers(mphx_ctx *ctx, double ms[4])
     cudaSetDevice(c->device);
     timer_resolve(c);
     ms[0] = c->ms[0]; ms[1] = c->ms[1] + c->ms[2]; ms[2] = c->ms[3]; ms[3] = c->ms[4];
+    return MPHX_OK;
+}
+
+/* Device-side timeline of the following steps: capacity > 0 gives the context a buffer of that many (code, ns) marks and
+   switches the markers on (a few one-thread kernels per step), 0 switches them off.  Codes: see trace_mark in kernels.cuh. */
+int mphx_trace_enable(mphx_ctx *ctx, int capacity)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || capacity < 0) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
+    CK(cudaStreamSynchronize(c->stream));
+    unsigned long long *buf = nullptr;
+    if (capacity > 0 && c->alloc(&buf, 2 * (size_t)capacity)) return MPHX_ERR_NOMEM;
+    const int zero = 0;
+    CK(cudaMemcpy(&c->ctl->trace, &buf, sizeof(buf), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&c->ctl->trace_cap, &capacity, sizeof(int), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(&c->ctl->trace_n, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    c->tracing = capacity > 0;
+    return MPHX_OK;
+}
+/* the marks recorded so far: out[2 i] = code, out[2 i + 1] = %globaltimer in ns; *count = marks written (<= max_marks) */
+int mphx_trace_read(mphx_ctx *ctx, unsigned long long *out, int max_marks, int *count)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(ctx);
+    if (!c || !out || !count || max_marks < 0) return MPHX_ERR_INVALID;
+    CK(cudaSetDevice(c->device));
+    { int jrc = join_solids(c); if (jrc) return jrc; }
+    CK(cudaStreamSynchronize(c->stream));
+    Ctl h;
+    CK(cudaMemcpy(&h, c->ctl, sizeof(Ctl), cudaMemcpyDeviceToHost));
+    const int n = std::min(std::min(h.trace_n, h.trace_cap), max_marks);
+    if (n > 0) CK(cudaMemcpy(out, h.trace, sizeof(unsigned long long) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
+    *count = n;
     return MPHX_OK;
 }
 

@@ -365,6 +365,18 @@ def bench_main(args, METRIC, UNIT, WORKLOAD, peaks, ClockSampler, cpu_reference_
     allp = [torch.empty_like(pt) for _ in range(world)]
     dist.all_gather(allp, pt)
     phases = [[round(float(v), 4) for v in t.cpu()] for t in allp]
+    if getattr(args, "trace", ""):   # device-side timeline of 3 steps (diagnostic; outside every timed region)
+        s._ck("mphx_trace_enable", s.lib.mphx_trace_enable(s.ctx, 8192))
+        dist.barrier()
+        s.step(3)
+        s.sync()
+        buf = np.zeros(2 * 8192, dtype=np.uint64)
+        cnt = C.c_int()
+        s._ck("mphx_trace_read", s.lib.mphx_trace_read(s.ctx, buf.ctypes.data, 8192, C.byref(cnt)))
+        s._ck("mphx_trace_enable", s.lib.mphx_trace_enable(s.ctx, 0))
+        marks = buf[: 2 * cnt.value].reshape(-1, 2)
+        with open(f"{args.trace}_rank{rank}.json", "w") as fh:
+            json.dump({"rank": rank, "world": world, "marks": [[int(a), int(b)] for a, b in marks]}, fh)
     launches = allsum(float(s.launch_count - l0))
     st = s.status()
     held = allmax(float(st["held"]))

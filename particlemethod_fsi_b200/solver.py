@@ -77,6 +77,8 @@ def _load():
     L.mphx_set_timing.argtypes = [vp, C.c_int]
     L.mphx_get_timers.argtypes = [vp, C.POINTER(C.c_double * 4)]
     L.mphx_get_kernel_timers.argtypes = [vp, C.POINTER(C.c_double * 5)]
+    L.mphx_trace_enable.argtypes = [vp, C.c_int]
+    L.mphx_trace_read.argtypes = [vp, vp, C.c_int, ip]
     L.mphx_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.mphx_count_pairs.argtypes = [vp, C.POINTER(C.c_ulonglong * 2)]
     L.mphx_get_virial_ms.argtypes = [vp]

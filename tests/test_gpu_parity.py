@@ -611,6 +611,27 @@ def test_candidate_list_fallbacks_agree(name, cap, monkeypatch):
         assert rel_err(b[f], a[f]) <= tol, (name, cap, f, rel_err(b[f], a[f]))
 
 
+@pytest.mark.parametrize("name", ["bar2d", "fsi2d", "fsi3d_mini"])
+def test_team_substep_kernels_equal_one_thread_per_solid(name, monkeypatch):
+    """The solid sub-step kernels with a team of 16 lanes per solid (terms in parallel, sums in the reference's serial
+    order) against the one-thread-per-solid kernels (MPHX_SOLID_TEAM=0): the same operations in the same order, so
+    every solid field is the same bits."""
+    case = getattr(cases, name)()
+    fields = ("position", "velocity", "stress", "strain", "deform_gradient", "force")
+    monkeypatch.setenv("MPHX_SOLID_TEAM", "2")   # (a single context uses one thread per solid by default: a team only pays on a rank's share)
+    a_s = Solver.from_case(case)
+    a_s.step(25, sync=True)
+    a = a_s.download(*fields)
+    a_s.close()
+    monkeypatch.setenv("MPHX_SOLID_TEAM", "0")
+    b_s = Solver.from_case(case)
+    b_s.step(25, sync=True)
+    b = b_s.download(*fields)
+    b_s.close()
+    for f in fields:
+        assert np.array_equal(a[f], b[f]), (name, f, float(np.abs(a[f] - b[f]).max()))
+
+
 def test_fsi2d_100k_matches_oracle_and_aggregates():
     """BASELINE.json configs[2]: 2D dam break on an elastic plate at ~100k particles (l0 = 5e-4).
     Per-step fields against the oracle over the first 100 steps, then final-state aggregates (stated
