@@ -1175,9 +1175,9 @@ __device__ __forceinline__ Rec ld_rec_ro(const Rec *p)
 // stress P after pass 1, the displacement u after pass 2 -- straight into their solid arrays over NVLink (Solid::pmask:
 // the ranks whose rows reference s), from the kernel that computes it.  The last block of a launch then raises this rank's
 // phase counter in every rank's mailbox; the next kernel of every rank is preceded by a one-warp wait for all counters.
+// (the threads that stored into peer memory have fenced after their stores: solid_pass*_finish)
 __device__ __forceinline__ void ring_complete(Ctl *ctl, int which, const SolidRing &ring)
 {
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence_system();
@@ -1191,9 +1191,10 @@ __device__ __forceinline__ void ring_complete(Ctl *ctl, int which, const SolidRi
 }
 template <int DIMS, bool RING>
 __device__ __forceinline__ void solid_pass1_finish(const Solid &so, const int s, const double (&G)[3][3], const SolidRing &ring);
-template <int DIMS, bool PACKED, bool RING>
+template <int DIMS, bool PACKED, bool RING, bool DEEP>
 __device__ __forceinline__ void solid_pass1_row(const Solid &so, const int s, const SolidRing &ring)
 {
+    constexpr int GI = DEEP ? 8 : 4; // pairs whose gathers are in flight together
     using namespace ex;
     const int ns = so.ns;
     const Rec uo = so.u[s];
@@ -1219,10 +1220,10 @@ __device__ __forceinline__ void solid_pass1_row(const Solid &so, const int s, co
         for (int u = 0; u < kSolidBatch; ++u) { jc[u] = jn[u]; tc[u] = tn[u]; }
         if (kk0 + kSolidBatch < len) fetch(kk0 + kSolidBatch);
 #pragma unroll
-        for (int h = 0; h < kSolidBatch; h += 4) { // four pairs' gathers in flight
-            Rec tt[4], un[4];
+        for (int h = 0; h < kSolidBatch; h += GI) {
+            Rec tt[GI], un[GI];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < GI; ++u) {
                 const size_t k = (size_t)(kk0 + h + u < len ? kk0 + h + u : 0) * ns + s;
                 if (PACKED) tt[u] = ld_rec_ro(so.ttab + tc[h + u]);
                 else {
@@ -1232,8 +1233,8 @@ __device__ __forceinline__ void solid_pass1_row(const Solid &so, const int s, co
                 un[u] = so.u[jc[h + u]];
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                if (kk0 + h + u >= len) break;
+            for (int u = 0; u < GI; ++u) {
+                if (kk0 + h + u >= len) { if (DEEP) continue; else break; } // (DEEP: straight-line code, the tail is predicated)
                 const double d0[3] = {tt[u].a, tt[u].b, DIMS == 3 ? tt[u].c : 0.0};
                 const double w = tt[u].d;
                 const double uj[3] = {un[u].a, un[u].b, DIMS == 3 ? un[u].c : 0.0};
@@ -1296,19 +1297,22 @@ __device__ __forceinline__ void solid_pass1_finish(const Solid &so, const int s,
 #pragma unroll
             for (int e = 0; e < 9; ++e) d[e] = Pv[e];
         }
+        __threadfence_system();
     }
 }
 // (RING: a rank's share is ~ns/nranks solids, about one block per SM, and its kernels run beside the fluid's share of pass 2
 // on a high-priority stream: blocks of kRingBlock threads with <= 128 registers need no more of an SM than ONE retiring
 // pass-2 block frees (80 registers x 128 threads) -- a 218-register block of 128 threads waited for three to retire at once,
 // which the scheduler does not arrange: the sub-steps stretched over the whole of pass 2)
-constexpr int kRingBlock = 64;
-template <int DIMS, bool PACKED, bool RING>
-__global__ void __launch_bounds__(RING ? kRingBlock : 128, RING ? 8 : MPHX_S1_MINB)
+// DEEP: eight pairs' gathers in flight per thread, one warp per block, up to 255 registers -- for a latency chain at about
+// one warp per SM (a rank's share) registers are free and only memory-level parallelism shortens the chain.
+constexpr int kRingBlock = 32;
+template <int DIMS, bool PACKED, bool RING, bool DEEP>
+__global__ void __launch_bounds__(DEEP ? kRingBlock : 128, DEEP ? 8 : MPHX_S1_MINB)
 k_solid_pass1(Ctl *ctl, Solid so, int s_lo, int s_hi, SolidRing ring)
 {
     const int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < s_hi) solid_pass1_row<DIMS, PACKED, RING>(so, s, ring);
+    if (s < s_hi) solid_pass1_row<DIMS, PACKED, RING, DEEP>(so, s, ring);
     if (RING) ring_complete(ctl, 0, ring);
 }
 
@@ -1335,10 +1339,11 @@ __host__ __device__ inline bool solid_clamped(int module, double x0, double y0)
 template <bool RING>
 __device__ __forceinline__ void solid_pass2_finish(const Solid &so, const int s, double (&v)[3], double W0, double W1, double W2, double edt,
                                                    int module, int double_update, const SolidRing &ring);
-template <int DIMS, bool PACKED, bool RING>
+template <int DIMS, bool PACKED, bool RING, bool DEEP>
 __device__ __forceinline__ void solid_pass2_row(const Solid &so, const int s, double W0, double W1, double W2, double edt, int module,
                                                 int double_update, const double *__restrict__ inv_density, const SolidRing &ring)
 {
+    constexpr int GI = DEEP ? 8 : MPHX_S2_G; // pairs whose gathers are in flight together
     using namespace ex;
     const int ns = so.ns;
     const double xi0 = so.x0[s], yi0 = so.y0[s], zi0 = so.z0[s];
@@ -1367,11 +1372,11 @@ __device__ __forceinline__ void solid_pass2_row(const Solid &so, const int s, do
             for (int u = 0; u < kSolidBatch; ++u) { jc[u] = jn[u]; tc[u] = tn[u]; }
             if (kk0 + kSolidBatch < ke) fetch(kk0 + kSolidBatch);
 #pragma unroll
-            for (int h = 0; h < kSolidBatch; h += MPHX_S2_G) {
-                Rec tt[MPHX_S2_G];
-                double Pj[MPHX_S2_G][9];
+            for (int h = 0; h < kSolidBatch; h += GI) {
+                Rec tt[GI];
+                double Pj[GI][9];
 #pragma unroll
-                for (int u = 0; u < MPHX_S2_G; ++u) {
+                for (int u = 0; u < GI; ++u) {
                     const size_t k = (size_t)(kk0 + h + u < ke ? kk0 + h + u : kb) * ns + s;
                     if (PACKED) tt[u] = ld_rec_ro(so.ttab + tc[h + u]);
                     else {
@@ -1385,8 +1390,8 @@ __device__ __forceinline__ void solid_pass2_row(const Solid &so, const int s, do
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < MPHX_S2_G; ++u) {
-                    if (kk0 + h + u >= ke) break;
+                for (int u = 0; u < GI; ++u) {
+                    if (kk0 + h + u >= ke) { if (DEEP) continue; else break; }
                     const double d0[3] = {tt[u].a, tt[u].b, DIMS == 3 ? tt[u].c : 0.0};
                     const double w = tt[u].d;
                     for (int a = 0; a < DIMS; ++a) {
@@ -1449,15 +1454,16 @@ __device__ __forceinline__ void solid_pass2_finish(const Solid &so, const int s,
                 ((double *)(b + ring.off_xv[0]))[s] = x[0]; ((double *)(b + ring.off_xv[1]))[s] = x[1]; ((double *)(b + ring.off_xv[2]))[s] = x[2];
                 ((double *)(b + ring.off_xv[3]))[s] = v[0]; ((double *)(b + ring.off_xv[4]))[s] = v[1]; ((double *)(b + ring.off_xv[5]))[s] = v[2];
             }
+        __threadfence_system();
     }
 }
-template <int DIMS, bool PACKED, bool RING>
-__global__ void __launch_bounds__(RING ? kRingBlock : 128, RING ? 8 : MPHX_S2_MINB)
+template <int DIMS, bool PACKED, bool RING, bool DEEP>
+__global__ void __launch_bounds__(DEEP ? kRingBlock : 128, DEEP ? 8 : MPHX_S2_MINB)
 k_solid_pass2(Ctl *ctl, Solid so, int s_lo, int s_hi, double W0, double W1, double W2, double edt, int module, int double_update,
               const double *__restrict__ inv_density, SolidRing ring)
 {
     const int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < s_hi) solid_pass2_row<DIMS, PACKED, RING>(so, s, W0, W1, W2, edt, module, double_update, inv_density, ring);
+    if (s < s_hi) solid_pass2_row<DIMS, PACKED, RING, DEEP>(so, s, W0, W1, W2, edt, module, double_update, inv_density, ring);
     if (RING) ring_complete(ctl, 1, ring);
 }
 

@@ -125,7 +125,8 @@ struct Ctx {
     // fluid's share (FP64 / issue bound; the sub-steps are HBM bound) is still being computed
     bool overlap_solid = true;
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_solid_ready = nullptr, ev_solid_done = nullptr;
+    cudaEvent_t ev_solid_ready = nullptr, ev_solid_done = nullptr, ev_u_ready = nullptr;
+    bool early_pass1 = true, early_done = false; // pass 1 of the first sub-step right after the solids' pre-step (second stream)
     bool solids_pending = false;  // sub-steps enqueued on `side`, not yet joined by the main stream
     std::vector<void *> allocs;
 
@@ -398,9 +399,11 @@ static void preload_kernels(int dim)
     preload(k_pass1_v3<D, false, false>); preload(k_pass1_v3<D, false, true>); preload(k_pass1_v3<D, true, false>);      \
     preload(k_pass1_v3<D, true, true>); preload(k_pass2_v3<D, false, false>); preload(k_pass2_v3<D, false, true>);       \
     preload(k_pass2_v3<D, true, false>); preload(k_pass2_v3<D, true, true>);                                             \
-    preload(k_solid_pass1<D, false, false>); preload(k_solid_pass2<D, false, false>); preload(k_solid_pass1<D, true, false>); \
-    preload(k_solid_pass2<D, true, false>); preload(k_solid_pass1<D, false, true>); preload(k_solid_pass2<D, false, true>); \
-    preload(k_solid_pass1<D, true, true>); preload(k_solid_pass2<D, true, true>);                                        \
+    preload(k_solid_pass1<D, false, false, false>); preload(k_solid_pass2<D, false, false, false>);                      \
+    preload(k_solid_pass1<D, true, false, false>); preload(k_solid_pass2<D, true, false, false>);                        \
+    preload(k_solid_pass1<D, false, true, true>); preload(k_solid_pass2<D, false, true, true>);                          \
+    preload(k_solid_pass1<D, true, true, true>); preload(k_solid_pass2<D, true, true, true>);                            \
+    preload(k_solid_pass1<D, true, false, true>); preload(k_solid_pass2<D, true, false, true>);                          \
     preload(k_solid_pass1_team<D, false>); preload(k_solid_pass1_team<D, true>); preload(k_solid_pass2_team<D, false>);  \
     preload(k_solid_pass2_team<D, true>)
     if (dim == 3) { PRELOAD_DIM(3); } else { PRELOAD_DIM(2); }
@@ -441,10 +444,6 @@ static int exchange_particles(Ctx *c, bool halo)
     const dim3 grid(kPushBlocks, 2);
     k_push<<<grid, kPushThreads, 0, c->stream>>>(ctl, c->epoch, halo ? kPushHaloL : kPushMigL, pp, kMsgDoubles, c->msg_cap, 1);
     ++c->launches;
-    if (halo) {
-        k_halo_resend<<<grid, kPushThreads, 0, c->stream>>>(ctl, c->epoch, kPushHaloL, c->S, c->haloSlot[0], c->haloSlot[1], pp);
-        ++c->launches;
-    }
     LAUNCH(c, k_wait<0>, 1, 32, ctl, c->epoch, halo ? c->mine.fhalo : c->mine.fmig, 2, halo ? kWaitHalo : kWaitMig, halo ? 0 : 1);
     CK(cudaGetLastError());
     return MPHX_OK;
@@ -452,7 +451,10 @@ static int exchange_particles(Ctx *c, bool halo)
 
 // ---- bucket rebuild / refresh: K0 pre-step, decision, K1 count (+ slab exchange), K2 scan, K3 scatter, K4 permute ---
 // motion: the step's calculateWall / calculatePeriodicBoundary (false: buckets over the positions as they are)
-static int stage_build(Ctx *c, bool motion)
+static int run_solid_substeps(Ctx *c, cudaStream_t strm, int part);
+static bool solid_split(const Ctx *c);
+// early_pass1: the step's sub-steps follow (one_step): their first pass 1 starts on the second stream once the solids' pre-step is done
+static int stage_build(Ctx *c, bool motion, bool early_pass1 = false)
 {
     Ctl *ctl = c->ctl;
     const int nb = nblk(c->nmax);
@@ -497,6 +499,12 @@ static int stage_build(Ctx *c, bool motion)
         if (rc) return rc;
         LAUNCH(c, k_prestep, nblk(c->ns), kBlock, ctl, c->S, c->sol, c->grid, wm, motion ? 1 : 0, c->ancx, c->ancy, c->ancz,
                (const int *)c->sol.slot, c->ns, 0);
+        if (early_pass1 && c->early_pass1) {
+            CK(cudaEventRecord(c->ev_u_ready, c->stream));
+            CK(cudaStreamWaitEvent(c->side, c->ev_u_ready, 0));
+            if ((rc = run_solid_substeps(c, c->side, 1))) return rc;
+            c->early_done = true;
+        }
     }
     if (motion) // :3066-3070 (host mirror of the wall centres)
         for (int t = 4; t < kTypeCount; ++t)
@@ -509,6 +517,11 @@ static int stage_build(Ctx *c, bool motion)
     } else {
         LAUNCH(c, k_need, 1, 1, ctl, da, (const int *)c->pl.flags);
         LAUNCH(c, k_decide, 1, 1, ctl, da, c->pl.flags);
+    }
+    if (c->slab) { // a step that reuses its list sends the halo particles' new state first: the rebuild-only kernels below return at once
+        k_halo_resend<<<dim3(kPushBlocks, 2), kPushThreads, 0, c->stream>>>(ctl, c->epoch, kPushHaloL, c->S, c->haloSlot[0], c->haloSlot[1],
+                                                                          push_pair(c, true));
+        ++c->launches;
     }
     SlabSend snd{};
     snd.buf[0] = c->stage_mig[0]; snd.buf[1] = c->stage_mig[1]; snd.capacity = c->msg_cap;
@@ -535,9 +548,9 @@ static int stage_build(Ctx *c, bool motion)
         SidePair hl{};
         hl.buf[0] = c->mine.halo[0]; hl.buf[1] = c->mine.halo[1];
         hl.xshift[0] = c->rank == 0 ? -W0 : 0.0; hl.xshift[1] = c->rank == c->nranks - 1 ? W0 : 0.0;
+        k_unpack_refresh<<<mb2, kBlock, 0, c->stream>>>(ctl, hl, c->S, c->ghostSlot[0], c->ghostSlot[1]);
         k_unpack_particles<<<mb2, kBlock, 0, c->stream>>>(ctl, hl, c->mine.cnt_halo, c->msg_cap, c->cap, kGhost, c->S, c->grid, c->cellCount, c->slot,
                                                           c->ancx, c->ancy, c->ancz);
-        k_unpack_refresh<<<mb2, kBlock, 0, c->stream>>>(ctl, hl, c->S, c->ghostSlot[0], c->ghostSlot[1]);
         c->launches += 2;
         LAUNCH(c, k_advance_n, 1, 1, ctl, c->mine.cnt_halo, c->msg_cap, c->cap, 1);
     }
@@ -688,7 +701,10 @@ static int run_pass2(Ctx *c)
     return MPHX_OK;
 }
 
-static int run_solid_substeps(Ctx *c, cudaStream_t strm)
+// part 0: the whole of the step's sub-steps; 1: only pass 1 of the first sub-step (it reads the displacements the pre-step
+// left, not the coupled velocities: on the second stream it starts right after the solids' pre-step, beside the bucket stage and
+// the fluid passes); 2: the rest (the owners' coupled velocities arrive first)
+static int run_solid_substeps(Ctx *c, cudaStream_t strm, int part = 0)
 {
     if (c->ns <= 0) return MPHX_OK;
     const int substeps = (int)(c->p.dt / c->p.elastic_dt + 0.5); // :653
@@ -704,51 +720,48 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm)
     if (!ring) rg.nranks = 0;
     if (ring && 2 * substeps + 1 >= kSubPhases) { set_last_error("too many solid sub-steps per step for the split exchange"); return MPHX_ERR_UNSUPPORTED; }
     const unsigned long long seq0 = c->epoch * (unsigned long long)kSubPhases;
-    if (c->slab) {
-        LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, c->epoch, c->mine.fsolV, c->nranks, kWaitSolV);
-        LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV, c->s_lo, c->s_hi, c->p.clamp_module);
-    }
     const int cnt = c->s_hi - c->s_lo;
-    const int threads = ring ? kRingBlock : kBlock;
-    const int grid = ring ? std::max(nblk(cnt, threads), 1) : nblk(cnt); // (an empty share still posts its phase counters)
-#define SOLID_STEP(D, PK, RG)                                                                                                          \
-    do {                                                                                                                                 \
-        LAUNCH_ON(c, strm, (k_solid_pass1<D, PK, RG>), grid, threads, c->ctl, c->sol, c->s_lo, c->s_hi, rg);                               \
-        if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
-        ++rg.seq;                                                                                                                        \
-        LAUNCH_ON(c, strm, (k_solid_pass2<D, PK, RG>), grid, threads, c->ctl, c->sol, c->s_lo, c->s_hi, k.domain_width[0],                 \
-                  k.domain_width[1], k.domain_width[2], c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density, rg);                  \
-        if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
-        ++rg.seq;                                                                                                                        \
-    } while (0)
-#define TEAM_STEP(D, RG)                                                                                                               \
-    do {                                                                                                                                 \
-        k_solid_pass1_team<D, RG><<<tgrid, kTeamBlock, 0, strm>>>(c->ctl, c->sol, c->s_lo, c->s_hi, rg);                                  \
-        ++c->launches;                                                                                                                   \
-        if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
-        ++rg.seq;                                                                                                                        \
-        k_solid_pass2_team<D, RG><<<tgrid, kTeamBlock, 0, strm>>>(c->ctl, c->sol, c->s_lo, c->s_hi, k.domain_width[0],                    \
-            k.domain_width[1], k.domain_width[2], c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density, rg);                        \
-        ++c->launches;                                                                                                                   \
-        if (RG) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);                                 \
-        ++rg.seq;                                                                                                                        \
-    } while (0)
-    // the team kernels need ~5x the instructions and L1 wavefronts (a team's gathers do not coalesce across lanes): on a full
-    // set of solids they lose to one thread per solid (113k solids: 116 + 211 us against 58 + 95 us per sub-step), on a
-    // rank's share -- about one warp per SM, a pure latency chain -- they win (28k solids: 72 + 52 us one thread per solid)
-    const bool team = c->team_ok && c->sol.packed && (c->solid_team_always || (ring && cnt * 2 <= ns));
+    const bool deep = ring || (c->sol.packed && std::getenv("MPHX_DEBUG_DEEP") != nullptr); // (the variable: developer timing of the deep variant)
+    const int threads = deep ? kRingBlock : kBlock;
+    const int grid = ring ? std::max(nblk(cnt, threads), 1) : nblk(cnt, threads); // (an empty share still posts its phase counters)
+    // Measured on B200 (tools/substep_bench.py, 113k solids, ms per step of 5 sub-steps, kernels alone):
+    //   share of the solids      1/1     1/2     1/4     1/8
+    //   one thread per solid     0.608   0.404   0.276   0.264     <- a latency chain of ~80 / ~160 dependent gathers per thread
+    //   ... 8 gathers in flight  0.681   0.416   0.195   0.162     <- DEEP: what a rank's share uses (ring)
+    //   team of 16 lanes         1.619   0.839   0.391   0.233     <- 5x the instructions and L1 wavefronts (a team's gathers do not
+    //                                                                  coalesce across lanes): kept for MPHX_SOLID_TEAM=2 only
+    const bool team = c->team_ok && c->sol.packed && c->solid_team_always;
     const int tgrid = std::max(nblk(cnt, kTeamBlock / kTeam), 1);
-#define SOLID_STEP_D(D) do { if (team) { if (ring) TEAM_STEP(D, true); else TEAM_STEP(D, false); }                         \
-                             else if (c->sol.packed) { if (ring) SOLID_STEP(D, true, true); else SOLID_STEP(D, true, false); } \
-                             else { if (ring) SOLID_STEP(D, false, true); else SOLID_STEP(D, false, false); } } while (0)
-    rg.seq = seq0 + 1;
-    for (int s = 0; s < substeps; ++s) {
-        rg.last = s == substeps - 1 ? 1 : 0;
-        if (c->p.dim == 3) SOLID_STEP_D(3); else SOLID_STEP_D(2);
+#define PASS1(D, PK, RG, DP) LAUNCH_ON(c, strm, (k_solid_pass1<D, PK, RG, DP>), grid, threads, c->ctl, c->sol, c->s_lo, c->s_hi, rg)
+#define PASS2(D, PK, RG, DP) LAUNCH_ON(c, strm, (k_solid_pass2<D, PK, RG, DP>), grid, threads, c->ctl, c->sol, c->s_lo, c->s_hi, k.domain_width[0], \
+                                       k.domain_width[1], k.domain_width[2], c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density, rg)
+#define TEAM1(D, RG) do { k_solid_pass1_team<D, RG><<<tgrid, kTeamBlock, 0, strm>>>(c->ctl, c->sol, c->s_lo, c->s_hi, rg); ++c->launches; } while (0)
+#define TEAM2(D, RG) do { k_solid_pass2_team<D, RG><<<tgrid, kTeamBlock, 0, strm>>>(c->ctl, c->sol, c->s_lo, c->s_hi, k.domain_width[0],            \
+                              k.domain_width[1], k.domain_width[2], c->p.elastic_dt, c->p.clamp_module, dbl, c->d_inv_density, rg); ++c->launches; } while (0)
+#define PHASE_D(D, WHICH)                                                                                                              \
+    do {                                                                                                                                \
+        if (team) { if (ring) TEAM##WHICH(D, true); else TEAM##WHICH(D, false); }                                                       \
+        else if (c->sol.packed) { if (ring) PASS##WHICH(D, true, true, true); else if (deep) PASS##WHICH(D, true, false, true);         \
+                                  else PASS##WHICH(D, true, false, false); }                                                            \
+        else { if (ring) PASS##WHICH(D, false, true, true); else PASS##WHICH(D, false, false, false); }                                 \
+    } while (0)
+    const int first = part == 2 ? 1 : 0, last = part == 1 ? 1 : 2 * substeps;
+    for (int ph = first; ph < last; ++ph) {
+        if (c->slab && ph == (part == 0 ? 0 : 1)) { // the owners' coupled velocities (pass 2 needs them, pass 1 does not)
+            LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, c->epoch, c->mine.fsolV, c->nranks, kWaitSolV);
+            LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV, c->s_lo, c->s_hi, c->p.clamp_module);
+        }
+        rg.seq = seq0 + 1 + ph;
+        rg.last = ph == 2 * substeps - 1 ? 1 : 0;
+        if (ph % 2 == 0) { if (c->p.dim == 3) PHASE_D(3, 1); else PHASE_D(2, 1); }
+        else             { if (c->p.dim == 3) PHASE_D(3, 2); else PHASE_D(2, 2); }
+        if (ring) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);
     }
-#undef SOLID_STEP_D
-#undef TEAM_STEP
-#undef SOLID_STEP
+#undef PHASE_D
+#undef TEAM2
+#undef TEAM1
+#undef PASS2
+#undef PASS1
     CK(cudaGetLastError());
     return MPHX_OK;
 }
@@ -800,7 +813,8 @@ static int one_step(Ctx *c, bool fluid_only)
     if (c->slab && !c->connected) { set_last_error("slab context is not connected to its peers (mphx_slab_connect)"); return MPHX_ERR_INVALID; }
     timer_mark(c);
     TRACE_ON(c->stream, 1);
-    if ((rc = stage_build(c, true))) return rc;     // calculateWall, PeriodicBoundary, resets, calculateNeighbor
+    c->early_done = false;
+    if ((rc = stage_build(c, true, !fluid_only))) return rc; // calculateWall, PeriodicBoundary, resets, calculateNeighbor
     timer_mark(c);
     TRACE_ON(c->stream, 2);
     if ((rc = run_pass1(c, true))) return rc;       // filter; DensityA..DivergenceP, coefficients, PressureP/A
@@ -816,7 +830,7 @@ static int one_step(Ctx *c, bool fluid_only)
             CK(cudaStreamWaitEvent(c->side, c->ev_solid_ready, 0));
             TRACE_ON(c->side, 7);
             if (c->timing) { cudaEvent_t e = timer_event(c); cudaEventRecord(e, c->side); c->side_marks.push_back(e); }
-            if ((rc = run_solid_substeps(c, c->side))) return rc;
+            if ((rc = run_solid_substeps(c, c->side, c->early_done ? 2 : 0))) return rc;
             TRACE_ON(c->side, 8);
             if (c->timing) { cudaEvent_t e = timer_event(c); cudaEventRecord(e, c->side); c->side_marks.push_back(e); }
             CK(cudaEventRecord(c->ev_solid_done, c->side));
@@ -1287,6 +1301,8 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
     }
     cudaEventCreateWithFlags(&c->ev_solid_ready, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&c->ev_solid_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_u_ready, cudaEventDisableTiming);
+    if (const char *e = std::getenv("MPHX_EARLY_PASS1")) c->early_pass1 = std::atoi(e) != 0;
     *out = reinterpret_cast<mphx_ctx *>(c);
     return MPHX_OK;
 }
@@ -1307,6 +1323,7 @@ void mphx_destroy(mphx_ctx *ctx)
     if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
     if (c->ev_solid_ready) cudaEventDestroy(c->ev_solid_ready);
     if (c->ev_solid_done) cudaEventDestroy(c->ev_solid_done);
+    if (c->ev_u_ready) cudaEventDestroy(c->ev_u_ready);
     for (void *q : c->allocs) cudaFree(q);
     if (c->stream && !c->external_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -1377,6 +1394,8 @@ static int upload_allocate(Ctx *c, int n, int nloc, const int r[6])
                 c->s_hi = (int)((long long)c->ns * (c->rank + 1) / c->nranks);
             }
         } else {
+            // (developer timing hook: advance only the first ns / k solids, as one rank of k would -- wrong physics, right kernel time)
+            if (const char *e2 = std::getenv("MPHX_DEBUG_SUBSTEP_SHARE")) c->s_hi = c->ns / std::max(1, std::atoi(e2));
             double **sx[] = {&so.x, &so.y, &so.z, &so.vx, &so.vy, &so.vz};
             for (double **q : sx) e |= c->alloc(q, ns);
             e |= c->alloc(&so.u, ns);
