@@ -615,13 +615,24 @@ __global__ void k_halo_resend(Ctl *ctl, unsigned long long epoch, int which0, Pa
                               const int *__restrict__ haloSlot1, PushPair pp)
 {
     if (ctl->rebuild) return;
+    // (a particle's 7 doubles are gathered into shared memory, the block's tile leaves as one contiguous stream: NVLink moves
+    //  128-byte packets about as fast as 8-byte ones)
+    __shared__ double tile[256 * kMsgDoubles];
     const int dir = blockIdx.y;
     const int cnt = ctl->halo_cnt[dir];
     const int *__restrict__ hs = dir == 0 ? haloSlot0 : haloSlot1;
     double *__restrict__ dst = pp.dst[dir];
-    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
-        const int i = hs[q];
-        pack_particle(dst + (size_t)kMsgDoubles * q, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], p.type[i], p.id[i]);
+    for (int q0 = blockIdx.x * blockDim.x; q0 < cnt; q0 += gridDim.x * blockDim.x) {
+        const int q = q0 + threadIdx.x;
+        if (q < cnt) {
+            const int i = hs[q];
+            pack_particle(tile + (size_t)kMsgDoubles * threadIdx.x, p.x[i], p.y[i], p.z[i], p.vx[i], p.vy[i], p.vz[i], p.type[i], p.id[i]);
+        }
+        __syncthreads();
+        const int nd = min((int)blockDim.x, cnt - q0) * kMsgDoubles;
+        double *__restrict__ out = dst + (size_t)kMsgDoubles * q0;
+        for (int k = threadIdx.x; k < nd; k += blockDim.x) out[k] = tile[k];
+        __syncthreads();
     }
     __threadfence_system();
     __syncthreads();
@@ -1183,16 +1194,17 @@ __device__ __forceinline__ void ring_complete(Ctl *ctl, int which, const SolidRi
         __threadfence_system();
         if (atomicAdd(&ctl->sub_done[which], 1u) == gridDim.x - 1) {
             ctl->sub_done[which] = 0;
+            trace_mark(ctl, 320 + which);
             __threadfence_system();
             for (int r = 0; r < ring.nranks; ++r) st_flag((unsigned long long *)(ring.base[r] + ring.off_flag) + ring.rank, ring.seq);
             trace_mark(ctl, 300 + which);
         }
     }
 }
-template <int DIMS, bool RING>
-__device__ __forceinline__ void solid_pass1_finish(const Solid &so, const int s, const double (&G)[3][3], const SolidRing &ring);
-template <int DIMS, bool PACKED, bool RING, bool DEEP>
-__device__ __forceinline__ void solid_pass1_row(const Solid &so, const int s, const SolidRing &ring)
+template <int DIMS>
+__device__ __forceinline__ void solid_pass1_finish(const Solid &so, const int s, const double (&G)[3][3], double (&Pv)[9]);
+template <int DIMS, bool PACKED, bool DEEP>
+__device__ __forceinline__ void solid_pass1_row(const Solid &so, const int s, double (&Pv)[9])
 {
     constexpr int GI = DEEP ? 8 : 4; // pairs whose gathers are in flight together
     using namespace ex;
@@ -1245,11 +1257,11 @@ __device__ __forceinline__ void solid_pass1_row(const Solid &so, const int s, co
             }
         }
     }
-    solid_pass1_finish<DIMS, RING>(so, s, G, ring);
+    solid_pass1_finish<DIMS>(so, s, G, Pv);
 }
-// F = G L^-1 (:2743), E (:2780), S (:2804), P = F S L^-1 (:2847) of solid s from its accumulated G
-template <int DIMS, bool RING>
-__device__ __forceinline__ void solid_pass1_finish(const Solid &so, const int s, const double (&G)[3][3], const SolidRing &ring)
+// F = G L^-1 (:2743), E (:2780), S (:2804), P = F S L^-1 (:2847) of solid s from its accumulated G; P also comes back in Pv
+template <int DIMS>
+__device__ __forceinline__ void solid_pass1_finish(const Solid &so, const int s, const double (&G)[3][3], double (&Pv)[9])
 {
     using namespace ex;
     const int ns = so.ns;
@@ -1288,17 +1300,39 @@ __device__ __forceinline__ void solid_pass1_finish(const Solid &so, const int s,
             MPHX_T(so.E, a, b, s, ns) = E[a][b];
             MPHX_T(so.S, a, b, s, ns) = S[a][b];
         }
-    if (RING) { // P of s -> the ranks whose pass 2 gathers it
-        double Pv[9];
 #pragma unroll
-        for (int e = 0; e < 9; ++e) Pv[e] = Pk[e];
-        for (unsigned m = so.pmask[s]; m; m &= m - 1) {
-            double *d = (double *)(ring.base[__ffs(m) - 1] + ring.off_pk) + 9 * (size_t)s;
+    for (int e = 0; e < 9; ++e) Pv[e] = Pk[e];
+}
+// P of s -> the ranks whose pass 2 gathers it: scattered (a thread stores its own nine doubles) ...
+__device__ __forceinline__ void ring_push_P(const Solid &so, const int s, const double (&Pv)[9], const SolidRing &ring)
+{
+    for (unsigned m = so.pmask[s]; m; m &= m - 1) {
+        double *d = (double *)(ring.base[__ffs(m) - 1] + ring.off_pk) + 9 * (size_t)s;
 #pragma unroll
-            for (int e = 0; e < 9; ++e) d[e] = Pv[e];
-        }
-        __threadfence_system();
+        for (int e = 0; e < 9; ++e) d[e] = Pv[e];
     }
+    __threadfence_system();
+}
+// ... or by the warp (one thread per solid, consecutive solids): the warp's 32 x 9 doubles are contiguous in PkA, so they
+// go through shared memory and leave as 256-byte rows to every rank that needs any of them (all lanes must call)
+__device__ __forceinline__ void ring_push_P_warp(const Solid &so, const int s, const bool active, const double (&Pv)[9], int s_hi,
+                                                 const SolidRing &ring, double *stage /* [32 * 9] of this warp */)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned um = __reduce_or_sync(0xffffffffu, active ? (unsigned)so.pmask[s] : 0u);
+    if (um == 0u) return;
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < 9; ++e) stage[lane * 9 + e] = Pv[e];
+    }
+    __syncwarp();
+    const int s0 = s - lane;
+    const int nd = min(32, s_hi - s0) * 9;
+    for (unsigned m = um; m; m &= m - 1) {
+        double *d = (double *)(ring.base[__ffs(m) - 1] + ring.off_pk) + 9 * (size_t)s0;
+        for (int k = lane; k < nd; k += 32) d[k] = stage[k];
+    }
+    __threadfence_system();
 }
 // (RING: a rank's share is ~ns/nranks solids, about one block per SM, and its kernels run beside the fluid's share of pass 2
 // on a high-priority stream: blocks of kRingBlock threads with <= 128 registers need no more of an SM than ONE retiring
@@ -1311,9 +1345,15 @@ template <int DIMS, bool PACKED, bool RING, bool DEEP>
 __global__ void __launch_bounds__(DEEP ? kRingBlock : 128, DEEP ? 8 : MPHX_S1_MINB)
 k_solid_pass1(Ctl *ctl, Solid so, int s_lo, int s_hi, SolidRing ring)
 {
+    __shared__ double stage[RING ? (DEEP ? kRingBlock : 128) * 9 : 1];
     const int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < s_hi) solid_pass1_row<DIMS, PACKED, RING, DEEP>(so, s, ring);
-    if (RING) ring_complete(ctl, 0, ring);
+    if (RING && threadIdx.x == 0 && blockIdx.x == 0) trace_mark(ctl, 310);
+    double Pv[9];
+    if (s < s_hi) solid_pass1_row<DIMS, PACKED, DEEP>(so, s, Pv);
+    if (RING) {
+        ring_push_P_warp(so, s, s < s_hi, Pv, s_hi, ring, stage + (threadIdx.x / 32) * 32 * 9);
+        ring_complete(ctl, 0, ring);
+    }
 }
 
 // the clamp variants of updateElasticPosition (MPHX_MODULE_*: Bar :1919, DAM :1968, Turek_Hron :1944, Rolling1 :1992,
@@ -1463,6 +1503,7 @@ k_solid_pass2(Ctl *ctl, Solid so, int s_lo, int s_hi, double W0, double W1, doub
               const double *__restrict__ inv_density, SolidRing ring)
 {
     const int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (RING && threadIdx.x == 0 && blockIdx.x == 0) trace_mark(ctl, 311);
     if (s < s_hi) solid_pass2_row<DIMS, PACKED, RING, DEEP>(so, s, W0, W1, W2, edt, module, double_update, inv_density, ring);
     if (RING) ring_complete(ctl, 1, ring);
 }
@@ -1534,7 +1575,9 @@ __global__ void __launch_bounds__(kTeamBlock, 6) k_solid_pass1_team(Ctl *ctl, So
             double G[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
             for (int a = 0; a < DIMS; ++a)
                 for (int b2 = 0; b2 < DIMS; ++b2) G[a][b2] = Gs[threadIdx.x][a * DIMS + b2];
-            solid_pass1_finish<DIMS, RING>(so, s2, G, ring);
+            double Pv[9];
+            solid_pass1_finish<DIMS>(so, s2, G, Pv);
+            if (RING) ring_push_P(so, s2, Pv, ring);
         }
     }
     if (RING) ring_complete(ctl, 0, ring);

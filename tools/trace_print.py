@@ -9,7 +9,9 @@ def name(c):
     if c < 100: return NAMES.get(c, str(c))
     if c < 200: return "wait " + TAGS[c - 100] + " begins"
     if c < 300: return "wait " + TAGS[c - 200] + " ends"
-    if c < 400: return "sub-step pass %d posted" % (c - 300 + 1)
+    if c < 310: return "sub-step pass %d posted" % (c - 300 + 1)
+    if c < 320: return "sub-step pass %d kernel starts" % (c - 310 + 1)
+    if c < 400: return "sub-step pass %d last block done" % (c - 320 + 1)
     return "push " + PUSH[c - 400] + " complete"
 d = json.load(open(sys.argv[1]))
 step = int(sys.argv[2]) if len(sys.argv) > 2 else 1
