@@ -313,6 +313,14 @@ int mphx_slab_mailbox(mphx_ctx *ctx, void *ipc_handle, void **device_ptr, long l
  * devices[r]: CUDA ordinal of rank r's GPU in this process (or NULL) */
 int mphx_slab_connect(mphx_ctx *ctx, const void *ipc_handles, void *const *device_ptrs, const int *devices);
 int mphx_slab_info(mphx_ctx *ctx, int out[4]);
+/* In-place re-balancing of a running ring: sum mphx_slab_column_histogram over the ranks, let
+ * mphx_rebalance_cuts move every interior cut towards the balanced position by at most one halo width, and hand every
+ * rank its new columns with mphx_slab_recut before the same step -- the particles that change owner travel with that
+ * step's ordinary migration (no host gather).  mphx_slab_columns: the columns a slab owns (out[0], out[1]). */
+int mphx_slab_column_histogram(mphx_ctx *ctx, long long *hist /* ncols */, int ncols);
+int mphx_rebalance_cuts(const long long *hist, int ncols, int nranks, int halo, const int *old_cuts, int *new_cuts, int *moved);
+int mphx_slab_recut(mphx_ctx *ctx, int col_lo, int col_hi);
+int mphx_slab_columns(mphx_ctx *ctx, int out[2]);
 
 /* one process, N devices -- what the reference's main() needs to drive a whole box (csrc/main.cpp, MPHX_NGPU):
  * same life cycle as a single context; devices may be NULL (0..ndev-1) and may repeat */
@@ -329,6 +337,7 @@ int mphx_multi_sync(mphx_multi *m);
 double mphx_multi_time(const mphx_multi *m);
 int mphx_multi_download(mphx_multi *m, const mphx_host_views *views);
 int mphx_multi_timed_steps(mphx_multi *m, int nsteps, double *elapsed_ms);
+int mphx_multi_rebalance(mphx_multi *m, int *moved /* interior cuts that moved; may be NULL */);
 
 #ifdef __cplusplus
 }

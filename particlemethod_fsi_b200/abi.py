@@ -111,7 +111,7 @@ EXPORTS = [
     "mphx_debug_neighbors", "mphx_debug_initial_structure_neighbors",
     "mphx_timed_steps", "mphx_set_timing", "mphx_get_timers", "mphx_get_kernel_timers", "mphx_trace_enable", "mphx_trace_read", "mphx_get_virial_ms", "mphx_measure_fp64_peak", "mphx_count_pairs", "mphx_set_overlap", "mphx_join", "mphx_launch_count", "mphx_algorithmic_bytes_per_step",
     "mphx_set_list_reuse", "mphx_get_status",
-    "mphx_set_stream", "mphx_partition_columns", "mphx_slab_configure", "mphx_slab_mailbox", "mphx_slab_connect", "mphx_slab_info",
+    "mphx_set_stream", "mphx_partition_columns", "mphx_slab_configure", "mphx_slab_mailbox", "mphx_slab_connect", "mphx_slab_info", "mphx_slab_column_histogram", "mphx_rebalance_cuts", "mphx_slab_recut", "mphx_slab_columns", "mphx_multi_rebalance",
     "mphx_multi_create", "mphx_multi_destroy", "mphx_multi_count", "mphx_multi_context", "mphx_multi_upload", "mphx_multi_init",
     "mphx_multi_step", "mphx_multi_sync", "mphx_multi_time", "mphx_multi_download", "mphx_multi_timed_steps",
 ]

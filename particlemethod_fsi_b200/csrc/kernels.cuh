@@ -1814,6 +1814,20 @@ __global__ void k_owned_mask(int n, Particles p, GridDesc g, int solids_too, int
     }
     mask[q] = own ? 1 : 0;
 }
+// owned fluid / wall particles per GLOBAL bucket column (the input of the slab re-balancing)
+__global__ void k_column_histogram(const Ctl *ctl, Particles p, GridDesc g, int *__restrict__ hist)
+{
+    const int n = ctl->n;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const int k = p.key[q], t = p.type[q];
+        if ((t & kGhost) || is_structure_type(t) || k >= g.ncells) continue;
+        const int col = key_column(g, k);
+        if (!column_owned(g, col)) continue;
+        int cx = col + g.xoff;
+        if (cx < 0) cx += g.nxg; else if (cx >= g.nxg) cx -= g.nxg;
+        atomicAdd(&hist[cx], 1);
+    }
+}
 // compact state of the masked slots: out row r = scan[q] for mask[q] != 0; solids report the solid arrays
 __global__ void k_compact_owned(int n, Particles p, Solid sol, const int *__restrict__ mask, const int *__restrict__ scan,
                                 int *__restrict__ slot_of_row, int *__restrict__ ids, double *__restrict__ x3, double *__restrict__ v3)

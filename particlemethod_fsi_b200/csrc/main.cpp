@@ -9,6 +9,7 @@
 // loop).  The reference fixes dimension and clamp module at compile time (src/main.cpp:50,54-55);
 // here they are the optional 7th/8th arguments or MPHX_DIM / MPHX_MODULE (defaults: 2, bar -- the
 // shipped configuration).  `nthreads` is accepted and ignored (there is no CPU path).
+// MPHX_REBALANCE_EVERY=K re-cuts the slabs of a multi-GPU run every K steps (mphx_multi_rebalance).
 // MPHX_NGPU=N (2..16) runs the case on N devices of the box as x-slabs (mphx_multi_*: one process, the
 // slabs exchange over NVLink inside the library); MPHX_DEVICE picks the device of a single-GPU run.
 #include <chrono>
@@ -189,7 +190,20 @@ int main(int argc, char *argv[])
         if ((rc = mphx_init(ctx))) die("mphx_init", rc);
     }
     mphx_set_timing(ctx, 1);
-    auto do_step = [&]() { return multi ? mphx_multi_step(multi, 1) : mphx_step(ctx, 1); };
+    // MPHX_REBALANCE_EVERY=K (multi-GPU): re-cut the slabs on the current particle distribution every K steps
+    const int rebalance_every = (multi && getenv("MPHX_REBALANCE_EVERY")) ? atoi(getenv("MPHX_REBALANCE_EVERY")) : 0;
+    long long steps_taken = 0;
+    auto do_step = [&]() {
+        if (!multi) return mphx_step(ctx, 1);
+        if (rebalance_every > 0 && steps_taken > 0 && steps_taken % rebalance_every == 0) {
+            int moved = 0;
+            const int r = mphx_multi_rebalance(multi, &moved);
+            if (r) return r;
+            if (moved) log_printf("re-balanced the slabs: %d cuts moved\n", moved);
+        }
+        ++steps_taken;
+        return mphx_multi_step(multi, 1);
+    };
     auto do_sync = [&]() { return multi ? mphx_multi_sync(multi) : mphx_sync(ctx); };
     auto do_download = [&](const mphx_host_views *v) { return multi ? mphx_multi_download(multi, v) : mphx_download(ctx, v); };
 

@@ -59,6 +59,8 @@ struct Ctx {
     // slab mode (multi-GPU): see slab.inc
     bool slab = false, connected = false;
     int rank = 0, nranks = 1, col_lo = 0, col_hi = 0, msg_cap = 0;
+    int pending_lo = -1, pending_hi = -1; // re-cut requested (mphx_slab_recut): takes effect at the start of the next step
+    size_t cells_cap = 0;                 // bucket arrays hold this many buckets (+ service buckets)
     void *mailbox = nullptr;
     size_t mailbox_bytes = 0;
     Mailbox mine{};
@@ -807,10 +809,12 @@ static void timer_resolve(Ctx *c)
 }
 
 #define TRACE_ON(strm, code) do { if (c->tracing) LAUNCH_ON(c, strm, k_mark, 1, 1, c->ctl, code); } while (0)
+static int apply_recut(Ctx *c);
 static int one_step(Ctx *c, bool fluid_only)
 {
     int rc;
     if (c->slab && !c->connected) { set_last_error("slab context is not connected to its peers (mphx_slab_connect)"); return MPHX_ERR_INVALID; }
+    if (c->pending_lo >= 0 && (rc = apply_recut(c))) return rc;
     timer_mark(c);
     TRACE_ON(c->stream, 1);
     c->early_done = false;
@@ -842,6 +846,38 @@ static int one_step(Ctx *c, bool fluid_only)
     timer_mark(c);
     if (c->ev.size() >= 6000) timer_resolve(c);
     return MPHX_OK;
+}
+
+// In-place re-balancing of the slabs: this slab's owned columns become [pending_lo, pending_hi).  A face moves by
+// at most one halo width per re-cut, so the particles that change owner are exactly what the ordinary MIGRATION of the next
+// (forced) rebuild hands to the ring neighbour -- no host gather, no new exchange path: the grid descriptor changes, the
+// bucket arrays grow if they must, and the step that follows rebuilds.  Applied at the start of a step so that everything
+// read between the request and the step (downloads, ownership masks) still refers to the grid the keys were made on.
+static int apply_recut(Ctx *c)
+{
+    const int lo = c->pending_lo, hi = c->pending_hi;
+    c->pending_lo = c->pending_hi = -1;
+    int rc;
+    if ((rc = join_solids(c))) return rc;
+    GridDesc &g = c->grid;
+    const int R = g.range;
+    const long long nc = (long long)((hi - lo) + 2 * R) * g.ny * g.nz;
+    if (nc > 2000000000LL) return MPHX_ERR_UNSUPPORTED;
+    if ((size_t)nc > c->cells_cap) { // (rare: the old arrays stay with the context until it is destroyed)
+        CK(cudaStreamSynchronize(c->stream));
+        const size_t cap = (size_t)nc + (size_t)nc / 8;
+        int *cc = nullptr, *cs = nullptr, *bs = nullptr;
+        if (c->alloc(&cc, cap + 2) || c->alloc(&cs, cap + 3) || c->alloc(&bs, (cap + 2 + kScanChunk - 1) / kScanChunk + 1)) return MPHX_ERR_NOMEM;
+        CK(cudaMemsetAsync(cc, 0, sizeof(int) * (cap + 2), c->stream)); // (the counters are all-zero outside a rebuild)
+        c->cellCount = cc; c->cellStart = cs; c->blockSums = bs; c->cells_cap = cap;
+    }
+    c->col_lo = lo; c->col_hi = hi;
+    g.nx = (hi - lo) + 2 * R;
+    g.xoff = lo - R;
+    g.mn[0] = g.mn0g + (double)g.xoff * g.cellw;
+    g.ncells = (int)nc;
+    c->scan_blocks = (int)((nc + 2 + kScanChunk - 1) / kScanChunk);
+    return request_rebuild(c);
 }
 
 // ---- exact neighbour sets (debug / VTK NeighborCount / the initial structure lists) -----------------------
@@ -1367,8 +1403,9 @@ static int upload_allocate(Ctx *c, int n, int nloc, const int r[6])
             e |= c->alloc(&c->brick_sums, (size_t)c->brick_scan_blocks + 1);
             if (!e) { cudaMemset(c->brick_ok, 0, (size_t)c->nbricks); cudaMemset(c->in_brick, 0, cap); }
         }
-        e |= c->alloc(&c->cellCount, (size_t)c->grid.ncells + 2);
-        e |= c->alloc(&c->cellStart, (size_t)c->grid.ncells + 3);
+        c->cells_cap = (size_t)c->grid.ncells;
+        e |= c->alloc(&c->cellCount, c->cells_cap + 2);
+        e |= c->alloc(&c->cellStart, c->cells_cap + 3);
         c->scan_blocks = (int)(((long long)c->grid.ncells + 2 + kScanChunk - 1) / kScanChunk);
         e |= c->alloc(&c->blockSums, (size_t)c->scan_blocks + 1);
         e |= c->alloc(&c->slot, cap); e |= c->alloc(&c->tmpIdx, cap); e |= c->alloc(&c->where, cap);

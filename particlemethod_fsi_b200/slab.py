@@ -175,6 +175,21 @@ class MultiSolver:
             res.append(dict(rank=r, held=a[0], capacity=a[1], ghosts=a[2], msg_capacity=a[3], err=st[0], builds=st[2], reuses=st[3]))
         return res
 
+    def rebalance(self) -> int:
+        """re-cut the slabs on the current particle distribution (every interior cut moves by at most one halo width; the
+        particles that change owner travel with the next step's migration); returns the number of cuts that moved"""
+        moved = C.c_int()
+        self._ck("mphx_multi_rebalance", self.lib.mphx_multi_rebalance(self._m, C.byref(moved)))
+        return moved.value
+
+    def columns(self):
+        out = []
+        for r in range(self.world):
+            a = (C.c_int * 2)()
+            self._ck("mphx_slab_columns", self.lib.mphx_slab_columns(self.context(r), C.byref(a)))
+            out.append((a[0], a[1]))
+        return out
+
     def download_owned(self, r: int):
         """(ids, position, velocity) rows of slab r (its owned fluid/wall particles + all replicated solids)"""
         cap = self.info()[r]["capacity"]
@@ -262,6 +277,29 @@ class DistSlab:
         self._ck("mphx_get_status", self.lib.mphx_get_status(self.ctx, C.byref(st)))
         self._ck("mphx_slab_info", self.lib.mphx_slab_info(self.ctx, C.byref(a)))
         return dict(err=st[0], held=st[1], builds=st[2], reuses=st[3], ghosts=st[7], capacity=a[1], msg_capacity=a[3])
+
+    def rebalance(self) -> int:
+        """In-place re-balancing: all-reduce the per-column histogram of the owned particles, move every interior cut towards
+        the balanced position by at most one halo width (mphx_rebalance_cuts: the rule lives in the library), and request the
+        new columns from this rank's context; the particles that change owner travel with the next step's migration.
+        Collective; returns the number of cuts that moved."""
+        from . import solver
+        k = solver.compute_constants(self.case.params)
+        ncols, R = k.cell_count[0], k.stencil_range
+        hist = np.zeros(ncols, dtype=np.int64)
+        self._ck("mphx_slab_column_histogram", self.lib.mphx_slab_column_histogram(self.ctx, hist.ctypes.data, ncols))
+        t = self.torch.from_numpy(hist).to(self.device if self.dist.get_backend(self.group) == "nccl" else "cpu")
+        self.dist.all_reduce(t, group=self.group)
+        hist = np.ascontiguousarray(t.cpu().numpy(), dtype=np.int64)
+        old = np.ascontiguousarray([p[0] for p in self.partition] + [self.partition[-1][1]], dtype=np.int32)
+        new = np.zeros(self.world + 1, dtype=np.int32)
+        moved = C.c_int()
+        self._ck("mphx_rebalance_cuts", self.lib.mphx_rebalance_cuts(hist.ctypes.data, ncols, self.world, R, old.ctypes.data, new.ctypes.data,
+                                                                     C.byref(moved)))
+        if moved.value:
+            self._ck("mphx_slab_recut", self.lib.mphx_slab_recut(self.ctx, int(new[self.rank]), int(new[self.rank + 1])))
+            self.partition = [(int(new[r]), int(new[r + 1])) for r in range(self.world)]
+        return moved.value
 
     def download(self, *names):
         """every rank reports the particles it owns (zeros elsewhere); the all-reduced sum is the case"""

@@ -97,6 +97,11 @@ def _load():
     L.mphx_slab_mailbox.argtypes = [vp, vp, C.POINTER(vp), C.POINTER(C.c_longlong)]
     L.mphx_slab_connect.argtypes = [vp, vp, vp, vp]
     L.mphx_slab_info.argtypes = [vp, C.POINTER(C.c_int * 4)]
+    L.mphx_slab_column_histogram.argtypes = [vp, vp, C.c_int]
+    L.mphx_rebalance_cuts.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, ip]
+    L.mphx_slab_recut.argtypes = [vp, C.c_int, C.c_int]
+    L.mphx_slab_columns.argtypes = [vp, C.POINTER(C.c_int * 2)]
+    L.mphx_multi_rebalance.argtypes = [vp, ip]
     L.mphx_multi_create.argtypes = [C.POINTER(vp), C.POINTER(abi.Params), C.c_int, vp]
     L.mphx_multi_destroy.argtypes = [vp]
     L.mphx_multi_destroy.restype = None

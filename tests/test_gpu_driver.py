@@ -105,3 +105,30 @@ def test_driver_on_several_slabs_writes_the_same_files(tmp_path):
                        timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     assert (d / "r003.vtk").exists()
+
+
+def test_driver_rebalances_the_slabs_in_place(tmp_path):
+    """MPHX_REBALANCE_EVERY: the driver re-cuts the slabs of a multi-GPU run while it steps (mphx_multi_rebalance); with the
+    reference's rebuild-every-step schedule the files stay byte-identical to the single-context run"""
+    c = cases.dam2d()
+    c.velocity[c.property < 2, 0] = 1.5
+    c.rc.end_time = 40.5 * c.params.dt
+    c.rc.output_interval = 40.0 * c.params.dt
+    c.rc.vtk_output_interval = 100.0 * c.params.dt
+    outs, logs = {}, {}
+    for tag, env in (("one", dict(MPHX_LIST_REUSE="0")),
+                     ("four", dict(MPHX_LIST_REUSE="0", MPHX_NGPU="4", MPHX_DEVICES="0,0,0,0", MPHX_REBALANCE_EVERY="10",
+                                   CUDA_DEVICE_MAX_CONNECTIONS="32"))):
+        d = tmp_path / tag
+        d.mkdir()
+        cases.write_grid_file(str(d / "c.grid"), c)
+        cases.write_data_file(str(d / "t.data"), c.params, c.rc)
+        r = subprocess.run([EXE, "t.data", "c.grid", "t%03d.prof", "t%03d.vtk", "t.log", "4", "2", "dam"], cwd=d, capture_output=True,
+                           text=True, env=dict(os.environ, **env), timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[tag] = {f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.endswith((".prof", ".vtk"))}
+        logs[tag] = (d / "t.log").read_text()
+    assert list(outs["one"]) == list(outs["four"]) and len(outs["one"]) >= 3
+    for f in outs["one"]:
+        assert outs["one"][f] == outs["four"][f], f
+    assert "re-balanced the slabs" in logs["four"]

@@ -99,3 +99,35 @@ def test_handles_travel_over_gloo(world):
     ok = mp.get_context("spawn").Array("i", [0] * world)
     mp.spawn(_gloo_worker, args=(world, _free_port(), ok), nprocs=world, join=True)
     assert list(ok) == [1] * world
+
+
+def test_rebalance_cuts_move_towards_balance_by_at_most_one_halo():
+    """mphx_rebalance_cuts: interior cuts move towards the balanced position of the CURRENT histogram by at most one halo
+    width per call, never below the minimum slab width, the periodic seam (cuts[0], cuts[n]) stays put; repeated calls
+    converge on mphx_partition_columns' cuts"""
+    import ctypes as C
+    from particlemethod_fsi_b200.solver import lib
+    ncols, world, R = 120, 4, 3
+    hist = np.zeros(ncols, dtype=np.int64)
+    hist[10:50] = 1000            # all particles sit in the first half now
+    old = np.array([0, 30, 60, 90, 120], dtype=np.int32)
+    target = np.array(slab.partition_columns(hist, world, R)).ravel()[[0, 2, 4, 6, 7]]
+    cuts = old.copy()
+    for it in range(40):
+        new = np.zeros(world + 1, dtype=np.int32)
+        moved = C.c_int()
+        rc = lib.mphx_rebalance_cuts(hist.ctypes.data, ncols, world, R, cuts.ctypes.data, new.ctypes.data, C.byref(moved))
+        assert rc == 0
+        assert new[0] == 0 and new[-1] == ncols
+        assert np.all(np.abs(new - cuts) <= R)
+        assert np.all(np.diff(new) >= R)
+        assert moved.value == int((new != cuts).sum())
+        if moved.value == 0:
+            break
+        cuts = new
+    assert np.array_equal(cuts, target), (cuts, target)
+    # an already balanced ring does not move
+    new = np.zeros(world + 1, dtype=np.int32)
+    moved = C.c_int(7)
+    assert lib.mphx_rebalance_cuts(hist.ctypes.data, ncols, world, R, cuts.ctypes.data, new.ctypes.data, C.byref(moved)) == 0
+    assert moved.value == 0 and np.array_equal(new, cuts)
