@@ -233,6 +233,7 @@ struct SolidRing {
     int nranks, rank;          // nranks = 0: single context, nothing is pushed
     int last;                  // pass 2: last sub-step of the step -> positions and velocities go to every rank
     unsigned long long seq;    // value this launch posts into every rank's fsub[rank] when its last block is done
+    unsigned long long wait_seq; // != 0: every block first waits until all ranks' fsub carry at least this value (the previous phase)
     char *base[kMaxRanks];
     size_t off_flag, off_xv[6], off_u, off_pk;
 };
@@ -1186,6 +1187,26 @@ __device__ __forceinline__ Rec ld_rec_ro(const Rec *p)
 // stress P after pass 1, the displacement u after pass 2 -- straight into their solid arrays over NVLink (Solid::pmask:
 // the ranks whose rows reference s), from the kernel that computes it.  The last block of a launch then raises this rank's
 // phase counter in every rank's mailbox; the next kernel of every rank is preceded by a one-warp wait for all counters.
+// The wait for the previous phase of every rank, inside the kernel that needs it: the kernel is launched (and its blocks
+// resident) while the slower ranks still compute, so the launch latency hides behind the skew between the ranks, and a phase
+// costs one launch instead of two.  All threads of the block call; the data the phase reads is only loaded afterwards.
+__device__ __forceinline__ void ring_wait(Ctl *ctl, const SolidRing &ring)
+{
+    if (ring.wait_seq == 0) return;
+    const bool marks = blockIdx.x == 0 && threadIdx.x == 0;
+    if (marks) trace_mark(ctl, 100 + kWaitSub);
+    if ((int)threadIdx.x < ring.nranks) {
+        const unsigned long long *f = (const unsigned long long *)(ring.base[ring.rank] + ring.off_flag) + threadIdx.x;
+        const unsigned long long t0 = global_ns();
+        while (ld_flag(f) < ring.wait_seq) {
+            if (global_ns() - t0 > kWaitTimeoutNs) { atomicOr(&ctl->err, kErrTimeout | (256 << kWaitSub)); break; }
+            __nanosleep(32);
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (marks) trace_mark(ctl, 200 + kWaitSub);
+}
 // (the threads that stored into peer memory have fenced after their stores: solid_pass*_finish)
 __device__ __forceinline__ void ring_complete(Ctl *ctl, int which, const SolidRing &ring)
 {
@@ -1347,6 +1368,7 @@ k_solid_pass1(Ctl *ctl, Solid so, int s_lo, int s_hi, SolidRing ring)
 {
     __shared__ double stage[RING ? (DEEP ? kRingBlock : 128) * 9 : 1];
     const int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (RING) ring_wait(ctl, ring);
     if (RING && threadIdx.x == 0 && blockIdx.x == 0) trace_mark(ctl, 310);
     double Pv[9];
     if (s < s_hi) solid_pass1_row<DIMS, PACKED, DEEP>(so, s, Pv);
@@ -1503,6 +1525,7 @@ k_solid_pass2(Ctl *ctl, Solid so, int s_lo, int s_hi, double W0, double W1, doub
               const double *__restrict__ inv_density, SolidRing ring)
 {
     const int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (RING) ring_wait(ctl, ring);
     if (RING && threadIdx.x == 0 && blockIdx.x == 0) trace_mark(ctl, 311);
     if (s < s_hi) solid_pass2_row<DIMS, PACKED, RING, DEEP>(so, s, W0, W1, W2, edt, module, double_update, inv_density, ring);
     if (RING) ring_complete(ctl, 1, ring);
@@ -1531,6 +1554,7 @@ __global__ void __launch_bounds__(kTeamBlock, 6) k_solid_pass1_team(Ctl *ctl, So
     __shared__ double Gs[TEAMS][NE];
     const int team = threadIdx.x / kTeam, lane = threadIdx.x % kTeam;
     const int s = s_lo + blockIdx.x * TEAMS + team;
+    if (RING) ring_wait(ctl, ring);
     if (s < s_hi) { // (a team is half a warp: both halves take the same number of trips only by chance, hence the masks)
         const unsigned mask = 0xffffu << (16 * ((threadIdx.x / kTeam) & 1));
         const int len = so.len[s], base = so.off[s];
@@ -1593,6 +1617,7 @@ k_solid_pass2_team(Ctl *ctl, Solid so, int s_lo, int s_hi, double W0, double W1,
     __shared__ double Vs[TEAMS][3];
     const int team = threadIdx.x / kTeam, lane = threadIdx.x % kTeam;
     const int s = s_lo + blockIdx.x * TEAMS + team;
+    if (RING) ring_wait(ctl, ring);
     if (s < s_hi) {
         const unsigned mask = 0xffffu << (16 * ((threadIdx.x / kTeam) & 1));
         // the reference's serial order (:2855-2887): rows j < s that list s, the own row, rows j > s

@@ -754,10 +754,12 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm, int part = 0)
             LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV, c->s_lo, c->s_hi, c->p.clamp_module);
         }
         rg.seq = seq0 + 1 + ph;
+        rg.wait_seq = (ring && ph > 0) ? seq0 + ph : 0; // every rank's previous phase, waited for inside the kernel
         rg.last = ph == 2 * substeps - 1 ? 1 : 0;
         if (ph % 2 == 0) { if (c->p.dim == 3) PHASE_D(3, 1); else PHASE_D(2, 1); }
         else             { if (c->p.dim == 3) PHASE_D(3, 2); else PHASE_D(2, 2); }
-        if (ring) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);
+        // after the step's last phase: everybody's final state has arrived before anything reads the solids
+        if (ring && ph == 2 * substeps - 1) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);
     }
 #undef PHASE_D
 #undef TEAM2
