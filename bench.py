@@ -245,6 +245,11 @@ def run_mphx(args):
     for nm, t in (("pass1", kms[2] / K), ("pass2", kms[3] / K)):
         tfl = sweep_flop / (t * 1e-3) / 1e12
         fp64[nm] = {"achieved_tflops": tfl, "frac": tfl / fp64_peak}
+    # the gather level (L1/L2, not HBM; SURVEY 8(d): "report HBM-level and L2-level throughput separately"): what the list
+    # kernels pull per candidate -- a 4-byte list entry and two 32-byte records -- counted from the live lists
+    gather_bytes = 68.0 * cand_n
+    gather = {"model": "per candidate: list entry 4 B + records 2 x 32 B, served by L1/L2 (not HBM traffic)", "bytes_per_sweep": gather_bytes,
+              "pass1_gbs": gather_bytes / (kms[2] / K * 1e-3) / 1e9, "pass2_gbs": gather_bytes / (kms[3] / K * 1e-3) / 1e9}
     # ncu counters of the dominant kernel: a committed capture (DRAM traffic per launch cannot be measured without the
     # profiler); the entry says which commit / round it was taken at
     traffic, ncu_facts = None, None
@@ -270,6 +275,7 @@ def run_mphx(args):
                 "whole_step": {"algorithmic_bytes": step_bytes, "achieved_gbs": step_bytes * K / (ms * 1e-3) / 1e9,
                                "frac": step_bytes * K / (ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
                 "fp64": fp64,
+                "gather_level": gather,
                 "ncu": ncu_facts,
                 "note": "frac is the HBM fraction the metric asks for; it is small by construction (370 algorithmic bytes but ~2e4 "
                         "fp64 flop per particle-step).  What binds the sweeps is under fp64 (live) and ncu (committed capture): FP64 "

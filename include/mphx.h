@@ -202,7 +202,10 @@ typedef struct mphx_cuboid {
     double lower[3], upper[3], spacing, velocity[3];
 } mphx_cuboid;
 long long mphx_generate_count(const mphx_cuboid *cuboids, int ncuboids); /* particles the cuboids hold (-1: invalid) */
-int mphx_upload_generated(mphx_ctx *ctx, const mphx_cuboid *cuboids, int ncuboids);
+int mphx_upload_generated(mphx_ctx *ctx, const mphx_cuboid *cuboids, int ncuboids); /* also on a configured slab: it keeps its share */
+/* fluid / wall particles of the cuboids per bucket column, from the axis tables alone: cuts the slabs of a generated case */
+int mphx_generate_column_histogram(const mphx_cuboid *cuboids, int ncuboids, double domain_min0, double cell_width, int ncols,
+                                   long long *hist /* ncols */);
 /* per-step variant of the above for a caller that keeps the state on the host: replaces Position
  * and Velocity only (original order, [N][3]); asynchronous on the context's stream, so pass
  * page-locked buffers and keep them alive until the next mphx_sync/mphx_download */
@@ -331,6 +334,7 @@ int mphx_multi_count(const mphx_multi *m);
 mphx_ctx *mphx_multi_context(mphx_multi *m, int i);
 int mphx_multi_upload(mphx_multi *m, int n, const int *property, const double *position,
                       const double *initial_position, const double *velocity);
+int mphx_multi_upload_generated(mphx_multi *m, const mphx_cuboid *cuboids, int ncuboids); /* no particle array on the host */
 int mphx_multi_init(mphx_multi *m);
 int mphx_multi_step(mphx_multi *m, int nsteps);
 int mphx_multi_sync(mphx_multi *m);

@@ -1771,6 +1771,26 @@ __global__ void k_generate(long long n, GenPlan plan, const double *__restrict__
     v3[o] = g.v[0]; v3[o + 1] = g.v[1]; v3[o + 2] = g.v[2];
 }
 
+// device-side generator on a slab: which of the generated particles this slab keeps (all solids + the fluid / wall particles
+// of its own columns: the rule of mphx_upload), and their ids once the mask is scanned
+__global__ void k_generated_keep(long long n, const int *__restrict__ type, const double *__restrict__ x3, GridDesc g, int *__restrict__ keep)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    bool k = is_structure_type(type[i]);
+    if (!k) {
+        int cx = cell_coord_exact(x3[3 * (size_t)i], g.mn0g, g.cellw, g.nxg) - g.xoff; // :1671
+        if (cx < 0) cx += g.nxg; else if (cx >= g.nxg) cx -= g.nxg;
+        k = cx >= g.range && cx < g.nx - g.range;
+    }
+    keep[i] = k ? 1 : 0;
+}
+__global__ void k_generated_ids(long long n, const int *__restrict__ keep, const int *__restrict__ scan, int *__restrict__ ids)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && keep[i]) ids[scan[i]] = (int)i;
+}
+
 // the solids in their reference configuration as a particle set (for the initial-list build)
 __global__ void k_solid_reference_particles(Solid so, Particles p)
 {

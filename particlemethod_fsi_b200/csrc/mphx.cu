@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -1595,11 +1596,34 @@ long long mphx_generate_count(const mphx_cuboid *cuboids, int ncuboids)
     return generator_plan(cuboids, ncuboids, plan, axes, total, r) == MPHX_OK ? total : -1;
 }
 
+// owned-by-column histogram of the fluid / wall particles the cuboids hold, from the axis tables alone (no particle arrays):
+// what cuts the slabs of a generated case (mphx_partition_columns)
+int mphx_generate_column_histogram(const mphx_cuboid *cuboids, int ncuboids, double domain_min0, double cell_width, int ncols, long long *hist)
+{
+    if (!hist || ncols < 1 || !(cell_width > 0.0)) return MPHX_ERR_INVALID;
+    GenPlan plan;
+    std::vector<double> axes;
+    long long total = 0;
+    int r[6];
+    int rc = generator_plan(cuboids, ncuboids, plan, axes, total, r);
+    if (rc) return rc;
+    for (int i = 0; i < ncols; ++i) hist[i] = 0;
+    for (int q = 0; q < plan.count; ++q) {
+        const GenCuboid &g = plan.c[q];
+        if (g.type >= 2 && g.type < 4) continue;
+        for (int ix = 0; ix < g.nx; ++ix) {
+            int cx = ((int)std::floor((axes[(size_t)g.ax + ix] - domain_min0) / cell_width)) % ncols; // :1671
+            cx = (cx % ncols + ncols) % ncols;
+            hist[cx] += (long long)g.ny * g.nz;
+        }
+    }
+    return MPHX_OK;
+}
+
 int mphx_upload_generated(mphx_ctx *ctx, const mphx_cuboid *cuboids, int ncuboids)
 {
     Ctx *c = reinterpret_cast<Ctx *>(ctx);
     if (!c || c->uploaded) return MPHX_ERR_INVALID;
-    if (c->slab) { set_last_error("mphx_upload_generated: single context only (slabs take host arrays)"); return MPHX_ERR_UNSUPPORTED; }
     CK(cudaSetDevice(c->device));
     GenPlan plan;
     std::vector<double> axes;
@@ -1608,7 +1632,6 @@ int mphx_upload_generated(mphx_ctx *ctx, const mphx_cuboid *cuboids, int ncuboid
     int rc = generator_plan(cuboids, ncuboids, plan, axes, total, r);
     if (rc) return rc;
     const int n = (int)total;
-    if ((rc = upload_allocate(c, n, n, r))) return rc;
     Scratch tmp;
     int *d_t;
     double *d_x, *d_x0, *d_v, *d_axes;
@@ -1618,7 +1641,27 @@ int mphx_upload_generated(mphx_ctx *ctx, const mphx_cuboid *cuboids, int ncuboid
     CK(cudaMemcpyAsync(d_axes, axes.data(), sizeof(double) * axes.size(), cudaMemcpyHostToDevice, c->stream));
     LAUNCH(c, k_generate, nblk(n), kBlock, (long long)n, plan, d_axes, d_t, d_x, d_x0, d_v);
     CK(cudaGetLastError());
-    return upload_finish(c, n, nullptr, d_t, d_x, d_x0, d_v);
+    if (!c->slab) {
+        if ((rc = upload_allocate(c, n, n, r))) return rc;
+        return upload_finish(c, n, nullptr, d_t, d_x, d_x0, d_v);
+    }
+    // a slab keeps all solids and the fluid / wall particles of its own columns: mask, scan, ids -- on the device
+    int *keep, *scan, *sums, *d_ids;
+    const int sb = (int)(((long long)n + 1 + kScanChunk - 1) / kScanChunk);
+    if (tmp.get(&keep, (size_t)n + 1) || tmp.get(&scan, (size_t)n + 2) || tmp.get(&sums, (size_t)sb + 1)) return MPHX_ERR_NOMEM;
+    CK(cudaMemsetAsync(keep + n, 0, sizeof(int), c->stream));
+    LAUNCH(c, k_generated_keep, nblk(n), kBlock, (long long)n, (const int *)d_t, (const double *)d_x, c->grid, keep);
+    LAUNCH(c, k_scan_reduce, sb, kScanThreads, (const Ctl *)nullptr, (const int *)keep, n + 1, sums);
+    LAUNCH(c, k_scan_top, 1, kScanThreads, (const Ctl *)nullptr, sums, sb);
+    LAUNCH(c, k_scan_apply, sb, kScanThreads, (const Ctl *)nullptr, keep, n + 1, (const int *)sums, scan, 0);
+    int nloc = 0;
+    CK(cudaMemcpyAsync(&nloc, scan + n, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if ((rc = upload_allocate(c, n, nloc, r))) return rc;
+    if (tmp.get(&d_ids, (size_t)std::max(nloc, 1))) return MPHX_ERR_NOMEM;
+    LAUNCH(c, k_generated_ids, nblk(n), kBlock, (long long)n, (const int *)keep, (const int *)scan, d_ids);
+    CK(cudaGetLastError());
+    return upload_finish(c, nloc, d_ids, d_t, d_x, d_x0, d_v);
 }
 
 // replace Position and Velocity of every particle (original order) on an initialised context:

@@ -113,7 +113,9 @@ class MultiSolver:
     """mphx_multi_*: the explicit step on `world` x-slabs driven by ONE process.  devices=None puts slab r
     on CUDA device r; a list may repeat a device (parity tests on a one-GPU box)."""
 
-    def __init__(self, case, world: int, devices=None, list_reuse: bool | None = None):
+    def __init__(self, case, world: int, devices=None, list_reuse: bool | None = None, generated: bool = False):
+        """generated=True: the particles come from the device-side generator (case.cuboids: mphx_multi_upload_generated) --
+        no particle array leaves the host"""
         from . import solver
         self.lib, self._ck = solver.lib, solver._ck
         self.case, self.n, self.world = case, case.n, world
@@ -127,9 +129,13 @@ class MultiSolver:
         if list_reuse is not None:
             for r in range(world):
                 self._ck("mphx_set_list_reuse", self.lib.mphx_set_list_reuse(self.context(r), 1 if list_reuse else 0, 0.0))
-        t = np.ascontiguousarray(case.property, dtype=np.int32)
-        x, x0, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (case.position, case.initial_position, case.velocity))
-        self._ck("mphx_multi_upload", self.lib.mphx_multi_upload(self._m, case.n, t.ctypes.data, x.ctypes.data, x0.ctypes.data, v.ctypes.data))
+        if generated:
+            arr = solver._cuboid_array(case.cuboids)
+            self._ck("mphx_multi_upload_generated", self.lib.mphx_multi_upload_generated(self._m, C.cast(arr, C.c_void_p), len(case.cuboids)))
+        else:
+            t = np.ascontiguousarray(case.property, dtype=np.int32)
+            x, x0, v = (np.ascontiguousarray(a, dtype=np.float64) for a in (case.position, case.initial_position, case.velocity))
+            self._ck("mphx_multi_upload", self.lib.mphx_multi_upload(self._m, case.n, t.ctypes.data, x.ctypes.data, x0.ctypes.data, v.ctypes.data))
         self._ck("mphx_multi_init", self.lib.mphx_multi_init(self._m))
 
     def context(self, r: int):

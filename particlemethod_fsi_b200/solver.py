@@ -59,6 +59,8 @@ def _load():
     L.mphx_generate_count.argtypes = [vp, C.c_int]
     L.mphx_generate_count.restype = C.c_longlong
     L.mphx_upload_generated.argtypes = [vp, vp, C.c_int]
+    L.mphx_generate_column_histogram.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, vp]
+    L.mphx_multi_upload_generated.argtypes = [vp, vp, C.c_int]
     L.mphx_upload_state.argtypes = [vp, vp, vp]
     L.mphx_init.argtypes = [vp]
     L.mphx_get_constants.argtypes = [vp, C.POINTER(abi.Constants)]

@@ -74,3 +74,22 @@ def test_generator_count_matches_the_lattice_rule():
     for c in (cases.dam2d(), cases.fsi3d_mini(), cases.tiny2d(), cases.bar2d()):
         assert solver.generate_count(c.cuboids) == c.n, c.name
     assert solver.generate_count([cases.Cuboid(9, (0, 0, 0), (1, 1, 1), 0.1)]) == -1     # invalid type
+
+
+def test_generated_column_histogram_equals_the_particle_histogram():
+    """mphx_generate_column_histogram (axis tables only) against the histogram of the generated particles (slab.plan)"""
+    import ctypes as C
+    from particlemethod_fsi_b200 import slab, solver
+    for case in (cases.fsi3d_mini(), cases.fsi2d(), cases.dam2d()):
+        k = solver.compute_constants(case.params)
+        ncols = k.cell_count[0]
+        want = slab.plan(case, 2, k)["hist"] if ncols >= 4 * k.stencil_range else None
+        arr = solver._cuboid_array(case.cuboids)
+        hist = np.zeros(ncols, dtype=np.int64)
+        rc = solver.lib.mphx_generate_column_histogram(C.cast(arr, C.c_void_p), len(case.cuboids), case.params.domain_min[0], k.cell_width, ncols,
+                                                       hist.ctypes.data)
+        assert rc == 0
+        t = case.property
+        assert hist.sum() == int(((t < 2) | (t >= 4)).sum())
+        if want is not None:
+            assert np.array_equal(hist, want)

@@ -223,3 +223,22 @@ def test_rebalance_with_list_reuse_stays_within_tolerance():
     assert all(i["err"] == 0 for i in ring.info())
     ref.close()
     ring.close()
+
+
+@pytest.mark.parametrize("name,world", [("fsi3d_mini", 3), ("fsi2d", 2)])
+def test_generated_ring_equals_uploaded_single_context(name, world):
+    """SURVEY 8(f) N4 on slabs: every slab fills the generator's lattice on its device and keeps its share (histogram from the
+    axis tables, keep mask + scan + ids on the device: no particle array on the host); the run equals the single context fed
+    with the .grid arrays, bit for bit"""
+    case = getattr(cases, name)()
+    ref = Solver.from_case(case)
+    ring = slab.MultiSolver(case, world, devices=[0] * world, generated=True)
+    ref.step(12, sync=True)
+    ring.step(12)
+    ring.sync()
+    a, b = ref.download(*FIELDS), ring.download(*FIELDS)
+    for f in FIELDS:
+        assert np.array_equal(a[f], b[f]), (f, float(np.abs(a[f] - b[f]).max()))
+    assert all(i["err"] == 0 for i in ring.info())
+    ref.close()
+    ring.close()
