@@ -134,6 +134,8 @@ struct Ctx {
     std::vector<void *> allocs;
 
     bool tracing = false; // device-side timeline (mphx_trace_enable)
+    unsigned long long *trace_buf = nullptr;
+    int trace_cap_alloc = 0;
     // phase timers (src/main.cpp:695-700 split)
     bool timing = false;
     std::vector<cudaEvent_t> ev, ev_pool;
@@ -2065,7 +2067,13 @@ int mphx_trace_enable(mphx_ctx *ctx, int capacity)
     { int jrc = join_solids(c); if (jrc) return jrc; }
     CK(cudaStreamSynchronize(c->stream));
     unsigned long long *buf = nullptr;
-    if (capacity > 0 && c->alloc(&buf, 2 * (size_t)capacity)) return MPHX_ERR_NOMEM;
+    if (capacity > 0) { // (the buffer is kept and reused by later calls)
+        if (capacity > c->trace_cap_alloc) {
+            if (c->alloc(&c->trace_buf, 2 * (size_t)capacity)) return MPHX_ERR_NOMEM;
+            c->trace_cap_alloc = capacity;
+        }
+        buf = c->trace_buf;
+    }
     const int zero = 0;
     CK(cudaMemcpy(&c->ctl->trace, &buf, sizeof(buf), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(&c->ctl->trace_cap, &capacity, sizeof(int), cudaMemcpyHostToDevice));
