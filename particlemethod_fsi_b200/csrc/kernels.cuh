@@ -1186,7 +1186,7 @@ __device__ __forceinline__ Rec ld_rec_ro(const Rec *p)
 // Split sub-steps (slab mode): rank r advances the solids [s_lo, s_hi) and stores what other ranks' rows read -- the
 // stress P after pass 1, the displacement u after pass 2 -- straight into their solid arrays over NVLink (Solid::pmask:
 // the ranks whose rows reference s), from the kernel that computes it.  The last block of a launch then raises this rank's
-// phase counter in every rank's mailbox; the next kernel of every rank is preceded by a one-warp wait for all counters.
+// phase counter in every rank's mailbox; the next kernel of every rank starts by waiting for all counters (ring_wait).
 // The wait for the previous phase of every rank, inside the kernel that needs it: the kernel is launched (and its blocks
 // resident) while the slower ranks still compute, so the launch latency hides behind the skew between the ranks, and a phase
 // costs one launch instead of two.  All threads of the block call; the data the phase reads is only loaded afterwards.

@@ -7,6 +7,8 @@ every slab context owns a mailbox that its peers write into over NVLink, and `mp
 context is a fixed sequence of kernel launches without a host synchronisation (csrc/slab.inc).
 This module is only the plumbing around it:
 
+  * `rebalance()`   (both classes) re-cuts a running ring in place: column histogram on the devices, one all-reduce, the
+                    library's rule (mphx_rebalance_cuts), mphx_slab_recut -- owners change through the ordinary migration;
   * `plan()`        cuts the bucket columns on the particle histogram (mphx_partition_columns) and
                     sizes the slots / messages -- the same rule as mphx_multi_upload;
   * `DistSlab`      one process per GPU (torchrun): creates its slab context and carries the 64-byte
