@@ -70,7 +70,7 @@ struct Ctx {
     // sub-step kernels with a team of lanes per solid (kernels.cuh); 0: one thread per solid
     bool solid_team = true, team_ok = false, solid_team_always = false;
     int sol_maxlen = 0, sol_rmaxlen = 0;
-    bool split_substeps = true;
+    bool split_substeps = true, ring_inkernel_wait = false;
     int s_lo = 0, s_hi = 0;
     SolidRing ring{};
     void *peer_base[kMaxRanks] = {};
@@ -757,12 +757,16 @@ static int run_solid_substeps(Ctx *c, cudaStream_t strm, int part = 0)
             LAUNCH_ON(c, strm, k_solid_apply_update, nblk(ns), kBlock, c->sol, c->mine.solV, c->s_lo, c->s_hi, c->p.clamp_module);
         }
         rg.seq = seq0 + 1 + ph;
-        rg.wait_seq = (ring && ph > 0) ? seq0 + ph : 0; // every rank's previous phase, waited for inside the kernel
+        // every rank's previous phase: waited for by a one-warp kernel after each phase (default), or inside the kernel that
+        // needs it (MPHX_RING_INKERNEL_WAIT=1: one launch per phase; measured equal at 8 GPUs, 2 % slower at 2, where a share
+        // is ~1800 one-warp blocks that hold their registers while they spin)
+        rg.wait_seq = (ring && c->ring_inkernel_wait && ph > 0) ? seq0 + ph : 0;
         rg.last = ph == 2 * substeps - 1 ? 1 : 0;
         if (ph % 2 == 0) { if (c->p.dim == 3) PHASE_D(3, 1); else PHASE_D(2, 1); }
         else             { if (c->p.dim == 3) PHASE_D(3, 2); else PHASE_D(2, 2); }
-        // after the step's last phase: everybody's final state has arrived before anything reads the solids
-        if (ring && ph == 2 * substeps - 1) LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);
+        // (after the step's last phase in any case: everybody's final state has arrived before anything reads the solids)
+        if (ring && (!c->ring_inkernel_wait || ph == 2 * substeps - 1))
+            LAUNCH_ON(c, strm, k_wait<0>, 1, 32, c->ctl, rg.seq, c->mine.fsub, c->nranks, kWaitSub);
     }
 #undef PHASE_D
 #undef TEAM2
@@ -1333,6 +1337,7 @@ int mphx_create(mphx_ctx **out, const mphx_params *p, int device)
         c->solid_team = std::atoi(e) != 0;
         c->solid_team_always = std::atoi(e) == 2;
     }
+    if (const char *e = std::getenv("MPHX_RING_INKERNEL_WAIT")) c->ring_inkernel_wait = std::atoi(e) != 0;
     if (const char *e = std::getenv("MPHX_SPLIT_SUBSTEPS")) c->split_substeps = std::atoi(e) != 0; // 0: every slab runs all solids' sub-steps
     {   // highest priority: the few blocks of a sub-step kernel must get SM slots as pass-2 blocks retire,
         // not after the whole pass-2 grid has been issued
