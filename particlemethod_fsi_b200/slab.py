@@ -100,6 +100,29 @@ def gather_handles(mine: bytes, dist=None, group=None, device=None):
     return [bytes(o.cpu().numpy().tobytes()) for o in out]
 
 
+def rebalance_collective(local_hist, partition, halo: int, dist=None, group=None, device=None):
+    """the collective half of an in-place re-balancing: all-reduce the ranks' column histograms (each rank counts the
+    particles it owns), then every rank applies the library's rule (mphx_rebalance_cuts) to the same global histogram.
+    Returns (new partition [(lo, hi)] * world, number of interior cuts that moved)."""
+    import torch
+    import torch.distributed as tdist
+    from .solver import lib
+    dist = dist or tdist
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(np.ascontiguousarray(local_hist, dtype=np.int64).copy())
+    if device is not None:
+        t = t.to(device)
+    dist.all_reduce(t, group=group)
+    hist = np.ascontiguousarray(t.cpu().numpy(), dtype=np.int64)
+    old = np.ascontiguousarray([p[0] for p in partition] + [partition[-1][1]], dtype=np.int32)
+    new = np.zeros(world + 1, dtype=np.int32)
+    moved = C.c_int()
+    rc = lib.mphx_rebalance_cuts(hist.ctypes.data, int(hist.shape[0]), world, halo, old.ctypes.data, new.ctypes.data, C.byref(moved))
+    if rc != abi.MPHX_OK:
+        raise RuntimeError(f"mphx_rebalance_cuts: {lib.mphx_last_error().decode()}")
+    return [(int(new[r]), int(new[r + 1])) for r in range(world)], moved.value
+
+
 def _views_for(n, names):
     out, hv = {}, abi.HostViews()
     for nm in names:
@@ -296,18 +319,12 @@ class DistSlab:
         ncols, R = k.cell_count[0], k.stencil_range
         hist = np.zeros(ncols, dtype=np.int64)
         self._ck("mphx_slab_column_histogram", self.lib.mphx_slab_column_histogram(self.ctx, hist.ctypes.data, ncols))
-        t = self.torch.from_numpy(hist).to(self.device if self.dist.get_backend(self.group) == "nccl" else "cpu")
-        self.dist.all_reduce(t, group=self.group)
-        hist = np.ascontiguousarray(t.cpu().numpy(), dtype=np.int64)
-        old = np.ascontiguousarray([p[0] for p in self.partition] + [self.partition[-1][1]], dtype=np.int32)
-        new = np.zeros(self.world + 1, dtype=np.int32)
-        moved = C.c_int()
-        self._ck("mphx_rebalance_cuts", self.lib.mphx_rebalance_cuts(hist.ctypes.data, ncols, self.world, R, old.ctypes.data, new.ctypes.data,
-                                                                     C.byref(moved)))
-        if moved.value:
-            self._ck("mphx_slab_recut", self.lib.mphx_slab_recut(self.ctx, int(new[self.rank]), int(new[self.rank + 1])))
-            self.partition = [(int(new[r]), int(new[r + 1])) for r in range(self.world)]
-        return moved.value
+        nccl = self.dist.get_backend(self.group) == "nccl"
+        new, moved = rebalance_collective(hist, self.partition, R, self.dist, self.group, self.device if nccl else None)
+        if moved:
+            self._ck("mphx_slab_recut", self.lib.mphx_slab_recut(self.ctx, new[self.rank][0], new[self.rank][1]))
+            self.partition = new
+        return moved
 
     def download(self, *names):
         """every rank reports the particles it owns (zeros elsewhere); the all-reduced sum is the case"""

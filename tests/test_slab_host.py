@@ -131,3 +131,44 @@ def test_rebalance_cuts_move_towards_balance_by_at_most_one_halo():
     moved = C.c_int(7)
     assert lib.mphx_rebalance_cuts(hist.ctypes.data, ncols, world, R, cuts.ctypes.data, new.ctypes.data, C.byref(moved)) == 0
     assert moved.value == 0 and np.array_equal(new, cuts)
+
+
+def _rebalance_worker(rank, world, port, ok):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ncols, R = 96, 3
+        full = np.zeros(ncols, dtype=np.int64)
+        full[8:40] = 700                      # the fluid has moved into the first slabs' columns
+        width = ncols // world
+        part = [(r * width, (r + 1) * width if r < world - 1 else ncols) for r in range(world)]
+        mine = np.zeros(ncols, dtype=np.int64)
+        lo, hi = part[rank]
+        mine[lo:hi] = full[lo:hi]             # every rank counts the particles it owns
+        new, moved = slab.rebalance_collective(mine, part, R)
+        # the same answer as one process with the whole histogram, on every rank
+        import ctypes as C
+        from particlemethod_fsi_b200.solver import lib
+        old = np.array([p[0] for p in part] + [ncols], dtype=np.int32)
+        want = np.zeros(world + 1, dtype=np.int32)
+        m = C.c_int()
+        assert lib.mphx_rebalance_cuts(full.ctypes.data, ncols, world, R, old.ctypes.data, want.ctypes.data, C.byref(m)) == 0
+        assert [c for lohi in new for c in lohi] == [int(c) for r in range(world) for c in (want[r], want[r + 1])]
+        assert moved == m.value and moved > 0
+        assert all(abs(new[r][0] - part[r][0]) <= R and abs(new[r][1] - part[r][1]) <= R for r in range(world))
+        t = torch.tensor([c for lohi in new for c in lohi], dtype=torch.int64)
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(t, ref)
+        ok[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_rebalance_collective_over_gloo(world):
+    """the collective half of DistSlab.rebalance(): per-rank histograms all-reduced over gloo, the library's rule applied by
+    every rank -- identical cuts everywhere, equal to the single-process result"""
+    ok = mp.get_context("spawn").Array("i", [0] * world)
+    mp.spawn(_rebalance_worker, args=(world, _free_port(), ok), nprocs=world, join=True)
+    assert list(ok) == [1] * world
