@@ -202,6 +202,9 @@ typedef struct mphx_cuboid {
     double lower[3], upper[3], spacing, velocity[3];
 } mphx_cuboid;
 long long mphx_generate_count(const mphx_cuboid *cuboids, int ncuboids); /* particles the cuboids hold (-1: invalid) */
+/* the pre-processor's own input file (generator/generator.cpp:127-262; StartCuboid blocks only): fills time0 (0),
+ * particle_spacing and the domain through the `%e` text the generator would write, mallocs the cuboids (mphx_free_host) */
+int mphx_read_boid_file(const char *filename, mphx_params *p, mphx_cuboid **cuboids, int *ncuboids);
 int mphx_upload_generated(mphx_ctx *ctx, const mphx_cuboid *cuboids, int ncuboids); /* also on a configured slab: it keeps its share */
 /* fluid / wall particles of the cuboids per bucket column, from the axis tables alone: cuts the slabs of a generated case */
 int mphx_generate_column_histogram(const mphx_cuboid *cuboids, int ncuboids, double domain_min0, double cell_width, int ncols,

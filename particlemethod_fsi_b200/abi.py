@@ -105,7 +105,7 @@ EXPORTS = [
     "mphx_params_default", "mphx_read_data_file", "mphx_read_grid_file", "mphx_free_host",
     "mphx_write_prof_file", "mphx_write_vtk_file", "mphx_write_checkpoint", "mphx_read_checkpoint", "mphx_class_ranges",
     "mphx_compute_constants",
-    "mphx_create", "mphx_destroy", "mphx_upload", "mphx_generate_count", "mphx_upload_generated", "mphx_generate_column_histogram", "mphx_multi_upload_generated", "mphx_upload_state", "mphx_init", "mphx_get_constants", "mphx_get_wall_centers",
+    "mphx_create", "mphx_destroy", "mphx_upload", "mphx_generate_count", "mphx_read_boid_file", "mphx_upload_generated", "mphx_generate_column_histogram", "mphx_multi_upload_generated", "mphx_upload_state", "mphx_init", "mphx_get_constants", "mphx_get_wall_centers",
     "mphx_step", "mphx_step_fluid_only", "mphx_sync", "mphx_time", "mphx_set_time", "mphx_download",
     "mphx_download_owned", "mphx_upload_owned",
     "mphx_debug_neighbors", "mphx_debug_initial_structure_neighbors",

@@ -305,6 +305,20 @@ def write_data_file(fn: str, p: abi.Params, rc: abi.RunControl):
                 " ".join("%.17g" % v for v in p.wall_omega[t])))
 
 
+def write_boid_file(fn: str, case: Case):
+    """the pre-processor's input for `case` (generator/generator.cpp:127-262): header + one StartCuboid block per cuboid"""
+    p = case.params
+    with open(fn, "w") as f:
+        f.write("# %s\n" % case.name)
+        f.write("ParticleDistance %.17g\n" % p.particle_spacing)
+        f.write("LowerDomain %.17g %.17g %.17g\n" % tuple(p.domain_min))
+        f.write("UpperDomain %.17g %.17g %.17g\n" % tuple(p.domain_max))
+        for cub in case.cuboids:
+            f.write("StartCuboid\n    Spacing %.17g\n    Type %d\n    RigidType 10\n    Lower %.17g %.17g %.17g\n"
+                    "    Upper %.17g %.17g %.17g\n    Velocity %.17g %.17g %.17g\n    Enthalpy 0.0\nEndCuboid\n"
+                    % ((cub.spacing, cub.type) + tuple(cub.lower) + tuple(cub.upper) + tuple(cub.velocity)))
+
+
 def write_grid_file(fn: str, case: Case):
     """generator/generator.cpp:839-862"""
     p = case.params

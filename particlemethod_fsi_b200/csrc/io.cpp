@@ -119,6 +119,78 @@ extern "C" int mphx_read_data_file(const char *filename, mphx_params *p, mphx_ru
 
 extern "C" void mphx_free_host(void *ptr) { std::free(ptr); }
 
+// The pre-processor's input (generator/generator.cpp:127-262: ParticleDistance, LowerDomain, UpperDomain and the
+// StartCuboid ... EndCuboid blocks with Spacing / Type / Lower / Upper / Velocity; RigidType and Enthalpy are read and
+// not used by the solver).  The header values take the same `%e` round trip the generator's .grid text gives them
+// (generator.cpp:839-847), so a run from the .boid equals a run from the generated .grid.  Other shapes (Cuboid2,
+// cylinders, rectangles) are not supported by the device-side generator.
+static double through_e_text(double v)
+{
+    char b[64];
+    std::snprintf(b, sizeof(b), "%e", v);
+    return std::strtod(b, nullptr);
+}
+extern "C" int mphx_read_boid_file(const char *filename, mphx_params *p, mphx_cuboid **cuboids, int *ncuboids)
+{
+    if (!filename || !p || !cuboids || !ncuboids) return MPHX_ERR_INVALID;
+    *cuboids = nullptr;
+    *ncuboids = 0;
+    FILE *fp = std::fopen(filename, "r");
+    if (!fp) {
+        mphx::set_last_error(std::string("cannot open boid file ") + filename);
+        return MPHX_ERR_IO;
+    }
+    std::vector<mphx_cuboid> cubs;
+    char buf[1024], token[256];
+    bool in_cuboid = false, have_pd = false, have_lo = false, have_hi = false;
+    unsigned seen = 0; // Spacing 1, Type 2, Lower 4, Upper 8
+    mphx_cuboid cur{};
+    int rc = MPHX_OK;
+    double pd = 0.0, lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
+    while (std::fgets(buf, sizeof(buf), fp)) {
+        if (buf[0] == '#') continue;
+        if (std::sscanf(buf, "%255s", token) != 1) continue;
+        const std::string t = token;
+        if (!in_cuboid) {
+            if (t == "ParticleDistance") have_pd = std::sscanf(buf, " %*s %lf", &pd) == 1;
+            else if (t == "LowerDomain") have_lo = std::sscanf(buf, " %*s %lf %lf %lf", &lo[0], &lo[1], &lo[2]) == 3;
+            else if (t == "UpperDomain") have_hi = std::sscanf(buf, " %*s %lf %lf %lf", &hi[0], &hi[1], &hi[2]) == 3;
+            else if (t == "StartCuboid") { in_cuboid = true; cur = mphx_cuboid{}; seen = 0; }
+            else if (t.compare(0, 5, "Start") == 0) {
+                mphx::set_last_error("boid file: shape '" + t + "' is not supported (cuboids only)");
+                rc = MPHX_ERR_UNSUPPORTED;
+                break;
+            }
+            continue;
+        }
+        if (t == "EndCuboid") {
+            if (seen != 15u) { mphx::set_last_error("boid file: a cuboid lacks Spacing, Type, Lower or Upper"); rc = MPHX_ERR_IO; break; }
+            cubs.push_back(cur);
+            in_cuboid = false;
+        } else if (t == "Spacing") { if (std::sscanf(buf, " %*s %lf", &cur.spacing) == 1) seen |= 1u; }
+        else if (t == "Type") { if (std::sscanf(buf, " %*s %d", &cur.type) == 1) seen |= 2u; }
+        else if (t == "Lower") { if (std::sscanf(buf, " %*s %lf %lf %lf", &cur.lower[0], &cur.lower[1], &cur.lower[2]) == 3) seen |= 4u; }
+        else if (t == "Upper") { if (std::sscanf(buf, " %*s %lf %lf %lf", &cur.upper[0], &cur.upper[1], &cur.upper[2]) == 3) seen |= 8u; }
+        else if (t == "Velocity") std::sscanf(buf, " %*s %lf %lf %lf", &cur.velocity[0], &cur.velocity[1], &cur.velocity[2]);
+        // RigidType, Enthalpy: pre-processor fields the solver does not read
+    }
+    std::fclose(fp);
+    if (rc) return rc;
+    if (in_cuboid || !have_pd || !have_lo || !have_hi || cubs.empty()) {
+        mphx::set_last_error("boid file: ParticleDistance, LowerDomain, UpperDomain and at least one complete cuboid are required");
+        return MPHX_ERR_IO;
+    }
+    p->time0 = 0.0; // generator.cpp:841
+    p->particle_spacing = through_e_text(pd);
+    for (int d = 0; d < 3; ++d) { p->domain_min[d] = through_e_text(lo[d]); p->domain_max[d] = through_e_text(hi[d]); }
+    mphx_cuboid *out = (mphx_cuboid *)std::calloc(cubs.size(), sizeof(mphx_cuboid));
+    if (!out) return MPHX_ERR_NOMEM;
+    std::memcpy(out, cubs.data(), sizeof(mphx_cuboid) * cubs.size());
+    *cuboids = out;
+    *ncuboids = (int)cubs.size();
+    return MPHX_OK;
+}
+
 extern "C" void mphx_class_ranges(int n, const int *property, int ranges[6])
 {
     for (int i = 0; i < 6; ++i) ranges[i] = -1;

@@ -9,6 +9,7 @@
 // loop).  The reference fixes dimension and clamp module at compile time (src/main.cpp:50,54-55);
 // here they are the optional 7th/8th arguments or MPHX_DIM / MPHX_MODULE (defaults: 2, bar -- the
 // shipped configuration).  `nthreads` is accepted and ignored (there is no CPU path).
+// A grid argument ending in .boid (the pre-processor's input) generates the particles on the device(s) instead of reading a .grid.
 // MPHX_REBALANCE_EVERY=K re-cuts the slabs of a multi-GPU run every K steps (mphx_multi_rebalance).
 // MPHX_NGPU=N (2..16) runs the case on N devices of the box as x-slabs (mphx_multi_*: one process, the
 // slabs exchange over NVLink inside the library); MPHX_DEVICE picks the device of a single-GPU run.
@@ -147,12 +148,24 @@ int main(int argc, char *argv[])
     if (rc) die("readDataFile", rc);
     int n = 0, *property = nullptr;
     double *position = nullptr, *initial_position = nullptr, *velocity = nullptr;
-    // a grid argument ending in .ckp is a lossless checkpoint of this driver (MPHX_CHECKPOINT), not the reference's text
+    // a grid argument ending in .ckp is a lossless checkpoint of this driver (MPHX_CHECKPOINT), not the reference's text;
+    // one ending in .boid is the PRE-PROCESSOR's input: the lattice is generated on the device(s) (mphx_upload_generated,
+    // SURVEY 8(f) N4) -- the run equals the one from the generator's .grid without that (12 GB at 10^8 particles) text
     const bool restart = gridfilename.size() > 4 && gridfilename.compare(gridfilename.size() - 4, 4, ".ckp") == 0;
-    rc = restart ? mphx_read_checkpoint(gridfilename.c_str(), &p, &n, &property, &position, &initial_position, &velocity)
-                 : mphx_read_grid_file(gridfilename.c_str(), &p, &n, &property, &position, &initial_position, &velocity);
-    if (rc) die("readGridFile", rc);
-    {
+    const bool from_boid = gridfilename.size() > 5 && gridfilename.compare(gridfilename.size() - 5, 5, ".boid") == 0;
+    mphx_cuboid *cuboids = nullptr;
+    int ncuboids = 0;
+    if (from_boid) {
+        if ((rc = mphx_read_boid_file(gridfilename.c_str(), &p, &cuboids, &ncuboids))) die("readBoidFile", rc);
+        const long long total = mphx_generate_count(cuboids, ncuboids);
+        if (total <= 0 || total > 0x7fffffffLL) die("mphx_generate_count", MPHX_ERR_INVALID);
+        n = (int)total;
+    } else {
+        rc = restart ? mphx_read_checkpoint(gridfilename.c_str(), &p, &n, &property, &position, &initial_position, &velocity)
+                     : mphx_read_grid_file(gridfilename.c_str(), &p, &n, &property, &position, &initial_position, &velocity);
+        if (rc) die("readGridFile", rc);
+    }
+    if (!from_boid) {
         int r[6];
         mphx_class_ranges(n, property, r); // :931-944
         printf("Fluid Particles: %d\n", r[0] != -1 ? r[1] - r[0] : 0);
@@ -183,11 +196,32 @@ int main(int argc, char *argv[])
     log_printf("N0a = %e, count=%d\n", k.n0a, k.n0a_count); // :1258
     log_printf("N0p = %e, count=%d\n", k.n0p, k.n0p_count); // :1303
     if (multi) {
-        if ((rc = mphx_multi_upload(multi, n, property, position, initial_position, velocity))) die("mphx_multi_upload", rc);
+        if (from_boid) { if ((rc = mphx_multi_upload_generated(multi, cuboids, ncuboids))) die("mphx_multi_upload_generated", rc); }
+        else if ((rc = mphx_multi_upload(multi, n, property, position, initial_position, velocity))) die("mphx_multi_upload", rc);
         if ((rc = mphx_multi_init(multi))) die("mphx_multi_init", rc);
     } else {
-        if ((rc = mphx_upload(ctx, n, property, position, initial_position, velocity))) die("mphx_upload", rc);
+        if (from_boid) { if ((rc = mphx_upload_generated(ctx, cuboids, ncuboids))) die("mphx_upload_generated", rc); }
+        else if ((rc = mphx_upload(ctx, n, property, position, initial_position, velocity))) die("mphx_upload", rc);
         if ((rc = mphx_init(ctx))) die("mphx_init", rc);
+    }
+    if (from_boid) { // the host copies the writers need (Property, InitialPosition) come back from the device(s)
+        const size_t nn = (size_t)n;
+        property = (int *)calloc(nn, sizeof(int));
+        position = (double *)calloc(3 * nn, sizeof(double));
+        initial_position = (double *)calloc(3 * nn, sizeof(double));
+        velocity = (double *)calloc(3 * nn, sizeof(double));
+        if (!property || !position || !initial_position || !velocity) die("malloc", MPHX_ERR_NOMEM);
+        mphx_host_views v0;
+        memset(&v0, 0, sizeof(v0));
+        v0.property = property; v0.position = position; v0.velocity = velocity;
+        if ((rc = multi ? mphx_multi_download(multi, &v0) : mphx_download(ctx, &v0))) die("mphx_download", rc);
+        memcpy(initial_position, position, sizeof(double) * 3 * nn);
+        mphx_free_host(cuboids);
+        int r[6];
+        mphx_class_ranges(n, property, r); // :931-944
+        printf("Fluid Particles: %d\n", r[0] != -1 ? r[1] - r[0] : 0);
+        printf("Structure Particles: %d\n", r[2] != -1 ? r[3] - r[2] : 0);
+        printf("Wall Particles: %d\n", r[4] != -1 ? r[5] - r[4] : 0);
     }
     mphx_set_timing(ctx, 1);
     // MPHX_REBALANCE_EVERY=K (multi-GPU): re-cut the slabs on the current particle distribution every K steps

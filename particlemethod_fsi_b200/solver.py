@@ -59,6 +59,7 @@ def _load():
     L.mphx_generate_count.argtypes = [vp, C.c_int]
     L.mphx_generate_count.restype = C.c_longlong
     L.mphx_upload_generated.argtypes = [vp, vp, C.c_int]
+    L.mphx_read_boid_file.argtypes = [C.c_char_p, vp, C.POINTER(vp), ip]
     L.mphx_generate_column_histogram.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, vp]
     L.mphx_multi_upload_generated.argtypes = [vp, vp, C.c_int]
     L.mphx_upload_state.argtypes = [vp, vp, vp]
@@ -243,6 +244,17 @@ def _cuboid_array(cuboids):
         for d in range(3):
             arr[q].lower[d], arr[q].upper[d], arr[q].velocity[d] = float(cb.lower[d]), float(cb.upper[d]), float(cb.velocity[d])
     return arr
+
+
+def read_boid_file(fn: str, params):
+    """the pre-processor's input: fills params' time0 / spacing / domain, returns [cases.Cuboid] (mphx_read_boid_file)"""
+    from . import cases
+    ptr, n = C.c_void_p(), C.c_int()
+    _ck("mphx_read_boid_file", lib.mphx_read_boid_file(fn.encode(), C.byref(params), C.byref(ptr), C.byref(n)))
+    arr = C.cast(ptr, C.POINTER(abi.CuboidC * n.value)).contents
+    out = [cases.Cuboid(int(c.type), tuple(c.lower), tuple(c.upper), float(c.spacing), tuple(c.velocity)) for c in arr]
+    lib.mphx_free_host(ptr)
+    return out
 
 
 def generate_count(cuboids) -> int:

@@ -51,16 +51,7 @@ def test_classes_contiguous_and_sizes():
                     reason="reference generator not built")
 def test_lattice_rule_matches_reference_generator(tmp_path):
     c = cases.tiny3d()
-    boid = tmp_path / "t.boid"
-    with open(boid, "w") as f:
-        p = c.params
-        f.write("ParticleDistance %.17g\n" % p.particle_spacing)
-        f.write("LowerDomain %.17g %.17g %.17g\n" % tuple(p.domain_min))
-        f.write("UpperDomain %.17g %.17g %.17g\n" % tuple(p.domain_max))
-        for cub in c.cuboids:
-            f.write("StartCuboid\n Spacing %.17g\n Type %d\n RigidType 10\n Lower %.17g %.17g %.17g\n"
-                    " Upper %.17g %.17g %.17g\n Velocity 0.0 0.0 0.0\n Enthalpy 0.0\nEndCuboid\n"
-                    % ((cub.spacing, cub.type) + tuple(cub.lower) + tuple(cub.upper)))
+    cases.write_boid_file(str(tmp_path / "t.boid"), c)   # (the same writer feeds mphx_read_boid_file: tests/test_io.py)
     subprocess.run([os.path.join(ROOT, "oracle", "_ref", "GeneratorForMph"), "t"], cwd=tmp_path, check=True,
                    stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     mine = tmp_path / "mine.grid"

@@ -132,3 +132,30 @@ def test_driver_rebalances_the_slabs_in_place(tmp_path):
     for f in outs["one"]:
         assert outs["one"][f] == outs["four"][f], f
     assert "re-balanced the slabs" in logs["four"]
+
+
+@pytest.mark.parametrize("ngpu", ["1", "2"])
+def test_driver_runs_from_the_preprocessor_input(ngpu, tmp_path):
+    """a grid argument ending in .boid: the particles are generated on the device(s) (mphx_upload_generated /
+    mphx_multi_upload_generated) from the pre-processor's own input -- every output file equals the run from the .grid text"""
+    c = cases.tiny3d()
+    c.rc.end_time = 3.5 * c.params.dt
+    c.rc.output_interval = 2.0 * c.params.dt
+    c.rc.vtk_output_interval = 3.0 * c.params.dt
+    outs = {}
+    env = dict(os.environ)
+    if ngpu != "1":
+        env.update(MPHX_NGPU=ngpu, MPHX_DEVICES=",".join(["0"] * int(ngpu)), CUDA_DEVICE_MAX_CONNECTIONS="32")
+    for tag, grid in (("grid", "c.grid"), ("boid", "c.boid")):
+        d = tmp_path / tag
+        d.mkdir()
+        cases.write_grid_file(str(d / "c.grid"), c)
+        cases.write_boid_file(str(d / "c.boid"), c)
+        cases.write_data_file(str(d / "t.data"), c.params, c.rc)
+        r = subprocess.run([EXE, "t.data", grid, "t%03d.prof", "t%03d.vtk", "t.log", "4", "3", "dam"], cwd=d, capture_output=True,
+                           text=True, env=env, timeout=300)
+        assert r.returncode == 0, (r.stdout[-1000:], r.stderr[-2000:])
+        outs[tag] = {f: (d / f).read_bytes() for f in sorted(os.listdir(d)) if f.endswith((".prof", ".vtk"))}
+    assert list(outs["grid"]) == list(outs["boid"]) and len(outs["grid"]) == 5
+    for f in outs["grid"]:
+        assert outs["grid"][f] == outs["boid"][f], f

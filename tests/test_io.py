@@ -119,3 +119,35 @@ def test_checkpoint_round_trip_is_lossless(tmp_path):
         f.write(b"not a checkpoint")
     with pytest.raises(solver.MphxError):
         solver.read_checkpoint(str(tmp_path / "bad.ckp"), q)
+
+
+def test_boid_reader_round_trip_and_errors(tmp_path):
+    """mphx_read_boid_file: the pre-processor's input (header + StartCuboid blocks) -> parameters and cuboids; the cuboids
+    generate exactly the case's particle count; unsupported shapes and incomplete files are errors"""
+    from particlemethod_fsi_b200 import cases, solver
+    for case in (cases.dam2d(), cases.fsi3d_mini(), cases.bar2d()):
+        fn = str(tmp_path / (case.name + ".boid"))
+        cases.write_boid_file(fn, case)
+        p = case.params.copy()
+        p.particle_spacing = -1.0
+        p.domain_min[0] = 123.0
+        cubs = solver.read_boid_file(fn, p)
+        assert len(cubs) == len(case.cuboids)
+        for a, b in zip(cubs, case.cuboids):
+            assert a.type == b.type and a.spacing == b.spacing
+            assert tuple(a.lower) == tuple(b.lower) and tuple(a.upper) == tuple(b.upper) and tuple(a.velocity) == tuple(b.velocity)
+        # header values come back through the `%e` text of the generator's .grid header (here: exactly representable in 7 digits)
+        assert p.particle_spacing == float("%e" % case.params.particle_spacing)
+        assert list(p.domain_min) == [float("%e" % v) for v in case.params.domain_min]
+        assert list(p.domain_max) == [float("%e" % v) for v in case.params.domain_max]
+        assert p.time0 == 0.0
+        assert solver.generate_count(cubs) == case.n
+    bad = tmp_path / "bad.boid"
+    bad.write_text("ParticleDistance 0.001\nLowerDomain 0 0 0\nUpperDomain 1 1 1\nStartCuboid2\nEndCuboid2\n")
+    with pytest.raises(Exception):
+        solver.read_boid_file(str(bad), cases.dam2d().params.copy())
+    bad.write_text("ParticleDistance 0.001\nLowerDomain 0 0 0\nUpperDomain 1 1 1\nStartCuboid\n Spacing 0.001\n Type 1\nEndCuboid\n")
+    with pytest.raises(Exception):
+        solver.read_boid_file(str(bad), cases.dam2d().params.copy())
+    with pytest.raises(Exception):
+        solver.read_boid_file(str(tmp_path / "missing.boid"), cases.dam2d().params.copy())
