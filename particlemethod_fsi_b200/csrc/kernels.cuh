@@ -1408,7 +1408,6 @@ __device__ __forceinline__ void solid_pass2_row(const Solid &so, const int s, do
     constexpr int GI = DEEP ? 8 : MPHX_S2_G; // pairs whose gathers are in flight together
     using namespace ex;
     const int ns = so.ns;
-    const double xi0 = so.x0[s], yi0 = so.y0[s], zi0 = so.z0[s];
     const double ir = inv_density[so.type[s]];
     double v[3] = {so.vx[s], so.vy[s], so.vz[s]};
     // one row (own: sign +, P of s itself; transposed: sign -, P of the listing row j), pipelined like pass 1
